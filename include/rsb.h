@@ -1,0 +1,200 @@
+/*
+ * rsb.h — C ABI of the B200-native CTR hot path (librsb.so).
+ *
+ * Drop-in boundary for chenxing1999/recsys-benchmark: these are the entry
+ * points a Python/ctypes (or any FFI) binding behind the reference's
+ * IEmbedding plugin API (src/models/embeddings/base.py:8-20) and its
+ * DeepFM / DCN_Mix models (src/models/deepfm.py:79-105, src/models/dcn.py:76-96,
+ * src/models/layer_dcn.py:8-115) calls.  Every function cites the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch / C++ types.
+ *  - all data pointers are DEVICE pointers on the current CUDA device unless
+ *    the parameter name starts with `h_` (host).
+ *  - `stream` is a cudaStream_t passed as void*.  Nothing synchronises the
+ *    host; nothing allocates or frees; scratch memory is a caller-provided
+ *    workspace sized by the matching `*_workspace_bytes` query.
+ *  - return value: 0 = ok, 1..9999 = cudaError_t of the failed launch,
+ *    >= 10000 = rsb_status.  No exception crosses this ABI.
+ *  - floating point is fp32, row ids are int64 (or int32 where stated).
+ */
+#ifndef RSB_H_
+#define RSB_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RSB_API __attribute__((visibility("default")))
+#else
+#define RSB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RSB_OK = 0,
+  RSB_ERR_BAD_ARG = 10001,     /* null pointer / negative size / unknown enum */
+  RSB_ERR_UNSUPPORTED = 10002, /* row width outside the kernels' range (see rsb_row_width_supported) */
+  RSB_ERR_WORKSPACE = 10003    /* workspace too small */
+} rsb_status;
+
+/* Which lightweight-embedding variant is applied INSIDE the gather. */
+typedef enum {
+  RSB_KIND_VANILLA = 0,  /* VanillaEmbedding            src/models/embeddings/base.py:23-75          */
+  RSB_KIND_QR_MULT = 1,  /* QRHashingEmbedding "mult"   src/models/embeddings/qr_embedding.py:95-109 */
+  RSB_KIND_QR_ADD = 2,   /*                   "add"                                                  */
+  RSB_KIND_QR_CAT = 3,   /*                   "cat" (concat on the FIELD axis, like the reference)   */
+  RSB_KIND_PEP = 4,      /* PepEmbeeding soft threshold src/models/embeddings/pep_embedding.py:82-92 */
+  RSB_KIND_MASK = 5,     /* RetrainPepEmbedding / RetrainOptEmbed: weight * bool mask
+                            pep_embedding.py:215-221 ; deepfm_opt_embed.py:693-706                   */
+  RSB_KIND_OPTEMBED = 6  /* OptEmbed supernet training  deepfm_opt_embed.py:219-226 ; optembed_utils.py:101-104 */
+} rsb_kind;
+
+/* PEP threshold shapes (pep_embedding.py:94-117): value of `aux_mode` for RSB_KIND_PEP. */
+typedef enum {
+  RSB_PEP_GLOBAL = 0,     /* s[1]    */
+  RSB_PEP_DIMENSION = 1,  /* s[D]    */
+  RSB_PEP_FEATURE = 2,    /* s[N,1]  */
+  RSB_PEP_FEATURE_DIM = 3 /* s[N,D]  */
+} rsb_pep_threshold;
+
+/* What the segmented reduction does with each unique row's summed gradient. */
+typedef enum {
+  RSB_APPLY_DENSE = 0,       /* dst[row,:] = sum  (dst is a zero-filled dense [N,E] grad:
+                                aten embedding_dense_backward semantics, base.py:53-57)             */
+  RSB_APPLY_SPARSE_ADAM = 1, /* torch.optim.SparseAdam row update (src/models/deepfm.py:173-184;
+                                torch/optim/_functional.py:24-84)                                    */
+  RSB_APPLY_SPARSE_SGD = 2   /* sparse SGD, p += -lr*g (src/models/deepfm.py:203-216)              */
+} rsb_apply;
+
+RSB_API const char* rsb_version(void);
+/* Human-readable text for a non-zero return value (cudaGetErrorString for CUDA codes). */
+RSB_API const char* rsb_error_string(int code);
+/* 1 if a row of `width` floats (16-byte aligned when width % 4 == 0) is handled. */
+RSB_API int rsb_row_width_supported(int32_t width);
+
+/* ------------------------------------------------------------------------
+ * Forward: fused gather (+ variant transform) (+ FM second order + first order).
+ *
+ * Replaces, in one launch: `x + offsets` (deepfm.py:88 / dcn.py:84),
+ * IEmbedding.forward (F.embedding call sites base.py:75, qr_embedding.py:99-107,
+ * pep_embedding.py:82-89,215-221, deepfm_opt_embed.py:219-226,704),
+ * the EmbeddingBag first-order term + bias (deepfm.py:49,95) and the FM
+ * interaction (deepfm.py:91-92,98).
+ *
+ *  idx        [B,F] per-field ids, int32 if idx_is_i32 else int64
+ *  offsets    [F] int64 field offsets added to idx, or NULL (ids already global)
+ *  D          embedding width (num_factor).  QR_CAT: out is [B,2F,D/2]
+ *  table      main table [n_rows, E]   (QR: emb2 [(N-1)/divider+1, E])
+ *  table1     QR only: emb1 [divider, E]; divider = QR divider
+ *  aux        PEP: s ; MASK: uint8/bool mask [n_rows,D] ; OPTEMBED: t_param [F] or NULL (mask-E off)
+ *  aux_mode   PEP: rsb_pep_threshold ; OPTEMBED: norm (1 or 2)
+ *  mask_d_idx OPTEMBED: int64 [B,F] draw of torch.randint(0,D) (dims 0..k kept) or NULL
+ *  fc, bias   first-order weights [N_global,1] and bias [1]; NULL -> no FM head (DCN-Mix)
+ *  out_emb    [B,F,D] fp32 (always written)
+ *  out_yfm    [B]  y_fm = first order + 0.5*sum_d((sum_f e)^2 - sum_f e^2), or NULL
+ *  out_sum    [B,E] S = sum_f e, saved for the backward, or NULL
+ *  out_rows   [B,F] int64 global row ids (idx + offsets), or NULL
+ *  err_flag   device int32, set to 1 when an id is out of [0, n_global) (the read is
+ *             clamped to row 0 instead of faulting; torch raises IndexError there)
+ *  n_global   number of addressable ids (sum(field_dims)); for non-QR kinds == n_rows
+ * ---------------------------------------------------------------------- */
+RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx_is_i32, const int64_t* offsets,
+                   int64_t B, int32_t F, int32_t D,
+                   const float* table, int64_t n_rows, int64_t n_global,
+                   const float* table1, int64_t divider,
+                   const void* aux, int32_t aux_mode, const int64_t* mask_d_idx,
+                   const float* fc, const float* bias,
+                   float* out_emb, float* out_yfm, float* out_sum, int64_t* out_rows,
+                   int32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward, stage 1: per-lookup row gradients.
+ *
+ * g_out[b,f,:] = g_deep[b,f,:] + g_yfm[b] * (S[b,:] - emb[b,f,:])   (autograd of deepfm.py:91-102)
+ * then the variant's chain rule, written as one compact row per lookup:
+ *   VANILLA   rg_main = g_out
+ *   MASK      rg_main = g_out * mask[row]
+ *   QR_MULT   rg_main(emb2) = g_out * emb1[i1] ; rg_aux(emb1) = g_out * emb2[i2]
+ *   QR_ADD    rg_main = rg_aux = g_out (rg_aux may be NULL: same array)
+ *   QR_CAT    rg_aux = g_out[:, :F] ; rg_main = g_out[:, F:]
+ *   PEP       rg_main = g_out * 1[|v|>sig(s)] ; rg_aux = -g_out*sign(v)*1[..]*sig(s)(1-sig(s))
+ *   OPTEMBED  rg_main = d/d weight row incl. the BinaryStep surrogate (optembed_utils.py:35-44);
+ *             rg_aux[b,f] (ONE float per lookup) = g_z, so that g_t[f] = -sum_b rg_aux[b,f]
+ * Also accumulates the first-order weight gradient: fc_grad[row] += g_yfm[b] (atomic, dense [N,1]).
+ *
+ *  rows      [B,F] int64 global ids saved by the forward
+ *  emb, S    forward outputs (emb may be NULL when g_yfm is NULL and the kind does not need it)
+ *  g_yfm     [B] or NULL ; g_deep [B,F*D] or NULL (at least one non-NULL)
+ * ---------------------------------------------------------------------- */
+RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                        const float* table, int64_t n_rows, const float* table1, int64_t divider,
+                        const void* aux, int32_t aux_mode, const int64_t* mask_d_idx,
+                        const float* emb, const float* S, const float* g_yfm, const float* g_deep,
+                        float* rg_main, float* rg_aux, float* fc_grad, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward, stage 2: stable LSD radix sort of the lookups by target row.
+ *
+ *  keys       [n] int64 row ids in [0, n_rows)  (optionally transformed: key = id / key_div
+ *             when key_div > 1, key = id % key_mod when key_mod > 0 — the bit-exact QR index
+ *             math of qr_embedding.py:96-97)
+ *  sorted_keys [n] uint32, perm [n] uint32 (perm[j] = original lookup position)
+ * ---------------------------------------------------------------------- */
+RSB_API int64_t rsb_sort_workspace_bytes(int64_t n);
+RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_rows, int64_t key_div, int64_t key_mod,
+                  uint32_t* sorted_keys, uint32_t* perm, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * Backward, stage 3: deterministic segmented reduction over the sorted lookups
+ * and application of the result (dense grad row / fused SparseAdam / fused SGD).
+ * Replaces aten embedding_dense_backward resp. coalesce + torch.optim.SparseAdam /
+ * SGD (src/models/deepfm.py:173-216).
+ *
+ *  row_grads  [n, E] per-lookup gradients (stage 1), E = row width
+ *  dst        APPLY_DENSE: zero-filled dense grad [n_rows,E]; ADAM/SGD: the weight table
+ *  exp_avg, exp_avg_sq   SparseAdam state [n_rows,E] (ADAM only)
+ *  lr, beta1, beta2, eps, step   optimizer hyper-parameters; step is the 1-based step count
+ * ---------------------------------------------------------------------- */
+RSB_API int64_t rsb_segment_workspace_bytes(int64_t n, int32_t E);
+RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
+                             const float* row_grads, int32_t E,
+                             float* dst, float* exp_avg, float* exp_avg_sq,
+                             float lr, float beta1, float beta2, float eps, int64_t step,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Small-table gradient (QR emb1 has `divider` = 2..~1000 rows; qr_embedding.py:59): shared-memory
+ * accumulation per CTA, fixed-order cross-CTA reduction.  dst[n_rows,E] is overwritten.
+ * keys as in rsb_sort_rows (key_div / key_mod transform).  */
+RSB_API int64_t rsb_small_table_workspace_bytes(int64_t n_rows, int32_t E);
+RSB_API int rsb_small_table_grad(const int64_t* keys, int64_t n, int64_t key_div, int64_t key_mod,
+                         const float* row_grads, int32_t E, int64_t n_rows, float* dst,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Full-table helpers of the variants.
+ * ---------------------------------------------------------------------- */
+/* PEP get_weight / get_num_params (pep_embedding.py:78-80,127-130): out (may be NULL) =
+ * soft_threshold(weight, s); *count (device int64, may be NULL) += number of non-zeros. */
+RSB_API int rsb_pep_threshold_table(const float* weight, const float* s, int32_t threshold_type, int64_t n_rows,
+                            int32_t D, float* out, int64_t* count, void* stream);
+/* PEP dense backward epilogue: given g_table (dense grad wrt the thresholded table) produce
+ * g_weight and g_s_full [N,D] in one pass (autograd of pep_embedding.py:91-92). */
+RSB_API int rsb_pep_dense_bwd(const float* weight, const float* s, int32_t threshold_type, int64_t n_rows, int32_t D,
+                      const float* g_table, float* g_weight, float* g_s_full, void* stream);
+/* OptEmbed eval-mode weight (deepfm_opt_embed.py:148-202; optembed_utils.py:88-99):
+ * out[row,:] = weight[row,:] * 1[norm(weight[row]) - t_row[row] > 0] * tril[d <= mask_d_row[row]].
+ * t_row [N] per-feature thresholds or NULL; mask_d_row [N] int64 or NULL. count as above. */
+RSB_API int rsb_optembed_eval_weight(const float* weight, const float* t_row, const int64_t* mask_d_row, int32_t norm,
+                             int64_t n_rows, int32_t D, float* out, int64_t* count, void* stream);
+/* out = weight * mask (uint8) : RetrainPepEmbedding.get_weight / RetrainOptEmbed.get_weight. */
+RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, int64_t numel, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSB_H_ */

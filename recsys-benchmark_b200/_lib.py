@@ -1,0 +1,104 @@
+"""ctypes binding of librsb.so (include/rsb.h).  No torch types cross the boundary:
+tensors are passed as raw device pointers + sizes, the stream as a void*.
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librsb.so")
+
+# enums of include/rsb.h
+KIND_VANILLA, KIND_QR_MULT, KIND_QR_ADD, KIND_QR_CAT, KIND_PEP, KIND_MASK, KIND_OPTEMBED = range(7)
+PEP_GLOBAL, PEP_DIMENSION, PEP_FEATURE, PEP_FEATURE_DIM = range(4)
+APPLY_DENSE, APPLY_SPARSE_ADAM, APPLY_SPARSE_SGD = range(3)
+
+PEP_TYPES = {"global": PEP_GLOBAL, "dimension": PEP_DIMENSION, "feature": PEP_FEATURE,
+             "feature_dim": PEP_FEATURE_DIM}
+QR_KINDS = {"mult": KIND_QR_MULT, "add": KIND_QR_ADD, "cat": KIND_QR_CAT}
+
+_p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/rsb.h declares
+PROTOTYPES = {
+    "rsb_version": (C.c_char_p, []),
+    "rsb_error_string": (C.c_char_p, [C.c_int]),
+    "rsb_row_width_supported": (C.c_int, [_i32]),
+    "rsb_lookup_fwd": (C.c_int, [_i32, _p, _i32, _p, _i64, _i32, _i32, _p, _i64, _i64, _p, _i64, _p, _i32, _p,
+                                 _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rsb_lookup_bwd_rows": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p,
+                                      _p, _p, _p, _p]),
+    "rsb_sort_workspace_bytes": (_i64, [_i64]),
+    "rsb_sort_rows": (C.c_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
+    "rsb_segment_workspace_bytes": (_i64, [_i64, _i32]),
+    "rsb_segment_reduce_apply": (C.c_int, [_i32, _p, _p, _i64, _p, _i32, _p, _p, _p, _f, _f, _f, _f, _i64, _p,
+                                           _i64, _p]),
+    "rsb_small_table_workspace_bytes": (_i64, [_i64, _i32]),
+    "rsb_small_table_grad": (C.c_int, [_p, _i64, _i64, _i64, _p, _i32, _i64, _p, _p, _i64, _p]),
+    "rsb_pep_threshold_table": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    "rsb_pep_dense_bwd": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
+    "rsb_optembed_eval_weight": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
+    "rsb_mask_table": (C.c_int, [_p, _p, _i64, _p, _p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load librsb.so (built in-tree by build.py).  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"rsb: {LIB_PATH} not found. Build it with `python recsys-benchmark_b200/build.py` "
+            "(or __graft_entry__.build()). There is no CPU / PyTorch fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def version() -> str:
+    return load().rsb_version().decode()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().rsb_error_string(int(rc)).decode()
+        raise RuntimeError(f"rsb {what} failed (code {rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def require_cuda(*tensors) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("rsb: the hot path runs on CUDA tensors only (no CPU fallback); "
+                               "move the module and its inputs to a B200 device")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"rsb: tensors on different devices ({dev} vs {t.device})")
+    return dev

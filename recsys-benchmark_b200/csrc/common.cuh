@@ -1,0 +1,148 @@
+// Shared device helpers for librsb (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rsb.h"
+
+#define RSB_CHECK_LAUNCH()                         \
+  do {                                             \
+    cudaError_t _e = cudaGetLastError();           \
+    if (_e != cudaSuccess) return (int)_e;         \
+  } while (0)
+
+namespace rsb {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// A row chunk of V floats held in registers. V = 4 -> one 128-bit access.
+template <int V>
+struct FV {
+  float v[V];
+  __device__ __forceinline__ static FV zero() {
+    FV r;
+#pragma unroll
+    for (int i = 0; i < V; ++i) r.v[i] = 0.f;
+    return r;
+  }
+};
+
+template <int V>
+__device__ __forceinline__ FV<V> ldg(const float* p);
+template <>
+__device__ __forceinline__ FV<4> ldg<4>(const float* p) {
+  float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  FV<4> r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+template <>
+__device__ __forceinline__ FV<1> ldg<1>(const float* p) {
+  FV<1> r;
+  r.v[0] = __ldg(p);
+  return r;
+}
+// plain (coherent) load: for tables that this same kernel also writes
+template <int V>
+__device__ __forceinline__ FV<V> ld(const float* p);
+template <>
+__device__ __forceinline__ FV<4> ld<4>(const float* p) {
+  float4 t = *reinterpret_cast<const float4*>(p);
+  FV<4> r;
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  return r;
+}
+template <>
+__device__ __forceinline__ FV<1> ld<1>(const float* p) {
+  FV<1> r;
+  r.v[0] = *p;
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void st(float* p, const FV<V>& x);
+template <>
+__device__ __forceinline__ void st<4>(float* p, const FV<4>& x) {
+  *reinterpret_cast<float4*>(p) = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+}
+template <>
+__device__ __forceinline__ void st<1>(float* p, const FV<1>& x) {
+  *p = x.v[0];
+}
+// streaming store: written once, not re-read by this kernel
+template <int V>
+__device__ __forceinline__ void st_cs(float* p, const FV<V>& x);
+template <>
+__device__ __forceinline__ void st_cs<4>(float* p, const FV<4>& x) {
+  __stcs(reinterpret_cast<float4*>(p), make_float4(x.v[0], x.v[1], x.v[2], x.v[3]));
+}
+template <>
+__device__ __forceinline__ void st_cs<1>(float* p, const FV<1>& x) {
+  __stcs(p, x.v[0]);
+}
+
+template <int V>
+__device__ __forceinline__ FV<V> shfl_xor(const FV<V>& x, int off) {
+  FV<V> r;
+#pragma unroll
+  for (int i = 0; i < V; ++i) r.v[i] = __shfl_xor_sync(kFull, x.v[i], off);
+  return r;
+}
+
+__device__ __forceinline__ float sigmoidf_exact(float s) { return 1.0f / (1.0f + expf(-s)); }
+
+// Lanes-per-row for a row of `chunks` vector chunks: next power of two, <= 32.
+inline int lanes_per_row(int chunks) {
+  int l = 1;
+  while (l < chunks) l <<= 1;
+  return l;
+}
+
+struct RowShape {
+  int V;    // floats per lane access (4 or 1)
+  int LPR;  // lanes per row (power of two)
+  bool ok;
+};
+inline RowShape row_shape(int E, bool aligned16) {
+  RowShape s;
+  s.ok = true;
+  if (E > 0 && E % 4 == 0 && aligned16 && E <= 128) {
+    s.V = 4;
+    s.LPR = lanes_per_row(E / 4);
+  } else if (E > 0 && E <= 32) {
+    s.V = 1;
+    s.LPR = lanes_per_row(E);
+  } else {
+    s.V = 0; s.LPR = 0; s.ok = false;
+  }
+  return s;
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int sm_count();
+
+// Dispatch helper: calls F.template run<V, LPR>() for the runtime shape.
+#define RSB_DISPATCH_SHAPE(shape, CALL)                       \
+  do {                                                        \
+    if ((shape).V == 4) {                                     \
+      switch ((shape).LPR) {                                  \
+        case 1: { CALL(4, 1); } break;                        \
+        case 2: { CALL(4, 2); } break;                        \
+        case 4: { CALL(4, 4); } break;                        \
+        case 8: { CALL(4, 8); } break;                        \
+        case 16: { CALL(4, 16); } break;                      \
+        default: { CALL(4, 32); } break;                      \
+      }                                                       \
+    } else {                                                  \
+      switch ((shape).LPR) {                                  \
+        case 1: { CALL(1, 1); } break;                        \
+        case 2: { CALL(1, 2); } break;                        \
+        case 4: { CALL(1, 4); } break;                        \
+        case 8: { CALL(1, 8); } break;                        \
+        case 16: { CALL(1, 16); } break;                      \
+        default: { CALL(1, 32); } break;                      \
+      }                                                       \
+    }                                                         \
+  } while (0)
+
+}  // namespace rsb

@@ -1,0 +1,488 @@
+// Fused gather (+ lightweight-embedding transform) + FM forward, and the per-lookup
+// backward (stage 1).  One warp per sample; a row of E floats is spread over LPR lanes
+// with 128-bit accesses (V = 4) so a warp touches 32/LPR random rows per instruction and
+// every 32-byte sector it requests is fully used.  Field-axis reductions are xor-shuffles
+// over the lane groups.
+//
+// Reference semantics (paths relative to /root/reference):
+//   offsets add          src/models/deepfm.py:88, src/models/dcn.py:84
+//   vanilla gather       src/models/embeddings/base.py:75
+//   QR                   src/models/embeddings/qr_embedding.py:95-109
+//   PEP soft threshold   src/models/embeddings/pep_embedding.py:82-92
+//   retrain masks        pep_embedding.py:215-221, deepfm_opt_embed.py:693-706
+//   OptEmbed supernet    deepfm_opt_embed.py:219-226, optembed_utils.py:25-44,101-104
+//   first order + FM     src/models/deepfm.py:49,91-98
+#include "common.cuh"
+
+namespace rsb {
+
+struct LookupArgs {
+  const void* idx;
+  int idx_i32;
+  const long long* offsets;
+  const long long* rows_in;  // backward: saved global rows
+  long long B;
+  int F, VF, E;
+  const float* table;
+  long long n_rows, n_global;
+  const float* table1;
+  long long divider;
+  int small32;
+  const void* aux;
+  int aux_mode;
+  const long long* mask_d;
+  const float* fc;
+  const float* bias;
+  // forward outputs
+  float* out_emb;
+  float* out_y;
+  float* out_sum;
+  long long* out_rows;
+  int* err;
+  // backward inputs / outputs
+  const float* emb;
+  const float* S;
+  const float* g_y;
+  const float* g_deep;
+  float* rg_main;
+  float* rg_aux;
+  float* fc_grad;
+};
+
+__device__ __forceinline__ void qr_split(const LookupArgs& a, long long row, long long& i1, long long& i2) {
+  if (a.small32) {
+    unsigned r = (unsigned)row, d = (unsigned)a.divider;
+    unsigned q = r / d;
+    i2 = q;
+    i1 = r - q * d;
+  } else {
+    i2 = row / a.divider;
+    i1 = row - i2 * a.divider;
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+  for (int off = 1; off < LPR; off <<= 1) x += __shfl_xor_sync(kFull, x, off);
+  return x;
+}
+
+__device__ __forceinline__ float pep_s(const LookupArgs& a, long long row, int d) {
+  const float* s = reinterpret_cast<const float*>(a.aux);
+  switch (a.aux_mode) {
+    case RSB_PEP_GLOBAL: return __ldg(s);
+    case RSB_PEP_DIMENSION: return __ldg(s + d);
+    case RSB_PEP_FEATURE: return __ldg(s + row);
+    default: return __ldg(s + row * a.E + d);
+  }
+}
+
+// BinaryStep surrogate gradient (optembed_utils.py:35-44)
+__device__ __forceinline__ float binary_step_grad(float z) {
+  float az = fabsf(z);
+  if (az > 1.0f) return 0.0f;
+  if (az > 0.4f) return 0.4f;
+  return 2.0f - 4.0f * az;
+}
+
+// Transformed row chunk for lookup (b, vf).  Must be called by ALL lanes of the warp
+// (OPTEMBED reduces over the lane group); `act` = this lane owns a valid (row, chunk).
+template <int K, int V, int LPR>
+__device__ __forceinline__ FV<V> load_transformed(const LookupArgs& a, long long row, long long b, int f, int vf,
+                                                  int c, bool act) {
+  FV<V> e = FV<V>::zero();
+  const int d0 = c * V;
+  if (K == RSB_KIND_VANILLA) {
+    if (act) e = ldg<V>(a.table + row * a.E + d0);
+  } else if (K == RSB_KIND_QR_MULT || K == RSB_KIND_QR_ADD) {
+    if (act) {
+      long long i1, i2;
+      qr_split(a, row, i1, i2);
+      FV<V> e1 = ldg<V>(a.table1 + i1 * a.E + d0);
+      FV<V> e2 = ldg<V>(a.table + i2 * a.E + d0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) e.v[i] = (K == RSB_KIND_QR_MULT) ? e1.v[i] * e2.v[i] : e1.v[i] + e2.v[i];
+    }
+  } else if (K == RSB_KIND_QR_CAT) {
+    if (act) {
+      long long i1, i2;
+      qr_split(a, row, i1, i2);
+      e = (vf < a.F) ? ldg<V>(a.table1 + i1 * a.E + d0) : ldg<V>(a.table + i2 * a.E + d0);
+    }
+  } else if (K == RSB_KIND_PEP) {
+    if (act) {
+      FV<V> w = ldg<V>(a.table + row * a.E + d0);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float sg = sigmoidf_exact(pep_s(a, row, d0 + i));
+        float m = fmaxf(fabsf(w.v[i]) - sg, 0.0f);
+        e.v[i] = (w.v[i] > 0.f) ? m : ((w.v[i] < 0.f) ? -m : 0.0f * m);
+      }
+    }
+  } else if (K == RSB_KIND_MASK) {
+    if (act) {
+      FV<V> w = ldg<V>(a.table + row * a.E + d0);
+      const unsigned char* m = reinterpret_cast<const unsigned char*>(a.aux) + row * a.E + d0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) e.v[i] = w.v[i] * (float)(m[i] != 0);
+    }
+  } else if (K == RSB_KIND_OPTEMBED) {
+    FV<V> w = FV<V>::zero();
+    if (act) w = ldg<V>(a.table + row * a.E + d0);
+    float keep = 1.0f;
+    if (a.aux != nullptr) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) part += (a.aux_mode == 2) ? w.v[i] * w.v[i] : fabsf(w.v[i]);
+      float nrm = group_sum<LPR>(part);
+      if (a.aux_mode == 2) nrm = sqrtf(nrm);
+      float t = act ? __ldg(reinterpret_cast<const float*>(a.aux) + f) : 0.f;
+      keep = (nrm - t > 0.0f) ? 1.0f : 0.0f;
+    }
+    long long k = (a.mask_d != nullptr && act) ? __ldg(a.mask_d + b * a.F + f) : (long long)a.E;
+#pragma unroll
+    for (int i = 0; i < V; ++i) e.v[i] = ((long long)(d0 + i) <= k) ? w.v[i] * keep : 0.0f * w.v[i];
+  }
+  return e;
+}
+
+__device__ __forceinline__ long long load_id(const LookupArgs& a, long long b, int f) {
+  long long id = a.idx_i32 ? (long long)__ldg(reinterpret_cast<const int*>(a.idx) + b * a.F + f)
+                           : __ldg(reinterpret_cast<const long long*>(a.idx) + b * a.F + f);
+  if (a.offsets) id += __ldg(a.offsets + f);
+  return id;
+}
+
+template <int K, int V, int LPR>
+__global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
+  constexpr int GPW = kWarp / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, c = lane % LPR;
+  const bool cact = c * V < a.E;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool fm = a.out_y != nullptr || a.out_sum != nullptr;
+
+  for (long long b = warp; b < a.B; b += nwarps) {
+    FV<V> S = FV<V>::zero(), Q = FV<V>::zero();
+    float first = 0.f;
+    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW) {
+      const int vf = vf0 + g;
+      const bool vact = vf < a.VF;
+      const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
+      long long row = 0;
+      if (vact) {
+        row = load_id(a, b, f);
+        if (row < 0 || row >= a.n_global) {
+          if (a.err) *a.err = 1;
+          row = 0;
+        }
+        if (c == 0 && vf < a.F) {
+          if (a.out_rows) a.out_rows[b * a.F + f] = row;
+          if (a.fc) first += __ldg(a.fc + row);
+        }
+      }
+      const bool act = vact && cact;
+      FV<V> e = load_transformed<K, V, LPR>(a, row, b, f, vf, c, act);
+      if (act) {
+        st<V>(a.out_emb + ((b * a.VF + vf) * (long long)a.E + c * V), e);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          S.v[i] += e.v[i];
+          Q.v[i] = fmaf(e.v[i], e.v[i], Q.v[i]);
+        }
+      }
+    }
+    if (fm) {
+#pragma unroll
+      for (int off = LPR; off < kWarp; off <<= 1) {
+        FV<V> s2 = shfl_xor<V>(S, off), q2 = shfl_xor<V>(Q, off);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          S.v[i] += s2.v[i];
+          Q.v[i] += q2.v[i];
+        }
+      }
+      float y2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) y2 += S.v[i] * S.v[i] - Q.v[i];
+      y2 = group_sum<LPR>(y2);
+#pragma unroll
+      for (int off = 1; off < kWarp; off <<= 1) first += __shfl_xor_sync(kFull, first, off);
+      if (a.out_sum && g == 0 && cact) st<V>(a.out_sum + b * a.E + c * V, S);
+      if (a.out_y && lane == 0) {
+        float x1 = first + (a.bias ? __ldg(a.bias) : 0.f);
+        a.out_y[b] = x1 + 0.5f * y2;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Backward stage 1
+// ---------------------------------------------------------------------------------
+template <int K, int V, int LPR>
+__global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
+  constexpr int GPW = kWarp / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, c = lane % LPR;
+  const bool cact = c * V < a.E;
+  const int d0 = c * V;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+
+  for (long long b = warp; b < a.B; b += nwarps) {
+    const float gy = a.g_y ? __ldg(a.g_y + b) : 0.f;
+    FV<V> S = FV<V>::zero();
+    if (a.g_y && cact) S = ldg<V>(a.S + b * a.E + d0);
+    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW) {
+      const int vf = vf0 + g;
+      const bool vact = vf < a.VF;
+      const bool act = vact && cact;
+      const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
+      const long long row = vact ? __ldg(a.rows_in + b * a.F + f) : 0;
+      const long long o = (b * a.VF + vf) * (long long)a.E + d0;  // offset into [B,VF,E]
+      const long long p = (b * a.F + f) * (long long)a.E + d0;    // offset into [n,E] per-lookup arrays
+      FV<V> go = FV<V>::zero();
+      if (act) {
+        if (a.g_deep) go = ldg<V>(a.g_deep + o);
+        if (a.g_y) {
+          FV<V> e = ldg<V>(a.emb + o);
+#pragma unroll
+          for (int i = 0; i < V; ++i) go.v[i] = fmaf(gy, S.v[i] - e.v[i], go.v[i]);
+        }
+      }
+      if (a.fc_grad && a.g_y && vact && c == 0 && vf < a.F) atomicAdd(a.fc_grad + row, gy);
+
+      if (K == RSB_KIND_VANILLA) {
+        if (act) st<V>(a.rg_main + p, go);
+      } else if (K == RSB_KIND_MASK) {
+        if (act) {
+          const unsigned char* m = reinterpret_cast<const unsigned char*>(a.aux) + row * a.E + d0;
+          FV<V> r;
+#pragma unroll
+          for (int i = 0; i < V; ++i) r.v[i] = go.v[i] * (float)(m[i] != 0);
+          st<V>(a.rg_main + p, r);
+        }
+      } else if (K == RSB_KIND_QR_MULT) {
+        if (act) {
+          long long i1, i2;
+          qr_split(a, row, i1, i2);
+          FV<V> e1 = ldg<V>(a.table1 + i1 * a.E + d0);
+          FV<V> e2 = ldg<V>(a.table + i2 * a.E + d0);
+          FV<V> r1, r2;
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            r2.v[i] = go.v[i] * e1.v[i];
+            r1.v[i] = go.v[i] * e2.v[i];
+          }
+          st<V>(a.rg_main + p, r2);
+          st<V>(a.rg_aux + p, r1);
+        }
+      } else if (K == RSB_KIND_QR_ADD) {
+        if (act) {
+          st<V>(a.rg_main + p, go);
+          if (a.rg_aux && a.rg_aux != a.rg_main) st<V>(a.rg_aux + p, go);
+        }
+      } else if (K == RSB_KIND_QR_CAT) {
+        if (act) st<V>((vf < a.F ? a.rg_aux : a.rg_main) + p, go);
+      } else if (K == RSB_KIND_PEP) {
+        if (act) {
+          FV<V> w = ldg<V>(a.table + row * a.E + d0);
+          FV<V> rw, rs;
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float sg = sigmoidf_exact(pep_s(a, row, d0 + i));
+            bool keep = (fabsf(w.v[i]) - sg) > 0.0f;
+            float sgn = (w.v[i] > 0.f) ? 1.f : ((w.v[i] < 0.f) ? -1.f : 0.f);
+            rw.v[i] = keep ? go.v[i] * sgn * sgn : 0.f;
+            rs.v[i] = keep ? -(go.v[i] * sgn) * (sg * (1.0f - sg)) : 0.f;
+          }
+          st<V>(a.rg_main + p, rw);
+          if (a.rg_aux) st<V>(a.rg_aux + p, rs);
+        }
+      } else if (K == RSB_KIND_OPTEMBED) {
+        FV<V> w = FV<V>::zero();
+        if (act) w = ldg<V>(a.table + row * a.E + d0);
+        long long k = (a.mask_d != nullptr && vact) ? __ldg(a.mask_d + b * a.F + f) : (long long)a.E;
+        FV<V> u;
+#pragma unroll
+        for (int i = 0; i < V; ++i) u.v[i] = ((long long)(d0 + i) <= k) ? go.v[i] : 0.f;
+        FV<V> r = u;
+        if (a.aux != nullptr) {
+          float pn = 0.f, pd = 0.f;
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            pn += (a.aux_mode == 2) ? w.v[i] * w.v[i] : fabsf(w.v[i]);
+            pd = fmaf(u.v[i], w.v[i], pd);
+          }
+          float nrm = group_sum<LPR>(pn);
+          float gme = group_sum<LPR>(pd);
+          if (a.aux_mode == 2) nrm = sqrtf(nrm);
+          float t = vact ? __ldg(reinterpret_cast<const float*>(a.aux) + f) : 0.f;
+          float z = nrm - t;
+          float me = (z > 0.f) ? 1.f : 0.f;
+          float gz = gme * binary_step_grad(z);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float dn;
+            if (a.aux_mode == 2) dn = (nrm > 0.f) ? w.v[i] / nrm : 0.f;
+            else dn = (w.v[i] > 0.f) ? 1.f : ((w.v[i] < 0.f) ? -1.f : 0.f);
+            r.v[i] = fmaf(gz, dn, u.v[i] * me);
+          }
+          if (a.rg_aux && vact && c == 0) a.rg_aux[b * a.F + f] = gz;
+        }
+        if (act) st<V>(a.rg_main + p, r);
+      }
+    }
+  }
+}
+
+template <int K>
+static int launch_fwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
+  const int threads = 256;
+  long long warps_needed = a.B;
+  long long blocks = (warps_needed * 32 + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 32;  // grid-stride beyond this
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define CALL(VV, LL) lookup_fwd_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
+  RSB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+  RSB_CHECK_LAUNCH();
+  return RSB_OK;
+}
+
+template <int K>
+static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
+  const int threads = 256;
+  long long blocks = (a.B * 32 + threads - 1) / threads;
+  long long cap = (long long)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define CALL(VV, LL) lookup_bwd_rows_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
+  RSB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+  RSB_CHECK_LAUNCH();
+  return RSB_OK;
+}
+
+static int fill_common(LookupArgs& a, int kind, long long B, int F, int D, const float* table, long long n_rows,
+                       long long n_global, const float* table1, long long divider, const void* aux, int aux_mode,
+                       RowShape& sh, bool extra_aligned) {
+  if (B < 0 || F <= 0 || D <= 0 || table == nullptr) return RSB_ERR_BAD_ARG;
+  if (kind < RSB_KIND_VANILLA || kind > RSB_KIND_OPTEMBED) return RSB_ERR_BAD_ARG;
+  a.B = B;
+  a.F = F;
+  a.E = D;
+  a.VF = F;
+  if (kind == RSB_KIND_QR_CAT) {
+    if (D % 2) return RSB_ERR_BAD_ARG;
+    a.E = D / 2;
+    a.VF = 2 * F;
+  }
+  if (kind >= RSB_KIND_QR_MULT && kind <= RSB_KIND_QR_CAT) {
+    if (table1 == nullptr || divider <= 0) return RSB_ERR_BAD_ARG;
+  }
+  if ((kind == RSB_KIND_PEP || kind == RSB_KIND_MASK) && aux == nullptr) return RSB_ERR_BAD_ARG;
+  if (kind == RSB_KIND_PEP && (aux_mode < RSB_PEP_GLOBAL || aux_mode > RSB_PEP_FEATURE_DIM)) return RSB_ERR_BAD_ARG;
+  if (kind == RSB_KIND_OPTEMBED && aux != nullptr && aux_mode != 1 && aux_mode != 2) return RSB_ERR_BAD_ARG;
+  a.table = table;
+  a.n_rows = n_rows;
+  a.n_global = n_global;
+  a.table1 = table1;
+  a.divider = divider;
+  a.small32 = (n_global < (1ll << 32) && divider < (1ll << 32)) ? 1 : 0;
+  a.aux = aux;
+  a.aux_mode = aux_mode;
+  bool al = aligned16(table) && (table1 == nullptr || aligned16(table1)) && extra_aligned;
+  sh = row_shape(a.E, al);
+  if (!sh.ok) return RSB_ERR_UNSUPPORTED;
+  return RSB_OK;
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,
+                              int32_t F, int32_t D, const float* table, int64_t n_rows, int64_t n_global,
+                              const float* table1, int64_t divider, const void* aux, int32_t aux_mode,
+                              const int64_t* mask_d_idx, const float* fc, const float* bias, float* out_emb,
+                              float* out_yfm, float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream) {
+  LookupArgs a = {};
+  RowShape sh;
+  if (idx == nullptr || out_emb == nullptr) return RSB_ERR_BAD_ARG;
+  bool al = aligned16(out_emb) && (out_sum == nullptr || aligned16(out_sum));
+  int rc = fill_common(a, kind, B, F, D, table, n_rows, n_global, table1, divider, aux, aux_mode, sh, al);
+  if (rc) return rc;
+  if (B == 0) return RSB_OK;
+  a.idx = idx;
+  a.idx_i32 = idx_is_i32;
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  a.mask_d = reinterpret_cast<const long long*>(mask_d_idx);
+  a.fc = fc;
+  a.bias = bias;
+  a.out_emb = out_emb;
+  a.out_y = out_yfm;
+  a.out_sum = out_sum;
+  a.out_rows = reinterpret_cast<long long*>(out_rows);
+  a.err = err_flag;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (kind) {
+    case RSB_KIND_VANILLA: return launch_fwd<RSB_KIND_VANILLA>(a, sh, s);
+    case RSB_KIND_QR_MULT: return launch_fwd<RSB_KIND_QR_MULT>(a, sh, s);
+    case RSB_KIND_QR_ADD: return launch_fwd<RSB_KIND_QR_ADD>(a, sh, s);
+    case RSB_KIND_QR_CAT: return launch_fwd<RSB_KIND_QR_CAT>(a, sh, s);
+    case RSB_KIND_PEP: return launch_fwd<RSB_KIND_PEP>(a, sh, s);
+    case RSB_KIND_MASK: return launch_fwd<RSB_KIND_MASK>(a, sh, s);
+    default: return launch_fwd<RSB_KIND_OPTEMBED>(a, sh, s);
+  }
+}
+
+extern "C" RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                                   const float* table, int64_t n_rows, const float* table1, int64_t divider,
+                                   const void* aux, int32_t aux_mode, const int64_t* mask_d_idx, const float* emb,
+                                   const float* S, const float* g_yfm, const float* g_deep, float* rg_main,
+                                   float* rg_aux, float* fc_grad, void* stream) {
+  LookupArgs a = {};
+  RowShape sh;
+  if (rows == nullptr || rg_main == nullptr) return RSB_ERR_BAD_ARG;
+  if (g_yfm == nullptr && g_deep == nullptr) return RSB_ERR_BAD_ARG;
+  if (g_yfm != nullptr && (emb == nullptr || S == nullptr)) return RSB_ERR_BAD_ARG;
+  if ((kind == RSB_KIND_QR_MULT || kind == RSB_KIND_QR_CAT) && rg_aux == nullptr) return RSB_ERR_BAD_ARG;
+  bool al = aligned16(rg_main) && (rg_aux == nullptr || kind == RSB_KIND_OPTEMBED || aligned16(rg_aux)) &&
+            (emb == nullptr || aligned16(emb)) && (S == nullptr || aligned16(S)) &&
+            (g_deep == nullptr || aligned16(g_deep));
+  int rc = fill_common(a, kind, B, F, D, table, n_rows, /*n_global=*/(1ll << 62), table1, divider, aux, aux_mode, sh,
+                       al);
+  if (rc) return rc;
+  if (B == 0) return RSB_OK;
+  // small32 must match the forward's index math: rows were validated there
+  a.small32 = (divider < (1ll << 32)) ? 1 : 0;
+  if (kind >= RSB_KIND_QR_MULT && kind <= RSB_KIND_QR_CAT) {
+    // emb2 has n_rows rows, so every id is < n_rows * divider
+    long double lim = (long double)n_rows * (long double)divider;
+    a.small32 = (lim < 4294967296.0L && divider < (1ll << 32)) ? 1 : 0;
+  }
+  a.rows_in = reinterpret_cast<const long long*>(rows);
+  a.mask_d = reinterpret_cast<const long long*>(mask_d_idx);
+  a.emb = emb;
+  a.S = S;
+  a.g_y = g_yfm;
+  a.g_deep = g_deep;
+  a.rg_main = rg_main;
+  a.rg_aux = rg_aux;
+  a.fc_grad = fc_grad;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (kind) {
+    case RSB_KIND_VANILLA: return launch_bwd<RSB_KIND_VANILLA>(a, sh, s);
+    case RSB_KIND_QR_MULT: return launch_bwd<RSB_KIND_QR_MULT>(a, sh, s);
+    case RSB_KIND_QR_ADD: return launch_bwd<RSB_KIND_QR_ADD>(a, sh, s);
+    case RSB_KIND_QR_CAT: return launch_bwd<RSB_KIND_QR_CAT>(a, sh, s);
+    case RSB_KIND_PEP: return launch_bwd<RSB_KIND_PEP>(a, sh, s);
+    case RSB_KIND_MASK: return launch_bwd<RSB_KIND_MASK>(a, sh, s);
+    default: return launch_bwd<RSB_KIND_OPTEMBED>(a, sh, s);
+  }
+}

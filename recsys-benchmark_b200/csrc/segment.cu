@@ -1,0 +1,248 @@
+// Backward stage 3: deterministic segmented reduction of per-lookup row gradients over
+// the row-sorted lookups, with the consumer fused in (dense grad row write, SparseAdam
+// row update, sparse SGD row update).
+//
+// Work is split by POSITION, not by segment, so hot rows (a 4-value field looked up by
+// every sample) cannot unbalance it: every lane group (LPR lanes = one row wide) walks a
+// chunk of kChunk consecutive sorted positions and sums runs of equal row ids in
+// registers.  A run that lies inside one chunk is final and is applied at once.  A run
+// that crosses a chunk boundary leaves one partial per chunk (part_first / part_last);
+// a second launch with one lane group per chunk boundary adds the partials of a run in
+// chunk order and applies the total.  No atomics, fixed summation order -> bit-reproducible.
+//
+// Reference semantics: aten embedding_dense_backward (dense grads of nn.Embedding,
+// src/models/embeddings/base.py:53-57), torch.optim.SparseAdam (coalesce + row update,
+// torch/optim/_functional.py:24-84, used at src/models/deepfm.py:173-184) and sparse SGD
+// (src/models/deepfm.py:203-216).
+#include "common.cuh"
+
+namespace rsb {
+
+constexpr int kChunk = 32;          // sorted positions per lane group
+constexpr int kSegThreads = 128;    // 4 warps per CTA
+constexpr unsigned kNoKey = 0xffffffffu;
+
+struct ApplyArgs {
+  int mode;
+  float* dst;
+  float* m;
+  float* v;
+  float one_minus_b1, one_minus_b2, eps, neg_step_size, neg_lr;
+  int E;
+};
+
+template <int V>
+__device__ __forceinline__ void apply_row(const ApplyArgs& ap, unsigned row, int d0, const FV<V>& g) {
+  const long long o = (long long)row * ap.E + d0;
+  if (ap.mode == RSB_APPLY_DENSE) {
+    st<V>(ap.dst + o, g);
+  } else if (ap.mode == RSB_APPLY_SPARSE_SGD) {
+    FV<V> w = ld<V>(ap.dst + o);
+#pragma unroll
+    for (int i = 0; i < V; ++i) w.v[i] = w.v[i] + ap.neg_lr * g.v[i];
+    st<V>(ap.dst + o, w);
+  } else {
+    // torch/optim/_functional.py:60-84, same operation order
+    FV<V> w = ld<V>(ap.dst + o), m = ld<V>(ap.m + o), v = ld<V>(ap.v + o);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float mu = __fmul_rn(__fsub_rn(g.v[i], m.v[i]), ap.one_minus_b1);
+      float vu = __fmul_rn(__fsub_rn(__fmul_rn(g.v[i], g.v[i]), v.v[i]), ap.one_minus_b2);
+      float mn = __fadd_rn(m.v[i], mu);
+      float vn = __fadd_rn(v.v[i], vu);
+      float numer = __fadd_rn(mu, m.v[i]);
+      float denom = __fadd_rn(sqrtf(__fadd_rn(vu, v.v[i])), ap.eps);
+      m.v[i] = mn;
+      v.v[i] = vn;
+      w.v[i] = __fadd_rn(w.v[i], __fmul_rn(ap.neg_step_size, __fdiv_rn(numer, denom)));
+    }
+    st<V>(ap.m + o, m);
+    st<V>(ap.v + o, v);
+    st<V>(ap.dst + o, w);
+  }
+}
+
+template <int V, int LPR>
+__global__ void __launch_bounds__(kSegThreads) seg_chunk_kernel(const unsigned* __restrict__ skeys,
+                                                                const unsigned* __restrict__ perm, long long n,
+                                                                const float* __restrict__ rg, ApplyArgs ap,
+                                                                float* part_first, float* part_last) {
+  constexpr int GPW = kWarp / LPR;
+  constexpr int WT = GPW * kChunk;  // positions per warp
+  constexpr int NW = kSegThreads / 32;
+  __shared__ unsigned s_key[NW][WT + 2];
+  __shared__ unsigned s_perm[NW][WT];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = lane / LPR, c = lane % LPR;
+  const int d0 = c * V;
+  const bool cact = d0 < ap.E;
+  const long long warp = (long long)blockIdx.x * NW + wib;
+  const long long base = warp * WT;
+  if (base >= n) return;
+
+  for (int i = lane; i < WT + 2; i += 32) {
+    long long p = base - 1 + i;
+    s_key[wib][i] = (p >= 0 && p < n) ? __ldg(skeys + p) : kNoKey;
+  }
+  for (int i = lane; i < WT; i += 32) {
+    long long p = base + i;
+    s_perm[wib][i] = (p < n) ? __ldg(perm + p) : 0u;
+  }
+  __syncwarp();
+
+  const int start = g * kChunk;
+  const long long chunk_id = warp * GPW + g;
+  if (base + start >= n) return;
+  const unsigned prev_key = s_key[wib][start];  // key just before this chunk (slot 0 == base-1)
+  unsigned cur = kNoKey;
+  bool began0 = false;
+  FV<V> acc = FV<V>::zero();
+
+  constexpr int U = 4;
+#pragma unroll 1
+  for (int i0 = 0; i0 < kChunk; i0 += U) {
+    FV<V> val[U];
+    unsigned key[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u;
+      key[u] = s_key[wib][1 + start + i];
+      val[u] = FV<V>::zero();
+      if (key[u] != kNoKey && cact) val[u] = ldg<V>(rg + (long long)s_perm[wib][start + i] * ap.E + d0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u;
+      if (key[u] == kNoKey) continue;  // past n (keys are < 2^32-1 only if n_rows < 2^32; see host check)
+      if (key[u] != cur) {
+        if (cur != kNoKey) {
+          // a run ended strictly inside the chunk: it cannot cross the chunk end
+          if (began0 && prev_key == cur) {
+            if (cact) st<V>(part_first + chunk_id * ap.E + d0, acc);
+          } else if (cact) {
+            apply_row<V>(ap, cur, d0, acc);
+          }
+        }
+        cur = key[u];
+        began0 = (i == 0);
+        acc = FV<V>::zero();
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc.v[k] += val[u].v[k];
+    }
+  }
+  if (cur != kNoKey) {
+    const unsigned next_key = s_key[wib][1 + start + kChunk];
+    const bool crosses_start = began0 && prev_key == cur;
+    const bool crosses_end = next_key == cur;
+    if (cact) {
+      if (crosses_start) st<V>(part_first + chunk_id * ap.E + d0, acc);
+      else if (crosses_end) st<V>(part_last + chunk_id * ap.E + d0, acc);
+      else apply_row<V>(ap, cur, d0, acc);
+    }
+  }
+}
+
+// One lane group per chunk boundary cb >= 1 (position P = cb * kChunk).
+template <int V, int LPR>
+__global__ void __launch_bounds__(kSegThreads) seg_boundary_kernel(const unsigned* __restrict__ skeys, long long n,
+                                                                   long long n_chunks, ApplyArgs ap,
+                                                                   const float* __restrict__ part_first,
+                                                                   const float* __restrict__ part_last) {
+  constexpr int GPW = kWarp / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, c = lane % LPR;
+  const int d0 = c * V;
+  const bool cact = d0 < ap.E;
+  const long long grp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / 32 * GPW + g;
+  const long long cb = grp + 1;
+  if (cb >= n_chunks) return;
+  const long long P = cb * kChunk;
+  if (P >= n) return;
+  const unsigned row = __ldg(skeys + P);
+  if (__ldg(skeys + P - 1) != row) return;                                    // no run crosses here
+  if (cb >= 2 && __ldg(skeys + (cb - 1) * kChunk - 1) == row) return;         // not the first crossing
+  if (!cact) return;
+  FV<V> tot = ldg<V>(part_last + (cb - 1) * ap.E + d0);
+  long long cc = cb;
+  while (true) {
+    FV<V> p = ldg<V>(part_first + cc * ap.E + d0);
+#pragma unroll
+    for (int k = 0; k < V; ++k) tot.v[k] += p.v[k];
+    const long long nextP = (cc + 1) * kChunk;
+    if (nextP < n && __ldg(skeys + nextP) == row) ++cc;
+    else break;
+  }
+  apply_row<V>(ap, row, d0, tot);
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+static long long seg_align(long long x) { return (x + 255) / 256 * 256; }
+
+extern "C" RSB_API int64_t rsb_segment_workspace_bytes(int64_t n, int32_t E) {
+  if (n < 0 || E <= 0) return 0;
+  long long n_chunks = (n + kChunk - 1) / kChunk + 1;
+  return 2 * seg_align(n_chunks * E * 4) + 256;
+}
+
+extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
+                                        const float* row_grads, int32_t E, float* dst, float* exp_avg,
+                                        float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                        int64_t step, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (n < 0 || E <= 0) return RSB_ERR_BAD_ARG;
+  if (apply < RSB_APPLY_DENSE || apply > RSB_APPLY_SPARSE_SGD) return RSB_ERR_BAD_ARG;
+  if (n == 0) return RSB_OK;
+  if (!sorted_keys || !perm || !row_grads || !dst || !workspace) return RSB_ERR_BAD_ARG;
+  if (apply == RSB_APPLY_SPARSE_ADAM && (!exp_avg || !exp_avg_sq || step < 1)) return RSB_ERR_BAD_ARG;
+  if (workspace_bytes < rsb_segment_workspace_bytes(n, E)) return RSB_ERR_WORKSPACE;
+  bool al = aligned16(row_grads) && aligned16(dst) && (!exp_avg || aligned16(exp_avg)) &&
+            (!exp_avg_sq || aligned16(exp_avg_sq));
+  RowShape sh = row_shape(E, al);
+  if (!sh.ok) return RSB_ERR_UNSUPPORTED;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+
+  ApplyArgs ap;
+  ap.mode = apply;
+  ap.dst = dst;
+  ap.m = exp_avg;
+  ap.v = exp_avg_sq;
+  ap.E = E;
+  // Scalars exactly as torch computes them (python doubles, then one rounding to fp32)
+  ap.one_minus_b1 = (float)(1.0 - (double)beta1);
+  ap.one_minus_b2 = (float)(1.0 - (double)beta2);
+  ap.eps = eps;
+  ap.neg_lr = -lr;
+  ap.neg_step_size = 0.f;
+  if (apply == RSB_APPLY_SPARSE_ADAM) {
+    double bc1 = 1.0 - pow((double)beta1, (double)step);
+    double bc2 = 1.0 - pow((double)beta2, (double)step);
+    ap.neg_step_size = (float)(-((double)lr * sqrt(bc2) / bc1));
+  }
+
+  const long long n_chunks = (n + kChunk - 1) / kChunk;
+  char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  float* part_first = reinterpret_cast<float*>(w);
+  float* part_last = reinterpret_cast<float*>(w + seg_align((n_chunks + 1) * E * 4));
+
+  const int gpw = 32 / sh.LPR;
+  const long long warp_tile = (long long)gpw * kChunk;
+  const long long warps = (n + warp_tile - 1) / warp_tile;
+  const int wpb = kSegThreads / 32;
+  const long long blocks1 = (warps + wpb - 1) / wpb;
+  const long long groups2 = n_chunks - 1;
+  const long long blocks2 = (groups2 + (long long)gpw * wpb - 1) / ((long long)gpw * wpb);
+
+#define CALL(VV, LL)                                                                                        \
+  seg_chunk_kernel<VV, LL><<<(unsigned)blocks1, kSegThreads, 0, s>>>(sorted_keys, perm, n, row_grads, ap,   \
+                                                                     part_first, part_last);                \
+  if (groups2 > 0)                                                                                          \
+    seg_boundary_kernel<VV, LL><<<(unsigned)blocks2, kSegThreads, 0, s>>>(sorted_keys, n, n_chunks, ap,     \
+                                                                          part_first, part_last)
+  RSB_DISPATCH_SHAPE(sh, CALL);
+#undef CALL
+  RSB_CHECK_LAUNCH();
+  return RSB_OK;
+}

@@ -1,0 +1,246 @@
+// Stable LSD radix sort of the lookups by target row (backward stage 2).
+//
+// keys are row ids < n_rows (so only bit_length(n_rows-1) bits are sorted, in passes of
+// <= 8 bits), values are the lookup positions.  Three launches per pass:
+//   histogram (per-CTA digit counts, digit-major) -> exclusive scan -> stable scatter.
+// The first pass reads the int64 ids directly and applies the optional QR index
+// transform (key = id / key_div or id % key_mod, qr_embedding.py:96-97, bit exact on
+// non-negative ids), so no separate key-extraction pass is needed.
+#include "common.cuh"
+
+namespace rsb {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // keys per CTA
+constexpr int kRadixMax = 256;
+
+struct SortSrc {
+  const long long* keys64;  // pass 0 source (or nullptr)
+  long long key_div, key_mod;
+  const unsigned* keys32;  // later passes
+  const unsigned* vals32;
+};
+
+__device__ __forceinline__ unsigned sort_key_at(const SortSrc& s, long long i) {
+  if (s.keys64) {
+    long long k = __ldg(s.keys64 + i);
+    if (s.key_div > 1) k = k / s.key_div;
+    if (s.key_mod > 0) k = k % s.key_mod;
+    return (unsigned)k;
+  }
+  return __ldg(s.keys32 + i);
+}
+
+// Each warp owns a contiguous run of kSortItems*32 keys of the tile, visited in kSortItems
+// rounds of 32 consecutive keys: (warp, round, lane) order == memory order, which is what
+// makes the ranking below stable.
+__device__ __forceinline__ long long sort_pos(long long tile_base, int warp, int round, int lane) {
+  return tile_base + (long long)warp * (kSortItems * 32) + round * 32 + lane;
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortSrc src, long long n, int shift, int radix_bits,
+                                                                 unsigned* hist, int nblk) {
+  __shared__ unsigned h[kRadixMax];
+  const int radix = 1 << radix_bits;
+  for (int i = threadIdx.x; i < radix; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const long long base = (long long)blockIdx.x * kSortTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int r = 0; r < kSortItems; ++r) {
+    long long p = sort_pos(base, warp, r, lane);
+    if (p < n) {
+      unsigned d = (sort_key_at(src, p) >> shift) & (radix - 1);
+      atomicAdd(&h[d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < radix; i += blockDim.x) hist[(long long)i * nblk + blockIdx.x] = h[i];
+}
+
+// Exclusive scan of `len` counters in place, one CTA, 16 items per thread per sweep.
+__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned* data, long long len) {
+  constexpr int IPT = 16;
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long base = 0; base < len; base += 1024 * IPT) {
+    long long i0 = base + (long long)threadIdx.x * IPT;
+    unsigned v[IPT];
+    unsigned sum = 0;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      v[i] = (i0 + i < len) ? data[i0 + i] : 0u;
+      sum += v[i];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned t = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = warp_tot[lane];
+      unsigned wi = w;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        unsigned t = __shfl_up_sync(kFull, wi, off);
+        if (lane >= off) wi += t;
+      }
+      warp_tot[lane] = wi - w;  // exclusive over warps
+      if (lane == 31) warp_tot[31] = wi - w;
+    }
+    __syncthreads();
+    unsigned carry = carry_s;
+    unsigned run = carry + warp_tot[warp] + (incl - sum);
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      if (i0 + i < len) data[i0 + i] = run;
+      run += v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;  // last thread's running total == sweep total + carry
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src, long long n, int shift,
+                                                                    int radix_bits, const unsigned* hist_scanned,
+                                                                    int nblk, unsigned* out_keys,
+                                                                    unsigned* out_vals) {
+  constexpr int NW = kSortThreads / 32;
+  __shared__ unsigned cnt[NW][kRadixMax];
+  const int radix = 1 << radix_bits;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NW * kRadixMax; i += blockDim.x) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+
+  const long long base = (long long)blockIdx.x * kSortTile;
+  unsigned key[kSortItems], rank[kSortItems];
+  unsigned short dig[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    long long p = sort_pos(base, warp, r, lane);
+    bool valid = p < n;
+    key[r] = valid ? sort_key_at(src, p) : 0xffffffffu;
+    unsigned d = valid ? ((key[r] >> shift) & (radix - 1)) : (unsigned)radix;  // invalid: own class
+    dig[r] = (unsigned short)d;
+    unsigned peers = __match_any_sync(kFull, d);
+    unsigned lower = peers & ((1u << lane) - 1u);
+    unsigned pre = 0;
+    if (valid) {
+      int leader = __ffs(peers) - 1;
+      if (lane == leader) {
+        pre = cnt[warp][d];
+        cnt[warp][d] = pre + __popc(peers);
+      }
+      pre = __shfl_sync(peers, pre, leader);
+    }
+    rank[r] = pre + __popc(lower);
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive scan over warps for each digit, plus this CTA's global base
+  for (int d = threadIdx.x; d < radix; d += blockDim.x) {
+    unsigned run = hist_scanned[(long long)d * nblk + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      unsigned t = cnt[w][d];
+      cnt[w][d] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    long long p = sort_pos(base, warp, r, lane);
+    if (p < n) {
+      unsigned dst = cnt[warp][dig[r]] + rank[r];
+      out_keys[dst] = key[r];
+      out_vals[dst] = src.vals32 ? __ldg(src.vals32 + p) : (unsigned)p;
+    }
+  }
+}
+
+static int bit_length(unsigned long long x) {
+  int b = 0;
+  while (x) {
+    ++b;
+    x >>= 1;
+  }
+  return b;
+}
+
+static long long align_up(long long x, long long a) { return (x + a - 1) / a * a; }
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" RSB_API int64_t rsb_sort_workspace_bytes(int64_t n) {
+  if (n < 0) return 0;
+  long long nblk = (n + kSortTile - 1) / kSortTile;
+  if (nblk < 1) nblk = 1;
+  long long bytes = 0;
+  bytes += align_up(2 * n * 4, 256);              // ping-pong keys
+  bytes += align_up(2 * n * 4, 256);              // ping-pong values
+  bytes += align_up(nblk * kRadixMax * 4, 256);   // histogram
+  return bytes + 256;
+}
+
+extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_rows, int64_t key_div, int64_t key_mod,
+                             uint32_t* sorted_keys, uint32_t* perm, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  // keys must stay below 0xffffffff: the segmented reduction uses it as its 'no key' sentinel
+  if (n < 0 || n_rows <= 0 || n >= (1ll << 32) || n_rows > 0xffffffffll) return RSB_ERR_BAD_ARG;
+  if (n == 0) return RSB_OK;
+  if (keys == nullptr || sorted_keys == nullptr || perm == nullptr || workspace == nullptr) return RSB_ERR_BAD_ARG;
+  if (workspace_bytes < rsb_sort_workspace_bytes(n)) return RSB_ERR_WORKSPACE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long nblk = (n + kSortTile - 1) / kSortTile;
+
+  char* w = reinterpret_cast<char*>(workspace);
+  w = reinterpret_cast<char*>(align_up(reinterpret_cast<long long>(w), 256));
+  unsigned* kbuf[2];
+  unsigned* vbuf[2];
+  kbuf[0] = reinterpret_cast<unsigned*>(w);
+  kbuf[1] = kbuf[0] + n;
+  w += align_up(2 * n * 4, 256);
+  vbuf[0] = reinterpret_cast<unsigned*>(w);
+  vbuf[1] = vbuf[0] + n;
+  w += align_up(2 * n * 4, 256);
+  unsigned* hist = reinterpret_cast<unsigned*>(w);
+
+  int bits = bit_length((unsigned long long)(n_rows - 1));
+  if (bits < 1) bits = 1;
+  const int passes = (bits + 7) / 8;
+  const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 8)
+
+  SortSrc src;
+  src.keys64 = reinterpret_cast<const long long*>(keys);
+  src.key_div = key_div;
+  src.key_mod = key_mod;
+  src.keys32 = nullptr;
+  src.vals32 = nullptr;
+  for (int p = 0; p < passes; ++p) {
+    const bool last = (p == passes - 1);
+    unsigned* ok = last ? sorted_keys : kbuf[p & 1];
+    unsigned* ov = last ? perm : vbuf[p & 1];
+    const int shift = p * rb;
+    sort_hist_kernel<<<(unsigned)nblk, kSortThreads, 0, s>>>(src, n, shift, rb, hist, (int)nblk);
+    RSB_CHECK_LAUNCH();
+    sort_scan_kernel<<<1, 1024, 0, s>>>(hist, (long long)(1 << rb) * nblk);
+    RSB_CHECK_LAUNCH();
+    sort_scatter_kernel<<<(unsigned)nblk, kSortThreads, 0, s>>>(src, n, shift, rb, hist, (int)nblk, ok, ov);
+    RSB_CHECK_LAUNCH();
+    src.keys64 = nullptr;
+    src.keys32 = ok;
+    src.vals32 = ov;
+  }
+  return RSB_OK;
+}

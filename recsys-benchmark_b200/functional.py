@@ -1,0 +1,291 @@
+"""Host-side glue between torch autograd and the C ABI (include/rsb.h).
+
+`fused_lookup` is the one differentiable entry point: gather (+ lightweight-embedding
+variant) (+ DeepFM first/second order) in one launch forward, and the three-stage
+backward (per-lookup row grads -> row sort -> deterministic segmented reduction with
+the consumer fused in).  torch is used for memory, streams and autograd plumbing only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+@dataclass
+class LookupSpec:
+    """Static description of one embedding variant (what the gather applies)."""
+
+    kind: int                      # L.KIND_*
+    num_global: int                # number of addressable ids (sum(field_dims))
+    dim: int                       # D (num_factor)
+    divider: int = 0               # QR
+    aux_mode: int = 0              # PEP threshold type / OptEmbed norm
+    sparse_grad: bool = False      # emit torch.sparse_coo grads for the main table (nn.Embedding(sparse=True))
+    module: object = None          # owner (for deferred fused updates / err flag)
+
+    @property
+    def is_qr(self) -> bool:
+        return self.kind in (L.KIND_QR_MULT, L.KIND_QR_ADD, L.KIND_QR_CAT)
+
+    @property
+    def row_width(self) -> int:
+        return self.dim // 2 if self.kind == L.KIND_QR_CAT else self.dim
+
+    def out_fields(self, f: int) -> int:
+        return 2 * f if self.kind == L.KIND_QR_CAT else f
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------
+# thin wrappers (one C call each)
+# ----------------------------------------------------------------------------
+def sort_rows(rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 0):
+    """Stable radix sort of int64 row ids -> (sorted_keys uint32-as-int32, perm)."""
+    lib = L.load()
+    n = rows.numel()
+    dev = rows.device
+    skeys = torch.empty(n, dtype=torch.int32, device=dev)
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    nb = lib.rsb_sort_workspace_bytes(n)
+    ws = _ws(nb, dev)
+    L.check(lib.rsb_sort_rows(L.ptr(rows), n, int(n_rows), int(key_div), int(key_mod), L.ptr(skeys), L.ptr(perm),
+                              L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "sort_rows")
+    return skeys, perm
+
+
+def segment_reduce_apply(apply: int, skeys, perm, row_grads, dst, exp_avg=None, exp_avg_sq=None, lr=0.0,
+                         beta1=0.9, beta2=0.999, eps=1e-8, step=1):
+    lib = L.load()
+    n = skeys.numel()
+    e = row_grads.shape[-1] if row_grads.dim() > 1 else 1
+    dev = row_grads.device
+    nb = lib.rsb_segment_workspace_bytes(n, e)
+    ws = _ws(nb, dev)
+    L.check(lib.rsb_segment_reduce_apply(apply, L.ptr(skeys), L.ptr(perm), n, L.ptr(row_grads), e, L.ptr(dst),
+                                         L.ptr(exp_avg), L.ptr(exp_avg_sq), lr, beta1, beta2, eps, int(step),
+                                         L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "segment_reduce_apply")
+
+
+def dense_row_grad(rows: torch.Tensor, row_grads: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 0,
+                   sorted_pair=None) -> torch.Tensor:
+    """Dense zero-filled [n_rows, E] gradient = scatter-add of per-lookup rows (deterministic)."""
+    e = row_grads.shape[-1]
+    out = torch.zeros(n_rows, e, dtype=torch.float32, device=row_grads.device)
+    if rows.numel() == 0:
+        return out
+    if sorted_pair is None:
+        sorted_pair = sort_rows(rows, n_rows, key_div, key_mod)
+    segment_reduce_apply(L.APPLY_DENSE, sorted_pair[0], sorted_pair[1], row_grads, out)
+    return out
+
+
+def small_table_grad(rows: torch.Tensor, row_grads: torch.Tensor, n_rows: int, key_div: int = 0,
+                     key_mod: int = 0) -> Optional[torch.Tensor]:
+    """Dense gradient of a table small enough to accumulate in shared memory; None if too big."""
+    lib = L.load()
+    e = row_grads.shape[-1]
+    nb = lib.rsb_small_table_workspace_bytes(n_rows, e)
+    if nb < 0:
+        return None
+    dev = row_grads.device
+    out = torch.empty(n_rows, e, dtype=torch.float32, device=dev)
+    ws = _ws(nb, dev)
+    L.check(lib.rsb_small_table_grad(L.ptr(rows), rows.numel(), int(key_div), int(key_mod), L.ptr(row_grads), e,
+                                     int(n_rows), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev)),
+            "small_table_grad")
+    return out
+
+
+def _err_flag(spec: LookupSpec, device) -> Optional[torch.Tensor]:
+    mod = spec.module
+    if mod is None:
+        return None
+    flag = getattr(mod, "_rsb_err_flag", None)
+    if flag is None or flag.device != device:
+        flag = torch.zeros(1, dtype=torch.int32, device=device)
+        mod._rsb_err_flag = flag
+    return flag
+
+
+def check_index_errors(module) -> None:
+    """Raise IndexError (like F.embedding does) if any id seen so far was out of range.
+    Synchronises the stream; called on demand (validate=True) or by tests."""
+    flag = getattr(module, "_rsb_err_flag", None)
+    if flag is not None and int(flag.item()) != 0:
+        flag.zero_()
+        raise IndexError("index out of range in self")
+
+
+# ----------------------------------------------------------------------------
+# the differentiable op
+# ----------------------------------------------------------------------------
+class _FusedLookup(torch.autograd.Function):
+    """(spec, x, offsets, mask_d, table, table1, aux, fc, bias) -> (emb [B,VF,E], y_fm [B] or empty)."""
+
+    @staticmethod
+    def forward(ctx, spec: LookupSpec, x, offsets, mask_d, table, table1, aux, fc, bias):
+        lib = L.load()
+        dev = L.require_cuda(x, table, table1, aux, fc, bias, offsets, mask_d)
+        if x.dim() != 2:
+            raise RuntimeError("rsb: x must be [B, F]")
+        if x.dtype not in (torch.int32, torch.int64):
+            raise RuntimeError(f"rsb: ids must be int32 or int64, got {x.dtype}")
+        x = x.contiguous()
+        b, f = x.shape
+        e = spec.row_width
+        vf = spec.out_fields(f)
+        fm = fc is not None
+        emb = torch.empty(b, vf, e, dtype=torch.float32, device=dev)
+        y = torch.empty(b, dtype=torch.float32, device=dev) if fm else None
+        s = torch.empty(b, e, dtype=torch.float32, device=dev) if fm else None
+        rows = torch.empty(b, f, dtype=torch.int64, device=dev)
+        aux_t = aux
+        if aux is not None and aux.dtype == torch.bool:
+            aux_t = aux.view(torch.uint8)
+        L.check(lib.rsb_lookup_fwd(
+            spec.kind, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, spec.dim,
+            L.ptr(table), table.shape[0], spec.num_global, L.ptr(table1), spec.divider,
+            L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(fc), L.ptr(bias),
+            L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows), L.ptr(_err_flag(spec, dev)), L.stream_ptr(dev)),
+            "lookup_fwd")
+        ctx.spec = spec
+        ctx.fm = fm
+        ctx.shape = (b, f)
+        ctx.save_for_backward(rows, emb, s, mask_d, table, table1, aux, fc)
+        ctx.mark_non_differentiable(rows)
+        if y is None:
+            y = emb.new_empty(0)
+        return emb, y, rows
+
+    @staticmethod
+    def backward(ctx, g_emb, g_y, _g_rows):
+        lib = L.load()
+        spec: LookupSpec = ctx.spec
+        rows, emb, s, mask_d, table, table1, aux, fc = ctx.saved_tensors
+        b, f = ctx.shape
+        dev = rows.device
+        e = spec.row_width
+        n = b * f
+        need = ctx.needs_input_grad  # (spec, x, offsets, mask_d, table, table1, aux, fc, bias)
+        use_gy = ctx.fm and g_y is not None and g_y.numel() == b
+        if g_emb is not None:
+            g_emb = g_emb.contiguous()
+        if use_gy:
+            g_y = g_y.contiguous()
+        if g_emb is None and not use_gy:
+            return (None,) * 9
+
+        g_fc = None
+        if ctx.fm and need[7] and use_gy:
+            g_fc = torch.zeros_like(fc)
+        g_bias = g_y.sum().reshape(1) if (ctx.fm and need[8] and use_gy) else None
+
+        kind = spec.kind
+        aux_t = aux.view(torch.uint8) if (aux is not None and aux.dtype == torch.bool) else aux
+        # ---- stage 1: per-lookup row gradients --------------------------------
+        skip_stage1 = (kind == L.KIND_VANILLA and not use_gy)
+        rg_main = rg_aux = None
+        if skip_stage1:
+            rg_main = g_emb.view(n, e)
+        else:
+            rg_main = torch.empty(n, e, dtype=torch.float32, device=dev)
+            if kind in (L.KIND_QR_MULT, L.KIND_QR_CAT) or (kind == L.KIND_PEP and need[6]):
+                rg_aux = torch.empty(n, e, dtype=torch.float32, device=dev)
+            elif kind == L.KIND_OPTEMBED and aux is not None:
+                rg_aux = torch.empty(b, f, dtype=torch.float32, device=dev)
+            L.check(lib.rsb_lookup_bwd_rows(
+                kind, L.ptr(rows), b, f, spec.dim, L.ptr(table), table.shape[0], L.ptr(table1), spec.divider,
+                L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
+                L.ptr(g_y) if use_gy else None, L.ptr(g_emb), L.ptr(rg_main), L.ptr(rg_aux), L.ptr(g_fc),
+                L.stream_ptr(dev)), "lookup_bwd_rows")
+            if kind == L.KIND_QR_ADD:
+                rg_aux = rg_main
+
+        # ---- stages 2+3: reduce by target row ---------------------------------
+        g_table = g_table1 = g_aux = None
+        n_rows = table.shape[0]
+        mod = spec.module
+        if spec.is_qr:
+            if need[4]:
+                g_table = dense_row_grad(rows, rg_main, n_rows, key_div=spec.divider)
+            if need[5]:
+                g_table1 = small_table_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
+                if g_table1 is None:
+                    g_table1 = dense_row_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
+        else:
+            if need[4]:
+                deferred = getattr(mod, "_rsb_fused_opt", None) if mod is not None else None
+                if deferred is not None:
+                    deferred.stash(table, rows, rg_main)          # consumed by FusedSparse*.step()
+                elif spec.sparse_grad:
+                    # same layout nn.Embedding(sparse=True) produces: uncoalesced COO, nnz = B*F
+                    g_table = torch.sparse_coo_tensor(rows.view(1, n), rg_main, (n_rows, e))
+                else:
+                    pair = sort_rows(rows, n_rows)
+                    g_table = dense_row_grad(rows, rg_main, n_rows, sorted_pair=pair)
+                    if kind == L.KIND_PEP and need[6] and spec.aux_mode == L.PEP_FEATURE_DIM:
+                        g_aux = dense_row_grad(rows, rg_aux, n_rows, sorted_pair=pair)
+                    elif kind == L.KIND_PEP and need[6] and spec.aux_mode == L.PEP_FEATURE:
+                        g_aux = dense_row_grad(rows, rg_aux.sum(dim=1, keepdim=True), n_rows, sorted_pair=pair)
+            if kind == L.KIND_PEP and need[6] and g_aux is None:
+                if spec.aux_mode == L.PEP_DIMENSION:
+                    g_aux = rg_aux.sum(dim=0)
+                elif spec.aux_mode == L.PEP_GLOBAL:
+                    g_aux = rg_aux.sum().reshape(1)
+                elif spec.aux_mode == L.PEP_FEATURE_DIM:
+                    g_aux = dense_row_grad(rows, rg_aux, n_rows)
+                else:
+                    g_aux = dense_row_grad(rows, rg_aux.sum(dim=1, keepdim=True), n_rows)
+            if kind == L.KIND_OPTEMBED and aux is not None and need[6]:
+                g_aux = -rg_aux.sum(dim=0)
+        return None, None, None, None, g_table, g_table1, g_aux, g_fc, g_bias
+
+
+def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tensor], table: torch.Tensor,
+                 table1: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+                 mask_d: Optional[torch.Tensor] = None, fc: Optional[torch.Tensor] = None,
+                 bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Differentiable fused gather.  Returns (emb [B,VF,E], y_fm [B] or None)."""
+    emb, y, _rows = _FusedLookup.apply(spec, x, offsets, mask_d, table, table1, aux, fc, bias)
+    return emb, (y if fc is not None else None)
+
+
+# ----------------------------------------------------------------------------
+# full-table helpers
+# ----------------------------------------------------------------------------
+def pep_threshold_table(weight, s, threshold_type: int, want_out=True, want_count=False):
+    lib = L.load()
+    dev = L.require_cuda(weight, s)
+    out = torch.empty_like(weight) if want_out else None
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev) if want_count else None
+    L.check(lib.rsb_pep_threshold_table(L.ptr(weight), L.ptr(s), threshold_type, weight.shape[0], weight.shape[1],
+                                        L.ptr(out), L.ptr(cnt), L.stream_ptr(dev)), "pep_threshold_table")
+    return out, cnt
+
+
+def optembed_eval_weight(weight, t_row, mask_d_row, norm: int, want_out=True, want_count=False):
+    lib = L.load()
+    dev = L.require_cuda(weight, t_row, mask_d_row)
+    out = torch.empty_like(weight) if want_out else None
+    cnt = torch.zeros(1, dtype=torch.int64, device=dev) if want_count else None
+    L.check(lib.rsb_optembed_eval_weight(L.ptr(weight), L.ptr(t_row), L.ptr(mask_d_row), norm, weight.shape[0],
+                                         weight.shape[1], L.ptr(out), L.ptr(cnt), L.stream_ptr(dev)),
+            "optembed_eval_weight")
+    return out, cnt
+
+
+def mask_table(weight, mask):
+    lib = L.load()
+    dev = L.require_cuda(weight, mask)
+    out = torch.empty_like(weight)
+    m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+    L.check(lib.rsb_mask_table(L.ptr(weight), L.ptr(m.contiguous()), weight.numel(), L.ptr(out), L.stream_ptr(dev)),
+            "mask_table")
+    return out

@@ -1,0 +1,350 @@
+"""GPU parity tests through the public (reference-shaped) API: our DeepFM / DCN_Mix and
+embedding plugins loaded with the reference's own state dicts (tests/golden/*.npz, made by
+the unmodified reference) must reproduce its logits, gradients and post-step weights.
+Plus edge cases (empty / ragged inputs, int32 ids, out-of-range ids, bag modes) and
+size-independent properties at the BASELINE.json sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ctr_oracle as O
+from tests.helpers import assert_close, load_golden, sub
+from tests.test_host_api import CASES, build_from_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+CRITEO_DIMS = [49, 101, 126, 45, 223, 118, 84, 76, 95, 9, 30, 40, 75, 1458, 555, 193949, 138801, 306, 19, 11970, 634,
+               4, 42646, 5178, 192773, 3175, 27, 11422, 181075, 11, 4654, 2032, 5, 189657, 18, 16, 59697, 86, 45571]
+
+
+@pytest.fixture(scope="module")
+def R():
+    import __graft_entry__ as G
+
+    G.build()
+    import recsys_benchmark_b200 as r
+
+    return r
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a)).to(DEV)
+
+
+def _grad_np(p):
+    g = p.grad
+    return (g.to_dense() if g.is_sparse else g).detach().cpu().numpy()
+
+
+def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, atol_scale=1e-5):
+    g, model, state = build_from_golden(name, emb_cfg)
+    model.load_state_dict(state, strict=True)
+    model.to(DEV)
+    # eval logits
+    model.eval()
+    if pre_step is not None:
+        pre_step(model, "eval", g)
+    with torch.no_grad():
+        logits = model(_t(g["x"]))
+    assert_close(logits.cpu().numpy(), g["logits_eval"], what=f"{name} eval logits", atol_scale=atol_scale)
+    opts = R.get_optimizers(model, opt_cfg) if opt_cfg else []
+    crit = torch.nn.BCEWithLogitsLoss()
+    model.train()
+    for s in range(steps):
+        if pre_step is not None:
+            pre_step(model, f"step{s}", g)
+        logits = model(_t(g[f"step{s}/x"]))
+        loss = crit(logits, _t(g[f"step{s}/y"]).float())
+        for o in opts:
+            o.zero_grad()
+        for p in model.parameters():
+            p.grad = None
+        loss.backward()
+        assert_close(logits.detach().cpu().numpy(), g[f"step{s}/logits"], what=f"{name} step{s} logits",
+                     atol_scale=atol_scale)
+        for k, p in model.named_parameters():
+            key = f"step{s}/grad/{k}"
+            if key in g:
+                assert p.grad is not None, f"{k} has no grad"
+                assert_close(_grad_np(p), g[key], what=f"{name} step{s} grad {k}", atol_scale=2e-5)
+            else:
+                assert p.grad is None or float(p.grad.abs().sum()) == 0.0 or not p.requires_grad, k
+        for o in opts:
+            o.step()
+        if opts:
+            after = sub(g, f"step{s}/after/")
+            cur = model.state_dict()
+            for k in ["embedding._emb_module.weight", "embedding.emb1.weight", "embedding.emb2.weight",
+                      "embedding.emb.weight", "embedding.s", "embedding._weight",
+                      "embedding._mask_e_module._t_param", "fc.weight", "_bias"]:
+                if k in after:
+                    assert_close(cur[k].cpu().numpy(), after[k], what=f"{name} step{s} after {k}", atol_scale=5e-5)
+    return g, model
+
+
+ADAM = dict(learning_rate=1e-2, weight_decay=1e-4)
+SPARSE_ADAM = dict(learning_rate=1e-2, weight_decay=1e-4, sparse=True)
+SPARSE_SGD = dict(learning_rate=1e-1, weight_decay=1e-4, sparse=True, optimizer="sgd")
+
+
+def test_deepfm_vanilla_dense_adam(R):
+    _run_steps(R, "deepfm_vanilla_adam", CASES["deepfm_vanilla_adam"], ADAM, 2)
+
+
+def test_deepfm_vanilla_int32_ids(R):
+    g, model = _run_steps(R, "deepfm_vanilla_int32", {"name": "vanilla"}, None, 1)
+    assert g["x"].dtype == np.int32
+
+
+def test_deepfm_vanilla_sparse_coo_grad_and_sparse_adam(R):
+    g, model = _run_steps(R, "deepfm_vanilla_sparse_adam", CASES["deepfm_vanilla_sparse_adam"], SPARSE_ADAM, 3)
+    gr = model.embedding._emb_module.weight.grad
+    b, f = g["step2/x"].shape
+    assert gr.is_sparse and not gr.is_coalesced() and gr._nnz() == b * f   # same layout as nn.Embedding(sparse=True)
+    assert gr._indices().dtype == torch.int64 and tuple(gr._indices().shape) == (1, b * f)
+
+
+@pytest.mark.parametrize("name,cfg", [("deepfm_vanilla_sparse_adam", dict(SPARSE_ADAM, fused_sparse=True)),
+                                      ("deepfm_vanilla_sparse_sgd", dict(SPARSE_SGD, fused_sparse=True))])
+def test_deepfm_fused_sparse_update_matches_reference_steps(R, name, cfg):
+    g, model, state = build_from_golden(name, {"name": "vanilla", "sparse": True})
+    model.load_state_dict(state, strict=True)
+    model.to(DEV).train()
+    opts = R.get_optimizers(model, cfg)
+    crit = torch.nn.BCEWithLogitsLoss()
+    steps = 3 if "adam" in name else 2
+    for s in range(steps):
+        logits = model(_t(g[f"step{s}/x"]))
+        loss = crit(logits, _t(g[f"step{s}/y"]).float())
+        for o in opts:
+            o.zero_grad()
+        loss.backward()
+        assert model.embedding._emb_module.weight.grad is None   # no gradient tensor is materialised
+        for o in opts:
+            o.step()
+        assert_close(model.embedding._emb_module.weight.detach().cpu().numpy(),
+                     g[f"step{s}/after/embedding._emb_module.weight"], what=f"fused step {s}", atol_scale=5e-5)
+
+
+def test_deepfm_vanilla_sparse_sgd(R):
+    _run_steps(R, "deepfm_vanilla_sparse_sgd", {"name": "vanilla", "sparse": True}, SPARSE_SGD, 2)
+
+
+@pytest.mark.parametrize("op", ["mult", "add", "cat"])
+def test_deepfm_qr(R, op):
+    _run_steps(R, f"deepfm_qr_{op}", CASES[f"deepfm_qr_{op}"], ADAM, 2)
+
+
+@pytest.mark.parametrize("tt", ["feature_dim", "feature", "dimension", "global"])
+def test_deepfm_pep(R, tt, tmp_path):
+    _run_steps(R, f"deepfm_pep_{tt}", {"name": "pep", "checkpoint_weight_dir": str(tmp_path), "threshold_type": tt},
+               ADAM, 1)
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_deepfm_pep_retrain(R, sparse, tmp_path):
+    ck = load_golden("pep_retrain_ckpt")
+    (tmp_path / "deepfm").mkdir()
+    torch.save({"emb.weight": torch.from_numpy(ck["weight"]), "s": torch.from_numpy(ck["s"])},
+               tmp_path / "deepfm" / "0.5.pth")
+    name = "deepfm_pep_retrain" + ("_sparse" if sparse else "")
+    g, model = _run_steps(R, name, {"name": "pep_retrain", "checkpoint_weight_dir": str(tmp_path), "sparsity": 0.5,
+                                    "sparse": sparse}, SPARSE_ADAM if sparse else ADAM, 1)
+    assert model.embedding.emb.weight.grad.is_sparse == sparse
+
+
+def _optembed_pre(model, tag, g):
+    if tag == "eval":
+        model.embedding.get_weight()
+        return
+    # replay the reference's mask-D draw: we make the same torch.randint call, so seeding the
+    # CPU generator is not enough on CUDA -> inject the recorded draw instead
+    k = _t(g[f"{tag}/mask_d_idx"])
+    model.embedding._mask_d_for = lambda b, f, device, _k=k: _k
+
+
+@pytest.mark.parametrize("name", ["deepfm_optembed", "deepfm_optembed_l2", "deepfm_optembed_d"])
+def test_deepfm_optembed(R, name):
+    steps = 2 if name == "deepfm_optembed" else 1
+    g, model = _run_steps(R, name, CASES[name], ADAM if name == "deepfm_optembed" else None, steps,
+                          pre_step=_optembed_pre)
+
+
+def test_optembed_draws_mask_with_the_reference_torch_call(R):
+    emb = R.get_embedding({"name": "deepfm_optembed"}, [5, 4, 6], 8).to(DEV).train()
+    torch.manual_seed(11)
+    k1 = emb._mask_d_for(7, 3, torch.device(DEV))
+    torch.manual_seed(11)
+    k2 = torch.randint(0, 8, size=(7, 3), device=DEV)
+    assert torch.equal(k1, k2) and k1.dtype == torch.int64
+
+
+def test_optembed_fresh_eval_raises_like_reference(R):
+    emb = R.get_embedding({"name": "deepfm_optembed"}, [5, 4, 6], 8).to(DEV).eval()
+    with pytest.raises(RuntimeError, match="2-D"):
+        emb(torch.zeros(2, 3, dtype=torch.long, device=DEV))
+
+
+def test_dcn_mix_matches_reference(R):
+    g = load_golden("dcn_mix")
+    fd = [int(v) for v in g["field_dims"]]
+    cfg = dict(name="dcn_mix", num_factor=4, hidden_sizes=[12], num_layers=2, num_experts=3, rank=5, p_dropout=0.0,
+               compile_model=False, embedding_config={"name": "vanilla"})
+    model = R.get_ctr_model(fd, cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sub(g, "state/").items()}, strict=True)
+    model.to(DEV).eval()
+    with torch.no_grad():
+        assert_close(model(_t(g["x"])).cpu().numpy(), g["logits_eval"], what="dcn eval logits")
+    model.train()
+    logits = model(_t(g["x"]))
+    torch.nn.BCEWithLogitsLoss()(logits, _t(g["y"]).float()).backward()
+    assert_close(logits.detach().cpu().numpy(), g["logits"], what="dcn logits")
+    for k, p in model.named_parameters():
+        if f"grad/{k}" in g:
+            assert_close(_grad_np(p), g[f"grad/{k}"], what=f"dcn grad {k}", atol_scale=3e-5)
+
+
+# ------------------------------------------------------------- plugin API ---
+def test_embedding_api_goldens(R, tmp_path):
+    a = load_golden("embedding_api")
+    fd = [int(v) for v in a["field_dims"]]
+    ids1, ids2 = _t(a["ids1"]), _t(a["ids2"])
+    for op in ["mult", "add", "cat"]:
+        emb = R.get_embedding({"name": "qr", "divider": 4, "operation": op}, fd, 6)
+        emb.load_state_dict({k[len(f"qr_{op}/state/"):]: torch.from_numpy(v) for k, v in a.items()
+                             if k.startswith(f"qr_{op}/state/")})
+        emb.to(DEV)
+        np.testing.assert_array_equal(emb(ids1).detach().cpu().numpy(), a[f"qr_{op}/out1"])
+        np.testing.assert_array_equal(emb(ids2).detach().cpu().numpy(), a[f"qr_{op}/out2"])
+        np.testing.assert_array_equal(emb.get_weight().detach().cpu().numpy(), a[f"qr_{op}/get_weight"])
+    # OptEmbed retrain
+    emb = R.get_embedding({"name": "deepfm_optembed_retrain"}, fd, 6)
+    with torch.no_grad():
+        emb._weight.copy_(torch.from_numpy(a["optretrain/weight"]))
+    m = emb.init_mask(mask_e=torch.from_numpy(a["optretrain/mask_e"]), mask_d=torch.from_numpy(a["optretrain/mask_d"]))
+    np.testing.assert_array_equal(m.cpu().numpy(), a["optretrain/mask"])
+    emb.to(DEV)
+    np.testing.assert_array_equal(emb(ids2).detach().cpu().numpy(), a["optretrain/out2"])
+    sp, nnz = emb.get_sparsity(True)
+    assert nnz == int(a["optretrain/nnz"]) and abs(sp - float(a["optretrain/sparsity"])) < 1e-12
+    # OptEmbed eval weight, explicit mask_d, bookkeeping
+    emb = R.get_embedding({"name": "deepfm_optembed"}, fd, 6)
+    with torch.no_grad():
+        emb._weight.copy_(torch.from_numpy(a["opteval/weight"]))
+        emb._mask_e_module._t_param.copy_(torch.from_numpy(a["opteval/t"]))
+    emb.to(DEV).eval()
+    np.testing.assert_array_equal(emb.get_weight().cpu().numpy(), a["opteval/w_plain"])
+    np.testing.assert_array_equal(emb.get_weight(torch.tensor([1, 4, 2])).cpu().numpy(), a["opteval/w_maskd"])
+    assert_close(emb.get_l_s().detach().cpu().numpy(), a["opteval/l_s"], what="l_s")
+    sp, nnz = emb.get_sparsity(True)
+    assert nnz == int(a["opteval/nnz"])
+    np.testing.assert_array_equal(emb.get_mask_e().numpy(), a["opteval/mask_e"])
+    np.testing.assert_array_equal(emb.get_submask().numpy(), a["opteval/submask"])
+    # PEP bookkeeping
+    emb = R.get_embedding({"name": "pep", "checkpoint_weight_dir": str(tmp_path)}, fd, 6, field_name="deepfm")
+    with torch.no_grad():
+        emb.emb.weight.copy_(torch.from_numpy(a["pep/weight"]))
+        emb.s.copy_(torch.from_numpy(a["pep/s"]))
+    emb.to(DEV)
+    sp, nnz = emb.get_sparsity(True)
+    assert nnz == int(a["pep/nnz"])
+    assert_close(emb.get_weight().cpu().numpy(), a["pep/get_weight"], what="pep get_weight")
+    assert_close(emb(ids1).detach().cpu().numpy(), a["pep/out1"], what="pep 1-D")
+    emb.sparsity = [0.1, 0.99]
+    emb.train_callback()
+    assert (tmp_path / "deepfm" / "0.1.pth").exists() and emb._cur_min_spar_idx == 1
+
+
+@pytest.mark.parametrize("name", ["vanilla", "qr", "deepfm_optembed_d"])
+def test_plugin_shapes_like_reference_tests(R, name):
+    """tests/test_emb.py:124-164 of the reference: [11,3] ids -> (11,3,7); 1-D ids -> (11,7)."""
+    emb = R.get_embedding({"name": name}, [5, 6, 7], 7).to(DEV)
+    x = torch.randint(0, 18, (11, 3), device=DEV)
+    assert tuple(emb(x).shape) == (11, 3, 7)
+    if name != "deepfm_optembed_d":
+        assert tuple(emb(x[:, 0]).shape) == (11, 7)
+    assert tuple(emb.get_weight().shape) == (18, 7)
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean", "max"])
+def test_bag_modes(R, mode):
+    emb = R.get_embedding({"name": "vanilla"}, [50], 16, mode=mode).to(DEV)
+    x = torch.randint(0, 50, (9, 4), device=DEV)
+    ref = torch.nn.functional.embedding(x, emb.get_weight())
+    ref = {"sum": ref.sum(1), "mean": ref.mean(1), "max": ref.max(1).values}[mode]
+    torch.testing.assert_close(emb(x), ref, rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------- edge cases ---
+def test_empty_batch(R):
+    model = R.get_ctr_model([5, 6, 7], dict(num_factor=16, hidden_sizes=[8], p_dropout=0.0)).to(DEV).eval()
+    out = model(torch.zeros(0, 3, dtype=torch.long, device=DEV))
+    assert tuple(out.shape) == (0,)
+
+
+def test_out_of_range_ids_raise_index_error_when_validating(R):
+    emb = R.get_embedding({"name": "vanilla"}, [5, 6], 16).to(DEV)
+    emb.validate = True
+    with pytest.raises(IndexError):
+        emb(torch.tensor([[0, 11]], device=DEV))
+    with pytest.raises(IndexError):
+        emb(torch.tensor([[-1, 3]], device=DEV))
+    assert tuple(emb(torch.tensor([[4, 10]], device=DEV)).shape) == (1, 2, 16)   # max valid ids
+
+
+def test_unsupported_row_width_fails_loudly(R):
+    emb = R.get_embedding({"name": "vanilla"}, [5, 6], 50).to(DEV)   # 50 % 4 != 0 and > 32
+    with pytest.raises(RuntimeError, match="unsupported row width"):
+        emb(torch.tensor([[0, 5]], device=DEV))
+
+
+@pytest.mark.parametrize("d", [7, 12, 16, 64])
+def test_odd_widths_match_torch(R, d):
+    model = R.get_ctr_model([50, 60, 70], dict(num_factor=d, hidden_sizes=[8], p_dropout=0.0)).to(DEV)
+    x = torch.stack([torch.randint(0, n, (33,), device=DEV) for n in [50, 60, 70]], 1)
+    logits = model(x)
+    w = model.embedding.get_weight()
+    rows = x + model.offsets
+    e = torch.nn.functional.embedding(rows, w)
+    y = model.fc(rows) + model._bias + 0.5 * (e.sum(1).pow(2) - e.pow(2).sum(1)).sum(1, keepdim=True)
+    ref = (y + model._deep_branch(e.reshape(33, -1))).squeeze(-1)
+    torch.testing.assert_close(logits, ref, rtol=1e-5, atol=1e-5)
+    g1 = torch.autograd.grad(logits.sum(), [w, model.fc.weight])
+    g2 = torch.autograd.grad(ref.sum(), [w, model.fc.weight])
+    torch.testing.assert_close(g1[0], g2[0], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(g1[1], g2[1], rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------- properties at BASELINE.json sizes ---
+@pytest.mark.parametrize("emb_cfg,b", [({"name": "vanilla"}, 2048), ({"name": "qr", "divider": 5}, 2048),
+                                       ({"name": "vanilla"}, 16384)])
+def test_criteo_shape_properties(R, emb_cfg, b):
+    torch.manual_seed(3)
+    model = R.get_ctr_model(CRITEO_DIMS, dict(num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=0.0,
+                                              use_batchnorm=False, embedding_config=dict(emb_cfg))).to(DEV)
+    gen = torch.Generator().manual_seed(2023)
+    x = torch.stack([torch.randint(0, d, (b,), generator=gen) for d in CRITEO_DIMS], 1).to(DEV)
+    # (1) fused forward == unfused composition of the plugin forward and torch FM ops
+    logits = model(x)
+    rows = x + model.offsets
+    e = model.embedding(rows)
+    y = model.fc(rows) + model._bias + 0.5 * (e.sum(1).pow(2) - e.pow(2).sum(1)).sum(1, keepdim=True)
+    ref = (y + model._deep_branch(e.reshape(b, -1))).squeeze(-1)
+    assert_close(logits.detach().cpu().numpy(), ref.detach().cpu().numpy(), what="fused vs composed", atol_scale=2e-5)
+    # (2) int32 ids give bit-identical logits
+    assert torch.equal(model(x.int()), logits)
+    # (3) gradients: fused backward == composed backward; checksum of checksums
+    params = [p for p in model.embedding.parameters()] + [model.fc.weight]
+    g1 = torch.autograd.grad(logits.square().sum(), params)
+    g2 = torch.autograd.grad(ref.square().sum(), params)
+    for a_, b_ in zip(g1, g2):
+        assert_close(a_.cpu().numpy(), b_.cpu().numpy(), what="grad fused vs composed", atol_scale=5e-5)
+    # (4) determinism of the sorted segmented scatter-add
+    g3 = torch.autograd.grad(model(x).square().sum(), params)
+    assert all(torch.equal(a_, b_) for a_, b_ in zip(g1[:-1], g3[:-1]))
+    # (5) untouched rows have exactly zero gradient
+    if emb_cfg["name"] == "vanilla":
+        touched = torch.zeros(sum(CRITEO_DIMS), dtype=torch.bool, device=DEV)
+        touched[rows.reshape(-1)] = True
+        assert float(g1[0][~touched].abs().sum()) == 0.0

@@ -1,0 +1,151 @@
+"""CPU tests of the host-side mirror of the reference API: registry / factory semantics,
+state-dict compatibility with the reference (from the golden files), optimizer grouping,
+and that the product path refuses to run without CUDA (no CPU fallback)."""
+import numpy as np
+import pytest
+import torch
+
+import recsys_benchmark_b200 as R
+from tests.helpers import load_golden, sub
+
+CASES = {
+    "deepfm_vanilla_adam": {"name": "vanilla"},
+    "deepfm_vanilla_sparse_adam": {"name": "vanilla", "sparse": True},
+    "deepfm_qr_mult": {"name": "qr", "divider": 4, "operation": "mult"},
+    "deepfm_qr_add": {"name": "qr", "divider": 4, "operation": "add"},
+    "deepfm_qr_cat": {"name": "qr", "divider": 4, "operation": "cat"},
+    "deepfm_optembed": {"name": "deepfm_optembed"},
+    "deepfm_optembed_l2": {"name": "deepfm_optembed", "norm": 2},
+    "deepfm_optembed_d": {"name": "deepfm_optembed_d"},
+}
+
+
+def build_from_golden(name, emb_cfg, tmp_path=None, **model_kw):
+    g = load_golden(name)
+    fd = [int(v) for v in g["field_dims"]]
+    st = sub(g, "state/")
+    use_bn = any(k.endswith("running_mean") for k in st)
+    d = 8
+    cfg = dict(num_factor=d, hidden_sizes=[16, 8], p_dropout=0.0, use_batchnorm=use_bn,
+               embedding_config=dict(emb_cfg))
+    cfg.update(model_kw)
+    model = R.get_ctr_model(fd, cfg)
+    return g, model, {k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_matches_reference(name):
+    g, model, state = build_from_golden(name, CASES[name])
+    ours = model.state_dict()
+    assert sorted(ours.keys()) == sorted(state.keys())
+    for k, v in state.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+        assert ours[k].dtype == v.dtype, k
+    model.load_state_dict(state, strict=True)
+    ref_grad_keys = {k[len("step0/grad/"):] for k in g if k.startswith("step0/grad/")}
+    trainable = {k for k, p in model.named_parameters() if p.requires_grad}
+    assert ref_grad_keys <= trainable
+
+
+@pytest.mark.parametrize("tt", ["feature_dim", "feature", "dimension", "global"])
+def test_pep_state_dict(tt, tmp_path):
+    g, model, state = build_from_golden(
+        f"deepfm_pep_{tt}", {"name": "pep", "checkpoint_weight_dir": str(tmp_path), "threshold_type": tt})
+    model.load_state_dict(state, strict=True)
+    assert (tmp_path / "deepfm").is_dir()  # constructor side effect kept (pep_embedding.py:73-75)
+    assert model.embedding.checkpoint_weight_dir.endswith("deepfm")
+    assert model.embedding.sparsity == [0.8, 0.9, 0.99] and model.embedding._cur_min_spar_idx == 0
+
+
+def test_pep_retrain_state_dict_and_mask(tmp_path):
+    ck = load_golden("pep_retrain_ckpt")
+    (tmp_path / "deepfm").mkdir()
+    torch.save({"emb.weight": torch.from_numpy(ck["weight"]), "s": torch.from_numpy(ck["s"])},
+               tmp_path / "deepfm" / "0.5.pth")
+    g, model, state = build_from_golden(
+        "deepfm_pep_retrain", {"name": "pep_retrain", "checkpoint_weight_dir": str(tmp_path), "sparsity": 0.5})
+    assert model.embedding.mask.dtype == torch.bool and not model.embedding.mask.requires_grad
+    np.testing.assert_array_equal(model.embedding.mask.numpy(), g["state/embedding.mask"])
+    model.load_state_dict(state, strict=True)
+
+
+def test_factory_semantics():
+    with pytest.raises(NotImplementedError):
+        R.get_embedding({"name": "nope"}, [3, 4], 8)
+    with pytest.raises(AssertionError):
+        R.get_embedding({"name": "vanilla"}, [3, 4], 8, mode="bad")
+    cfg = {"name": "deepfm_optembed_d"}
+    emb = R.get_embedding(cfg, [3, 4], 8)
+    assert cfg == {"name": "deepfm_optembed_d"}  # config not mutated
+    assert isinstance(emb._mask_e_module, torch.nn.Identity)
+    assert [k for k, _ in emb.named_parameters()] == ["_weight"]
+    qr = R.get_embedding({"name": "qr"}, [5, 4, 6], 6)
+    assert qr._divider == 3 and qr.emb2.weight.shape == (5, 6)
+    qr = R.get_embedding({"name": "qr", "divider": 4, "operation": "cat"}, [5, 4, 6], 6)
+    assert qr.emb1.weight.shape == (4, 3) and qr.emb2.weight.shape == (4, 3)
+    v = R.get_embedding({"name": "vanilla", "sparse": True}, 10, 4)
+    assert v._emb_module.sparse and v.get_weight().shape == (10, 4)
+
+
+def test_get_optimizers_grouping():
+    model = R.get_ctr_model([3, 4, 5], dict(num_factor=4, hidden_sizes=[8],
+                                            embedding_config={"name": "vanilla", "sparse": True}))
+    opts = R.get_optimizers(model, dict(learning_rate=1e-3, weight_decay=1e-6))
+    assert len(opts) == 1 and isinstance(opts[0], torch.optim.Adam)
+    opts = R.get_optimizers(model, dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True))
+    assert isinstance(opts[0], torch.optim.SparseAdam) and isinstance(opts[1], torch.optim.Adam)
+    emb_ids = {id(p) for p in model.embedding.parameters()}
+    assert {id(p) for g in opts[0].param_groups for p in g["params"]} == emb_ids
+    rest = {id(p) for g in opts[1].param_groups for p in g["params"]}
+    assert id(model.fc.weight) in rest and not (rest & emb_ids)   # fc stays under dense Adam
+    opts = R.get_optimizers(model, dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, optimizer="sgd"))
+    assert len(opts) == 1 and opts[0].param_groups[0]["weight_decay"] == 0
+    opts = R.get_optimizers(model, dict(learning_rate=1e-3, weight_decay=0, sparse=True, fused_sparse=True))
+    assert isinstance(opts[0], R.FusedSparseAdam) and model.embedding._rsb_fused_opt is opts[0]
+    with pytest.raises(ValueError):
+        R.get_optimizers(model, dict(learning_rate=1e-3, weight_decay=0, optimizer="lamb"))
+
+
+def test_cpu_tensors_are_refused_no_fallback():
+    model = R.get_ctr_model([3, 4, 5], dict(num_factor=4, hidden_sizes=[8]))
+    x = torch.zeros(2, 3, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        model(x)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        model.embedding(x)
+
+
+def test_dcn_mix_state_dict_and_orig_mod_prefix():
+    g = load_golden("dcn_mix")
+    fd = [int(v) for v in g["field_dims"]]
+    cfg = dict(name="dcn_mix", num_factor=4, hidden_sizes=[12], num_layers=2, num_experts=3, rank=5, p_dropout=0.0,
+               compile_model=True, embedding_config={"name": "vanilla"})
+    model = R.get_ctr_model(fd, cfg)
+    assert cfg["compile_model"] is True and "name" not in cfg
+    state = {k: torch.from_numpy(np.asarray(v)) for k, v in sub(g, "state/").items()}
+    assert sorted(model.state_dict()) == sorted(state)
+    model.load_state_dict(state, strict=True)
+    ck = {"field_dims": fd, "state_dict": {"_orig_mod." + k: v for k, v in state.items()},
+          "model_config": dict(num_factor=4, hidden_sizes=[12], num_layers=2, num_experts=3, rank=5, p_dropout=0.0,
+                               compile_model=True, embedding_config={"name": "vanilla"})}
+    m2 = R.DCN_Mix.load(ck)
+    torch.testing.assert_close(m2.cross_head.gates, model.cross_head.gates)
+
+
+def test_dcn_head_torch_math_matches_reference_golden_on_cpu():
+    """The restructured cross layer (single GEMM over U as [E*r, Dm]) equals the reference."""
+    g = load_golden("dcn_mix")
+    st = sub(g, "state/")
+    head = R.DCN_MixHead(3, 2, 5, 16)
+    head.load_state_dict({k[len("cross_head."):]: torch.from_numpy(v) for k, v in st.items()
+                          if k.startswith("cross_head.")})
+    x0 = torch.from_numpy(g["cross_in"]).requires_grad_(True)
+    out = head(x0)
+    torch.testing.assert_close(out, torch.from_numpy(g["cross_out"]), rtol=1e-5, atol=1e-6)
+    out.backward(torch.from_numpy(g["g_cross_out"]))
+    torch.testing.assert_close(x0.grad, torch.from_numpy(g["g_cross_in"]), rtol=1e-4, atol=1e-7)
+    for n in ["V", "C", "U", "biases"]:
+        for l in range(2):
+            torch.testing.assert_close(getattr(head, n)[l].grad, torch.from_numpy(g[f"grad/cross_head.{n}.{l}"]),
+                                       rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(head.gates.grad, torch.from_numpy(g["grad/cross_head.gates"]), rtol=1e-4, atol=1e-7)
