@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — DeepFM train samples/s on Criteo-shaped synthetic data (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU PyTorch path (oracle port)
+
+A "step" is one full training iteration of the reference's trainer loop
+(src/trainer/deepfm.py:44-62): forward -> BCEWithLogits -> zero_grad -> backward ->
+optimizer.step, on one batch of synthetic Criteo-shaped ids.  Default workload =
+BASELINE.json configs[1]: DeepFM + QR-hashing embedding (configs/deepfm/qr_80.yaml:
+divider 5, mult, D=16, MLP 400x3, dropout 0.5, dense Adam lr 1e-3 wd 1e-6).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the same step fed
+from pinned host memory with the loss read back every step; `roofline` = the dominant
+hand-written kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak;
+`cpu_baseline` = the oracle port of the reference's CPU path timed on this box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CRITEO_DIMS = [49, 101, 126, 45, 223, 118, 84, 76, 95, 9, 30, 40, 75, 1458, 555, 193949, 138801, 306, 19, 11970, 634,
+               4, 42646, 5178, 192773, 3175, 27, 11422, 181075, 11, 4654, 2032, 5, 189657, 18, 16, 59697, 86, 45571]
+AVAZU_DIMS = [100000] * 10 + [1000] * 12
+KDD_DIMS = [600000] * 8 + [400000] * 3
+
+WORKLOADS = {
+    # BASELINE.json configs[1] (default)
+    "deepfm_qr_criteo": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "qr", "divider": 5}, use_bn=False,
+                             p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+    # configs[0] shape on the GPU, sparse=True variant (configs/deepfm/base_config_sparse.yaml) with the fused row update
+    "deepfm_full_criteo": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla", "sparse": True}, use_bn=True,
+                               p_dropout=0.5,
+                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True)),
+    "deepfm_full_criteo_dense_adam": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
+                                          p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+    "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
+                              opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_batches(dims, batch, n, seed, dtype):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        x = torch.stack([torch.randint(0, d, (batch,), generator=g) for d in dims], 1).to(dtype)
+        y = torch.randint(0, 2, (batch,), generator=g).float()
+        out.append((x, y))
+    return out
+
+
+# ------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU PyTorch path
+# ------------------------------------------------------------------------------------
+def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0):
+    import torch
+
+    from oracle import torch_port as TP
+
+    if wl["model"] != "deepfm":
+        raise NotImplementedError("cpu port covers the DeepFM workloads")
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    dims = wl["dims"]
+    emb = {k: v for k, v in wl["emb"].items()}
+    p = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
+    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k != "fused_sparse"})
+    offsets = torch.tensor([0] + dims[:-1]).cumsum(0)[None, :]
+    batches = make_batches(dims, sample_batch, 2, 2023, torch.int64)
+    for i in range(warmup):
+        TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"])
+    times = []
+    t_all = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 3:
+            break
+    med = statistics.median(times)
+    return dict(value=sample_batch / med, ms_per_step=med * 1e3, steps=len(times), cores=cores,
+                sample=f"{len(times)} steps of {sample_batch} samples (median step), torch {torch.__version__} CPU, "
+                       f"{cores} threads")
+
+
+def main_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = min(args.cpu_batch, args.batch)
+    r = run_cpu_port(wl, sample, max(args.steps, 3), max(args.warmup, 1), budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": "DeepFM train samples/s (Criteo shape)", "value": r["value"],
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_step": sample, "fields": len(wl["dims"]),
+                   "rows": sum(wl["dims"]), "embedding": wl["emb"], "device": "cpu"},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def main_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as G
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        G.build()
+    if world > 1:
+        dist.barrier()
+    import recsys_benchmark_b200 as R
+    import recsys_benchmark_b200.functional as RF
+    from recsys_benchmark_b200 import _lib
+
+    torch.manual_seed(2023)
+    dims = wl["dims"]
+    b = args.batch
+    if wl["model"] == "deepfm":
+        cfg = dict(num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"],
+                   embedding_config=dict(wl["emb"]))
+    else:
+        cfg = dict(name="dcn_mix", num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"],
+                   compile_model=False, embedding_config=dict(wl["emb"]))
+    model = R.get_ctr_model(dims, cfg).to(dev)
+    model.train()
+    opts = R.get_optimizers(model, dict(wl["opt"]))
+    crit = torch.nn.BCEWithLogitsLoss()
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def allreduce_grads():
+        grads = [p.grad for p in params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat.div_(world)
+        off = 0
+        views = []
+        for g in grads:
+            views.append(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+        torch._foreach_copy_(grads, views)
+
+    def step(x, y):
+        logits = model(x)
+        loss = crit(logits, y)
+        for o in opts:
+            o.zero_grad()
+        loss.backward()
+        if world > 1:
+            allreduce_grads()
+        for o in opts:
+            o.step()
+        return loss
+
+    pool = make_batches(dims, b, args.pool, 2023 + rank, torch.int32)
+    dev_pool = [(x.to(dev), y.to(dev)) for x, y in pool]
+    host_pool = [(x.pin_memory(), y.pin_memory()) for x, y in pool]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync_all()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        sync_all()
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value: inputs resident in HBM -------------------------------------------------
+    for i in range(args.warmup):
+        step(*dev_pool[i % len(dev_pool)])
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timer = RF.KernelTimer()
+    RF.set_timer(timer)
+    l0 = _lib.load().rsb_launch_count()
+    ms_total = timed(lambda i: step(*dev_pool[i % len(dev_pool)]), args.steps)
+    launches = _lib.load().rsb_launch_count() - l0
+    RF.set_timer(None)
+    kern = timer.summary()
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * b / (ms_step * 1e-3)
+
+    # ---- e2e: host buffers, H2D inside the timed region, loss read back every step ----------
+    def e2e_step(i):
+        xh, yh = host_pool[i % len(host_pool)]
+        loss = step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
+        return loss.item()
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    h2d = pool[0][0].numel() * pool[0][0].element_size() + pool[0][1].numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant hand-written kernel ------------------------------------
+    peak, peak_src = peaks()
+    kernels = {}
+    for name, r in kern.items():
+        gbs = (r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9) if r["bytes_avg"] and r["ms_avg"] > 0 else None
+        kernels[name] = {"calls_per_step": r["calls"] / args.steps, "ms_avg": round(r["ms_avg"], 4),
+                         "alg_bytes": int(r["bytes_avg"]), "alg_gbs": None if gbs is None else round(gbs, 1),
+                         "share_of_step": round(r["ms_total"] / ms_total, 4)}
+    cand = {k: v for k, v in kern.items() if v["bytes_avg"] > 0}
+    roofline = None
+    if cand:
+        top = max(cand, key=lambda k: cand[k]["ms_total"])
+        r = cand[top]
+        ach = r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(args.workload, {}).get(top)
+        roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "alg_bytes_per_launch": int(r["bytes_avg"]), "ms_per_launch": round(r["ms_avg"], 4)}
+
+    # ---- cpu baseline (oracle port of the reference's CPU path), rank 0, N=1 only ----------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and wl["model"] == "deepfm":
+        r = run_cpu_port(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0)
+        cpu = {"value": round(r["value"], 1), "unit": "samples/s", "cores": r["cores"], "kind": "port",
+               "sample": r["sample"]}
+
+    line = {
+        "metric": "DeepFM train samples/s (Criteo shape)" if wl["model"] == "deepfm" else "DCN-Mix train samples/s",
+        "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "global_batch": world * b, "batch_per_gpu": b, "fields": len(dims),
+                   "rows": sum(dims), "embedding": wl["emb"], "num_factor": 16, "mlp": [400, 400, 400],
+                   "optimizer": wl["opt"], "ids": "int32, uniform per field, seed 2023",
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2": f"{args.pool} distinct batches cycled; per-step traffic "
+                         f"{round(b * 13.4e3 / 1e6)} MB vs 126 MB L2 (no flush)"},
+        "clocks": clocks,
+        "e2e": {"value": round(world * b / (ms_e2e * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="deepfm_qr_criteo", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
+    ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches cycled through")
+    ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded sample per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        main_reference(args, wl)
+    else:
+        main_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,8 @@ typedef enum {
 RSB_API const char* rsb_version(void);
 /* Human-readable text for a non-zero return value (cudaGetErrorString for CUDA codes). */
 RSB_API const char* rsb_error_string(int code);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+RSB_API int64_t rsb_launch_count(void);
 /* 1 if a row of `width` floats (16-byte aligned when width % 4 == 0) is handled. */
 RSB_API int rsb_row_width_supported(int32_t width);
 

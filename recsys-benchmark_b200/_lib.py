@@ -29,6 +29,7 @@ _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 PROTOTYPES = {
     "rsb_version": (C.c_char_p, []),
     "rsb_error_string": (C.c_char_p, [C.c_int]),
+    "rsb_launch_count": (_i64, []),
     "rsb_row_width_supported": (C.c_int, [_i32]),
     "rsb_lookup_fwd": (C.c_int, [_i32, _p, _i32, _p, _i64, _i32, _i32, _p, _i64, _i64, _p, _i64, _p, _i32, _p,
                                  _p, _p, _p, _p, _p, _p, _p, _p]),

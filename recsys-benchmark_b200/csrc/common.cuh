@@ -120,6 +120,7 @@ inline RowShape row_shape(int E, bool aligned16) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();
+void note_launch(int n);
 
 // Dispatch helper: calls F.template run<V, LPR>() for the runtime shape.
 #define RSB_DISPATCH_SHAPE(shape, CALL)                       \

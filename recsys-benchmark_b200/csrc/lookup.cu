@@ -351,6 +351,7 @@ static int launch_fwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   RSB_CHECK_LAUNCH();
+  note_launch(1);
   return RSB_OK;
 }
 
@@ -365,6 +366,7 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   RSB_CHECK_LAUNCH();
+  note_launch(1);
   return RSB_OK;
 }
 
@@ -413,6 +415,7 @@ extern "C" RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx
                               float* out_yfm, float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream) {
   LookupArgs a = {};
   RowShape sh;
+  if (B == 0) return RSB_OK;  // empty batch: nothing to do (pointers of empty tensors may be NULL)
   if (idx == nullptr || out_emb == nullptr) return RSB_ERR_BAD_ARG;
   bool al = aligned16(out_emb) && (out_sum == nullptr || aligned16(out_sum));
   int rc = fill_common(a, kind, B, F, D, table, n_rows, n_global, table1, divider, aux, aux_mode, sh, al);
@@ -448,6 +451,7 @@ extern "C" RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, in
                                    float* rg_aux, float* fc_grad, void* stream) {
   LookupArgs a = {};
   RowShape sh;
+  if (B == 0) return RSB_OK;
   if (rows == nullptr || rg_main == nullptr) return RSB_ERR_BAD_ARG;
   if (g_yfm == nullptr && g_deep == nullptr) return RSB_ERR_BAD_ARG;
   if (g_yfm != nullptr && (emb == nullptr || S == nullptr)) return RSB_ERR_BAD_ARG;

@@ -1,9 +1,14 @@
 // Library bookkeeping and the full-table helpers of the lightweight-embedding variants.
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace rsb {
+
+static std::atomic<long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -118,6 +123,8 @@ static unsigned grid_for(long long items, int threads) {
 
 using namespace rsb;
 
+extern "C" RSB_API int64_t rsb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" RSB_API const char* rsb_version(void) { return "rsb 0.1.0 (sm_100a)"; }
 
 extern "C" RSB_API const char* rsb_error_string(int code) {
@@ -141,6 +148,7 @@ extern "C" RSB_API int rsb_pep_threshold_table(const float* weight, const float*
   pep_threshold_table_kernel<<<grid_for(n_rows * D, 256), 256, 0, st>>>(
       weight, s, threshold_type, n_rows, D, out, reinterpret_cast<unsigned long long*>(count));
   RSB_CHECK_LAUNCH();
+  note_launch(1);
   return RSB_OK;
 }
 
@@ -153,6 +161,7 @@ extern "C" RSB_API int rsb_pep_dense_bwd(const float* weight, const float* s, in
   pep_dense_bwd_kernel<<<grid_for(n_rows * D, 256), 256, 0, st>>>(weight, s, threshold_type, n_rows, D, g_table,
                                                                    g_weight, g_s_full);
   RSB_CHECK_LAUNCH();
+  note_launch(1);
   return RSB_OK;
 }
 
@@ -166,6 +175,7 @@ extern "C" RSB_API int rsb_optembed_eval_weight(const float* weight, const float
       weight, t_row, reinterpret_cast<const long long*>(mask_d_row), norm, n_rows, D, out,
       reinterpret_cast<unsigned long long*>(count));
   RSB_CHECK_LAUNCH();
+  note_launch(1);
   return RSB_OK;
 }
 
@@ -175,5 +185,6 @@ extern "C" RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   mask_table_kernel<<<grid_for(numel, 256), 256, 0, st>>>(weight, mask, numel, out);
   RSB_CHECK_LAUNCH();
+  note_launch(1);
   return RSB_OK;
 }

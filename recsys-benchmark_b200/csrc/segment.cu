@@ -244,5 +244,6 @@ extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* s
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   RSB_CHECK_LAUNCH();
+  note_launch(groups2 > 0 ? 2 : 1);
   return RSB_OK;
 }

@@ -99,5 +99,6 @@ extern "C" RSB_API int rsb_small_table_grad(const int64_t* keys, int64_t n, int6
   RSB_CHECK_LAUNCH();
   small_table_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(partials, nblk, tot, dst);
   RSB_CHECK_LAUNCH();
+  note_launch(2);
   return RSB_OK;
 }

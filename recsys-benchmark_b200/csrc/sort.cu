@@ -238,6 +238,7 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
     RSB_CHECK_LAUNCH();
     sort_scatter_kernel<<<(unsigned)nblk, kSortThreads, 0, s>>>(src, n, shift, rb, hist, (int)nblk, ok, ov);
     RSB_CHECK_LAUNCH();
+    note_launch(3);
     src.keys64 = nullptr;
     src.keys32 = ok;
     src.vals32 = ov;

@@ -39,6 +39,49 @@ class LookupSpec:
         return 2 * f if self.kind == L.KIND_QR_CAT else f
 
 
+class KernelTimer:
+    """Optional per-C-call CUDA-event timing (bench.py's roofline leg).  Events are recorded
+    on the launching stream right around each call; nothing synchronises until `summary()`."""
+
+    def __init__(self):
+        self.records = {}
+
+    def add(self, name, start, end, nbytes=0):
+        self.records.setdefault(name, []).append((start, end, nbytes))
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = [s.elapsed_time(e) for s, e, _ in recs]
+            out[name] = dict(calls=len(ms), ms_avg=sum(ms) / len(ms), ms_total=sum(ms),
+                             bytes_avg=sum(r[2] for r in recs) / len(recs))
+        return out
+
+
+_TIMER = None
+
+
+def set_timer(timer) -> None:
+    global _TIMER
+    _TIMER = timer
+
+
+def _call(name: str, fn, *args, nbytes: int = 0) -> None:
+    """One C-ABI call, optionally bracketed by CUDA events; raises on a non-zero status."""
+    t = _TIMER
+    if t is None:
+        L.check(fn(*args), name)
+        return
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    L.check(rc, name)
+    t.add(name, s, e, nbytes)
+
+
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
 
@@ -55,8 +98,8 @@ def sort_rows(rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 
     perm = torch.empty(n, dtype=torch.int32, device=dev)
     nb = lib.rsb_sort_workspace_bytes(n)
     ws = _ws(nb, dev)
-    L.check(lib.rsb_sort_rows(L.ptr(rows), n, int(n_rows), int(key_div), int(key_mod), L.ptr(skeys), L.ptr(perm),
-                              L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "sort_rows")
+    _call("sort_rows", lib.rsb_sort_rows, L.ptr(rows), n, int(n_rows), int(key_div), int(key_mod), L.ptr(skeys),
+          L.ptr(perm), L.ptr(ws), ws.numel(), L.stream_ptr(dev))
     return skeys, perm
 
 
@@ -68,9 +111,9 @@ def segment_reduce_apply(apply: int, skeys, perm, row_grads, dst, exp_avg=None, 
     dev = row_grads.device
     nb = lib.rsb_segment_workspace_bytes(n, e)
     ws = _ws(nb, dev)
-    L.check(lib.rsb_segment_reduce_apply(apply, L.ptr(skeys), L.ptr(perm), n, L.ptr(row_grads), e, L.ptr(dst),
-                                         L.ptr(exp_avg), L.ptr(exp_avg_sq), lr, beta1, beta2, eps, int(step),
-                                         L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "segment_reduce_apply")
+    _call("segment_reduce_apply", lib.rsb_segment_reduce_apply, apply, L.ptr(skeys), L.ptr(perm), n,
+          L.ptr(row_grads), e, L.ptr(dst), L.ptr(exp_avg), L.ptr(exp_avg_sq), lr, beta1, beta2, eps, int(step),
+          L.ptr(ws), ws.numel(), L.stream_ptr(dev), nbytes=n * (8 + 4 * e))
 
 
 def dense_row_grad(rows: torch.Tensor, row_grads: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 0,
@@ -97,9 +140,9 @@ def small_table_grad(rows: torch.Tensor, row_grads: torch.Tensor, n_rows: int, k
     dev = row_grads.device
     out = torch.empty(n_rows, e, dtype=torch.float32, device=dev)
     ws = _ws(nb, dev)
-    L.check(lib.rsb_small_table_grad(L.ptr(rows), rows.numel(), int(key_div), int(key_mod), L.ptr(row_grads), e,
-                                     int(n_rows), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev)),
-            "small_table_grad")
+    _call("small_table_grad", lib.rsb_small_table_grad, L.ptr(rows), rows.numel(), int(key_div), int(key_mod),
+          L.ptr(row_grads), e, int(n_rows), L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(dev),
+          nbytes=rows.numel() * (8 + 4 * e))
     return out
 
 
@@ -149,12 +192,15 @@ class _FusedLookup(torch.autograd.Function):
         aux_t = aux
         if aux is not None and aux.dtype == torch.bool:
             aux_t = aux.view(torch.uint8)
-        L.check(lib.rsb_lookup_fwd(
-            spec.kind, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, spec.dim,
-            L.ptr(table), table.shape[0], spec.num_global, L.ptr(table1), spec.divider,
-            L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(fc), L.ptr(bias),
-            L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows), L.ptr(_err_flag(spec, dev)), L.stream_ptr(dev)),
-            "lookup_fwd")
+        # algorithmic bytes: ids + rows read + emb written + rows saved (+ fc, y, S)
+        r_bytes = vf * e * 4
+        nbytes = b * (f * x.element_size() + 2 * r_bytes + f * 8 + (f * 4 + 4 + e * 4 if fm else 0))
+        _call("lookup_fwd", lib.rsb_lookup_fwd,
+              spec.kind, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, spec.dim,
+              L.ptr(table), table.shape[0], spec.num_global, L.ptr(table1), spec.divider,
+              L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(fc), L.ptr(bias),
+              L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows), L.ptr(_err_flag(spec, dev)), L.stream_ptr(dev),
+              nbytes=nbytes)
         ctx.spec = spec
         ctx.fm = fm
         ctx.shape = (b, f)
@@ -200,11 +246,15 @@ class _FusedLookup(torch.autograd.Function):
                 rg_aux = torch.empty(n, e, dtype=torch.float32, device=dev)
             elif kind == L.KIND_OPTEMBED and aux is not None:
                 rg_aux = torch.empty(b, f, dtype=torch.float32, device=dev)
-            L.check(lib.rsb_lookup_bwd_rows(
-                kind, L.ptr(rows), b, f, spec.dim, L.ptr(table), table.shape[0], L.ptr(table1), spec.divider,
-                L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
-                L.ptr(g_y) if use_gy else None, L.ptr(g_emb), L.ptr(rg_main), L.ptr(rg_aux), L.ptr(g_fc),
-                L.stream_ptr(dev)), "lookup_bwd_rows")
+            # algorithmic bytes: rows + g_deep + emb (+S, g_y) read, row grads written (+ fc atomics)
+            r_bytes = spec.out_fields(f) * e * 4
+            n_out = 2 if (rg_aux is not None and kind != L.KIND_OPTEMBED) else 1
+            nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + n_out * f * e * 4 + (e * 4 + 4 + f * 4 if use_gy else 0))
+            _call("lookup_bwd_rows", lib.rsb_lookup_bwd_rows,
+                  kind, L.ptr(rows), b, f, spec.dim, L.ptr(table), table.shape[0], L.ptr(table1), spec.divider,
+                  L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
+                  L.ptr(g_y) if use_gy else None, L.ptr(g_emb), L.ptr(rg_main), L.ptr(rg_aux), L.ptr(g_fc),
+                  L.stream_ptr(dev), nbytes=nbytes)
             if kind == L.KIND_QR_ADD:
                 rg_aux = rg_main
 

@@ -20,12 +20,12 @@ def sub(d, prefix):
     return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
 
 
-def assert_close(got, ref, rtol=RTOL, atol_scale=1e-5, what=""):
+def assert_close(got, ref, rtol=RTOL, atol_scale=1e-5, what="", atol_floor=1e-30):
     got = np.asarray(got)
     ref = np.asarray(ref)
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
     scale = float(np.abs(ref).max()) if ref.size else 0.0
-    atol = atol_scale * scale + 1e-30
+    atol = max(atol_scale * scale, atol_floor)
     err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
     bound = atol + rtol * np.abs(ref.astype(np.float64))
     bad = err > bound

@@ -67,7 +67,8 @@ def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, a
             key = f"step{s}/grad/{k}"
             if key in g:
                 assert p.grad is not None, f"{k} has no grad"
-                assert_close(_grad_np(p), g[key], what=f"{name} step{s} grad {k}", atol_scale=2e-5)
+                # atol floor: gradients that are zero by construction (a Linear bias feeding BatchNorm) are fp32 noise ~1e-8
+                assert_close(_grad_np(p), g[key], what=f"{name} step{s} grad {k}", atol_scale=2e-5, atol_floor=2e-7)
             else:
                 assert p.grad is None or float(p.grad.abs().sum()) == 0.0 or not p.requires_grad, k
         for o in opts:
@@ -202,7 +203,7 @@ def test_dcn_mix_matches_reference(R):
     assert_close(logits.detach().cpu().numpy(), g["logits"], what="dcn logits")
     for k, p in model.named_parameters():
         if f"grad/{k}" in g:
-            assert_close(_grad_np(p), g[f"grad/{k}"], what=f"dcn grad {k}", atol_scale=3e-5)
+            assert_close(_grad_np(p), g[f"grad/{k}"], what=f"dcn grad {k}", atol_scale=3e-5, atol_floor=2e-7)
 
 
 # ------------------------------------------------------------- plugin API ---
@@ -340,9 +341,11 @@ def test_criteo_shape_properties(R, emb_cfg, b):
     g2 = torch.autograd.grad(ref.square().sum(), params)
     for a_, b_ in zip(g1, g2):
         assert_close(a_.cpu().numpy(), b_.cpu().numpy(), what="grad fused vs composed", atol_scale=5e-5)
-    # (4) determinism of the sorted segmented scatter-add
+    # (4) determinism of the sorted segmented scatter-add (the big table: vanilla weight / QR emb2;
+    #     QR emb1 accumulates in shared memory with float atomics and fc with global atomics)
     g3 = torch.autograd.grad(model(x).square().sum(), params)
-    assert all(torch.equal(a_, b_) for a_, b_ in zip(g1[:-1], g3[:-1]))
+    big = max(range(len(params) - 1), key=lambda i: params[i].numel())
+    assert torch.equal(g1[big], g3[big])
     # (5) untouched rows have exactly zero gradient
     if emb_cfg["name"] == "vanilla":
         touched = torch.zeros(sum(CRITEO_DIMS), dtype=torch.bool, device=DEV)
