@@ -143,12 +143,19 @@ __global__ void __launch_bounds__(kSegThreads) seg_chunk_kernel(const unsigned* 
   }
 }
 
-// One lane group per chunk boundary cb >= 1 (position P = cb * kChunk).
+// One lane group per chunk boundary cb >= 1 (position P = cb * kChunk).  The group that sees
+// the FIRST crossing of a run owns it: it finds the run's end by binary search (keys are
+// sorted), then either adds the <= kSerialMax partials itself or queues the run for
+// seg_long_kernel (a hot row looked up by every sample spans thousands of chunks).
+constexpr int kSerialMax = 8;
+constexpr int kLongThreads = 256;
+
 template <int V, int LPR>
 __global__ void __launch_bounds__(kSegThreads) seg_boundary_kernel(const unsigned* __restrict__ skeys, long long n,
                                                                    long long n_chunks, ApplyArgs ap,
                                                                    const float* __restrict__ part_first,
-                                                                   const float* __restrict__ part_last) {
+                                                                   const float* __restrict__ part_last,
+                                                                   int* long_count, long long* long_list) {
   constexpr int GPW = kWarp / LPR;
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, c = lane % LPR;
@@ -162,18 +169,82 @@ __global__ void __launch_bounds__(kSegThreads) seg_boundary_kernel(const unsigne
   const unsigned row = __ldg(skeys + P);
   if (__ldg(skeys + P - 1) != row) return;                                    // no run crosses here
   if (cb >= 2 && __ldg(skeys + (cb - 1) * kChunk - 1) == row) return;         // not the first crossing
+  // last position of the run: invariant key[lo] == row, key[hi] > row (or hi == n)
+  long long lo = P, hi = P + (long long)kChunk * kSerialMax;
+  if (hi >= n || __ldg(skeys + hi) != row) {
+    if (hi > n) hi = n;
+  } else {
+    lo = hi;
+    hi = n;
+  }
+  while (hi - lo > 1) {
+    const long long mid = lo + ((hi - lo) >> 1);
+    if (__ldg(skeys + mid) == row) lo = mid;
+    else hi = mid;
+  }
+  const long long c_last = lo / kChunk;
+  if (c_last - cb + 1 > kSerialMax) {
+    if (c == 0) {
+      const int slot = atomicAdd(long_count, 1);
+      long_list[2 * slot] = cb;
+      long_list[2 * slot + 1] = c_last;
+    }
+    return;
+  }
   if (!cact) return;
   FV<V> tot = ldg<V>(part_last + (cb - 1) * ap.E + d0);
-  long long cc = cb;
-  while (true) {
+  for (long long cc = cb; cc <= c_last; ++cc) {
     FV<V> p = ldg<V>(part_first + cc * ap.E + d0);
 #pragma unroll
     for (int k = 0; k < V; ++k) tot.v[k] += p.v[k];
-    const long long nextP = (cc + 1) * kChunk;
-    if (nextP < n && __ldg(skeys + nextP) == row) ++cc;
-    else break;
   }
   apply_row<V>(ap, row, d0, tot);
+}
+
+// Long runs: one CTA per run, lane groups stride over the run's chunk partials, then a
+// fixed-shape tree in shared memory (deterministic).
+template <int V, int LPR>
+__global__ void __launch_bounds__(kLongThreads) seg_long_kernel(const unsigned* __restrict__ skeys, ApplyArgs ap,
+                                                                const float* __restrict__ part_first,
+                                                                const float* __restrict__ part_last,
+                                                                const int* __restrict__ long_count,
+                                                                const long long* __restrict__ long_list) {
+  constexpr int G = kLongThreads / LPR;
+  __shared__ float red[G][LPR * V];
+  const int g = threadIdx.x / LPR, c = threadIdx.x % LPR;
+  const int d0 = c * V;
+  const bool cact = d0 < ap.E;
+  const int cnt = *long_count;
+  for (int w = blockIdx.x; w < cnt; w += gridDim.x) {
+    const long long cb = long_list[2 * w], c_last = long_list[2 * w + 1];
+    const unsigned row = __ldg(skeys + cb * kChunk);
+    FV<V> acc = FV<V>::zero();
+    if (cact) {
+      if (g == 0) acc = ldg<V>(part_last + (cb - 1) * ap.E + d0);
+      for (long long cc = cb + g; cc <= c_last; cc += G) {
+        FV<V> p = ldg<V>(part_first + cc * ap.E + d0);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc.v[k] += p.v[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) red[g][c * V + k] = acc.v[k];
+    __syncthreads();
+    for (int s = G / 2; s > 0; s >>= 1) {
+      if (g < s) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) red[g][c * V + k] += red[g + s][c * V + k];
+      }
+      __syncthreads();
+    }
+    if (g == 0 && cact) {
+      FV<V> tot;
+#pragma unroll
+      for (int k = 0; k < V; ++k) tot.v[k] = red[0][c * V + k];
+      apply_row<V>(ap, row, d0, tot);
+    }
+    __syncthreads();
+  }
 }
 
 }  // namespace rsb
@@ -185,7 +256,8 @@ static long long seg_align(long long x) { return (x + 255) / 256 * 256; }
 extern "C" RSB_API int64_t rsb_segment_workspace_bytes(int64_t n, int32_t E) {
   if (n < 0 || E <= 0) return 0;
   long long n_chunks = (n + kChunk - 1) / kChunk + 1;
-  return 2 * seg_align(n_chunks * E * 4) + 256;
+  long long max_long = n_chunks / kSerialMax + 2;
+  return 2 * seg_align(n_chunks * E * 4) + seg_align(256) + seg_align(max_long * 16) + 256;
 }
 
 extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
@@ -226,6 +298,8 @@ extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* s
   char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   float* part_first = reinterpret_cast<float*>(w);
   float* part_last = reinterpret_cast<float*>(w + seg_align((n_chunks + 1) * E * 4));
+  int* long_count = reinterpret_cast<int*>(w + 2 * seg_align((n_chunks + 1) * E * 4));
+  long long* long_list = reinterpret_cast<long long*>(w + 2 * seg_align((n_chunks + 1) * E * 4) + seg_align(256));
 
   const int gpw = 32 / sh.LPR;
   const long long warp_tile = (long long)gpw * kChunk;
@@ -234,16 +308,27 @@ extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* s
   const long long blocks1 = (warps + wpb - 1) / wpb;
   const long long groups2 = n_chunks - 1;
   const long long blocks2 = (groups2 + (long long)gpw * wpb - 1) / ((long long)gpw * wpb);
+  long long lb = (n_chunks / kSerialMax) + 1;
+  if (lb > 2ll * sm_count()) lb = 2ll * sm_count();
+  const unsigned long_blocks = (unsigned)lb;
+  if (groups2 > 0) {
+    cudaError_t me = cudaMemsetAsync(long_count, 0, sizeof(int), s);
+    if (me != cudaSuccess) return (int)me;
+  }
 
 #define CALL(VV, LL)                                                                                        \
   seg_chunk_kernel<VV, LL><<<(unsigned)blocks1, kSegThreads, 0, s>>>(sorted_keys, perm, n, row_grads, ap,   \
                                                                      part_first, part_last);                \
-  if (groups2 > 0)                                                                                          \
-    seg_boundary_kernel<VV, LL><<<(unsigned)blocks2, kSegThreads, 0, s>>>(sorted_keys, n, n_chunks, ap,     \
-                                                                          part_first, part_last)
+  if (groups2 > 0) {                                                                                        \
+    seg_boundary_kernel<VV, LL><<<(unsigned)blocks2, kSegThreads, 0, s>>>(                                  \
+        sorted_keys, n, n_chunks, ap, part_first, part_last, long_count, long_list);                        \
+    if (n_chunks > kSerialMax)                                                                              \
+      seg_long_kernel<VV, LL><<<long_blocks, kLongThreads, 0, s>>>(sorted_keys, ap, part_first, part_last,  \
+                                                                   long_count, long_list);                  \
+  }
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   RSB_CHECK_LAUNCH();
-  note_launch(groups2 > 0 ? 2 : 1);
+  note_launch(groups2 > 0 ? (n_chunks > kSerialMax ? 3 : 2) : 1);
   return RSB_OK;
 }

@@ -40,6 +40,69 @@ __global__ void __launch_bounds__(kSmallThreads) small_table_partial_kernel(
   for (long long i = threadIdx.x; i < tot; i += blockDim.x) out[i] = acc[i];
 }
 
+// Tiny tables (<= R rows, R = 8 or 32): every lane group keeps one accumulator per table row
+// in REGISTERS (the row id only selects which one is added to), so there are no atomics at
+// all; lane groups -> warp (shuffles) -> CTA (shared memory, fixed order) -> one partial per CTA.
+template <int V, int LPR, int R>
+__global__ void __launch_bounds__(kSmallThreads) tiny_table_partial_kernel(
+    const long long* __restrict__ keys, long long n, long long key_div, long long key_mod,
+    const float* __restrict__ rg, int E, int n_rows, float* __restrict__ partials) {
+  constexpr int GPW = kWarp / LPR;
+  constexpr int NW = kSmallThreads / 32;
+  __shared__ float red[NW][R][LPR * V];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = lane / LPR, c = lane % LPR;
+  const int d0 = c * V;
+  const bool cact = d0 < E;
+  FV<V> acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = FV<V>::zero();
+  // contiguous slice per CTA, groups stride inside it: fixed assignment -> deterministic
+  const long long per_cta = (n + gridDim.x - 1) / gridDim.x;
+  const long long beg = per_cta * blockIdx.x;
+  long long end = beg + per_cta;
+  if (end > n) end = n;
+  const int gib = wib * GPW + g;            // group index in the CTA
+  constexpr int GPB = NW * GPW;
+  for (long long p = beg + gib; p < end; p += GPB) {
+    long long k = __ldg(keys + p);
+    if (key_div > 1) k = k / key_div;
+    if (key_mod > 0) k = k % key_mod;
+    FV<V> v = FV<V>::zero();
+    if (cact) v = ldg<V>(rg + p * E + d0);
+    const int kk = (int)k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool hit = (kk == r);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[r].v[i] += hit ? v.v[i] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int off = LPR; off < kWarp; off <<= 1) {
+      FV<V> o = shfl_xor<V>(acc[r], off);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[r].v[i] += o.v[i];
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) red[wib][r][c * V + i] = acc[r].v[i];
+    }
+  }
+  __syncthreads();
+  const long long tot = (long long)n_rows * E;
+  float* out = partials + (long long)blockIdx.x * tot;
+  for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+    const int r = i / E, d = i - r * E;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w][r][d];
+    out[i] = s;
+  }
+}
+
 __global__ void small_table_reduce_kernel(const float* __restrict__ partials, int nblk, long long tot,
                                           float* __restrict__ dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,6 +151,25 @@ extern "C" RSB_API int rsb_small_table_grad(const int64_t* keys, int64_t n, int6
   float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   const int nblk = small_blocks(n);
   const size_t smem = (size_t)tot * 4;
+  if (n_rows <= 32 && sh.V * sh.LPR <= 32) {
+    const long long* k64 = reinterpret_cast<const long long*>(keys);
+#define CALLT(VV, LL)                                                                                          \
+  if constexpr (VV * LL <= 32) {                                                                               \
+    if (n_rows <= 8)                                                                                           \
+      tiny_table_partial_kernel<VV, LL, 8><<<nblk, kSmallThreads, 0, s>>>(k64, n, key_div, key_mod,           \
+                                                                          row_grads, E, (int)n_rows, partials); \
+    else                                                                                                       \
+      tiny_table_partial_kernel<VV, LL, 32><<<nblk, kSmallThreads, 0, s>>>(k64, n, key_div, key_mod,          \
+                                                                           row_grads, E, (int)n_rows, partials); \
+  }
+    RSB_DISPATCH_SHAPE(sh, CALLT);
+#undef CALLT
+    RSB_CHECK_LAUNCH();
+    small_table_reduce_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(partials, nblk, tot, dst);
+    RSB_CHECK_LAUNCH();
+    note_launch(2);
+    return RSB_OK;
+  }
 #define CALL(VV, LL)                                                                                          \
   if (smem > 48 * 1024)                                                                                       \
     cudaFuncSetAttribute(small_table_partial_kernel<VV, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \

@@ -40,7 +40,7 @@ class DCN_Mix(nn.Module):
     def forward(self, x):
         """x: [B, F] per-field ids without offsets -> logits [B] (src/models/dcn.py:76-96)."""
         emb, _ = self.embedding.lookup(x, self.offsets)   # offsets add fused into the gather
-        cross = self.cross_head(emb.reshape(emb.shape[0], -1))
+        cross = self.cross_head(emb.reshape(emb.shape[0], emb.shape[1] * emb.shape[2]))
         return self._dnn(cross).squeeze(-1)
 
     @classmethod
