@@ -46,6 +46,10 @@ WORKLOADS = {
                                opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True)),
     "deepfm_full_criteo_dense_adam": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
                                           p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+    # BASELINE.json configs[4]: full table row-sharded over the GPUs (NVLink peer gathers + shard atomics),
+    # dense Adam on each shard (= configs/deepfm/base_config.yaml semantics), dense MLP grads allreduced
+    "deepfm_full_criteo_sharded": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
+                                       p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6), sharded=True),
     "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
                               opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
 }
@@ -212,7 +216,13 @@ def main_ours(args, wl):
     else:
         cfg = dict(name="dcn_mix", num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"],
                    compile_model=False, embedding_config=dict(wl["emb"]))
-    model = R.get_ctr_model(dims, cfg).to(dev)
+    sharded = bool(wl.get("sharded", False))
+    if sharded:
+        from recsys_benchmark_b200.sharded import ShardedDeepFM
+
+        model = ShardedDeepFM(dims, 16, [400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"]).to(dev)
+    else:
+        model = R.get_ctr_model(dims, cfg).to(dev)
     model.train()
     opts = R.get_optimizers(model, dict(wl["opt"]))
     crit = torch.nn.BCEWithLogitsLoss()
@@ -236,10 +246,14 @@ def main_ours(args, wl):
         for o in opts:
             o.zero_grad()
         loss.backward()
-        if world > 1:
+        if sharded:
+            model.sync_gradients()
+        elif world > 1:
             allreduce_grads()
         for o in opts:
             o.step()
+        if sharded:
+            model.finish_step()
         return loss
 
     pool = make_batches(dims, b, args.pool, 2023 + rank, torch.int32)
@@ -337,7 +351,9 @@ def main_ours(args, wl):
         "config": {"workload": args.workload, "global_batch": world * b, "batch_per_gpu": b, "fields": len(dims),
                    "rows": sum(dims), "embedding": wl["emb"], "num_factor": 16, "mlp": [400, 400, 400],
                    "optimizer": wl["opt"], "ids": "int32, uniform per field, seed 2023",
-                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "parallelism": (f"row-sharded tables x{world} (NVLink peer gather / shard atomics) + dp{world} dense"
+                                   if sharded else (f"dp{world} (replicated compressed tables, flat grad allreduce)"
+                                                    if world > 1 else "single")),
                    "l2": f"{args.pool} distinct batches cycled; per-step traffic "
                          f"{round(b * 13.4e3 / 1e6)} MB vs 126 MB L2 (no flush)"},
         "clocks": clocks,

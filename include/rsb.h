@@ -67,7 +67,8 @@ typedef enum {
                                 aten embedding_dense_backward semantics, base.py:53-57)             */
   RSB_APPLY_SPARSE_ADAM = 1, /* torch.optim.SparseAdam row update (src/models/deepfm.py:173-184;
                                 torch/optim/_functional.py:24-84)                                    */
-  RSB_APPLY_SPARSE_SGD = 2   /* sparse SGD, p += -lr*g (src/models/deepfm.py:203-216)              */
+  RSB_APPLY_SPARSE_SGD = 2,  /* sparse SGD, p += -lr*g (src/models/deepfm.py:203-216)              */
+  RSB_APPLY_SHARD_ATOMIC = 3 /* (internal to rsb_segment_scatter_shards) vector atomic add into the owner's shard */
 } rsb_apply;
 
 RSB_API const char* rsb_version(void);
@@ -195,6 +196,34 @@ RSB_API int rsb_optembed_eval_weight(const float* weight, const float* t_row, co
                              int64_t n_rows, int32_t D, float* out, int64_t* count, void* stream);
 /* out = weight * mask (uint8) : RetrainPepEmbedding.get_weight / RetrainOptEmbed.get_weight. */
 RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, int64_t numel, float* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Row-sharded tables over the GPUs of one box (no reference
+ * counterpart: the reference is single-device).  Rank g owns the rows r of the concatenated
+ * table with r % G == g, stored at local row r / G.  Shards live in cudaMalloc'ed buffers
+ * exported with CUDA IPC; peers read (forward gather) and atomically add (backward) through
+ * the mapped pointers, i.e. directly over NVLink / NVSwitch — the index / row / row-grad
+ * exchange of an all-to-all design happens inside the gather and scatter kernels.
+ * ---------------------------------------------------------------------- */
+#define RSB_IPC_HANDLE_BYTES 64
+/* The only allocating calls of the library: peer-shareable buffers (zero-filled). */
+RSB_API int rsb_shared_alloc(int64_t bytes, void** dev_ptr_out /* host */);
+RSB_API int rsb_shared_free(void* dev_ptr);
+RSB_API int rsb_ipc_get_handle(const void* dev_ptr, uint8_t* h_handle /* [64] host */);
+RSB_API int rsb_ipc_open_handle(const uint8_t* h_handle /* [64] host */, void** dev_ptr_out /* host */);
+RSB_API int rsb_ipc_close_handle(void* dev_ptr);
+/* rsb_lookup_fwd(kind = VANILLA) over G shards: table_shards / fc_shards are DEVICE arrays of
+ * G device pointers (own shard + IPC-mapped peers); fc_shards may be NULL (no FM head). */
+RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B, int32_t F,
+                                   int32_t D, const float* const* table_shards, const float* const* fc_shards,
+                                   int32_t G, int64_t n_global, const float* bias, float* out_emb, float* out_yfm,
+                                   float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream);
+/* Backward: segmented reduction of this rank's sorted lookups (rsb_sort_rows on GLOBAL row
+ * ids), each locally-unique row's sum * scale added into the owner's dense shard gradient
+ * with one 128-bit red.global.add per 4 floats. */
+RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
+                                       const float* row_grads, int32_t E, float* const* grad_shards, int32_t G,
+                                       float scale, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "librsb.so")
 # enums of include/rsb.h
 KIND_VANILLA, KIND_QR_MULT, KIND_QR_ADD, KIND_QR_CAT, KIND_PEP, KIND_MASK, KIND_OPTEMBED = range(7)
 PEP_GLOBAL, PEP_DIMENSION, PEP_FEATURE, PEP_FEATURE_DIM = range(4)
-APPLY_DENSE, APPLY_SPARSE_ADAM, APPLY_SPARSE_SGD = range(3)
+APPLY_DENSE, APPLY_SPARSE_ADAM, APPLY_SPARSE_SGD, APPLY_SHARD_ATOMIC = range(4)
 
 PEP_TYPES = {"global": PEP_GLOBAL, "dimension": PEP_DIMENSION, "feature": PEP_FEATURE,
              "feature_dim": PEP_FEATURE_DIM}
@@ -46,6 +46,14 @@ PROTOTYPES = {
     "rsb_pep_dense_bwd": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "rsb_optembed_eval_weight": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "rsb_mask_table": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "rsb_shared_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
+    "rsb_shared_free": (C.c_int, [_p]),
+    "rsb_ipc_get_handle": (C.c_int, [_p, C.c_char_p]),
+    "rsb_ipc_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "rsb_ipc_close_handle": (C.c_int, [_p]),
+    "rsb_lookup_fwd_sharded": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p,
+                                         _p]),
+    "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i64, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -47,7 +47,23 @@ struct LookupArgs {
   float* rg_main;
   float* rg_aux;
   float* fc_grad;
+  // row-sharded tables (VANILLA only): shard g holds rows r with r % G == g at r / G
+  const float* const* table_shards;
+  const float* const* fc_shards;
+  int G;
 };
+
+__device__ __forceinline__ void shard_split(const LookupArgs& a, long long row, int& owner, long long& lrow) {
+  if (a.small32) {
+    unsigned r = (unsigned)row, g = (unsigned)a.G;
+    unsigned q = r / g;
+    lrow = q;
+    owner = (int)(r - q * g);
+  } else {
+    lrow = row / a.G;
+    owner = (int)(row - lrow * a.G);
+  }
+}
 
 __device__ __forceinline__ void qr_split(const LookupArgs& a, long long row, long long& i1, long long& i2) {
   if (a.small32) {
@@ -94,7 +110,16 @@ __device__ __forceinline__ FV<V> load_transformed(const LookupArgs& a, long long
   FV<V> e = FV<V>::zero();
   const int d0 = c * V;
   if (K == RSB_KIND_VANILLA) {
-    if (act) e = ldg<V>(a.table + row * a.E + d0);
+    if (act) {
+      if (a.table_shards != nullptr) {
+        int owner;
+        long long lrow;
+        shard_split(a, row, owner, lrow);
+        e = ldg<V>(a.table_shards[owner] + lrow * a.E + d0);   // peer shard: the load crosses NVLink
+      } else {
+        e = ldg<V>(a.table + row * a.E + d0);
+      }
+    }
   } else if (K == RSB_KIND_QR_MULT || K == RSB_KIND_QR_ADD) {
     if (act) {
       long long i1, i2;
@@ -181,6 +206,12 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
         if (c == 0 && vf < a.F) {
           if (a.out_rows) a.out_rows[b * a.F + f] = row;
           if (a.fc) first += __ldg(a.fc + row);
+          if (a.fc_shards) {
+            int owner;
+            long long lrow;
+            shard_split(a, row, owner, lrow);
+            first += __ldg(a.fc_shards[owner] + lrow);
+          }
         }
       }
       const bool act = vact && cact;
@@ -489,4 +520,35 @@ extern "C" RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, in
     case RSB_KIND_MASK: return launch_bwd<RSB_KIND_MASK>(a, sh, s);
     default: return launch_bwd<RSB_KIND_OPTEMBED>(a, sh, s);
   }
+}
+
+extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,
+                                              int32_t F, int32_t D, const float* const* table_shards,
+                                              const float* const* fc_shards, int32_t G, int64_t n_global,
+                                              const float* bias, float* out_emb, float* out_yfm, float* out_sum,
+                                              int64_t* out_rows, int32_t* err_flag, void* stream) {
+  LookupArgs a = {};
+  RowShape sh;
+  if (B == 0) return RSB_OK;
+  if (idx == nullptr || out_emb == nullptr || table_shards == nullptr || G < 1) return RSB_ERR_BAD_ARG;
+  bool al = aligned16(out_emb) && (out_sum == nullptr || aligned16(out_sum));
+  // shard base pointers come from cudaMalloc (256 B aligned); use a non-null dummy for the common checks
+  int rc = fill_common(a, RSB_KIND_VANILLA, B, F, D, reinterpret_cast<const float*>(out_emb), n_global, n_global,
+                       nullptr, 0, nullptr, 0, sh, al);
+  if (rc) return rc;
+  a.table = nullptr;
+  a.table_shards = table_shards;
+  a.fc_shards = fc_shards;
+  a.G = G;
+  a.small32 = (n_global < (1ll << 32)) ? 1 : 0;
+  a.idx = idx;
+  a.idx_i32 = idx_is_i32;
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  a.bias = bias;
+  a.out_emb = out_emb;
+  a.out_y = out_yfm;
+  a.out_sum = out_sum;
+  a.out_rows = reinterpret_cast<long long*>(out_rows);
+  a.err = err_flag;
+  return launch_fwd<RSB_KIND_VANILLA>(a, sh, reinterpret_cast<cudaStream_t>(stream));
 }

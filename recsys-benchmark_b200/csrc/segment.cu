@@ -29,10 +29,28 @@ struct ApplyArgs {
   float* v;
   float one_minus_b1, one_minus_b2, eps, neg_step_size, neg_lr;
   int E;
+  // RSB_APPLY_SHARD_ATOMIC: dst row lives on rank row % G at local row row / G (peer memory)
+  float* const* shards;
+  int G;
+  float scale;
 };
+
+__device__ __forceinline__ void atomic_add_row(float* p, const FV<4>& g) {
+  atomicAdd(reinterpret_cast<float4*>(p), make_float4(g.v[0], g.v[1], g.v[2], g.v[3]));  // red.global.add.v4.f32
+}
+__device__ __forceinline__ void atomic_add_row(float* p, const FV<1>& g) { atomicAdd(p, g.v[0]); }
 
 template <int V>
 __device__ __forceinline__ void apply_row(const ApplyArgs& ap, unsigned row, int d0, const FV<V>& g) {
+  if (ap.mode == RSB_APPLY_SHARD_ATOMIC) {
+    const unsigned q = row / (unsigned)ap.G;
+    const unsigned owner = row - q * (unsigned)ap.G;
+    FV<V> s;
+#pragma unroll
+    for (int i = 0; i < V; ++i) s.v[i] = g.v[i] * ap.scale;
+    atomic_add_row(ap.shards[owner] + (long long)q * ap.E + d0, s);
+    return;
+  }
   const long long o = (long long)row * ap.E + d0;
   if (ap.mode == RSB_APPLY_DENSE) {
     st<V>(ap.dst + o, g);
@@ -260,6 +278,28 @@ extern "C" RSB_API int64_t rsb_segment_workspace_bytes(int64_t n, int32_t E) {
   return 2 * seg_align(n_chunks * E * 4) + seg_align(256) + seg_align(max_long * 16) + 256;
 }
 
+static int segment_launch(ApplyArgs ap, RowShape sh, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
+                          const float* row_grads, int32_t E, void* workspace, cudaStream_t s);
+
+extern "C" RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
+                                                  const float* row_grads, int32_t E, float* const* grad_shards,
+                                                  int32_t G, float scale, void* workspace, int64_t workspace_bytes,
+                                                  void* stream) {
+  if (n < 0 || E <= 0 || G < 1) return RSB_ERR_BAD_ARG;
+  if (n == 0) return RSB_OK;
+  if (!sorted_keys || !perm || !row_grads || !grad_shards || !workspace) return RSB_ERR_BAD_ARG;
+  if (workspace_bytes < rsb_segment_workspace_bytes(n, E)) return RSB_ERR_WORKSPACE;
+  RowShape sh = row_shape(E, aligned16(row_grads));
+  if (!sh.ok) return RSB_ERR_UNSUPPORTED;
+  ApplyArgs ap = {};
+  ap.mode = RSB_APPLY_SHARD_ATOMIC;
+  ap.E = E;
+  ap.shards = grad_shards;
+  ap.G = G;
+  ap.scale = scale;
+  return segment_launch(ap, sh, sorted_keys, perm, n, row_grads, E, workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
 extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
                                         const float* row_grads, int32_t E, float* dst, float* exp_avg,
                                         float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
@@ -276,7 +316,7 @@ extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* s
   if (!sh.ok) return RSB_ERR_UNSUPPORTED;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 
-  ApplyArgs ap;
+  ApplyArgs ap = {};
   ap.mode = apply;
   ap.dst = dst;
   ap.m = exp_avg;
@@ -293,6 +333,11 @@ extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* s
     double bc2 = 1.0 - pow((double)beta2, (double)step);
     ap.neg_step_size = (float)(-((double)lr * sqrt(bc2) / bc1));
   }
+  return segment_launch(ap, sh, sorted_keys, perm, n, row_grads, E, workspace, s);
+}
+
+static int segment_launch(ApplyArgs ap, RowShape sh, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
+                          const float* row_grads, int32_t E, void* workspace, cudaStream_t s) {
 
   const long long n_chunks = (n + kChunk - 1) / kChunk;
   char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
