@@ -198,6 +198,28 @@ RSB_API int rsb_optembed_eval_weight(const float* weight, const float* t_row, co
 RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, int64_t numel, float* out, void* stream);
 
 /* ------------------------------------------------------------------------
+ * fp32-accurate tensor-core GEMM (tcgen05 + TMA; every fp32 operand split into 3 bf16 terms,
+ * 9 MMAs accumulated in fp32 TMEM).  Used for the DCN-Mix low-rank expert projections
+ * (src/models/layer_dcn.py:20-23: x@V, H@C, H@U, and their backward GEMMs) and for the
+ * dense tails (nn.Linear of the MLPs), which the reference runs as true-fp32 cuBLAS SGEMM
+ * (TF32 off), so plain TF32/bf16 MMA would break the 1e-5 parity gate.
+ *
+ *   D[l] = alpha * op(A[l]) * op(B[l]) + beta * C[l] + bias      l = 0..batch-1, D/C row-major [M,N] (ldd)
+ *   trans_a = 0: A is [M,K] row-major (lda)      trans_a = 1: A is stored [K,M] row-major (lda)
+ *   trans_b = 0: B is [K,N] row-major (ldb)      trans_b = 1: B is stored [N,K] row-major (ldb)  (nn.Linear weight)
+ *   (trans_a = trans_b = 1 is not provided.)  bias: per column [N] or NULL.  C may be NULL when beta == 0.
+ * TMA constraints: 16-byte aligned pointers; lda/ldb/ldd/batch strides and the contiguous
+ * extents multiples of 4 floats -> otherwise RSB_ERR_UNSUPPORTED (callers use a library GEMM).
+ * ---------------------------------------------------------------------- */
+RSB_API int64_t rsb_gemm_f32_workspace_bytes(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N, int64_t K,
+                                             int64_t batch);
+RSB_API int rsb_gemm_f32(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N, int64_t K, int64_t batch,
+                         const float* A, int64_t lda, int64_t stride_a, const float* B, int64_t ldb,
+                         int64_t stride_b, const float* C, float* D, int64_t ldd, int64_t stride_d,
+                         const float* bias, float alpha, float beta, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------------------
  * Row-sharded tables over the GPUs of one box (no reference
  * counterpart: the reference is single-device).  Rank g owns the rows r of the concatenated
  * table with r % G == g, stored at local row r / G.  Shards live in cudaMalloc'ed buffers

@@ -46,6 +46,9 @@ PROTOTYPES = {
     "rsb_pep_dense_bwd": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "rsb_optembed_eval_weight": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "rsb_mask_table": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "rsb_gemm_f32_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64]),
+    "rsb_gemm_f32": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64,
+                               _i64, _p, _f, _f, _p, _i64, _p]),
     "rsb_shared_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
     "rsb_shared_free": (C.c_int, [_p]),
     "rsb_ipc_get_handle": (C.c_int, [_p, C.c_char_p]),

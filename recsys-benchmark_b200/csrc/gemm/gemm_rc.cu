@@ -1,0 +1,9 @@
+// FastF32 GEMM instantiation: A RowMajor, B ColumnMajor (see fast_f32_gemm.cuh).
+#include "fast_f32_gemm.cuh"
+
+namespace rsb_gemm {
+int64_t gemm_rc(const Problem& p, bool query_ws) {
+  if (p.N <= 64) return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::ColumnMajor, 64>, true, true>(p, query_ws);
+  return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::ColumnMajor, 128>, true, true>(p, query_ws);
+}
+}  // namespace rsb_gemm

@@ -1,0 +1,9 @@
+// FastF32 GEMM instantiation: A RowMajor, B RowMajor (see fast_f32_gemm.cuh).
+#include "fast_f32_gemm.cuh"
+
+namespace rsb_gemm {
+int64_t gemm_rr(const Problem& p, bool query_ws) {
+  if (p.N <= 64) return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::RowMajor, 64>, true, false>(p, query_ws);
+  return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::RowMajor, 128>, true, false>(p, query_ws);
+}
+}  // namespace rsb_gemm

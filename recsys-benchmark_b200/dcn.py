@@ -8,6 +8,7 @@ from torch import nn
 
 from .embeddings import IEmbedding
 from .layer_dcn import DCN_MixHead
+from .linalg import run_sequential
 
 
 class DCN_Mix(nn.Module):
@@ -41,7 +42,7 @@ class DCN_Mix(nn.Module):
         """x: [B, F] per-field ids without offsets -> logits [B] (src/models/dcn.py:76-96)."""
         emb, _ = self.embedding.lookup(x, self.offsets)   # offsets add fused into the gather
         cross = self.cross_head(emb.reshape(emb.shape[0], emb.shape[1] * emb.shape[2]))
-        return self._dnn(cross).squeeze(-1)
+        return run_sequential(self._dnn, cross).squeeze(-1)
 
     @classmethod
     def load(cls, checkpoint: Union[str, Dict[str, Any]], strict=True, *, empty_embedding=False):

@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from .embeddings import IEmbedding
+from .linalg import run_sequential
 
 
 class DeepFM(nn.Module):
@@ -53,7 +54,7 @@ class DeepFM(nn.Module):
         """x: [B, F] per-field ids (int32 or int64, WITHOUT offsets) -> logits [B]."""
         emb, y_fm = self.embedding.lookup(x, self.offsets, self.fc.weight, self._bias)
         b = emb.shape[0]
-        scores = y_fm.unsqueeze(1) + self._deep_branch(emb.reshape(b, emb.shape[1] * emb.shape[2]))
+        scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]))
         return scores.squeeze(-1)
 
     def get_ranks(self, x) -> torch.Tensor:

@@ -14,18 +14,25 @@ from typing import Optional
 import torch
 from torch import nn
 
+from . import linalg as LA
+
 
 def forward_mixture_layer(x0, xl, V, C, U, bias, gates, gate_softmax: bool):
-    """One cross layer. x0, xl [B,Dm]; V [E,Dm,r]; C [E,r,r]; U [E,r,Dm]; bias [1,Dm]; gates [E,Dm,1]."""
+    """One cross layer. x0, xl [B,Dm]; V [E,Dm,r]; C [E,r,r]; U [E,r,Dm]; bias [1,Dm]; gates [E,Dm,1].
+
+    The three genuine GEMMs (x_l V, H1 C block-diagonal, G2 U) run on the fp32-accurate
+    tensor-core kernel (linalg.py); the [B,E] gate product (N = E = 4) stays a library call."""
     e, dm, r = V.shape
-    h1 = torch.tanh(torch.matmul(xl, V))                # [E,B,r]   (layer_dcn.py:20)
-    h2 = torch.tanh(torch.bmm(h1, C))                   # [E,B,r]   (:22)
-    g = torch.matmul(xl, gates.squeeze(2).t())          # [B,E]     (:107-109)
+    bsz = xl.shape[0]
+    vcat = V.permute(1, 0, 2).reshape(dm, e * r)           # [Dm, E*r]: column e*r+k = V[e,:,k]
+    h1 = torch.tanh(LA.matmul(xl, vcat))                   # [B, E*r]   (layer_dcn.py:20-21)
+    h2 = torch.tanh(LA.expert_matmul(h1, C))               # [B, E*r]   (:22)
+    g = torch.matmul(xl, gates.squeeze(2).t())             # [B, E]     (:107-109)
     if gate_softmax:
         g = torch.softmax(g, dim=1)
-    g2 = (h2 * g.t().unsqueeze(2)).permute(1, 0, 2).reshape(xl.shape[0], e * r)
-    t = torch.addmm(g.sum(1, keepdim=True) * bias, g2, U.reshape(e * r, dm))   # sum_e g_e (Eo_e + b)
-    return x0 * t + xl                                   # (:103,113)
+    g2 = (h2.view(bsz, e, r) * g.unsqueeze(2)).reshape(bsz, e * r)
+    t = LA.matmul(g2, U.reshape(e * r, dm)) + g.sum(1, keepdim=True) * bias   # sum_e g_e (Eo_e + b)  (:23,102)
+    return x0 * t + xl                                     # (:103,113)
 
 
 class DCN_MixHead(nn.Module):

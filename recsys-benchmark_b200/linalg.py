@@ -1,0 +1,232 @@
+"""fp32-accurate tensor-core GEMMs (rsb_gemm_f32: tcgen05 + TMA, 9xBF16 split) behind
+`matmul` / `linear` autograd functions.
+
+`gemm()` is the raw call (row-major operands with optional "stored transposed" flags,
+batched through strides, fused alpha / beta*C / per-column bias).  Shapes TMA cannot take
+(a leading dimension or contiguous extent not divisible by 4, e.g. the final Linear(400->1)
+or the toy sizes of the unit tests) go to the library GEMM (torch.matmul -> cuBLAS fp32);
+that is a shape dispatch between two fp32 GEMMs, not a CPU fallback."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import functional as RF
+
+MIN_FLOPS = 1 << 22   # below this a library call is launch-latency-equivalent
+
+
+def _aligned(*tensors) -> bool:
+    return all(t is None or t.data_ptr() % 16 == 0 for t in tensors)
+
+
+def gemm_supported(m: int, n: int, k: int, lda: int, ldb: int, ldd: int, trans_a: bool, trans_b: bool) -> bool:
+    if trans_a and trans_b:
+        return False
+    if min(m, n, k) <= 0 or n % 4 or lda % 4 or ldb % 4 or ldd % 4:
+        return False
+    if (m if trans_a else k) % 4 or (k if trans_b else n) % 4:
+        return False
+    return True
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
+         bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
+         beta: float = 0.0, c: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
+    """D = alpha * op(a) @ op(b) + beta * c + bias for 2-D fp32 CUDA tensors (contiguous rows).
+
+    trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K].  split_k > 1 splits the
+    reduction dimension into that many batched partial GEMMs (summed by the caller's dtype,
+    fixed order) — for weight-gradient GEMMs whose K is the batch size."""
+    lib = L.load()
+    dev = L.require_cuda(a, b, bias, c)
+    assert a.dim() == 2 and b.dim() == 2 and a.dtype == torch.float32 and b.dtype == torch.float32
+    a = a if a.stride(1) == 1 else a.contiguous()
+    b = b if b.stride(1) == 1 else b.contiguous()
+    k, m = (a.shape if trans_a else a.shape[::-1])
+    kb, n = (b.shape[::-1] if trans_b else b.shape)
+    assert k == kb, f"inner dimensions differ: {k} vs {kb}"
+    lda, ldb = a.stride(0), b.stride(0)
+    if split_k > 1 and (k % split_k or (k // split_k) % 4 or bias is not None or beta != 0.0):
+        split_k = 1
+    if not gemm_supported(m, n, k, lda, ldb, n if out is None else out.stride(0), trans_a, trans_b) or \
+            not _aligned(a, b, bias, c, out):
+        raise RuntimeError("rsb gemm: shape not supported by the TMA kernel")
+    if split_k > 1:
+        kc = k // split_k
+        part = torch.empty(split_k, m, n, dtype=torch.float32, device=dev)
+        sa = kc * lda if trans_a else kc          # A stored [K,M]: advance rows; A [M,K]: advance columns
+        sb = kc if trans_b else kc * ldb
+        nb = lib.rsb_gemm_f32_workspace_bytes(int(trans_a), int(trans_b), m, n, kc, split_k)
+        ws = RF._ws(nb, dev)
+        RF._call("gemm_f32", lib.rsb_gemm_f32, int(trans_a), int(trans_b), m, n, kc, split_k, L.ptr(a), lda, sa,
+                 L.ptr(b), ldb, sb, None, L.ptr(part), n, m * n, None, alpha, 0.0, L.ptr(ws), ws.numel(),
+                 L.stream_ptr(dev))
+        res = part.sum(0)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=dev)
+    nb = lib.rsb_gemm_f32_workspace_bytes(int(trans_a), int(trans_b), m, n, k, 1)
+    ws = RF._ws(nb, dev)
+    RF._call("gemm_f32", lib.rsb_gemm_f32, int(trans_a), int(trans_b), m, n, k, 1, L.ptr(a), lda, 0, L.ptr(b), ldb, 0,
+             L.ptr(c), L.ptr(out), out.stride(0), 0, L.ptr(bias), alpha, beta, L.ptr(ws), ws.numel(),
+             L.stream_ptr(dev))
+    return out
+
+
+def gemm_strided(m, n, k, batch, a, a_off, lda, sa, b, b_off, ldb, sb, out, d_off, ldd, sd, trans_a=False,
+                 trans_b=False, alpha=1.0) -> None:
+    """Raw strided-batched call: element offsets / leading dimensions / batch strides given explicitly
+    (all multiples of 4 floats).  out[d_off + l*sd + i*ldd + j] = alpha * sum_k op(A_l)[i,k] op(B_l)[k,j]."""
+    lib = L.load()
+    dev = a.device
+    nb = lib.rsb_gemm_f32_workspace_bytes(int(trans_a), int(trans_b), m, n, k, batch)
+    ws = RF._ws(nb, dev)
+    RF._call("gemm_f32", lib.rsb_gemm_f32, int(trans_a), int(trans_b), m, n, k, batch, a.data_ptr() + 4 * a_off, lda,
+             sa, b.data_ptr() + 4 * b_off, ldb, sb, None, out.data_ptr() + 4 * d_off, ldd, sd, None, alpha, 0.0,
+             L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+
+
+class _ExpertMatMul(torch.autograd.Function):
+    """Block-diagonal product of the DCN-Mix experts (src/models/layer_dcn.py:22):
+    out[b, e, :] = h[b, e, :] @ C[e]   for h [B, E*r] (expert-major columns), C [E, r, r2].
+    One strided-batched tensor-core GEMM (batch = experts) forward and for dh; the weight
+    gradient is one split-K batched GEMM per expert."""
+
+    @staticmethod
+    def forward(ctx, h, c):
+        e, r, r2 = c.shape
+        bsz = h.shape[0]
+        h = h.contiguous()
+        c = c.contiguous()
+        out = torch.empty(bsz, e * r2, dtype=torch.float32, device=h.device)
+        gemm_strided(bsz, r2, r, e, h, 0, e * r, r, c, 0, r2, r * r2, out, 0, e * r2, r2)
+        ctx.save_for_backward(h, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, c = ctx.saved_tensors
+        e, r, r2 = c.shape
+        bsz = h.shape[0]
+        g = g.contiguous()
+        gh = gc = None
+        if ctx.needs_input_grad[0]:
+            gh = torch.empty(bsz, e * r, dtype=torch.float32, device=h.device)
+            # gh[:, e, :] = g[:, e, :] @ C[e]^T : B operand "stored [N,K]" = C[e] as is
+            gemm_strided(bsz, r, r2, e, g, 0, e * r2, r2, c, 0, r2, r * r2, gh, 0, e * r, r, trans_b=True)
+        if ctx.needs_input_grad[1]:
+            split = 1
+            for s in (64, 32, 16, 8, 4, 2):
+                if bsz % s == 0 and (bsz // s) % 4 == 0 and bsz // s >= 256:
+                    split = s
+                    break
+            kc = bsz // split
+            part = torch.empty(e, split, r, r2, dtype=torch.float32, device=h.device)
+            for ei in range(e):
+                # C_grad[e] = h[:, e, :]^T @ g[:, e, :], reduction over the batch split into `split` partial GEMMs
+                gemm_strided(r, r2, kc, split, h, ei * r, e * r, kc * e * r, g, ei * r2, e * r2, kc * e * r2,
+                             part, ei * split * r * r2, r2, r * r2, trans_a=True)
+            gc = part.sum(1)
+        return gh, gc
+
+
+def expert_matmul(h: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """h [B, E*r] x C [E, r, r2] -> [B, E*r2] (block diagonal)."""
+    e, r, r2 = c.shape
+    bsz = h.shape[0]
+    if r % 4 == 0 and r2 % 4 == 0 and bsz % 4 == 0 and 2 * bsz * e * r * r2 >= MIN_FLOPS and h.is_cuda and \
+            _aligned(h, c):
+        return _ExpertMatMul.apply(h, c)
+    return torch.bmm(h.view(bsz, e, r).transpose(0, 1), c).transpose(0, 1).reshape(bsz, e * r2)
+
+
+def _use_kernel(m, n, k, *tensors) -> bool:
+    return (2 * m * n * k >= MIN_FLOPS and m % 4 == 0 and n % 4 == 0 and k % 4 == 0 and _aligned(*tensors)
+            and all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in tensors))
+
+
+class _Linear(torch.autograd.Function):
+    """y = x @ W^T + b with W [out, in] (nn.Linear layout); all three GEMMs on the tensor-core kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return gemm(x, weight, trans_b=True, bias=bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm(gy, weight)                                   # [B,out] @ [out,in]
+        if ctx.needs_input_grad[1]:
+            bsz = x.shape[0]
+            split = 1
+            for s in (32, 16, 8, 4, 2):
+                if bsz % s == 0 and (bsz // s) % 4 == 0 and bsz // s >= 512:
+                    split = s
+                    break
+            gw = gemm(gy, x, trans_a=True, split_k=split)           # gy^T [out,B] @ x [B,in]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy.sum(0)
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Drop-in for F.linear on 2-D inputs: tensor-core kernel when the shape allows, cuBLAS otherwise."""
+    if x.dim() == 2 and _use_kernel(x.shape[0], weight.shape[0], weight.shape[1], x, weight, bias) and \
+            x.stride(1) == 1 and x.stride(0) % 4 == 0:
+        return _Linear.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+class _MatMul(torch.autograd.Function):
+    """c = a @ b for 2-D row-major a [M,K], b [K,N]."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return gemm(a, b)
+
+    @staticmethod
+    def backward(ctx, gc):
+        a, b = ctx.saved_tensors
+        gc = gc.contiguous()
+        ga = gb = None
+        if ctx.needs_input_grad[0]:
+            ga = gemm(gc, b, trans_b=True)                          # gc [M,N] @ b^T (b stored [K,N] = "[N',K']" with N'=K)
+        if ctx.needs_input_grad[1]:
+            m = a.shape[0]
+            split = 1
+            for s in (32, 16, 8, 4, 2):
+                if m % s == 0 and (m // s) % 4 == 0 and m // s >= 512:
+                    split = s
+                    break
+            gb = gemm(a, gc, trans_a=True, split_k=split)           # a^T [K,M] @ gc [M,N]
+        return ga, gb
+
+
+def matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    if a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1 and a.stride(0) % 4 == 0 and \
+            b.stride(0) % 4 == 0 and _use_kernel(a.shape[0], b.shape[1], a.shape[1], a, b):
+        return _MatMul.apply(a, b)
+    return torch.matmul(a, b)
+
+
+def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """nn.Sequential forward with every nn.Linear routed through `linear` (same parameters,
+    same state dict); the other modules (BatchNorm1d / ReLU / Dropout) run unchanged."""
+    for m in seq:
+        if isinstance(m, torch.nn.Linear):
+            x = linear(x, m.weight, m.bias)
+        else:
+            x = m(x)
+    return x

@@ -29,6 +29,7 @@ from . import _lib as L
 from . import functional as RF
 from .deepfm import DeepFM
 from .embeddings import IEmbedding
+from .linalg import run_sequential
 
 
 # ------------------------------------------------------------------ host-side shard math ---
@@ -288,7 +289,7 @@ class ShardedDeepFM(DeepFM):
     def forward(self, x):
         emb, y_fm = self.embedding.lookup(x, self.offsets, None, self._bias)
         b = emb.shape[0]
-        scores = y_fm.unsqueeze(1) + self._deep_branch(emb.reshape(b, emb.shape[1] * emb.shape[2]))
+        scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]))
         return scores.squeeze(-1)
 
     # -- step protocol ---------------------------------------------------------------

@@ -1,0 +1,159 @@
+"""GPU tests of the fp32-accurate tensor-core GEMM (rsb_gemm_f32, tcgen05 9xBF16 split)
+through the C ABI wrappers: every layout, batching, fused epilogue, and fp32-level accuracy
+(error vs an fp64 product must be of the same order as cuBLAS fp32 SGEMM's)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def LA():
+    import __graft_entry__ as G
+
+    G.build()
+    import recsys_benchmark_b200.linalg as la
+
+    return la
+
+
+def _err(got, ref64):
+    return float((got.double() - ref64).abs().max() / ref64.abs().max())
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 400, 624), (2048, 400, 400), (1000, 64, 352), (4096, 256, 352),
+                                   (520, 352, 256), (4, 4, 4), (132, 12, 20)])
+@pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False)])
+def test_gemm_layouts_match_fp64(LA, m, n, k, ta, tb):
+    torch.manual_seed(m + n + k)
+    a = torch.randn((k, m) if ta else (m, k), device=DEV)
+    b = torch.randn((n, k) if tb else (k, n), device=DEV)
+    bias = torch.randn(n, device=DEV)
+    out = LA.gemm(a, b, trans_a=ta, trans_b=tb, bias=bias)
+    ref = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double()) + bias.double()
+    cublas = (a.t() if ta else a) @ (b.t() if tb else b) + bias
+    e_ours, e_cublas = _err(out, ref), _err(cublas, ref)
+    assert out.shape == (m, n)
+    assert e_ours < 2e-6, f"relative error {e_ours:.2e} (cuBLAS fp32: {e_cublas:.2e})"
+    assert e_ours < max(4 * e_cublas, 5e-7)
+
+
+def test_gemm_alpha_beta_c(LA):
+    a, b = torch.randn(256, 64, device=DEV), torch.randn(64, 128, device=DEV)
+    c = torch.randn(256, 128, device=DEV)
+    out = LA.gemm(a, b, alpha=0.5, beta=2.0, c=c)
+    ref = 0.5 * (a.double() @ b.double()) + 2.0 * c.double()
+    assert _err(out, ref) < 2e-6
+
+
+def test_gemm_split_k_and_strided_batches(LA):
+    a, b = torch.randn(65536, 400, device=DEV), torch.randn(65536, 624, device=DEV)
+    out = LA.gemm(a, b, trans_a=True, split_k=32)              # a^T b : weight-gradient shape
+    ref = a.double().t() @ b.double()
+    assert _err(out, ref) < 2e-6
+    h, c = torch.randn(2048, 4 * 64, device=DEV), torch.randn(4, 64, 64, device=DEV)
+    out = LA.expert_matmul(h, c)
+    ref = torch.einsum("ber,ers->bes", h.double().view(2048, 4, 64), c.double()).reshape(2048, 256)
+    assert _err(out, ref) < 2e-6
+
+
+def test_unsupported_shapes_fail_loudly_in_raw_call_and_dispatch_in_linear(LA):
+    a, b = torch.randn(64, 30, device=DEV), torch.randn(30, 64, device=DEV)
+    with pytest.raises(RuntimeError):
+        LA.gemm(a, b)
+    w = torch.randn(1, 400, device=DEV)
+    x = torch.randn(64, 400, device=DEV)
+    torch.testing.assert_close(LA.linear(x, w, None), x @ w.t())   # N = 1 -> library GEMM
+
+
+def test_linear_matmul_expert_autograd_match_torch(LA):
+    torch.manual_seed(0)
+    x = torch.randn(4096, 624, device=DEV, requires_grad=True)
+    w = (torch.randn(400, 624, device=DEV) * 0.05).requires_grad_(True)
+    b = torch.randn(400, device=DEV, requires_grad=True)
+    gy = torch.randn(4096, 400, device=DEV)
+    y = LA.linear(x, w, b)
+    g1 = torch.autograd.grad(y, [x, w, b], gy)
+    y2 = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    g2 = torch.autograd.grad(y2, [x, w, b], gy.double())
+    assert _err(y, y2) < 2e-6
+    for a_, b_ in zip(g1, g2):
+        assert _err(a_, b_) < 2e-6
+    a = torch.randn(2048, 256, device=DEV, requires_grad=True)
+    m = torch.randn(256, 352, device=DEV, requires_grad=True)
+    g = torch.randn(2048, 352, device=DEV)
+    g1 = torch.autograd.grad(LA.matmul(a, m), [a, m], g)
+    g2 = torch.autograd.grad(a.double() @ m.double(), [a, m], g.double())
+    for a_, b_ in zip(g1, g2):
+        assert _err(a_, b_) < 2e-6
+    h = torch.randn(2048, 256, device=DEV, requires_grad=True)
+    c = torch.randn(4, 64, 64, device=DEV, requires_grad=True)
+    go = torch.randn(2048, 256, device=DEV)
+    g1 = torch.autograd.grad(LA.expert_matmul(h, c), [h, c], go)
+    ref = torch.einsum("ber,ers->bes", h.double().view(2048, 4, 64), c.double()).reshape(2048, 256)
+    g2 = torch.autograd.grad(ref, [h, c], go.double())
+    for a_, b_ in zip(g1, g2):
+        assert _err(a_, b_) < 2e-6
+
+
+def test_dcn_mix_head_avazu_shape_matches_reference_formulation():
+    """Avazu-shaped cross head (Dm=352, E=4, r=64, L=3, B=2048) on the tensor-core kernel vs the
+    reference's own formulation (src/models/layer_dcn.py:8-24,90-115) evaluated in fp64."""
+    import recsys_benchmark_b200 as R
+
+    torch.manual_seed(1)
+    head = R.DCN_MixHead(4, 3, 64, 352).to(DEV)
+    with torch.no_grad():
+        for bia in head.biases:
+            bia.normal_(0, 0.1)
+    x0 = (torch.randn(2048, 352, device=DEV) * 0.3).requires_grad_(True)
+    out = head(x0)
+    gout = torch.randn_like(out)
+    params = [x0] + list(head.parameters())
+    g1 = torch.autograd.grad(out, params, gout)
+
+    def ref_forward(x0d):
+        xl = x0d
+        x0u = x0d.unsqueeze(1)
+        for l in range(3):
+            V, C, U, bl = (head.V[l].double(), head.C[l].double(), head.U[l].double(), head.biases[l].double())
+            E = torch.tanh(xl @ V).permute(1, 0, 2)
+            E = torch.tanh(torch.einsum("ber,ers->bes", E, C))
+            E = torch.einsum("ber,erd->bed", E, U)
+            E = x0u * (E + bl)
+            gts = (xl @ head.gates.double()).squeeze(2).permute(1, 0)
+            xl = torch.einsum("be,bed->bd", gts, E) + xl
+        return xl
+
+    ref = ref_forward(x0.double())
+    g2 = torch.autograd.grad(ref, params, gout.double())
+    assert _err(out, ref) < 5e-6
+    for a_, b_, p in zip(g1, g2, params):
+        assert _err(a_, b_) < 2e-5, tuple(p.shape)
+
+
+def test_gemm_speed_report(LA, capsys):
+    """Not an assertion on speed: prints TFLOP/s of the tensor-core kernel vs cuBLAS fp32 for the MLP shapes."""
+    res = []
+    for (m, n, k, ta, tb, sk) in [(65536, 400, 624, False, True, 1), (65536, 400, 400, False, True, 1),
+                                  (65536, 624, 400, False, False, 1), (400, 624, 65536, True, False, 32),
+                                  (65536, 256, 352, False, False, 1), (65536, 352, 256, False, False, 1)]:
+        a = torch.randn((k, m) if ta else (m, k), device=DEV)
+        b = torch.randn((n, k) if tb else (k, n), device=DEV)
+        at, bt = (a.t() if ta else a), (b.t() if tb else b)
+        for fn, name in [(lambda: LA.gemm(a, b, trans_a=ta, trans_b=tb, split_k=sk), "rsb"), (lambda: at @ bt, "cublas")]:
+            for _ in range(3):
+                fn()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / 10
+            res.append((m, n, k, name, ms, 2 * m * n * k / ms / 1e9))
+    with capsys.disabled():
+        for r in res:
+            print("GEMM %6d x %4d x %6d %-6s %8.3f ms %7.1f TFLOP/s" % r)
