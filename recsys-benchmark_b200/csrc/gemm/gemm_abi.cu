@@ -59,6 +59,14 @@ extern "C" RSB_API int rsb_gemm_f32(int32_t trans_a, int32_t trans_b, int64_t M,
   p.ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   p.ws_bytes = workspace ? (size_t)(workspace_bytes > 256 ? workspace_bytes - 256 : 0) : 0;
   p.stream = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // The TMA descriptors are encoded with a DRIVER API call, which needs a context current on the
+    // calling thread; autograd worker threads may not have touched the runtime yet (error 201).
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return (int)e;
+  }
   int64_t r = dispatch(p, trans_a, trans_b, false);
   if (r == 0) {
     rsb::note_launch(1);
