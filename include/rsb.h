@@ -127,7 +127,8 @@ RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx_is_i32, co
  *   PEP       rg_main = g_out * 1[|v|>sig(s)] ; rg_aux = -g_out*sign(v)*1[..]*sig(s)(1-sig(s))
  *   OPTEMBED  rg_main = d/d weight row incl. the BinaryStep surrogate (optembed_utils.py:35-44);
  *             rg_aux[b,f] (ONE float per lookup) = g_z, so that g_t[f] = -sum_b rg_aux[b,f]
- * Also accumulates the first-order weight gradient: fc_grad[row] += g_yfm[b] (atomic, dense [N,1]).
+ * Also accumulates the first-order weight gradient fc_grad[row] += g_yfm[b] (dense [N,1]; a second
+ * launch that merges equal rows of 32 consecutive samples per field before one atomic per distinct row).
  *
  *  rows      [B,F] int64 global ids saved by the forward
  *  emb, S    forward outputs (emb may be NULL when g_yfm is NULL and the kind does not need it)
@@ -138,6 +139,18 @@ RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, in
                         const void* aux, int32_t aux_mode, const int64_t* mask_d_idx,
                         const float* emb, const float* S, const float* g_yfm, const float* g_deep,
                         float* rg_main, float* rg_aux, float* fc_grad, void* stream);
+
+/* QR (mult / add) variant of stage 1 with the emb1 gradient fused in: emb1 has only `divider`
+ * rows (2/5/20 in configs/deepfm/qr_*.yaml), so every lane group keeps one accumulator per emb1
+ * row in registers while it streams the lookups; no per-lookup emb1 gradient is written and no
+ * second pass over the lookups is needed.  divider <= 8, else RSB_ERR_UNSUPPORTED (callers then
+ * use rsb_lookup_bwd_rows + rsb_small_table_grad).  table1_grad [divider, D] is overwritten. */
+RSB_API int64_t rsb_qr_bwd_fused_workspace_bytes(int64_t B, int32_t D);
+RSB_API int rsb_qr_bwd_fused(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                             const float* table, int64_t n_rows, const float* table1, int64_t divider,
+                             const float* emb, const float* S, const float* g_yfm, const float* g_deep,
+                             float* rg_main, float* table1_grad, float* fc_grad, void* workspace,
+                             int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Backward, stage 2: stable LSD radix sort of the lookups by target row.

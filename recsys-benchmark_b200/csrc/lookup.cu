@@ -51,7 +51,11 @@ struct LookupArgs {
   const float* const* table_shards;
   const float* const* fc_shards;
   int G;
+  // QR emb1 gradient accumulated in registers (divider <= kTinyRows): per-CTA partials [grid][kTinyRows][E]
+  float* tiny_partials;
 };
+
+constexpr int kTinyRows = 8;
 
 __device__ __forceinline__ void shard_split(const LookupArgs& a, long long row, int& owner, long long& lrow) {
   if (a.small32) {
@@ -253,9 +257,58 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
 // ---------------------------------------------------------------------------------
 // Backward stage 1
 // ---------------------------------------------------------------------------------
-template <int K, int V, int LPR>
+// First-order weight gradient fc_grad[row] += g_y[b] without hot-address atomics: a warp takes ONE
+// field of 32 consecutive samples, lanes holding the same row (small fields: a 4-value field is hit
+// by every sample) are combined with match_any + a masked warp sum, one atomic per distinct row.
+// (Per-lookup atomics serialise ~B updates on each hot row inside L2 and stall the whole gather.)
+__global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restrict__ rows,
+                                                      const float* __restrict__ g_y, long long B, int F,
+                                                      float* __restrict__ fc_grad) {
+  extern __shared__ long long tile[];  // [32][F]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long b0 = (long long)blockIdx.x * 32;
+  const long long nvalid = (B - b0 < 32) ? (B - b0) : 32;
+  for (long long i = threadIdx.x; i < nvalid * F; i += blockDim.x) tile[i] = __ldg(rows + b0 * F + i);
+  __syncthreads();
+  const bool valid = lane < nvalid;
+  const float gy = valid ? __ldg(g_y + b0 + lane) : 0.f;
+  for (int f = warp; f < F; f += 8) {
+    const long long row = valid ? tile[(long long)lane * F + f] : (long long)(-1 - lane);
+    const unsigned peers = __match_any_sync(kFull, row);
+    const int leader = __ffs(peers) - 1;
+    const bool dup = __popc(peers) > 1;
+    if (valid && !dup) atomicAdd(fc_grad + row, gy);
+    unsigned todo = __ballot_sync(kFull, valid && dup && lane == leader);
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      const unsigned m = __shfl_sync(kFull, peers, l);
+      float v = ((m >> lane) & 1u) ? gy : 0.f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+      if (lane == l) atomicAdd(fc_grad + row, v);
+      todo &= todo - 1;
+    }
+  }
+}
+
+// Sum of per-CTA partial tables in CTA order: one warp per output element.
+__global__ void partials_reduce_kernel(const float* __restrict__ partials, int nblk, int tot, float* __restrict__ dst,
+                                       int dst_elems) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= dst_elems) return;
+  float s = 0.f;
+  for (int b = lane; b < nblk; b += 32) s += partials[(long long)b * tot + w];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+  if (lane == 0) dst[w] = s;
+}
+
+template <int K, int V, int LPR, bool TINY = false>
 __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
+  FV<V> tacc[TINY ? kTinyRows : 1];
+#pragma unroll
+  for (int r = 0; r < (TINY ? kTinyRows : 1); ++r) tacc[r] = FV<V>::zero();
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, c = lane % LPR;
   const bool cact = c * V < a.E;
@@ -284,8 +337,6 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
           for (int i = 0; i < V; ++i) go.v[i] = fmaf(gy, S.v[i] - e.v[i], go.v[i]);
         }
       }
-      if (a.fc_grad && a.g_y && vact && c == 0 && vf < a.F) atomicAdd(a.fc_grad + row, gy);
-
       if (K == RSB_KIND_VANILLA) {
         if (act) st<V>(a.rg_main + p, go);
       } else if (K == RSB_KIND_MASK) {
@@ -309,12 +360,32 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
             r1.v[i] = go.v[i] * e2.v[i];
           }
           st<V>(a.rg_main + p, r2);
-          st<V>(a.rg_aux + p, r1);
+          if (TINY) {
+            const int k1 = (int)i1;
+#pragma unroll
+            for (int r = 0; r < kTinyRows; ++r) {
+#pragma unroll
+              for (int i = 0; i < V; ++i) tacc[TINY ? r : 0].v[i] += (k1 == r) ? r1.v[i] : 0.f;
+            }
+          } else {
+            st<V>(a.rg_aux + p, r1);
+          }
         }
       } else if (K == RSB_KIND_QR_ADD) {
         if (act) {
           st<V>(a.rg_main + p, go);
-          if (a.rg_aux && a.rg_aux != a.rg_main) st<V>(a.rg_aux + p, go);
+          if (TINY) {
+            long long i1, i2;
+            qr_split(a, row, i1, i2);
+            const int k1 = (int)i1;
+#pragma unroll
+            for (int r = 0; r < kTinyRows; ++r) {
+#pragma unroll
+              for (int i = 0; i < V; ++i) tacc[TINY ? r : 0].v[i] += (k1 == r) ? go.v[i] : 0.f;
+            }
+          } else if (a.rg_aux && a.rg_aux != a.rg_main) {
+            st<V>(a.rg_aux + p, go);
+          }
         }
       } else if (K == RSB_KIND_QR_CAT) {
         if (act) st<V>((vf < a.F ? a.rg_aux : a.rg_main) + p, go);
@@ -368,6 +439,34 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
       }
     }
   }
+  if constexpr (TINY) {
+    // lane groups -> warp (shuffles) -> CTA (shared memory, fixed order) -> one partial table per CTA
+    __shared__ float tred[8][kTinyRows][LPR * V];
+    const int wib = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < kTinyRows; ++r) {
+#pragma unroll
+      for (int off = LPR; off < kWarp; off <<= 1) {
+        FV<V> o = shfl_xor<V>(tacc[r], off);
+#pragma unroll
+        for (int i = 0; i < V; ++i) tacc[r].v[i] += o.v[i];
+      }
+      if (g == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) tred[wib][r][c * V + i] = tacc[r].v[i];
+      }
+    }
+    __syncthreads();
+    const int tot = kTinyRows * a.E;
+    float* out = a.tiny_partials + (long long)blockIdx.x * tot;
+    for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+      const int r = i / a.E, d = i - r * a.E;
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += tred[w][r][d];
+      out[i] = sum;
+    }
+  }
 }
 
 template <int K>
@@ -386,16 +485,42 @@ static int launch_fwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   return RSB_OK;
 }
 
-template <int K>
-static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
-  const int threads = 256;
-  long long blocks = (a.B * 32 + threads - 1) / threads;
+static long long bwd_blocks(long long B) {
+  long long blocks = (B * 32 + 255) / 256;
   long long cap = (long long)sm_count() * 32;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  return blocks;
+}
+
+template <int K>
+static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
+  const int threads = 256;
+  const long long blocks = bwd_blocks(a.B);
+  if constexpr (K == RSB_KIND_QR_MULT || K == RSB_KIND_QR_ADD) {
+    if (a.tiny_partials != nullptr) {
+#define CALLT(VV, LL) lookup_bwd_rows_kernel<K, VV, LL, true><<<(unsigned)blocks, threads, 0, stream>>>(a)
+      RSB_DISPATCH_SHAPE(sh, CALLT);
+#undef CALLT
+      RSB_CHECK_LAUNCH();
+      note_launch(1);
+      return RSB_OK;
+    }
+  }
 #define CALL(VV, LL) lookup_bwd_rows_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
+  RSB_CHECK_LAUNCH();
+  note_launch(1);
+  return RSB_OK;
+}
+
+static int launch_fc_grad(const long long* rows, const float* g_y, long long B, int F, float* fc_grad,
+                          cudaStream_t stream) {
+  const size_t smem = (size_t)32 * F * sizeof(long long);
+  if (smem > 200 * 1024) return RSB_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(fc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  fc_grad_kernel<<<(unsigned)((B + 31) / 32), 256, smem, stream>>>(rows, g_y, B, F, fc_grad);
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;
@@ -475,18 +600,21 @@ extern "C" RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx
   }
 }
 
-extern "C" RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
-                                   const float* table, int64_t n_rows, const float* table1, int64_t divider,
-                                   const void* aux, int32_t aux_mode, const int64_t* mask_d_idx, const float* emb,
-                                   const float* S, const float* g_yfm, const float* g_deep, float* rg_main,
-                                   float* rg_aux, float* fc_grad, void* stream) {
+extern "C" RSB_API int64_t rsb_qr_bwd_fused_workspace_bytes(int64_t B, int32_t D);
+
+static int bwd_rows_impl(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D, const float* table,
+                         int64_t n_rows, const float* table1, int64_t divider, const void* aux, int32_t aux_mode,
+                         const int64_t* mask_d_idx, const float* emb, const float* S, const float* g_yfm,
+                         const float* g_deep, float* rg_main, float* rg_aux, float* fc_grad, float* table1_grad,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
   LookupArgs a = {};
   RowShape sh;
   if (B == 0) return RSB_OK;
   if (rows == nullptr || rg_main == nullptr) return RSB_ERR_BAD_ARG;
   if (g_yfm == nullptr && g_deep == nullptr) return RSB_ERR_BAD_ARG;
   if (g_yfm != nullptr && (emb == nullptr || S == nullptr)) return RSB_ERR_BAD_ARG;
-  if ((kind == RSB_KIND_QR_MULT || kind == RSB_KIND_QR_CAT) && rg_aux == nullptr) return RSB_ERR_BAD_ARG;
+  if ((kind == RSB_KIND_QR_MULT || kind == RSB_KIND_QR_CAT) && rg_aux == nullptr && table1_grad == nullptr)
+    return RSB_ERR_BAD_ARG;
   bool al = aligned16(rg_main) && (rg_aux == nullptr || kind == RSB_KIND_OPTEMBED || aligned16(rg_aux)) &&
             (emb == nullptr || aligned16(emb)) && (S == nullptr || aligned16(S)) &&
             (g_deep == nullptr || aligned16(g_deep));
@@ -511,15 +639,60 @@ extern "C" RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, in
   a.rg_aux = rg_aux;
   a.fc_grad = fc_grad;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  switch (kind) {
-    case RSB_KIND_VANILLA: return launch_bwd<RSB_KIND_VANILLA>(a, sh, s);
-    case RSB_KIND_QR_MULT: return launch_bwd<RSB_KIND_QR_MULT>(a, sh, s);
-    case RSB_KIND_QR_ADD: return launch_bwd<RSB_KIND_QR_ADD>(a, sh, s);
-    case RSB_KIND_QR_CAT: return launch_bwd<RSB_KIND_QR_CAT>(a, sh, s);
-    case RSB_KIND_PEP: return launch_bwd<RSB_KIND_PEP>(a, sh, s);
-    case RSB_KIND_MASK: return launch_bwd<RSB_KIND_MASK>(a, sh, s);
-    default: return launch_bwd<RSB_KIND_OPTEMBED>(a, sh, s);
+  if (table1_grad != nullptr) {
+    // fused small-table gradient: per-CTA register accumulators -> partials in the workspace
+    if (!(kind == RSB_KIND_QR_MULT || kind == RSB_KIND_QR_ADD) || divider > kTinyRows) return RSB_ERR_UNSUPPORTED;
+    if (workspace == nullptr || workspace_bytes < rsb_qr_bwd_fused_workspace_bytes(B, D)) return RSB_ERR_WORKSPACE;
+    a.tiny_partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   }
+  switch (kind) {
+    case RSB_KIND_VANILLA: rc = launch_bwd<RSB_KIND_VANILLA>(a, sh, s); break;
+    case RSB_KIND_QR_MULT: rc = launch_bwd<RSB_KIND_QR_MULT>(a, sh, s); break;
+    case RSB_KIND_QR_ADD: rc = launch_bwd<RSB_KIND_QR_ADD>(a, sh, s); break;
+    case RSB_KIND_QR_CAT: rc = launch_bwd<RSB_KIND_QR_CAT>(a, sh, s); break;
+    case RSB_KIND_PEP: rc = launch_bwd<RSB_KIND_PEP>(a, sh, s); break;
+    case RSB_KIND_MASK: rc = launch_bwd<RSB_KIND_MASK>(a, sh, s); break;
+    default: rc = launch_bwd<RSB_KIND_OPTEMBED>(a, sh, s); break;
+  }
+  if (rc) return rc;
+  if (table1_grad != nullptr) {
+    const int nblk = (int)bwd_blocks(B);
+    const int tot = kTinyRows * a.E;
+    const int dst_elems = (int)divider * a.E;   // rows >= divider are never hit
+    partials_reduce_kernel<<<(dst_elems * 32 + 255) / 256, 256, 0, s>>>(a.tiny_partials, nblk, tot, table1_grad,
+                                                                       dst_elems);
+    RSB_CHECK_LAUNCH();
+    note_launch(1);
+  }
+  if (fc_grad != nullptr && g_yfm != nullptr) {
+    rc = launch_fc_grad(reinterpret_cast<const long long*>(rows), g_yfm, B, F, fc_grad, s);
+    if (rc) return rc;
+  }
+  return RSB_OK;
+}
+
+extern "C" RSB_API int64_t rsb_qr_bwd_fused_workspace_bytes(int64_t B, int32_t D) {
+  if (B < 0 || D <= 0) return 0;
+  return (int64_t)bwd_blocks(B) * kTinyRows * D * 4 + 256;
+}
+
+extern "C" RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                                   const float* table, int64_t n_rows, const float* table1, int64_t divider,
+                                   const void* aux, int32_t aux_mode, const int64_t* mask_d_idx, const float* emb,
+                                   const float* S, const float* g_yfm, const float* g_deep, float* rg_main,
+                                   float* rg_aux, float* fc_grad, void* stream) {
+  return bwd_rows_impl(kind, rows, B, F, D, table, n_rows, table1, divider, aux, aux_mode, mask_d_idx, emb, S, g_yfm,
+                       g_deep, rg_main, rg_aux, fc_grad, nullptr, nullptr, 0, stream);
+}
+
+extern "C" RSB_API int rsb_qr_bwd_fused(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                                        const float* table, int64_t n_rows, const float* table1, int64_t divider,
+                                        const float* emb, const float* S, const float* g_yfm, const float* g_deep,
+                                        float* rg_main, float* table1_grad, float* fc_grad, void* workspace,
+                                        int64_t workspace_bytes, void* stream) {
+  if (table1_grad == nullptr) return RSB_ERR_BAD_ARG;
+  return bwd_rows_impl(kind, rows, B, F, D, table, n_rows, table1, divider, nullptr, 0, nullptr, emb, S, g_yfm, g_deep,
+                       rg_main, nullptr, fc_grad, table1_grad, workspace, workspace_bytes, stream);
 }
 
 extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,

@@ -114,7 +114,7 @@ __global__ void small_table_reduce_kernel(const float* __restrict__ partials, in
 
 static int small_blocks(long long n) {
   long long want = (n + 2047) / 2048;
-  long long cap = 2ll * sm_count();
+  long long cap = 8ll * sm_count();   // enough resident warps to keep the row-gradient loads in flight
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
@@ -130,7 +130,7 @@ static const long long kSmallTableMaxBytes = 96 * 1024;
 extern "C" RSB_API int64_t rsb_small_table_workspace_bytes(int64_t n_rows, int32_t E) {
   if (n_rows <= 0 || E <= 0) return 0;
   if (n_rows * E * 4 > kSmallTableMaxBytes) return -1;  // not a small table: use the sorted path
-  return (int64_t)2 * sm_count() * n_rows * E * 4 + 256;
+  return (int64_t)8 * sm_count() * n_rows * E * 4 + 256;
 }
 
 extern "C" RSB_API int rsb_small_table_grad(const int64_t* keys, int64_t n, int64_t key_div, int64_t key_mod,

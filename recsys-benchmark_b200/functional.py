@@ -238,15 +238,27 @@ class _FusedLookup(torch.autograd.Function):
         # ---- stage 1: per-lookup row gradients --------------------------------
         skip_stage1 = (kind == L.KIND_VANILLA and not use_gy)
         rg_main = rg_aux = None
+        g_table1_fused = None
         if skip_stage1:
             rg_main = g_emb.view(n, e)
+        elif kind in (L.KIND_QR_MULT, L.KIND_QR_ADD) and spec.divider <= 8 and need[5]:
+            # emb1 (<= 8 rows) gradient accumulated in registers inside stage 1: no per-lookup emb1 rows
+            rg_main = torch.empty(n, e, dtype=torch.float32, device=dev)
+            g_table1_fused = torch.empty_like(table1)
+            ws = _ws(lib.rsb_qr_bwd_fused_workspace_bytes(b, spec.dim), dev)
+            r_bytes = f * e * 4
+            nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + f * e * 4 + (e * 4 + 4 + f * 4 if use_gy else 0))
+            _call("lookup_bwd_rows", lib.rsb_qr_bwd_fused, kind, L.ptr(rows), b, f, spec.dim, L.ptr(table),
+                  table.shape[0], L.ptr(table1), spec.divider, L.ptr(emb), L.ptr(s), L.ptr(g_y) if use_gy else None,
+                  L.ptr(g_emb), L.ptr(rg_main), L.ptr(g_table1_fused), L.ptr(g_fc), L.ptr(ws), ws.numel(),
+                  L.stream_ptr(dev), nbytes=nbytes)
         else:
             rg_main = torch.empty(n, e, dtype=torch.float32, device=dev)
             if kind in (L.KIND_QR_MULT, L.KIND_QR_CAT) or (kind == L.KIND_PEP and need[6]):
                 rg_aux = torch.empty(n, e, dtype=torch.float32, device=dev)
             elif kind == L.KIND_OPTEMBED and aux is not None:
                 rg_aux = torch.empty(b, f, dtype=torch.float32, device=dev)
-            # algorithmic bytes: rows + g_deep + emb (+S, g_y) read, row grads written (+ fc atomics)
+            # algorithmic bytes: rows + g_deep + emb (+S, g_y) read, row grads written (+ fc)
             r_bytes = spec.out_fields(f) * e * 4
             n_out = 2 if (rg_aux is not None and kind != L.KIND_OPTEMBED) else 1
             nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + n_out * f * e * 4 + (e * 4 + 4 + f * 4 if use_gy else 0))
@@ -265,7 +277,9 @@ class _FusedLookup(torch.autograd.Function):
         if spec.is_qr:
             if need[4]:
                 g_table = dense_row_grad(rows, rg_main, n_rows, key_div=spec.divider)
-            if need[5]:
+            if need[5] and g_table1_fused is not None:
+                g_table1 = g_table1_fused
+            elif need[5]:
                 g_table1 = small_table_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
                 if g_table1 is None:
                     g_table1 = dense_row_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)

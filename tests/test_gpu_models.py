@@ -338,7 +338,9 @@ def test_odd_widths_match_torch(R, d):
 
 # ----------------------------------------- properties at BASELINE.json sizes ---
 @pytest.mark.parametrize("emb_cfg,b", [({"name": "vanilla"}, 2048), ({"name": "qr", "divider": 5}, 2048),
-                                       ({"name": "vanilla"}, 16384)])
+                                       ({"name": "vanilla"}, 16384), ({"name": "qr", "divider": 20}, 2048),
+                                       ({"name": "qr"}, 4096), ({"name": "qr", "divider": 2, "operation": "add"}, 2048),
+                                       ({"name": "qr", "divider": 5}, 65536)])
 def test_criteo_shape_properties(R, emb_cfg, b):
     torch.manual_seed(3)
     model = R.get_ctr_model(CRITEO_DIMS, dict(num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=0.0,
