@@ -39,19 +39,19 @@ KDD_DIMS = [600000] * 8 + [400000] * 3
 WORKLOADS = {
     # BASELINE.json configs[1] (default)
     "deepfm_qr_criteo": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "qr", "divider": 5}, use_bn=False,
-                             p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+                             p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
     # configs[0] shape on the GPU, sparse=True variant (configs/deepfm/base_config_sparse.yaml) with the fused row update
     "deepfm_full_criteo": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla", "sparse": True}, use_bn=True,
                                p_dropout=0.5,
-                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True)),
+                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam=True)),
     "deepfm_full_criteo_dense_adam": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
-                                          p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+                                          p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
     # BASELINE.json configs[4]: full table row-sharded over the GPUs (NVLink peer gathers + shard atomics),
     # dense Adam on each shard (= configs/deepfm/base_config.yaml semantics), dense MLP grads allreduced
     "deepfm_full_criteo_sharded": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
-                                       p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6), sharded=True),
+                                       p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True), sharded=True),
     "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
-                              opt=dict(learning_rate=1e-3, weight_decay=1e-6)),
+                              opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
 }
 
 
@@ -90,7 +90,7 @@ def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0):
     dims = wl["dims"]
     emb = {k: v for k, v in wl["emb"].items()}
     p = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
-    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k != "fused_sparse"})
+    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
     offsets = torch.tensor([0] + dims[:-1]).cumsum(0)[None, :]
     batches = make_batches(dims, sample_batch, 2, 2023, torch.int64)
     for i in range(warmup):

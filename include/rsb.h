@@ -233,6 +233,23 @@ RSB_API int rsb_gemm_f32(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N,
                          void* stream);
 
 /* ------------------------------------------------------------------------
+ * Bandwidth-bound glue of the dense tails (Linear -> [BatchNorm1d] -> ReLU -> Dropout,
+ * src/models/deepfm.py:55-66, src/models/dcn.py:56-66), one pass per direction.
+ *  rsb_relu_dropout_fwd  y = dropout_p(relu(x)), mask[i] = 1 iff x[i] > 0 and kept (Philox4x32-10 keyed by
+ *                        seed/offset; numel % 4 == 0, 16-byte aligned)
+ *  rsb_relu_dropout_bwd  gx = g * mask / (1-p) for g [M,N]; colsum [N] (may be NULL) = column sums of gx,
+ *                        i.e. the bias gradient of the preceding Linear, accumulated in the same pass
+ *  rsb_colsum            out[N] = sum over rows of x [M,N] (row stride ld), deterministic two-stage
+ * ---------------------------------------------------------------------- */
+RSB_API int rsb_relu_dropout_fwd(const float* x, int64_t numel, float p, uint64_t seed, uint64_t offset, float* y,
+                                 uint8_t* mask, void* stream);
+RSB_API int rsb_relu_dropout_bwd(const float* g, const uint8_t* mask, int64_t M, int32_t N, float p, float* gx,
+                                 float* colsum, void* workspace, int64_t workspace_bytes, void* stream);
+RSB_API int64_t rsb_colsum_workspace_bytes(int64_t M, int32_t N);
+RSB_API int rsb_colsum(const float* x, int64_t M, int32_t N, int64_t ld, float* out, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Row-sharded tables over the GPUs of one box (no reference
  * counterpart: the reference is single-device).  Rank g owns the rows r of the concatenated
  * table with r % G == g, stored at local row r / G.  Shards live in cudaMalloc'ed buffers

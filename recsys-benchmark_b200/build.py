@@ -49,9 +49,12 @@ def sources():
 
 
 def _deps(src):
-    deps = [src, os.path.join(ROOT, "include", "rsb.h")]
+    deps = [src]
     d = os.path.dirname(src)
     deps += sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cuh"))
+    text = "".join(open(f).read() for f in deps)
+    if "rsb.h" in text:   # the CUTLASS instantiations (gemm_rc/rr/cr.cu) do not see the C header
+        deps.append(os.path.join(ROOT, "include", "rsb.h"))
     return deps
 
 

@@ -1,0 +1,195 @@
+// Bandwidth-bound glue of the dense tails (src/models/deepfm.py:55-66, src/models/dcn.py:56-66:
+// Linear -> [BatchNorm1d] -> ReLU -> Dropout), fused so that every activation tensor is read and
+// written once per direction:
+//   relu_dropout_fwd : y = dropout(relu(x)) + a 1-byte keep mask        (torch: clamp + fused_dropout)
+//   relu_dropout_bwd : gx = g * mask * 1/(1-p), and the column sums of gx (= the bias gradient of the
+//                      preceding Linear) accumulated in the same pass     (torch: masked_scale + threshold_backward + sum)
+//   colsum           : deterministic two-stage column sum (bias gradients, split-K partial sums)
+// Dropout uses a counter-based Philox4x32-10 stream keyed by (seed, offset); the mask is random by
+// definition, so only its statistics (keep probability 1-p, scale 1/(1-p)) are part of the contract.
+#include "common.cuh"
+
+namespace rsb {
+
+struct Philox {
+  unsigned k0, k1;
+  __device__ __forceinline__ uint4 operator()(unsigned long long ctr) const {
+    unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+    unsigned a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ a;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ b;
+      c3 = lo0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
+// numel must be a multiple of 4 and x/y 16-byte aligned (checked by the host function)
+__global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float4* __restrict__ x, long long n4,
+                                                               float p, float scale, unsigned long long seed,
+                                                               unsigned long long offset, float4* __restrict__ y,
+                                                               uchar4* __restrict__ mask) {
+  Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
+  const unsigned thr = (unsigned)(p * 4294967296.0);  // keep iff r >= thr
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    const uint4 r = rng(offset + (unsigned long long)i);
+    uchar4 m;
+    m.x = (v.x > 0.f) && (r.x >= thr);
+    m.y = (v.y > 0.f) && (r.y >= thr);
+    m.z = (v.z > 0.f) && (r.z >= thr);
+    m.w = (v.w > 0.f) && (r.w >= thr);
+    float4 o;
+    o.x = m.x ? v.x * scale : 0.f;
+    o.y = m.y ? v.y * scale : 0.f;
+    o.z = m.z ? v.z * scale : 0.f;
+    o.w = m.w ? v.w * scale : 0.f;
+    y[i] = o;
+    mask[i] = m;
+  }
+}
+
+// One CTA owns a slab of rows; thread t owns the float4 column groups t, t+256, ... so that a row is
+// read with fully coalesced 128-bit loads and the column sums stay in registers until the end.
+constexpr int kColsPerThread = 2;  // float4 groups per thread: supports N <= 256*4*2 = 2048 columns per pass
+
+template <bool MASKED>
+__global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restrict__ g,
+                                                          const unsigned char* __restrict__ mask, float scale,
+                                                          long long M, int N, long long ld, float* __restrict__ gx,
+                                                          float* __restrict__ partials, int col0) {
+  const int n4 = N / 4;
+  const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
+  const long long r0 = rows_per * blockIdx.x;
+  long long r1 = r0 + rows_per;
+  if (r1 > M) r1 = M;
+  float4 acc[kColsPerThread];
+#pragma unroll
+  for (int j = 0; j < kColsPerThread; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int j = 0; j < kColsPerThread; ++j) {
+      const int c4 = col0 / 4 + threadIdx.x + j * 256;
+      if (c4 < n4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(g + r * ld) + c4);
+        if (MASKED) {
+          const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + r * (long long)N) + c4);
+          v.x = m.x ? v.x * scale : 0.f;
+          v.y = m.y ? v.y * scale : 0.f;
+          v.z = m.z ? v.z * scale : 0.f;
+          v.w = m.w ? v.w * scale : 0.f;
+          reinterpret_cast<float4*>(gx + r * (long long)N)[c4] = v;
+        }
+        acc[j].x += v.x;
+        acc[j].y += v.y;
+        acc[j].z += v.z;
+        acc[j].w += v.w;
+      }
+    }
+  }
+  if (partials) {
+#pragma unroll
+    for (int j = 0; j < kColsPerThread; ++j) {
+      const int c4 = col0 / 4 + threadIdx.x + j * 256;
+      if (c4 < n4) reinterpret_cast<float4*>(partials + (long long)blockIdx.x * N)[c4] = acc[j];
+    }
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partials, int nblk, int N, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partials[(long long)b * N + c];
+  out[c] = s;
+}
+
+static int slab_blocks(long long M) {
+  long long b = 2ll * sm_count();
+  if (b > M) b = M;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" RSB_API int rsb_relu_dropout_fwd(const float* x, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                                            float* y, uint8_t* mask, void* stream) {
+  if (numel < 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  if (numel == 0) return RSB_OK;
+  if (!x || !y || !mask) return RSB_ERR_BAD_ARG;
+  if (numel % 4 || !aligned16(x) || !aligned16(y) || (reinterpret_cast<uintptr_t>(mask) & 3u)) return RSB_ERR_UNSUPPORTED;
+  const long long n4 = numel / 4;
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  relu_dropout_fwd_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(x), n4, p, 1.0f / (1.0f - p), seed, offset, reinterpret_cast<float4*>(y),
+      reinterpret_cast<uchar4*>(mask));
+  RSB_CHECK_LAUNCH();
+  note_launch(1);
+  return RSB_OK;
+}
+
+extern "C" RSB_API int64_t rsb_colsum_workspace_bytes(int64_t M, int32_t N) {
+  if (M < 0 || N <= 0) return 0;
+  return (int64_t)slab_blocks(M) * N * 4 + 256;
+}
+
+static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t M, int32_t N, int64_t ld, float* gx,
+                       float* colsum, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+  if (M < 0 || N <= 0) return RSB_ERR_BAD_ARG;
+  if (M == 0) {
+    if (colsum) cudaMemsetAsync(colsum, 0, (size_t)N * 4, s);
+    return RSB_OK;
+  }
+  if (!g) return RSB_ERR_BAD_ARG;
+  if (N % 4 || ld % 4 || !aligned16(g) || (gx && !aligned16(gx)) || (mask && (reinterpret_cast<uintptr_t>(mask) & 3u)))
+    return RSB_ERR_UNSUPPORTED;
+  float* partials = nullptr;
+  const int nblk = slab_blocks(M);
+  if (colsum) {
+    if (!workspace || workspace_bytes < rsb_colsum_workspace_bytes(M, N)) return RSB_ERR_WORKSPACE;
+    partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  }
+  const int per_pass = 256 * 4 * kColsPerThread;
+  for (int col0 = 0; col0 < N; col0 += per_pass) {
+    if (mask)
+      colsum_slab_kernel<true><<<nblk, 256, 0, s>>>(g, mask, scale, M, N, ld, gx, partials, col0);
+    else
+      colsum_slab_kernel<false><<<nblk, 256, 0, s>>>(g, nullptr, 1.f, M, N, ld, nullptr, partials, col0);
+    RSB_CHECK_LAUNCH();
+    note_launch(1);
+  }
+  if (colsum) {
+    colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(partials, nblk, N, colsum);
+    RSB_CHECK_LAUNCH();
+    note_launch(1);
+  }
+  return RSB_OK;
+}
+
+extern "C" RSB_API int rsb_colsum(const float* x, int64_t M, int32_t N, int64_t ld, float* out, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  if (!out) return RSB_ERR_BAD_ARG;
+  return colsum_impl(x, nullptr, 1.f, M, N, ld, nullptr, out, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" RSB_API int rsb_relu_dropout_bwd(const float* g, const uint8_t* mask, int64_t M, int32_t N, float p,
+                                            float* gx, float* colsum, void* workspace, int64_t workspace_bytes,
+                                            void* stream) {
+  if (!mask || !gx || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  return colsum_impl(g, mask, 1.0f / (1.0f - p), M, N, N, gx, colsum, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream));
+}

@@ -100,10 +100,12 @@ def get_optimizers(model: nn.Module, config: Dict) -> List[torch.optim.Optimizer
         emb_opt = (FusedSparseAdam(model.embedding, lr=lr_emb) if fused
                    else torch.optim.SparseAdam(no_decay_param, lr=lr_emb))
         return [emb_opt,
-                torch.optim.Adam(decay_param, lr=config["learning_rate"], weight_decay=config["weight_decay"])]
+                torch.optim.Adam(decay_param, lr=config["learning_rate"], weight_decay=config["weight_decay"],
+                                 fused=bool(config.get("fused_adam", False)))]
     if optimizer_name == "adam":
+        # `fused_adam: true` (opt-in) selects torch's single-kernel multi-tensor Adam (same arithmetic)
         return [torch.optim.Adam(model.parameters(), lr=config["learning_rate"],
-                                 weight_decay=config["weight_decay"])]
+                                 weight_decay=config["weight_decay"], fused=bool(config.get("fused_adam", False)))]
     if optimizer_name == "sgd":
         if not sparse:
             return [torch.optim.SGD(model.parameters(), lr=config["learning_rate"],

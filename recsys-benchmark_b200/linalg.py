@@ -146,6 +146,115 @@ def expert_matmul(h: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     return torch.bmm(h.view(bsz, e, r).transpose(0, 1), c).transpose(0, 1).reshape(bsz, e * r2)
 
 
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a 2-D fp32 CUDA tensor (deterministic two-stage kernel); torch.sum for odd shapes."""
+    if x.dim() == 2 and x.is_cuda and x.shape[1] % 4 == 0 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and \
+            x.data_ptr() % 16 == 0 and x.shape[0] >= 256:
+        lib = L.load()
+        m, n = x.shape
+        out = torch.empty(n, dtype=torch.float32, device=x.device)
+        ws = RF._ws(lib.rsb_colsum_workspace_bytes(m, n), x.device)
+        RF._call("colsum", lib.rsb_colsum, L.ptr(x), m, n, x.stride(0), L.ptr(out), L.ptr(ws), ws.numel(),
+                 L.stream_ptr(x.device), nbytes=m * n * 4)
+        return out
+    return x.sum(0)
+
+
+_DROPOUT_CALLS = 0
+
+
+def _dropout_stream(numel: int):
+    """(seed, offset) of the next Philox stream: seeded by torch's global seed, advanced per call."""
+    global _DROPOUT_CALLS
+    _DROPOUT_CALLS += 1
+    seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + _DROPOUT_CALLS * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    return seed, (_DROPOUT_CALLS * 0x100000000) & 0xFFFFFFFFFFFFFFFF
+
+
+def _relu_dropout_fwd(x: torch.Tensor, p: float):
+    lib = L.load()
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    seed, off = _dropout_stream(x.numel())
+    RF._call("relu_dropout_fwd", lib.rsb_relu_dropout_fwd, L.ptr(x), x.numel(), float(p), seed, off, L.ptr(y),
+             L.ptr(mask), L.stream_ptr(x.device), nbytes=x.numel() * 9)
+    return y, mask
+
+
+def _relu_dropout_bwd(g: torch.Tensor, mask: torch.Tensor, p: float, want_colsum: bool):
+    lib = L.load()
+    m, n = g.shape
+    g = g.contiguous()
+    gx = torch.empty_like(g)
+    cs = torch.empty(n, dtype=torch.float32, device=g.device) if want_colsum else None
+    ws = RF._ws(lib.rsb_colsum_workspace_bytes(m, n), g.device) if want_colsum else None
+    RF._call("relu_dropout_bwd", lib.rsb_relu_dropout_bwd, L.ptr(g), L.ptr(mask), m, n, float(p), L.ptr(gx), L.ptr(cs),
+             L.ptr(ws), ws.numel() if ws is not None else 0, L.stream_ptr(g.device), nbytes=m * n * 9)
+    return gx, cs
+
+
+def _fusable(x: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.shape[1] % 4 == 0
+            and x.shape[1] <= 2048 and x.data_ptr() % 16 == 0)
+
+
+class _ReluDropout(torch.autograd.Function):
+    """y = dropout_p(relu(x)) in one pass each way (torch: clamp + fused_dropout / masked_scale + threshold_backward)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        y, mask = _relu_dropout_fwd(x, p)
+        ctx.save_for_backward(mask)
+        ctx.p = p
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        gx, _ = _relu_dropout_bwd(g, mask, ctx.p, False)
+        return gx, None
+
+
+def relu_dropout(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    if training and 0.0 < p < 1.0 and _fusable(x):
+        return _ReluDropout.apply(x, p)
+    return torch.nn.functional.dropout(torch.relu(x), p, training)
+
+
+class _LinearReluDropout(torch.autograd.Function):
+    """dropout_p(relu(x @ W^T + b)): tensor-core GEMM with the bias in its epilogue, one fused
+    ReLU+dropout pass, and a backward whose single elementwise pass also produces the bias gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p):
+        z = gemm(x, weight, trans_b=True, bias=bias)
+        y, mask = _relu_dropout_fwd(z, p)
+        ctx.save_for_backward(x, weight, mask)
+        ctx.p = p
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, mask = ctx.saved_tensors
+        gz, gb = _relu_dropout_bwd(gy, mask, ctx.p, ctx.has_bias and ctx.needs_input_grad[2])
+        gx = gemm(gz, weight) if ctx.needs_input_grad[0] else None
+        gw = gemm(gz, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1])) \
+            if ctx.needs_input_grad[1] else None
+        return gx, gw, gb, None
+
+
+def _split_for(k: int, m: int, n: int) -> int:
+    """Split-K factor for a weight-gradient GEMM [m,n] with reduction length k: enough partial GEMMs to
+    fill the SMs with 128x128 tiles, each still >= 512 deep."""
+    tiles = ((m + 127) // 128) * ((n + 127) // 128)
+    best = 1
+    for s in (2, 4, 8, 16, 32, 64):
+        if k % s == 0 and (k // s) % 4 == 0 and k // s >= 512 and tiles * s <= 2 * 148 + tiles:
+            best = s
+    return best
+
+
 def _use_kernel(m, n, k, *tensors) -> bool:
     return (2 * m * n * k >= MIN_FLOPS and m % 4 == 0 and n % 4 == 0 and k % 4 == 0 and _aligned(*tensors)
             and all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in tensors))
@@ -168,15 +277,9 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = gemm(gy, weight)                                   # [B,out] @ [out,in]
         if ctx.needs_input_grad[1]:
-            bsz = x.shape[0]
-            split = 1
-            for s in (32, 16, 8, 4, 2):
-                if bsz % s == 0 and (bsz // s) % 4 == 0 and bsz // s >= 512:
-                    split = s
-                    break
-            gw = gemm(gy, x, trans_a=True, split_k=split)           # gy^T [out,B] @ x [B,in]
+            gw = gemm(gy, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1]))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy.sum(0)
+            gb = colsum(gy)
         return gx, gw, gb
 
 
@@ -204,13 +307,7 @@ class _MatMul(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             ga = gemm(gc, b, trans_b=True)                          # gc [M,N] @ b^T (b stored [K,N] = "[N',K']" with N'=K)
         if ctx.needs_input_grad[1]:
-            m = a.shape[0]
-            split = 1
-            for s in (32, 16, 8, 4, 2):
-                if m % s == 0 and (m // s) % 4 == 0 and m // s >= 512:
-                    split = s
-                    break
-            gb = gemm(a, gc, trans_a=True, split_k=split)           # a^T [K,M] @ gc [M,N]
+            gb = gemm(a, gc, trans_a=True, split_k=_split_for(a.shape[0], a.shape[1], gc.shape[1]))  # a^T @ gc
         return ga, gb
 
 
@@ -222,11 +319,31 @@ def matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-    """nn.Sequential forward with every nn.Linear routed through `linear` (same parameters,
-    same state dict); the other modules (BatchNorm1d / ReLU / Dropout) run unchanged."""
-    for m in seq:
+    """nn.Sequential forward of the dense tails with the same parameters / state dict, but
+    Linear -> tensor-core GEMM, and (Linear ->) ReLU -> Dropout fused into single passes.
+    BatchNorm1d (and anything else) runs unchanged."""
+    mods = list(seq)
+    i = 0
+    training = seq.training
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        nx2 = mods[i + 2] if i + 2 < len(mods) else None
         if isinstance(m, torch.nn.Linear):
+            ok = x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and \
+                _use_kernel(x.shape[0], m.weight.shape[0], m.weight.shape[1], x, m.weight, m.bias)
+            if ok and isinstance(nxt, torch.nn.ReLU) and isinstance(nx2, torch.nn.Dropout) and training and \
+                    0.0 < nx2.p < 1.0 and m.weight.shape[0] <= 2048:
+                x = _LinearReluDropout.apply(x, m.weight, m.bias, float(nx2.p))
+                i += 3
+                continue
             x = linear(x, m.weight, m.bias)
-        else:
-            x = m(x)
+            i += 1
+            continue
+        if isinstance(m, torch.nn.ReLU) and isinstance(nxt, torch.nn.Dropout):
+            x = relu_dropout(x, float(nxt.p), training)
+            i += 2
+            continue
+        x = m(x)
+        i += 1
     return x

@@ -157,3 +157,58 @@ def test_gemm_speed_report(LA, capsys):
     with capsys.disabled():
         for r in res:
             print("GEMM %6d x %4d x %6d %-6s %8.3f ms %7.1f TFLOP/s" % r)
+
+
+def test_colsum_matches_fp64(LA):
+    x = torch.randn(65536, 400, device=DEV)
+    ref = x.double().sum(0)
+    assert _err(LA.colsum(x), ref) < 1e-6
+    assert torch.equal(LA.colsum(x), LA.colsum(x))          # deterministic
+    y = torch.randn(1000, 2400, device=DEV)                 # more than one column pass
+    assert _err(LA.colsum(y), y.double().sum(0)) < 1e-6
+
+
+def test_relu_dropout_statistics_and_backward(LA):
+    torch.manual_seed(3)
+    x = torch.randn(8192, 400, device=DEV, requires_grad=True)
+    y = LA.relu_dropout(x, 0.5, True)
+    pos = x.detach() > 0
+    assert float(y.detach()[~pos].abs().sum()) == 0.0
+    kept = y.detach() != 0
+    assert torch.equal(y.detach()[kept], (2.0 * x.detach())[kept])
+    frac = float(kept.sum()) / float(pos.sum())
+    assert abs(frac - 0.5) < 0.01, frac
+    g = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, g)
+    assert torch.equal(gx, torch.where(kept, 2.0 * g, torch.zeros_like(g)))
+    y2 = LA.relu_dropout(x, 0.5, True)
+    assert not torch.equal(y2, y)                            # a new stream every call
+    torch.testing.assert_close(LA.relu_dropout(x, 0.5, False), torch.relu(x))   # eval mode = relu
+
+
+def test_fused_linear_relu_dropout_block_matches_composition(LA):
+    torch.manual_seed(4)
+    seq = torch.nn.Sequential(torch.nn.Linear(624, 400), torch.nn.ReLU(), torch.nn.Dropout(0.5),
+                              torch.nn.Linear(400, 400), torch.nn.BatchNorm1d(400), torch.nn.ReLU(),
+                              torch.nn.Dropout(0.2), torch.nn.Linear(400, 1)).to(DEV).train()
+    x = torch.randn(4096, 624, device=DEV, requires_grad=True)
+    out = LA.run_sequential(seq, x)
+    assert tuple(out.shape) == (4096, 1)
+    go = torch.randn_like(out)
+    params = [x] + list(seq.parameters())
+    g1 = torch.autograd.grad(out, params, go)
+    # first block in isolation against an fp64 composition that reuses the mask the kernel drew
+    lin = seq[0]
+    y = LA._LinearReluDropout.apply(x, lin.weight, lin.bias, 0.5)
+    keep = (y.detach() != 0).double()
+    z = torch.nn.functional.linear(x.double(), lin.weight.double(), lin.bias.double())
+    ref = z * keep * 2.0
+    assert _err(y, ref) < 2e-6
+    gy = torch.randn_like(y)
+    ga = torch.autograd.grad(y, [x, lin.weight, lin.bias], gy)
+    gb = torch.autograd.grad(ref, [x, lin.weight, lin.bias], gy.double())
+    for a_, b_ in zip(ga, gb):
+        assert _err(a_, b_) < 2e-6
+    assert all(torch.isfinite(g).all() for g in g1)
+    seq.eval()
+    torch.testing.assert_close(LA.run_sequential(seq, x), seq(x), rtol=1e-4, atol=1e-5)
