@@ -74,24 +74,44 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
   float4 acc[kColsPerThread];
 #pragma unroll
   for (int j = 0; j < kColsPerThread; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long r = r0; r < r1; ++r) {
+  constexpr int RU = 4;  // rows in flight per thread
+  for (long long rb = r0; rb < r1; rb += RU) {
+    float4 v[RU][kColsPerThread];
+    uchar4 m[RU][kColsPerThread];
 #pragma unroll
-    for (int j = 0; j < kColsPerThread; ++j) {
-      const int c4 = col0 / 4 + threadIdx.x + j * 256;
-      if (c4 < n4) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(g + r * ld) + c4);
-        if (MASKED) {
-          const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + r * (long long)N) + c4);
-          v.x = m.x ? v.x * scale : 0.f;
-          v.y = m.y ? v.y * scale : 0.f;
-          v.z = m.z ? v.z * scale : 0.f;
-          v.w = m.w ? v.w * scale : 0.f;
-          reinterpret_cast<float4*>(gx + r * (long long)N)[c4] = v;
+    for (int u = 0; u < RU; ++u) {
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; ++j) {
+        const int c4 = col0 / 4 + threadIdx.x + j * 256;
+        const long long r = rb + u;
+        v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        m[u][j] = make_uchar4(0, 0, 0, 0);
+        if (c4 < n4 && r < r1) {
+          v[u][j] = __ldg(reinterpret_cast<const float4*>(g + r * ld) + c4);
+          if (MASKED) m[u][j] = __ldg(reinterpret_cast<const uchar4*>(mask + r * (long long)N) + c4);
         }
-        acc[j].x += v.x;
-        acc[j].y += v.y;
-        acc[j].z += v.z;
-        acc[j].w += v.w;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; ++j) {
+        const int c4 = col0 / 4 + threadIdx.x + j * 256;
+        const long long r = rb + u;
+        if (c4 < n4 && r < r1) {
+          float4 x = v[u][j];
+          if (MASKED) {
+            x.x = m[u][j].x ? x.x * scale : 0.f;
+            x.y = m[u][j].y ? x.y * scale : 0.f;
+            x.z = m[u][j].z ? x.z * scale : 0.f;
+            x.w = m[u][j].w ? x.w * scale : 0.f;
+            reinterpret_cast<float4*>(gx + r * (long long)N)[c4] = x;
+          }
+          acc[j].x += x.x;
+          acc[j].y += x.y;
+          acc[j].z += x.z;
+          acc[j].w += x.w;
+        }
       }
     }
   }
@@ -104,17 +124,20 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
   }
 }
 
+// one warp per column: lanes stride over the CTA partials, fixed-shape shuffle tree
 __global__ void colsum_final_kernel(const float* __restrict__ partials, int nblk, int N, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (c >= N) return;
   float s = 0.f;
-  for (int b = 0; b < nblk; ++b) s += partials[(long long)b * N + c];
-  out[c] = s;
+  for (int b = lane; b < nblk; b += 32) s += partials[(long long)b * N + c];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
+  if (lane == 0) out[c] = s;
 }
 
 static int slab_blocks(long long M) {
-  long long b = 2ll * sm_count();
-  if (b > M) b = M;
+  long long b = 16ll * sm_count();     // >= 2 resident CTAs per SM x several waves; >= 16 rows per CTA
+  if (b > M / 16) b = M / 16;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -172,7 +195,7 @@ static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t
     note_launch(1);
   }
   if (colsum) {
-    colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(partials, nblk, N, colsum);
+    colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(partials, nblk, N, colsum);
     RSB_CHECK_LAUNCH();
     note_launch(1);
   }

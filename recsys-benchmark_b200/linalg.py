@@ -244,14 +244,20 @@ class _LinearReluDropout(torch.autograd.Function):
         return gx, gw, gb, None
 
 
-def _split_for(k: int, m: int, n: int) -> int:
-    """Split-K factor for a weight-gradient GEMM [m,n] with reduction length k: enough partial GEMMs to
-    fill the SMs with 128x128 tiles, each still >= 512 deep."""
+def _split_for(k: int, m: int, n: int, sms: int = 148) -> int:
+    """Split-K factor for a weight-gradient GEMM [m,n] with reduction length k (the batch): the
+    persistent scheduler hands out (128x128 tile, split) units, so pick the split whose unit count
+    fills whole waves of SMs; each split stays >= 256 deep."""
     tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    best = 1
-    for s in (2, 4, 8, 16, 32, 64):
-        if k % s == 0 and (k // s) % 4 == 0 and k // s >= 512 and tiles * s <= 2 * 148 + tiles:
-            best = s
+    best, best_score = 1, -1.0
+    for sp in (1, 2, 4, 8, 16, 32, 64, 128):
+        if k % sp or (k // sp) % 4 or (k // sp < 256 and sp > 1):
+            continue
+        units = tiles * sp
+        eff = units / (((units + sms - 1) // sms) * sms)
+        score = eff - 0.001 * sp
+        if score > best_score:
+            best, best_score = sp, score
     return best
 
 
