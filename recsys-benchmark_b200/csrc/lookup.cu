@@ -183,6 +183,12 @@ __device__ __forceinline__ long long load_id(const LookupArgs& a, long long b, i
   return id;
 }
 
+// Field iterations are processed in batches of kIter: all ids of a batch are loaded first, then all
+// first-order weights and table rows, then the arithmetic and the stores.  (A plain per-field loop
+// serialises id -> row -> store round trips, because the compiler may not hoist the next id load
+// above the previous emb store; ncu showed the warps stalled on exactly those three loads.)
+constexpr int kIter = 4;
+
 template <int K, int V, int LPR>
 __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
@@ -196,36 +202,56 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
   for (long long b = warp; b < a.B; b += nwarps) {
     FV<V> S = FV<V>::zero(), Q = FV<V>::zero();
     float first = 0.f;
-    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW) {
-      const int vf = vf0 + g;
-      const bool vact = vf < a.VF;
-      const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
-      long long row = 0;
-      if (vact) {
-        row = load_id(a, b, f);
-        if (row < 0 || row >= a.n_global) {
-          if (a.err) *a.err = 1;
-          row = 0;
-        }
-        if (c == 0 && vf < a.F) {
-          if (a.out_rows) a.out_rows[b * a.F + f] = row;
-          if (a.fc) first += __ldg(a.fc + row);
-          if (a.fc_shards) {
-            int owner;
-            long long lrow;
-            shard_split(a, row, owner, lrow);
-            first += __ldg(a.fc_shards[owner] + lrow);
+    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW * kIter) {
+      long long rowv[kIter];
+      int fv[kIter];
+      bool vactv[kIter];
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int vf = vf0 + it * GPW + g;
+        vactv[it] = vf < a.VF;
+        fv[it] = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
+        rowv[it] = vactv[it] ? load_id(a, b, fv[it]) : 0;
+      }
+      float fcv[kIter];
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int vf = vf0 + it * GPW + g;
+        fcv[it] = 0.f;
+        if (vactv[it]) {
+          if (rowv[it] < 0 || rowv[it] >= a.n_global) {
+            if (a.err) *a.err = 1;
+            rowv[it] = 0;
+          }
+          if (c == 0 && vf < a.F) {
+            if (a.out_rows) a.out_rows[b * a.F + fv[it]] = rowv[it];
+            if (a.fc) fcv[it] = __ldg(a.fc + rowv[it]);
+            if (a.fc_shards) {
+              int owner;
+              long long lrow;
+              shard_split(a, rowv[it], owner, lrow);
+              fcv[it] = __ldg(a.fc_shards[owner] + lrow);
+            }
           }
         }
       }
-      const bool act = vact && cact;
-      FV<V> e = load_transformed<K, V, LPR>(a, row, b, f, vf, c, act);
-      if (act) {
-        st<V>(a.out_emb + ((b * a.VF + vf) * (long long)a.E + c * V), e);
+      FV<V> ev[kIter];
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          S.v[i] += e.v[i];
-          Q.v[i] = fmaf(e.v[i], e.v[i], Q.v[i]);
+      for (int it = 0; it < kIter; ++it) {
+        const int vf = vf0 + it * GPW + g;
+        ev[it] = load_transformed<K, V, LPR>(a, rowv[it], b, fv[it], vf, c, vactv[it] && cact);
+      }
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int vf = vf0 + it * GPW + g;
+        first += fcv[it];
+        if (vactv[it] && cact) {
+          st<V>(a.out_emb + ((b * a.VF + vf) * (long long)a.E + c * V), ev[it]);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            S.v[i] += ev[it].v[i];
+            Q.v[i] = fmaf(ev[it].v[i], ev[it].v[i], Q.v[i]);
+          }
         }
       }
     }
@@ -320,22 +346,51 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
     const float gy = a.g_y ? __ldg(a.g_y + b) : 0.f;
     FV<V> S = FV<V>::zero();
     if (a.g_y && cact) S = ldg<V>(a.S + b * a.E + d0);
-    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW) {
-      const int vf = vf0 + g;
+    for (int vfb = 0; vfb < a.VF; vfb += GPW * kIter) {
+      // ---- load phase: every load of the batch is issued before the first store ----
+      long long rowv[kIter];
+      FV<V> gdv[kIter], eev[kIter], t1v[kIter], t2v[kIter];
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int vf = vfb + it * GPW + g;
+        const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
+        rowv[it] = (vf < a.VF) ? __ldg(a.rows_in + b * a.F + f) : 0;
+      }
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+        const int vf = vfb + it * GPW + g;
+        const bool act = (vf < a.VF) && cact;
+        const long long o = (b * a.VF + vf) * (long long)a.E + d0;
+        gdv[it] = FV<V>::zero();
+        eev[it] = FV<V>::zero();
+        t1v[it] = FV<V>::zero();
+        t2v[it] = FV<V>::zero();
+        if (act) {
+          if (a.g_deep) gdv[it] = ldg<V>(a.g_deep + o);
+          if (a.g_y) eev[it] = ldg<V>(a.emb + o);
+          if (K == RSB_KIND_QR_MULT) {
+            long long i1, i2;
+            qr_split(a, rowv[it], i1, i2);
+            t1v[it] = ldg<V>(a.table1 + i1 * a.E + d0);
+            t2v[it] = ldg<V>(a.table + i2 * a.E + d0);
+          } else if (K == RSB_KIND_PEP || K == RSB_KIND_OPTEMBED) {
+            t1v[it] = ldg<V>(a.table + rowv[it] * a.E + d0);
+          }
+        }
+      }
+      // ---- compute + store phase ----
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
+      const int vf = vfb + it * GPW + g;
       const bool vact = vf < a.VF;
       const bool act = vact && cact;
       const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
-      const long long row = vact ? __ldg(a.rows_in + b * a.F + f) : 0;
-      const long long o = (b * a.VF + vf) * (long long)a.E + d0;  // offset into [B,VF,E]
+      const long long row = rowv[it];
       const long long p = (b * a.F + f) * (long long)a.E + d0;    // offset into [n,E] per-lookup arrays
-      FV<V> go = FV<V>::zero();
-      if (act) {
-        if (a.g_deep) go = ldg<V>(a.g_deep + o);
-        if (a.g_y) {
-          FV<V> e = ldg<V>(a.emb + o);
+      FV<V> go = gdv[it];
+      if (act && a.g_y) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) go.v[i] = fmaf(gy, S.v[i] - e.v[i], go.v[i]);
-        }
+        for (int i = 0; i < V; ++i) go.v[i] = fmaf(gy, S.v[i] - eev[it].v[i], go.v[i]);
       }
       if (K == RSB_KIND_VANILLA) {
         if (act) st<V>(a.rg_main + p, go);
@@ -351,8 +406,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
         if (act) {
           long long i1, i2;
           qr_split(a, row, i1, i2);
-          FV<V> e1 = ldg<V>(a.table1 + i1 * a.E + d0);
-          FV<V> e2 = ldg<V>(a.table + i2 * a.E + d0);
+          const FV<V> e1 = t1v[it], e2 = t2v[it];
           FV<V> r1, r2;
 #pragma unroll
           for (int i = 0; i < V; ++i) {
@@ -391,7 +445,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
         if (act) st<V>((vf < a.F ? a.rg_aux : a.rg_main) + p, go);
       } else if (K == RSB_KIND_PEP) {
         if (act) {
-          FV<V> w = ldg<V>(a.table + row * a.E + d0);
+          const FV<V> w = t1v[it];
           FV<V> rw, rs;
 #pragma unroll
           for (int i = 0; i < V; ++i) {
@@ -405,8 +459,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
           if (a.rg_aux) st<V>(a.rg_aux + p, rs);
         }
       } else if (K == RSB_KIND_OPTEMBED) {
-        FV<V> w = FV<V>::zero();
-        if (act) w = ldg<V>(a.table + row * a.E + d0);
+        const FV<V> w = t1v[it];
         long long k = (a.mask_d != nullptr && vact) ? __ldg(a.mask_d + b * a.F + f) : (long long)a.E;
         FV<V> u;
 #pragma unroll
@@ -437,6 +490,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
         }
         if (act) st<V>(a.rg_main + p, r);
       }
+      }  // it
     }
   }
   if constexpr (TINY) {
