@@ -57,15 +57,20 @@ __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float4* __r
   }
 }
 
-// One CTA owns a slab of rows; thread t owns the float4 column groups t, t+256, ... so that a row is
-// read with fully coalesced 128-bit loads and the column sums stay in registers until the end.
-constexpr int kColsPerThread = 2;  // float4 groups per thread: supports N <= 256*4*2 = 2048 columns per pass
+// One CTA owns a slab of rows.  The 256 threads are arranged as (row lane ty) x (column group tx):
+// tx owns the float4 column groups tx, tx+ctx, ... (a row is read with coalesced 128-bit loads), the
+// cty row lanes interleave over the slab's rows; column sums stay in registers, are folded over ty in
+// shared memory (fixed order) and leave the CTA as one partial row.
+constexpr int kColsPerThread = 2;  // float4 groups per thread per pass
 
 template <bool MASKED>
 __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restrict__ g,
                                                           const unsigned char* __restrict__ mask, float scale,
                                                           long long M, int N, long long ld, float* __restrict__ gx,
                                                           float* __restrict__ partials, int col0) {
+  __shared__ float4 red[256][kColsPerThread];
+  const int ctx = blockDim.x, cty = blockDim.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;
   const int n4 = N / 4;
   const long long rows_per = (M + gridDim.x - 1) / gridDim.x;
   const long long r0 = rows_per * blockIdx.x;
@@ -75,15 +80,15 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
 #pragma unroll
   for (int j = 0; j < kColsPerThread; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   constexpr int RU = 4;  // rows in flight per thread
-  for (long long rb = r0; rb < r1; rb += RU) {
+  for (long long rb = r0 + ty; rb < r1; rb += (long long)cty * RU) {
     float4 v[RU][kColsPerThread];
     uchar4 m[RU][kColsPerThread];
 #pragma unroll
     for (int u = 0; u < RU; ++u) {
 #pragma unroll
       for (int j = 0; j < kColsPerThread; ++j) {
-        const int c4 = col0 / 4 + threadIdx.x + j * 256;
-        const long long r = rb + u;
+        const int c4 = col0 / 4 + tx + j * ctx;
+        const long long r = rb + (long long)u * cty;
         v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
         m[u][j] = make_uchar4(0, 0, 0, 0);
         if (c4 < n4 && r < r1) {
@@ -96,8 +101,8 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
     for (int u = 0; u < RU; ++u) {
 #pragma unroll
       for (int j = 0; j < kColsPerThread; ++j) {
-        const int c4 = col0 / 4 + threadIdx.x + j * 256;
-        const long long r = rb + u;
+        const int c4 = col0 / 4 + tx + j * ctx;
+        const long long r = rb + (long long)u * cty;
         if (c4 < n4 && r < r1) {
           float4 x = v[u][j];
           if (MASKED) {
@@ -116,10 +121,21 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
     }
   }
   if (partials) {
+    const int t = ty * ctx + tx;
 #pragma unroll
-    for (int j = 0; j < kColsPerThread; ++j) {
-      const int c4 = col0 / 4 + threadIdx.x + j * 256;
-      if (c4 < n4) reinterpret_cast<float4*>(partials + (long long)blockIdx.x * N)[c4] = acc[j];
+    for (int j = 0; j < kColsPerThread; ++j) red[t][j] = acc[j];
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+      for (int j = 0; j < kColsPerThread; ++j) {
+        const int c4 = col0 / 4 + tx + j * ctx;
+        float4 s4 = red[tx][j];
+        for (int y = 1; y < cty; ++y) {
+          const float4 o = red[y * ctx + tx][j];
+          s4.x += o.x; s4.y += o.y; s4.z += o.z; s4.w += o.w;
+        }
+        if (c4 < n4) reinterpret_cast<float4*>(partials + (long long)blockIdx.x * N)[c4] = s4;
+      }
     }
   }
 }
@@ -185,12 +201,16 @@ static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t
     if (!workspace || workspace_bytes < rsb_colsum_workspace_bytes(M, N)) return RSB_ERR_WORKSPACE;
     partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   }
-  const int per_pass = 256 * 4 * kColsPerThread;
+  // thread arrangement: enough column threads for one pass over the row, the rest as row lanes
+  int ctx = 256;
+  while (ctx > 32 && ctx * kColsPerThread / 2 >= N / 4) ctx >>= 1;   // smallest power of two with ctx*kCols >= n4
+  const dim3 block(ctx, 256 / ctx);
+  const int per_pass = ctx * 4 * kColsPerThread;
   for (int col0 = 0; col0 < N; col0 += per_pass) {
     if (mask)
-      colsum_slab_kernel<true><<<nblk, 256, 0, s>>>(g, mask, scale, M, N, ld, gx, partials, col0);
+      colsum_slab_kernel<true><<<nblk, block, 0, s>>>(g, mask, scale, M, N, ld, gx, partials, col0);
     else
-      colsum_slab_kernel<false><<<nblk, 256, 0, s>>>(g, nullptr, 1.f, M, N, ld, nullptr, partials, col0);
+      colsum_slab_kernel<false><<<nblk, block, 0, s>>>(g, nullptr, 1.f, M, N, ld, nullptr, partials, col0);
     RSB_CHECK_LAUNCH();
     note_launch(1);
   }

@@ -332,6 +332,8 @@ __global__ void partials_reduce_kernel(const float* __restrict__ partials, int n
 template <int K, int V, int LPR, bool TINY = false>
 __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
+  // the register-accumulating QR variant keeps its registers for the emb1 accumulators: no batching there
+  constexpr int KI = TINY ? 1 : kIter;
   FV<V> tacc[TINY ? kTinyRows : 1];
 #pragma unroll
   for (int r = 0; r < (TINY ? kTinyRows : 1); ++r) tacc[r] = FV<V>::zero();
@@ -346,18 +348,18 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
     const float gy = a.g_y ? __ldg(a.g_y + b) : 0.f;
     FV<V> S = FV<V>::zero();
     if (a.g_y && cact) S = ldg<V>(a.S + b * a.E + d0);
-    for (int vfb = 0; vfb < a.VF; vfb += GPW * kIter) {
+    for (int vfb = 0; vfb < a.VF; vfb += GPW * KI) {
       // ---- load phase: every load of the batch is issued before the first store ----
-      long long rowv[kIter];
-      FV<V> gdv[kIter], eev[kIter], t1v[kIter], t2v[kIter];
+      long long rowv[KI];
+      FV<V> gdv[KI], eev[KI], t1v[KI], t2v[KI];
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
         const int vf = vfb + it * GPW + g;
         const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
         rowv[it] = (vf < a.VF) ? __ldg(a.rows_in + b * a.F + f) : 0;
       }
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
         const int vf = vfb + it * GPW + g;
         const bool act = (vf < a.VF) && cact;
         const long long o = (b * a.VF + vf) * (long long)a.E + d0;
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
       }
       // ---- compute + store phase ----
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
       const int vf = vfb + it * GPW + g;
       const bool vact = vf < a.VF;
       const bool act = vact && cact;

@@ -1,8 +1,11 @@
 // Stable LSD radix sort of the lookups by target row (backward stage 2).
 //
 // keys are row ids < n_rows (so only bit_length(n_rows-1) bits are sorted, in passes of
-// <= 8 bits), values are the lookup positions.  Three launches per pass:
-//   histogram (per-CTA digit counts, digit-major) -> exclusive scan -> stable scatter.
+// <= 11 bits: two passes for tables up to 4 M rows), values are the lookup positions.
+// Three launches per pass:
+//   histogram (per-CTA digit counts, digit-major)
+//   -> row scan (one CTA per digit: exclusive prefix over the CTAs + the digit total)
+//   -> stable scatter (digit bases scanned in shared memory, match-any ranking).
 // The first pass reads the int64 ids directly and applies the optional QR index
 // transform (key = id / key_div or id % key_mod, qr_embedding.py:96-97, bit exact on
 // non-negative ids), so no separate key-extraction pass is needed.
@@ -13,7 +16,8 @@ namespace rsb {
 constexpr int kSortThreads = 256;
 constexpr int kSortItems = 16;
 constexpr int kSortTile = kSortThreads * kSortItems;  // keys per CTA
-constexpr int kRadixMax = 256;
+constexpr int kRadixBitsMax = 11;
+constexpr int kRadixMax = 1 << kRadixBitsMax;
 
 struct SortSrc {
   const long long* keys64;  // pass 0 source (or nullptr)
@@ -59,21 +63,21 @@ __global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortSrc src, lo
   for (int i = threadIdx.x; i < radix; i += blockDim.x) hist[(long long)i * nblk + blockIdx.x] = h[i];
 }
 
-// Exclusive scan of `len` counters in place, one CTA, 16 items per thread per sweep.
-__global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned* data, long long len) {
-  constexpr int IPT = 16;
-  __shared__ unsigned warp_tot[32];
+// One CTA per digit d: exclusive prefix of hist[d][0..nblk) in place, digit total to totals[d].
+__global__ void __launch_bounds__(256) sort_rowscan_kernel(unsigned* __restrict__ hist, int nblk,
+                                                          unsigned* __restrict__ totals) {
+  __shared__ unsigned warp_tot[8];
   __shared__ unsigned carry_s;
+  unsigned* row = hist + (long long)blockIdx.x * nblk;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (long long base = 0; base < len; base += 1024 * IPT) {
-    long long i0 = base + (long long)threadIdx.x * IPT;
-    unsigned v[IPT];
-    unsigned sum = 0;
+  for (int base = 0; base < nblk; base += 256 * 4) {
+    const int i0 = base + threadIdx.x * 4;
+    unsigned v[4], sum = 0;
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      v[i] = (i0 + i < len) ? data[i0 + i] : 0u;
+    for (int i = 0; i < 4; ++i) {
+      v[i] = (i0 + i < nblk) ? row[i0 + i] : 0u;
       sum += v[i];
     }
     unsigned incl = sum;
@@ -84,40 +88,64 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(unsigned* data, long lo
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-      unsigned w = warp_tot[lane];
-      unsigned wi = w;
+    unsigned wbase = 0;
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        unsigned t = __shfl_up_sync(kFull, wi, off);
-        if (lane >= off) wi += t;
-      }
-      warp_tot[lane] = wi - w;  // exclusive over warps
-      if (lane == 31) warp_tot[31] = wi - w;
-    }
-    __syncthreads();
-    unsigned carry = carry_s;
-    unsigned run = carry + warp_tot[warp] + (incl - sum);
+    for (int w = 0; w < 8; ++w) wbase += (w < warp) ? warp_tot[w] : 0u;
+    unsigned run = carry_s + wbase + (incl - sum);
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      if (i0 + i < len) data[i0 + i] = run;
+    for (int i = 0; i < 4; ++i) {
+      if (i0 + i < nblk) row[i0 + i] = run;
       run += v[i];
     }
     __syncthreads();
-    if (threadIdx.x == 1023) carry_s = run;  // last thread's running total == sweep total + carry
+    if (threadIdx.x == 255) carry_s = run;
     __syncthreads();
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src, long long n, int shift,
                                                                     int radix_bits, const unsigned* hist_scanned,
-                                                                    int nblk, unsigned* out_keys,
-                                                                    unsigned* out_vals) {
+                                                                    const unsigned* totals, int nblk,
+                                                                    unsigned* out_keys, unsigned* out_vals) {
   constexpr int NW = kSortThreads / 32;
-  __shared__ unsigned cnt[NW][kRadixMax];
+  extern __shared__ unsigned sort_smem[];
   const int radix = 1 << radix_bits;
+  unsigned* dbase = sort_smem;                 // [radix] exclusive scan of the digit totals
+  unsigned(*cnt)[kRadixMax] = reinterpret_cast<unsigned(*)[kRadixMax]>(sort_smem + kRadixMax);  // [NW][kRadixMax]
+  __shared__ unsigned wtot[NW];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NW * kRadixMax; i += blockDim.x) (&cnt[0][0])[i] = 0;
+  {
+    // digit bases: thread t scans its radix/256 consecutive totals, then a 256-wide block scan
+    const int per = (radix + kSortThreads - 1) / kSortThreads;
+    unsigned loc[kRadixMax / kSortThreads];
+    unsigned sum = 0;
+#pragma unroll
+    for (int i = 0; i < kRadixMax / kSortThreads; ++i) {
+      const int d = threadIdx.x * per + i;
+      loc[i] = (i < per && d < radix) ? __ldg(totals + d) : 0u;
+      sum += loc[i];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      unsigned t = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) wbase += (w < warp) ? wtot[w] : 0u;
+    unsigned run = wbase + (incl - sum);
+#pragma unroll
+    for (int i = 0; i < kRadixMax / kSortThreads; ++i) {
+      const int d = threadIdx.x * per + i;
+      if (i < per && d < radix) dbase[d] = run;
+      run += loc[i];
+    }
+  }
   __syncthreads();
 
   const long long base = (long long)blockIdx.x * kSortTile;
@@ -147,7 +175,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src,
   __syncthreads();
   // exclusive scan over warps for each digit, plus this CTA's global base
   for (int d = threadIdx.x; d < radix; d += blockDim.x) {
-    unsigned run = hist_scanned[(long long)d * nblk + blockIdx.x];
+    unsigned run = dbase[d] + hist_scanned[(long long)d * nblk + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       unsigned t = cnt[w][d];
@@ -190,6 +218,7 @@ extern "C" RSB_API int64_t rsb_sort_workspace_bytes(int64_t n) {
   bytes += align_up(2 * n * 4, 256);              // ping-pong keys
   bytes += align_up(2 * n * 4, 256);              // ping-pong values
   bytes += align_up(nblk * kRadixMax * 4, 256);   // histogram
+  bytes += align_up(kRadixMax * 4, 256);          // digit totals
   return bytes + 256;
 }
 
@@ -215,11 +244,15 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
   vbuf[1] = vbuf[0] + n;
   w += align_up(2 * n * 4, 256);
   unsigned* hist = reinterpret_cast<unsigned*>(w);
+  w += align_up(nblk * kRadixMax * 4, 256);
+  unsigned* totals = reinterpret_cast<unsigned*>(w);
 
   int bits = bit_length((unsigned long long)(n_rows - 1));
   if (bits < 1) bits = 1;
-  const int passes = (bits + 7) / 8;
-  const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 8)
+  const int passes = (bits + kRadixBitsMax - 1) / kRadixBitsMax;
+  const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 11)
+  const size_t scatter_smem = (size_t)(kRadixMax + (kSortThreads / 32) * kRadixMax) * sizeof(unsigned);
+  cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
 
   SortSrc src;
   src.keys64 = reinterpret_cast<const long long*>(keys);
@@ -234,9 +267,10 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
     const int shift = p * rb;
     sort_hist_kernel<<<(unsigned)nblk, kSortThreads, 0, s>>>(src, n, shift, rb, hist, (int)nblk);
     RSB_CHECK_LAUNCH();
-    sort_scan_kernel<<<1, 1024, 0, s>>>(hist, (long long)(1 << rb) * nblk);
+    sort_rowscan_kernel<<<1 << rb, 256, 0, s>>>(hist, (int)nblk, totals);
     RSB_CHECK_LAUNCH();
-    sort_scatter_kernel<<<(unsigned)nblk, kSortThreads, 0, s>>>(src, n, shift, rb, hist, (int)nblk, ok, ov);
+    sort_scatter_kernel<<<(unsigned)nblk, kSortThreads, scatter_smem, s>>>(src, n, shift, rb, hist, totals, (int)nblk,
+                                                                          ok, ov);
     RSB_CHECK_LAUNCH();
     note_launch(3);
     src.keys64 = nullptr;
