@@ -140,19 +140,30 @@ __global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restric
   }
 }
 
-// one warp per column: lanes stride over the CTA partials, fixed-shape shuffle tree
-__global__ void colsum_final_kernel(const float* __restrict__ partials, int nblk, int N, float* __restrict__ out) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (c >= N) return;
+// final reduction of the CTA partials: 32 columns x 32 row lanes per CTA, coalesced along the columns,
+// fixed-order fold over the row lanes in shared memory
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partials, int nblk, int N,
+                                                            float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = lane; b < nblk; b += 32) s += partials[(long long)b * N + c];
+  if (c < N) {
+#pragma unroll 4
+    for (int b = ty; b < nblk; b += 32) s += __ldg(partials + (long long)b * N + c);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = 0.f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
-  if (lane == 0) out[c] = s;
+    for (int y = 0; y < 32; ++y) t += red[y][tx];
+    out[c] = t;
+  }
 }
 
 static int slab_blocks(long long M) {
-  long long b = 16ll * sm_count();     // >= 2 resident CTAs per SM x several waves; >= 16 rows per CTA
+  long long b = 4ll * sm_count();      // a few resident CTAs per SM; >= 16 rows per CTA
   if (b > M / 16) b = M / 16;
   if (b < 1) b = 1;
   return (int)b;
@@ -215,7 +226,7 @@ static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t
     note_launch(1);
   }
   if (colsum) {
-    colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(partials, nblk, N, colsum);
+    colsum_final_kernel<<<(N + 31) / 32, dim3(32, 32), 0, s>>>(partials, nblk, N, colsum);
     RSB_CHECK_LAUNCH();
     note_launch(1);
   }
