@@ -182,6 +182,83 @@ class ClockSampler:
         return out
 
 
+def small_batch_leg(args, wl, dims, cfg, dev, R, crit):
+    """The reference yaml batch (configs/deepfm/*.yaml: 2048) is launch-latency-bound on a B200
+    (~70 launches of a few microseconds each), so the same training step is also measured captured in
+    ONE CUDA graph (static input buffers, capturable Adam, dropout stream position in device memory)."""
+    import torch
+
+    import recsys_benchmark_b200.linalg as LA
+
+    b = args.small_batch
+    torch.manual_seed(2023)
+    model = R.get_ctr_model(dims, {k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}).to(dev)
+    model.train()
+    opt_cfg = dict(wl["opt"])
+    opt_cfg.update(capturable=True, fused_adam=True)
+    opt_cfg.pop("fused_sparse", None)
+    if opt_cfg.get("sparse"):
+        opt_cfg.pop("sparse")          # the sparse optimizers are not capturable: dense Adam for this leg
+    opts = R.get_optimizers(model, opt_cfg)
+    pool = make_batches(dims, b, 8, 77, torch.int32)
+    dev_pool = [(x.to(dev), y.to(dev)) for x, y in pool]
+    sx, sy = dev_pool[0][0].clone(), dev_pool[0][1].clone()
+
+    def step(x, y):
+        logits = model(x)
+        loss = crit(logits, y)
+        for o in opts:
+            o.zero_grad(set_to_none=True)
+        loss.backward()
+        for o in opts:
+            o.step()
+        return loss
+
+    def run(fn, steps):
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / steps
+
+    steps = max(args.steps, 20)
+    for i in range(5):
+        step(*dev_pool[i % 8])
+    eager_ms = run(lambda i: step(*dev_pool[i % 8]), steps)
+
+    LA.use_device_dropout_counter(dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(sx, sy)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        LA.advance_dropout_counter()
+        static_loss = step(sx, sy)
+
+    def replay(i):
+        x, y = dev_pool[i % 8]
+        sx.copy_(x)
+        sy.copy_(y)
+        graph.replay()
+
+    for i in range(5):
+        replay(i)
+    graph_ms = run(replay, steps)
+    l1 = float(static_loss.item())
+    replay(1)
+    l2 = float(static_loss.item())
+    return {"batch": b, "eager_ms_per_step": round(eager_ms, 4), "eager_samples_per_s": round(b / eager_ms * 1e3, 1),
+            "cuda_graph_ms_per_step": round(graph_ms, 4), "cuda_graph_samples_per_s": round(b / graph_ms * 1e3, 1),
+            "loss_changes_between_replays": l1 != l2,
+            "note": "whole step (fwd, BCE, bwd, Adam) captured in one CUDA graph; inputs copied into static buffers"}
+
+
 def main_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -307,6 +384,14 @@ def main_ours(args, wl):
     ms_e2e = timed(e2e_step, args.steps) / args.steps
     h2d = pool[0][0].numel() * pool[0][0].element_size() + pool[0][1].numel() * 4
 
+    # ---- reference-yaml batch (2048): launch-bound -> whole step captured in a CUDA graph -------------
+    small = None
+    if world == 1 and args.small_batch > 0 and not sharded:
+        try:
+            small = small_batch_leg(args, wl, dims, cfg, dev, R, crit)
+        except Exception as exc:  # noqa: BLE001 - a secondary number must never break the main line
+            small = {"batch": args.small_batch, "error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -390,6 +475,7 @@ def main_ours(args, wl):
         "roofline_gemm": roofline_gemm,
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "small_batch": small,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -408,6 +494,8 @@ def main():
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches cycled through")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded sample per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small-batch", type=int, default=2048,
+                    help="also time this (reference yaml) batch eagerly and as one CUDA graph; 0 = skip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]

@@ -241,7 +241,8 @@ RSB_API int rsb_gemm_f32(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N,
  *                        i.e. the bias gradient of the preceding Linear, accumulated in the same pass
  *  rsb_colsum            out[N] = sum over rows of x [M,N] (row stride ld), deterministic two-stage
  * ---------------------------------------------------------------------- */
-RSB_API int rsb_relu_dropout_fwd(const float* x, int64_t numel, float p, uint64_t seed, uint64_t offset, float* y,
+RSB_API int rsb_relu_dropout_fwd(const float* x, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                                 const uint64_t* offset_dev /* device, added to offset; may be NULL */, float* y,
                                  uint8_t* mask, void* stream);
 RSB_API int rsb_relu_dropout_bwd(const float* g, const uint8_t* mask, int64_t M, int32_t N, float p, float* gx,
                                  float* colsum, void* workspace, int64_t workspace_bytes, void* stream);

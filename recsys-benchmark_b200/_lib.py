@@ -52,7 +52,7 @@ PROTOTYPES = {
     "rsb_gemm_f32_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64]),
     "rsb_gemm_f32": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64,
                                _i64, _p, _f, _f, _p, _i64, _p]),
-    "rsb_relu_dropout_fwd": (C.c_int, [_p, _i64, _f, C.c_uint64, C.c_uint64, _p, _p, _p]),
+    "rsb_relu_dropout_fwd": (C.c_int, [_p, _i64, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p]),
     "rsb_relu_dropout_bwd": (C.c_int, [_p, _p, _i64, _i32, _f, _p, _p, _p, _i64, _p]),
     "rsb_colsum_workspace_bytes": (_i64, [_i64, _i32]),
     "rsb_colsum": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i64, _p]),

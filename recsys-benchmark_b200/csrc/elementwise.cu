@@ -34,9 +34,11 @@ struct Philox {
 // numel must be a multiple of 4 and x/y 16-byte aligned (checked by the host function)
 __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float4* __restrict__ x, long long n4,
                                                                float p, float scale, unsigned long long seed,
-                                                               unsigned long long offset, float4* __restrict__ y,
-                                                               uchar4* __restrict__ mask) {
+                                                               unsigned long long offset,
+                                                               const unsigned long long* __restrict__ offset_dev,
+                                                               float4* __restrict__ y, uchar4* __restrict__ mask) {
   Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
+  if (offset_dev) offset += *offset_dev;   // CUDA-graph replays: the stream position lives in device memory
   const unsigned thr = (unsigned)(p * 4294967296.0);  // keep iff r >= thr
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -174,7 +176,7 @@ static int slab_blocks(long long M) {
 using namespace rsb;
 
 extern "C" RSB_API int rsb_relu_dropout_fwd(const float* x, int64_t numel, float p, uint64_t seed, uint64_t offset,
-                                            float* y, uint8_t* mask, void* stream) {
+                                            const uint64_t* offset_dev, float* y, uint8_t* mask, void* stream) {
   if (numel < 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
   if (numel == 0) return RSB_OK;
   if (!x || !y || !mask) return RSB_ERR_BAD_ARG;
@@ -184,7 +186,8 @@ extern "C" RSB_API int rsb_relu_dropout_fwd(const float* x, int64_t numel, float
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   relu_dropout_fwd_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float4*>(x), n4, p, 1.0f / (1.0f - p), seed, offset, reinterpret_cast<float4*>(y),
+      reinterpret_cast<const float4*>(x), n4, p, 1.0f / (1.0f - p), seed, offset,
+      reinterpret_cast<const unsigned long long*>(offset_dev), reinterpret_cast<float4*>(y),
       reinterpret_cast<uchar4*>(mask));
   RSB_CHECK_LAUNCH();
   note_launch(1);

@@ -317,16 +317,26 @@ __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restric
   }
 }
 
-// Sum of per-CTA partial tables in CTA order: one warp per output element.
-__global__ void partials_reduce_kernel(const float* __restrict__ partials, int nblk, int tot, float* __restrict__ dst,
-                                       int dst_elems) {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= dst_elems) return;
+// Sum of the per-CTA partial tables: 32 columns x 32 row lanes per CTA, coalesced along the columns,
+// fixed-order fold over the row lanes.
+__global__ void __launch_bounds__(1024) partials_reduce_kernel(const float* __restrict__ partials, int nblk, int N,
+                                                               float* __restrict__ dst) {
+  __shared__ float red[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int b = lane; b < nblk; b += 32) s += partials[(long long)b * tot + w];
+  if (c < N) {
+#pragma unroll 4
+    for (int b = ty; b < nblk; b += 32) s += __ldg(partials + (long long)b * N + c);
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < N) {
+    float t = 0.f;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFull, s, off);
-  if (lane == 0) dst[w] = s;
+    for (int y = 0; y < 32; ++y) t += red[y][tx];
+    dst[c] = t;
+  }
 }
 
 template <int K, int V, int LPR, bool TINY = false>
@@ -513,7 +523,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
       }
     }
     __syncthreads();
-    const int tot = kTinyRows * a.E;
+    const int tot = (int)a.divider * a.E;   // rows >= divider are never hit
     float* out = a.tiny_partials + (long long)blockIdx.x * tot;
     for (int i = threadIdx.x; i < tot; i += blockDim.x) {
       const int r = i / a.E, d = i - r * a.E;
@@ -713,10 +723,9 @@ static int bwd_rows_impl(int32_t kind, const int64_t* rows, int64_t B, int32_t F
   if (rc) return rc;
   if (table1_grad != nullptr) {
     const int nblk = (int)bwd_blocks(B);
-    const int tot = kTinyRows * a.E;
-    const int dst_elems = (int)divider * a.E;   // rows >= divider are never hit
-    partials_reduce_kernel<<<(dst_elems * 32 + 255) / 256, 256, 0, s>>>(a.tiny_partials, nblk, tot, table1_grad,
-                                                                       dst_elems);
+    const int dst_elems = (int)divider * a.E;
+    partials_reduce_kernel<<<(dst_elems + 31) / 32, dim3(32, 32), 0, s>>>(a.tiny_partials, nblk, dst_elems,
+                                                                          table1_grad);
     RSB_CHECK_LAUNCH();
     note_launch(1);
   }

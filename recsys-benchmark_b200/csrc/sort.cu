@@ -252,7 +252,11 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
   const int passes = (bits + kRadixBitsMax - 1) / kRadixBitsMax;
   const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 11)
   const size_t scatter_smem = (size_t)(kRadixMax + (kSortThreads / 32) * kRadixMax) * sizeof(unsigned);
-  cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
+  static bool attr_set = false;   // one process drives one device
+  if (!attr_set) {
+    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
+    attr_set = true;
+  }
 
   SortSrc src;
   src.keys64 = reinterpret_cast<const long long*>(keys);

@@ -105,7 +105,8 @@ def get_optimizers(model: nn.Module, config: Dict) -> List[torch.optim.Optimizer
     if optimizer_name == "adam":
         # `fused_adam: true` (opt-in) selects torch's single-kernel multi-tensor Adam (same arithmetic)
         return [torch.optim.Adam(model.parameters(), lr=config["learning_rate"],
-                                 weight_decay=config["weight_decay"], fused=bool(config.get("fused_adam", False)))]
+                                 weight_decay=config["weight_decay"], fused=bool(config.get("fused_adam", False)),
+                                 capturable=bool(config.get("capturable", False)))]
     if optimizer_name == "sgd":
         if not sparse:
             return [torch.optim.SGD(model.parameters(), lr=config["learning_rate"],

@@ -161,6 +161,21 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
 
 
 _DROPOUT_CALLS = 0
+_DROPOUT_DEV_COUNTER = None   # int64 device tensor: Philox stream position for CUDA-graph replays
+
+
+def use_device_dropout_counter(device) -> torch.Tensor:
+    """CUDA-graph mode: the dropout stream position is read from device memory, so that every replay
+    of a captured step draws fresh masks.  Call `advance_dropout_counter()` once per step INSIDE the
+    captured region."""
+    global _DROPOUT_DEV_COUNTER
+    _DROPOUT_DEV_COUNTER = torch.zeros(1, dtype=torch.int64, device=device)
+    return _DROPOUT_DEV_COUNTER
+
+
+def advance_dropout_counter():
+    if _DROPOUT_DEV_COUNTER is not None:
+        _DROPOUT_DEV_COUNTER.add_(1 << 40)
 
 
 def _dropout_stream(numel: int):
@@ -176,8 +191,8 @@ def _relu_dropout_fwd(x: torch.Tensor, p: float):
     y = torch.empty_like(x)
     mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     seed, off = _dropout_stream(x.numel())
-    RF._call("relu_dropout_fwd", lib.rsb_relu_dropout_fwd, L.ptr(x), x.numel(), float(p), seed, off, L.ptr(y),
-             L.ptr(mask), L.stream_ptr(x.device), nbytes=x.numel() * 9)
+    RF._call("relu_dropout_fwd", lib.rsb_relu_dropout_fwd, L.ptr(x), x.numel(), float(p), seed, off,
+             L.ptr(_DROPOUT_DEV_COUNTER), L.ptr(y), L.ptr(mask), L.stream_ptr(x.device), nbytes=x.numel() * 9)
     return y, mask
 
 
