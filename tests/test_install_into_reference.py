@@ -1,0 +1,51 @@
+"""Drop-in check against the real reference checkout (build container only: skipped on the GPU
+box, where /root/reference does not exist): after install_into_reference() the reference's own
+registry / factories hand out the B200-native classes, with the reference's yaml configs."""
+import os
+import sys
+import types
+
+import pytest
+
+REF = os.environ.get("RSB_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "models")),
+                                reason="reference checkout not present")
+
+
+def test_registry_is_rebound_and_reference_yaml_builds_our_model():
+    import yaml
+
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("lmdb", types.ModuleType("lmdb"))
+    try:
+        import src.models as ref_models
+        import src.models.embeddings as ref_emb
+
+        import recsys_benchmark_b200 as R
+
+        saved = (dict(ref_emb.NAME_TO_CLS), ref_emb.VanillaEmbedding, ref_models.DeepFM, ref_models.get_ctr_model)
+        R.install_into_reference()
+        try:
+            assert ref_emb.NAME_TO_CLS["qr"] is R.QRHashingEmbedding
+            assert ref_emb.VanillaEmbedding is R.VanillaEmbedding
+            assert ref_models.DeepFM is R.DeepFM and ref_models.DCN_Mix is R.DCN_Mix
+            # the reference's own factory (unchanged code) now returns our plugin classes
+            emb = ref_emb.get_embedding({"name": "vanilla"}, [3, 4], 8)
+            assert isinstance(emb, R.VanillaEmbedding)
+            emb = ref_emb.get_embedding({"name": "qr", "divider": 2}, [3, 4], 8)
+            assert isinstance(emb, R.QRHashingEmbedding)
+            for cfg_name in ["base_config.yaml", "qr_80.yaml", "base_config_sparse.yaml"]:
+                with open(os.path.join(REF, "configs", "deepfm", cfg_name)) as fh:
+                    cfg = yaml.safe_load(fh)
+                model = ref_models.get_ctr_model([5, 6, 7], dict(cfg["model"]))
+                assert isinstance(model, R.DeepFM)
+                opts = ref_models.deepfm.get_optimizers(model, cfg)
+                assert len(opts) == (2 if cfg.get("sparse") else 1)
+        finally:
+            ref_emb.NAME_TO_CLS.clear()
+            ref_emb.NAME_TO_CLS.update(saved[0])
+            ref_emb.VanillaEmbedding = saved[1]
+            ref_models.DeepFM = saved[2]
+            ref_models.get_ctr_model = saved[3]
+    finally:
+        sys.path.remove(REF)
