@@ -302,18 +302,18 @@ __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restric
     const long long row = valid ? tile[(long long)lane * F + f] : (long long)(-1 - lane);
     const unsigned peers = __match_any_sync(kFull, row);
     const int leader = __ffs(peers) - 1;
-    const bool dup = __popc(peers) > 1;
-    if (valid && !dup) atomicAdd(fc_grad + row, gy);
-    unsigned todo = __ballot_sync(kFull, valid && dup && lane == leader);
-    while (todo) {
-      const int l = __ffs(todo) - 1;
-      const unsigned m = __shfl_sync(kFull, peers, l);
-      float v = ((m >> lane) & 1u) ? gy : 0.f;
+    float sum = gy;
+    if (__any_sync(kFull, __popc(peers) > 1)) {
+      // every lane sums its peer set in lane order: 32 INDEPENDENT broadcasts (they pipeline), instead of a
+      // dependent shuffle tree per distinct row
+      sum = 0.f;
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
-      if (lane == l) atomicAdd(fc_grad + row, v);
-      todo &= todo - 1;
+      for (int j = 0; j < 32; ++j) {
+        const float v = __shfl_sync(kFull, gy, j);
+        sum += ((peers >> j) & 1u) ? v : 0.f;
+      }
     }
+    if (valid && lane == leader) atomicAdd(fc_grad + row, sum);
   }
 }
 
@@ -343,7 +343,7 @@ template <int K, int V, int LPR, bool TINY = false>
 __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
   // the register-accumulating QR variant keeps its registers for the emb1 accumulators: no batching there
-  constexpr int KI = TINY ? 1 : kIter;
+  constexpr int KI = TINY ? 2 : kIter;
   FV<V> tacc[TINY ? kTinyRows : 1];
 #pragma unroll
   for (int r = 0; r < (TINY ? kTinyRows : 1); ++r) tacc[r] = FV<V>::zero();
@@ -559,13 +559,21 @@ static long long bwd_blocks(long long B) {
   return blocks;
 }
 
+// the register-accumulating QR variant writes one partial table per CTA: a few resident CTAs per SM
+static long long tiny_blocks(long long B) {
+  long long blocks = bwd_blocks(B);
+  const long long cap = (long long)sm_count() * 8;
+  return blocks > cap ? cap : blocks;
+}
+
 template <int K>
 static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   const int threads = 256;
   const long long blocks = bwd_blocks(a.B);
   if constexpr (K == RSB_KIND_QR_MULT || K == RSB_KIND_QR_ADD) {
     if (a.tiny_partials != nullptr) {
-#define CALLT(VV, LL) lookup_bwd_rows_kernel<K, VV, LL, true><<<(unsigned)blocks, threads, 0, stream>>>(a)
+      const long long tblocks = tiny_blocks(a.B);
+#define CALLT(VV, LL) lookup_bwd_rows_kernel<K, VV, LL, true><<<(unsigned)tblocks, threads, 0, stream>>>(a)
       RSB_DISPATCH_SHAPE(sh, CALLT);
 #undef CALLT
       RSB_CHECK_LAUNCH();
@@ -722,7 +730,7 @@ static int bwd_rows_impl(int32_t kind, const int64_t* rows, int64_t B, int32_t F
   }
   if (rc) return rc;
   if (table1_grad != nullptr) {
-    const int nblk = (int)bwd_blocks(B);
+    const int nblk = (int)tiny_blocks(B);
     const int dst_elems = (int)divider * a.E;
     partials_reduce_kernel<<<(dst_elems + 31) / 32, dim3(32, 32), 0, s>>>(a.tiny_partials, nblk, dst_elems,
                                                                           table1_grad);
