@@ -382,6 +382,28 @@ def main_ours(args, wl):
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps) / args.steps
+
+    # same, with the library's own input staging (data.DevicePrefetcher: H2D of step i+1 on a side
+    # stream under the compute of step i); still host buffers in, loss read back every step
+    from recsys_benchmark_b200.data import DevicePrefetcher
+
+    def prefetched_run(steps):
+        src = (host_pool[i % len(host_pool)] for i in range(steps))
+        for xd, yd in DevicePrefetcher(src, dev):
+            step(xd, yd).item()
+
+    prefetched_run(3)
+    sync_all()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    prefetched_run(args.steps)
+    e_ev.record()
+    sync_all()
+    ms_e2e_pf = s_ev.elapsed_time(e_ev) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_e2e_pf], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e_pf = float(t.item())
     h2d = pool[0][0].numel() * pool[0][0].element_size() + pool[0][1].numel() * 4
 
     # ---- reference-yaml batch (2048): launch-bound -> whole step captured in a CUDA graph -------------
@@ -468,8 +490,13 @@ def main_ours(args, wl):
                    "l2": f"{args.pool} distinct batches cycled; per-step traffic "
                          f"{round(b * 13.4e3 / 1e6)} MB vs 126 MB L2 (no flush)"},
         "clocks": clocks,
-        "e2e": {"value": round(world * b / (ms_e2e * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms_e2e, 4),
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "e2e": {"value": round(world * b / (ms_e2e_pf * 1e-3), 1), "unit": "samples/s",
+                "ms_per_step": round(ms_e2e_pf, 4), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "input_staging": "recsys_benchmark_b200.data.DevicePrefetcher (pinned host ids, H2D one step ahead "
+                                 "on a side stream); loss.item() every step",
+                "blocking_to_device": {"value": round(world * b / (ms_e2e * 1e-3), 1),
+                                       "ms_per_step": round(ms_e2e, 4),
+                                       "note": "the reference trainer's inputs.to(device) on the compute stream"}},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_gemm": roofline_gemm,

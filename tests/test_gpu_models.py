@@ -372,3 +372,15 @@ def test_criteo_shape_properties(R, emb_cfg, b):
         touched = torch.zeros(sum(CRITEO_DIMS), dtype=torch.bool, device=DEV)
         touched[rows.reshape(-1)] = True
         assert float(g1[0][~touched].abs().sum()) == 0.0
+
+
+def test_device_prefetcher_yields_the_same_batches_in_order(R):
+    from recsys_benchmark_b200.data import DevicePrefetcher
+
+    batches = [(torch.randint(0, 100, (64, 5), dtype=torch.int32), torch.rand(64)) for _ in range(7)]
+    got = list(DevicePrefetcher(iter(batches), DEV))
+    assert len(got) == 7
+    for (x, y), (xd, yd) in zip(batches, got):
+        assert xd.is_cuda and yd.is_cuda
+        assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
+    assert list(DevicePrefetcher(iter([]), DEV)) == []
