@@ -94,7 +94,9 @@ RSB_API int rsb_row_width_supported(int32_t width);
  *  table      main table [n_rows, E]   (QR: emb2 [(N-1)/divider+1, E])
  *  table1     QR only: emb1 [divider, E]; divider = QR divider
  *  aux        PEP: s ; MASK: uint8/bool mask [n_rows,D] ; OPTEMBED: t_param [F] or NULL (mask-E off)
- *  aux_mode   PEP: rsb_pep_threshold ; OPTEMBED: norm (1 or 2)
+ *  aux_mode   PEP: rsb_pep_threshold ; OPTEMBED: norm (1 or 2) ; QR kinds: if > 0, the modulus of the
+ *             remainder index (i1 = id % aux_mode, i2 = id / divider): CERP's bucket size
+ *             (src/models/embeddings/cerp_embedding.py:142-153); 0 = divider (plain QR)
  *  mask_d_idx OPTEMBED: int64 [B,F] draw of torch.randint(0,D) (dims 0..k kept) or NULL
  *  fc, bias   first-order weights [N_global,1] and bias [1]; NULL -> no FM head (DCN-Mix)
  *  out_emb    [B,F,D] fp32 (always written)

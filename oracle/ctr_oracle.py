@@ -255,6 +255,44 @@ def masked_backward(weight, mask, rows, g_out) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# f-1. CERP (src/models/embeddings/cerp_embedding.py:142-207)
+# --------------------------------------------------------------------------
+
+
+def cerp_indices(rows: np.ndarray, num_item: int, bucket_size: int) -> Tuple[np.ndarray, np.ndarray]:
+    """q_idx = trunc(x / ceil(num_item / bucket)), p_idx = x % bucket (cerp_embedding.py:69,145-146)."""
+    per_row = int(np.ceil(num_item / bucket_size))
+    r = rows.astype(np.int64)
+    return r // np.int64(per_row), r % np.int64(bucket_size)
+
+
+def cerp_forward(p_w, q_w, p_t, q_t, rows, num_item: int) -> np.ndarray:
+    """emb = soft(Q)[q_idx] + soft(P)[p_idx] (cerp_embedding.py:134-153)."""
+    qi, pi = cerp_indices(rows, num_item, p_w.shape[0])
+    return pep_soft_threshold(q_w, q_t)[qi] + pep_soft_threshold(p_w, p_t)[pi]
+
+
+def cerp_backward(p_w, q_w, p_t, q_t, rows, num_item: int, g_out):
+    """Returns dense (g_p_w, g_p_t, g_q_w, g_q_t)."""
+    qi, pi = cerp_indices(rows, num_item, p_w.shape[0])
+    n = p_w.shape[0]
+    res = []
+    for w, t, idx in ((p_w, p_t, pi), (q_w, q_t, qi)):
+        g_table = scatter_add_dense(idx, g_out, n)
+        sg = sigmoid(t)
+        keep = (np.abs(w) - sg) > 0
+        res.append(np.where(keep, np.sign(w) ** 2 * g_table, 0).astype(w.dtype))
+        res.append(np.where(keep, -np.sign(w) * g_table * sg * (1 - sg), 0).astype(w.dtype))
+    return tuple(res)
+
+
+def cerp_prune_loss(p_w, q_w, p_t, q_t, K=100):
+    """get_prune_loss (cerp_embedding.py:205-207)."""
+    emb = pep_soft_threshold(p_w, p_t) + pep_soft_threshold(q_w, q_t)
+    return -np.sum(np.tanh(emb * K) ** 2)
+
+
+# --------------------------------------------------------------------------
 # a9/a10. OptEmbed (deepfm_opt_embed.py:40-307,633-718 ; optembed_utils.py)
 # --------------------------------------------------------------------------
 

@@ -15,7 +15,7 @@ from typing import Dict, List, Optional, Union
 import torch
 
 from . import _lib
-from .embeddings import (IEmbedding, OptEmbed, PepEmbeeding, QRHashingEmbedding, RetrainOptEmbed,
+from .embeddings import (CerpEmbedding, IEmbedding, OptEmbed, RetrainCerpEmbedding, PepEmbeeding, QRHashingEmbedding, RetrainOptEmbed,
                          RetrainPepEmbedding, VanillaEmbedding)
 
 __version__ = "0.1.0"
@@ -30,6 +30,8 @@ NAME_TO_CLS = {
     "deepfm_optembed": OptEmbed,
     "deepfm_optembed_d": OptEmbed,
     "deepfm_optembed_retrain": RetrainOptEmbed,
+    "cerp": CerpEmbedding,
+    "cerp_retrain": RetrainCerpEmbedding,
 }
 
 
@@ -42,7 +44,7 @@ def get_embedding(embedding_config: Dict, field_dims: Union[int, List[int]], hid
     cfg.pop("name")
     if name not in NAME_TO_CLS:
         raise NotImplementedError(f"{name} not found in mapping from name to class")
-    if name.startswith("pep"):
+    if name.startswith("pep") or name.startswith("cerp"):
         cfg["field_name"] = field_name
     if name == "deepfm_optembed_d":
         cfg["t_init"] = None

@@ -27,6 +27,7 @@ struct LookupArgs {
   long long n_rows, n_global;
   const float* table1;
   long long divider;
+  long long modulus;  // i1 = row % modulus (== divider for QR; the CERP bucket size otherwise)
   int small32;
   const void* aux;
   int aux_mode;
@@ -74,10 +75,10 @@ __device__ __forceinline__ void qr_split(const LookupArgs& a, long long row, lon
     unsigned r = (unsigned)row, d = (unsigned)a.divider;
     unsigned q = r / d;
     i2 = q;
-    i1 = r - q * d;
+    i1 = (a.modulus == a.divider) ? r - q * d : r % (unsigned)a.modulus;
   } else {
     i2 = row / a.divider;
-    i1 = row - i2 * a.divider;
+    i1 = (a.modulus == a.divider) ? row - i2 * a.divider : row % a.modulus;
   }
 }
 
@@ -625,6 +626,8 @@ static int fill_common(LookupArgs& a, int kind, long long B, int F, int D, const
   a.n_global = n_global;
   a.table1 = table1;
   a.divider = divider;
+  a.modulus = divider;
+  if (kind >= RSB_KIND_QR_MULT && kind <= RSB_KIND_QR_CAT && aux_mode > 0) a.modulus = aux_mode;
   a.small32 = (n_global < (1ll << 32) && divider < (1ll << 32)) ? 1 : 0;
   a.aux = aux;
   a.aux_mode = aux_mode;

@@ -580,3 +580,171 @@ class RetrainOptEmbed(IOptEmbed):
 
     def get_num_params(self):
         return torch.count_nonzero(self._mask).item()
+
+
+# ------------------------------------------------------------------------------
+class CerpEmbedding(IEmbedding):
+    """CERP (src/models/embeddings/cerp_embedding.py:14-207): two bucket tables P, Q, each PEP
+    soft-thresholded with element-wise thresholds, composed by QR-style index math
+    (q = x // q_entity_per_row, p = x % bucket_size) and summed.  The two small tables are
+    thresholded in one pass each (differentiable), the index math + both gathers + the add run
+    inside the fused gather kernel (QR "add" with a separate modulus)."""
+
+    def __init__(self, field_dims: Union[List[int], int], hidden_size: int, mode: Optional[str] = None,
+                 bucket_size: int = 8000, threshold_init: float = -100.0, threshold_init_method="all-ones",
+                 field_name: str = ""):
+        super().__init__()
+        field_dims = _as_list(field_dims)
+        assert mode in [None, "sum", "mean", "max"]
+        num_item = sum(field_dims)
+        self._field_dims = torch.tensor(field_dims)
+        self._mode = mode
+        self.field_name: str = field_name
+        self.p_weight = nn.Parameter(torch.zeros(bucket_size, hidden_size))
+        self.q_weight = nn.Parameter(torch.zeros(bucket_size, hidden_size))
+        nn.init.xavier_uniform_(self.p_weight)
+        nn.init.xavier_uniform_(self.q_weight)
+        self.q_threshold = self.init_threshold("element-wise", threshold_init, bucket_size, hidden_size,
+                                               threshold_init_method)
+        self.p_threshold = self.init_threshold("element-wise", threshold_init, bucket_size, hidden_size,
+                                               threshold_init_method)
+        self._num_item = num_item
+        self._hidden_size = hidden_size
+        self._bucket_size = bucket_size
+        self.q_entity_per_row = int(math.ceil(self._num_item / self._bucket_size))
+        self.sparse_q_weight = None
+        self.sparse_p_weight = None
+
+    @staticmethod
+    def init_threshold(threshold_type, init: float, row_size: int, col_size: int,
+                       threshold_init_method="all_ones") -> nn.Parameter:
+        """Same initialisers as the reference (cerp_embedding.py:76-140)."""
+        requires_scaling = True
+        if threshold_type == "global":
+            mat = torch.ones(1)
+            if threshold_init_method == "uniform":
+                mat = mat * torch.rand(1)
+                requires_scaling = False
+            elif threshold_init_method == "normal":
+                mat = mat * torch.normal(mean=0.0, std=1.0, size=(1,))
+            elif threshold_init_method == "xavier_uniform":
+                raise NotImplementedError
+            else:
+                requires_scaling = False
+            if requires_scaling:
+                mat = torch.sigmoid(mat)
+            return nn.Parameter(mat * init)
+        if threshold_type == "element-wise":
+            mat = torch.ones([row_size, col_size])
+            if threshold_init_method == "uniform":
+                mat = mat * torch.nn.init.uniform_(torch.zeros((row_size, col_size)))
+            elif threshold_init_method == "normal":
+                mat = mat * torch.normal(mean=0.0, std=1.0, size=mat.shape)
+            elif threshold_init_method == "xavier_uniform":
+                mat = mat * nn.init.xavier_uniform_(torch.zeros(size=mat.shape))
+            else:
+                requires_scaling = False
+            if requires_scaling:
+                mat_min, _ = mat.min(dim=1, keepdim=True)
+                mat_max, _ = mat.max(dim=1, keepdim=True)
+                mat = (mat - mat_min) / (mat_max - mat_min)
+            assert (0 <= mat).all() and (1 >= mat).all()
+            return nn.Parameter(init * mat)
+        raise ValueError("Invalid threshold_type: {}".format(threshold_type))
+
+    def apply_pruning(self):
+        self.sparse_q_weight = RF.soft_threshold_table(self.q_weight, self.q_threshold)
+        self.sparse_p_weight = RF.soft_threshold_table(self.p_weight, self.p_threshold)
+
+    def _spec(self):
+        return RF.LookupSpec(L.KIND_QR_ADD, self._num_item, self._hidden_size, divider=self.q_entity_per_row,
+                             modulus=self._bucket_size, module=self)
+
+    def _tensors(self):
+        self.apply_pruning()
+        return self.sparse_q_weight, self.sparse_p_weight, None
+
+    def _count(self) -> int:
+        n = 0
+        for w, t in ((self.p_weight, self.p_threshold), (self.q_weight, self.q_threshold)):
+            _, cnt = RF.pep_threshold_table(w.detach(), t.detach(), L.PEP_FEATURE_DIM, want_out=False, want_count=True)
+            n += int(cnt.item())
+        return n
+
+    def get_sparsity(self, get_n_params=False):
+        total_params = self._num_item * self._hidden_size
+        n_params = self._count()
+        if get_n_params:
+            return (1 - n_params / total_params), n_params
+        return 1 - n_params / total_params
+
+    def get_num_params(self):
+        return self._count()
+
+    def get_weight(self):
+        return self(torch.arange(self._num_item, device=self.p_weight.device))
+
+    def get_prune_loss(self, K=100):
+        emb = self.sparse_p_weight + self.sparse_q_weight
+        return -torch.tanh(emb * K).norm(2) ** 2
+
+
+class RetrainCerpEmbedding(IEmbedding):
+    """CERP retrain (cerp_embedding.py:210-378): P, Q re-initialised from `initial.pth`, fixed bool masks
+    from the searched checkpoint; the masked tables feed the same fused gather."""
+
+    def __init__(self, field_dims: Union[List[int], int], hidden_size: int, mode: Optional[str],
+                 checkpoint_weight_dir: str, field_name: str = "", weight_name: str = "target",
+                 bucket_size: int = 8000, sparse: bool = False):
+        super().__init__()
+        field_dims = _as_list(field_dims)
+        mask_weight_path = os.path.join(checkpoint_weight_dir, field_name, f"{weight_name}.pth")
+        init_weight_path = os.path.join(checkpoint_weight_dir, field_name, "initial.pth")
+        assert os.path.exists(mask_weight_path), f"Weight not found at {mask_weight_path} to re-init mask"
+        assert os.path.exists(init_weight_path), f"Weight not found at {init_weight_path} to re-init original weight"
+        num_item = sum(field_dims)
+        self._field_dims = torch.tensor(field_dims)
+        self._mode = mode
+        self.field_name: str = field_name
+        self._bucket_size = bucket_size
+        self._hidden_size = hidden_size
+        self.p_weight = nn.Parameter(torch.zeros(bucket_size, hidden_size))
+        self.q_weight = nn.Parameter(torch.zeros(bucket_size, hidden_size))
+        init_weight = torch.load(init_weight_path)
+        self.q_mask, self.p_mask = None, None
+        assert init_weight["q_weight"].shape == (bucket_size, hidden_size)
+        assert init_weight["p_weight"].shape == (bucket_size, hidden_size)
+        self.q_weight.data = init_weight["q_weight"]
+        self.p_weight.data = init_weight["p_weight"]
+        self.q_mask, self.p_mask = self.load_mask(mask_weight_path)
+        self.sparse_q_weight, self.sparse_p_weight = None, None
+        self._num_item = num_item
+        self.q_entity_per_row = int(math.ceil(self._num_item / self._bucket_size))
+        self._sparse = sparse
+
+    def load_mask(self, weight_path: str):
+        checkpoint = torch.load(weight_path, map_location="cpu")
+        masks = []
+        for weight_name, threshold_name in (("q_weight", "q_threshold"), ("p_weight", "p_threshold")):
+            mask = (checkpoint[weight_name].abs() - torch.sigmoid(checkpoint[threshold_name])) > 0
+            assert mask.shape == (self._bucket_size, self._hidden_size)
+            masks.append(nn.Parameter(mask, False))
+        return masks
+
+    def _spec(self):
+        return RF.LookupSpec(L.KIND_QR_ADD, self._num_item, self._hidden_size, divider=self.q_entity_per_row,
+                             modulus=self._bucket_size, module=self)
+
+    def _tensors(self):
+        if self.sparse_q_weight is None or self.training:
+            self.sparse_q_weight = self.q_weight * self.q_mask
+            self.sparse_p_weight = self.p_weight * self.p_mask
+        return self.sparse_q_weight, self.sparse_p_weight, None
+
+    def get_weight(self):
+        return self(torch.arange(self._num_item, device=self.p_weight.device))
+
+    def get_num_params(self):
+        if self.sparse_p_weight is None:
+            return (torch.count_nonzero(self.q_mask) + torch.count_nonzero(self.p_mask)).item()
+        return (torch.count_nonzero(self.sparse_p_weight) + torch.count_nonzero(self.sparse_q_weight)).item()

@@ -22,7 +22,8 @@ class LookupSpec:
     kind: int                      # L.KIND_*
     num_global: int                # number of addressable ids (sum(field_dims))
     dim: int                       # D (num_factor)
-    divider: int = 0               # QR
+    divider: int = 0               # QR quotient divisor (CERP: q_entity_per_row)
+    modulus: int = 0               # remainder modulus if different from divider (CERP bucket size)
     aux_mode: int = 0              # PEP threshold type / OptEmbed norm
     sparse_grad: bool = False      # emit torch.sparse_coo grads for the main table (nn.Embedding(sparse=True))
     module: object = None          # owner (for deferred fused updates / err flag)
@@ -192,13 +193,14 @@ class _FusedLookup(torch.autograd.Function):
         aux_t = aux
         if aux is not None and aux.dtype == torch.bool:
             aux_t = aux.view(torch.uint8)
+        aux_mode = spec.modulus if spec.is_qr else spec.aux_mode
         # algorithmic bytes: ids + rows read + emb written + rows saved (+ fc, y, S)
         r_bytes = vf * e * 4
         nbytes = b * (f * x.element_size() + 2 * r_bytes + f * 8 + (f * 4 + 4 + e * 4 if fm else 0))
         _call("lookup_fwd", lib.rsb_lookup_fwd,
               spec.kind, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, spec.dim,
               L.ptr(table), table.shape[0], spec.num_global, L.ptr(table1), spec.divider,
-              L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(fc), L.ptr(bias),
+              L.ptr(aux_t), aux_mode, L.ptr(mask_d), L.ptr(fc), L.ptr(bias),
               L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows), L.ptr(_err_flag(spec, dev)), L.stream_ptr(dev),
               nbytes=nbytes)
         ctx.spec = spec
@@ -241,7 +243,7 @@ class _FusedLookup(torch.autograd.Function):
         g_table1_fused = None
         if skip_stage1:
             rg_main = g_emb.view(n, e)
-        elif kind in (L.KIND_QR_MULT, L.KIND_QR_ADD) and spec.divider <= 8 and need[5]:
+        elif kind in (L.KIND_QR_MULT, L.KIND_QR_ADD) and spec.divider <= 8 and spec.modulus == 0 and need[5]:
             # emb1 (<= 8 rows) gradient accumulated in registers inside stage 1: no per-lookup emb1 rows
             rg_main = torch.empty(n, e, dtype=torch.float32, device=dev)
             g_table1_fused = torch.empty_like(table1)
@@ -264,7 +266,7 @@ class _FusedLookup(torch.autograd.Function):
             nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + n_out * f * e * 4 + (e * 4 + 4 + f * 4 if use_gy else 0))
             _call("lookup_bwd_rows", lib.rsb_lookup_bwd_rows,
                   kind, L.ptr(rows), b, f, spec.dim, L.ptr(table), table.shape[0], L.ptr(table1), spec.divider,
-                  L.ptr(aux_t), spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
+                  L.ptr(aux_t), spec.modulus if spec.is_qr else spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
                   L.ptr(g_y) if use_gy else None, L.ptr(g_emb), L.ptr(rg_main), L.ptr(rg_aux), L.ptr(g_fc),
                   L.stream_ptr(dev), nbytes=nbytes)
             if kind == L.KIND_QR_ADD:
@@ -280,9 +282,10 @@ class _FusedLookup(torch.autograd.Function):
             if need[5] and g_table1_fused is not None:
                 g_table1 = g_table1_fused
             elif need[5]:
-                g_table1 = small_table_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
+                kmod = spec.modulus or spec.divider
+                g_table1 = small_table_grad(rows, rg_aux, table1.shape[0], key_mod=kmod)
                 if g_table1 is None:
-                    g_table1 = dense_row_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
+                    g_table1 = dense_row_grad(rows, rg_aux, table1.shape[0], key_mod=kmod)
         else:
             if need[4]:
                 deferred = getattr(mod, "_rsb_fused_opt", None) if mod is not None else None
@@ -324,6 +327,32 @@ def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tens
 # ----------------------------------------------------------------------------
 # full-table helpers
 # ----------------------------------------------------------------------------
+class _SoftThresholdTable(torch.autograd.Function):
+    """sign(w) * relu(|w| - sigmoid(s)) over a whole (small) table, differentiable in w and s
+    (element-wise thresholds); one pass forward, one pass backward."""
+
+    @staticmethod
+    def forward(ctx, w, s):
+        out, _ = pep_threshold_table(w.detach(), s.detach(), L.PEP_FEATURE_DIM)
+        ctx.save_for_backward(w, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        w, s = ctx.saved_tensors
+        lib = L.load()
+        g = g.contiguous()
+        gw = torch.empty_like(w)
+        gs = torch.empty_like(w)
+        _call("pep_dense_bwd", lib.rsb_pep_dense_bwd, L.ptr(w), L.ptr(s), L.PEP_FEATURE_DIM, w.shape[0], w.shape[1],
+              L.ptr(g), L.ptr(gw), L.ptr(gs), L.stream_ptr(w.device))
+        return gw, gs
+
+
+def soft_threshold_table(w: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    return _SoftThresholdTable.apply(w, s)
+
+
 def pep_threshold_table(weight, s, threshold_type: int, want_out=True, want_count=False):
     lib = L.load()
     dev = L.require_cuda(weight, s)

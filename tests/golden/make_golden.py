@@ -152,6 +152,16 @@ def tweak_pep(scale_s=-2.0):
     return f
 
 
+def tweak_cerp(model):
+    g = torch.Generator().manual_seed(55)
+    emb = model.embedding
+    with torch.no_grad():
+        emb.p_weight.uniform_(-0.5, 0.5, generator=g)
+        emb.q_weight.uniform_(-0.5, 0.5, generator=g)
+        emb.p_threshold.copy_(-2.0 + 0.7 * torch.randn(emb.p_threshold.shape, generator=g).clamp_(-2, 2))
+        emb.q_threshold.copy_(-2.0 + 0.7 * torch.randn(emb.q_threshold.shape, generator=g).clamp_(-2, 2))
+
+
 def tweak_optembed(model):
     g = torch.Generator().manual_seed(77)
     lo, span = (0.3, 0.8) if getattr(model.embedding._mask_e_module, "_norm", 1) == 1 else (0.2, 0.25)
@@ -326,6 +336,8 @@ def main():
                     tweak=tweak_optembed, steps=1, pre_forward=optembed_pre_forward)
     run_deepfm_case("deepfm_optembed_d", {"name": "deepfm_optembed_d"}, opt_cfg=None, tweak=tweak_optembed,
                     steps=1, pre_forward=optembed_pre_forward)
+    run_deepfm_case("deepfm_cerp", {"name": "cerp", "bucket_size": 5, "threshold_init": -2.0,
+                                    "threshold_init_method": "uniform"}, opt_cfg=adam, tweak=tweak_cerp, steps=2)
     run_dcn_case()
     run_embedding_api_case()
 

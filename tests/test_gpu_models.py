@@ -94,7 +94,8 @@ def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, a
         if opts:
             after = sub(g, f"step{s}/after/")
             cur = model.state_dict()
-            for k in ["embedding._emb_module.weight", "embedding.emb1.weight", "embedding.emb2.weight",
+            for k in ["embedding.p_weight", "embedding.q_weight", "embedding.p_threshold", "embedding.q_threshold",
+                      "embedding._emb_module.weight", "embedding.emb1.weight", "embedding.emb2.weight",
                       "embedding.emb.weight", "embedding.s", "embedding._weight",
                       "embedding._mask_e_module._t_param", "fc.weight", "_bias"]:
                 if k in after:
@@ -171,6 +172,22 @@ def test_deepfm_pep_retrain(R, sparse, tmp_path):
     g, model = _run_steps(R, name, {"name": "pep_retrain", "checkpoint_weight_dir": str(tmp_path), "sparsity": 0.5,
                                     "sparse": sparse}, SPARSE_ADAM if sparse else ADAM, 1)
     assert model.embedding.emb.weight.grad.is_sparse == sparse
+
+
+def test_deepfm_cerp(R):
+    g, model = _run_steps(R, "deepfm_cerp", CASES["deepfm_cerp"], ADAM, 2)
+    emb = model.embedding
+    # bookkeeping the CERP trainer calls (src/trainer/deepfm.py:142-248)
+    sp, nnz = emb.get_sparsity(True)
+    st = {k: v.detach().cpu().numpy() for k, v in emb.state_dict().items()}
+    ref_nnz = int(np.count_nonzero(O.pep_soft_threshold(st["p_weight"], st["p_threshold"])) +
+                  np.count_nonzero(O.pep_soft_threshold(st["q_weight"], st["q_threshold"])))
+    assert abs(nnz - ref_nnz) <= 1
+    loss = emb.get_prune_loss()
+    ref = O.cerp_prune_loss(st["p_weight"].astype(np.float64), st["q_weight"].astype(np.float64),
+                            st["p_threshold"].astype(np.float64), st["q_threshold"].astype(np.float64))
+    assert abs(float(loss) - ref) < 1e-3 * abs(ref) + 1e-6
+    assert tuple(emb.get_weight().shape) == (int(g["field_dims"].sum()), 8)
 
 
 def _optembed_pre(model, tag, g):

@@ -17,6 +17,7 @@ CASES = {
     "deepfm_optembed": {"name": "deepfm_optembed"},
     "deepfm_optembed_l2": {"name": "deepfm_optembed", "norm": 2},
     "deepfm_optembed_d": {"name": "deepfm_optembed_d"},
+    "deepfm_cerp": {"name": "cerp", "bucket_size": 5, "threshold_init": -2.0, "threshold_init_method": "uniform"},
 }
 
 
