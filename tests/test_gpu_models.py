@@ -183,6 +183,7 @@ def test_deepfm_cerp(R):
     ref_nnz = int(np.count_nonzero(O.pep_soft_threshold(st["p_weight"], st["p_threshold"])) +
                   np.count_nonzero(O.pep_soft_threshold(st["q_weight"], st["q_threshold"])))
     assert abs(nnz - ref_nnz) <= 1
+    emb.apply_pruning()   # get_prune_loss reads the tables pruned by the last forward (cerp_embedding.py:205-207)
     loss = emb.get_prune_loss()
     ref = O.cerp_prune_loss(st["p_weight"].astype(np.float64), st["q_weight"].astype(np.float64),
                             st["p_threshold"].astype(np.float64), st["q_threshold"].astype(np.float64))
