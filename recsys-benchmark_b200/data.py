@@ -12,44 +12,56 @@ import torch
 
 
 class DevicePrefetcher:
+    """Double-buffered: two persistent device buffers per tensor; the copy of batch i+1 is issued on a
+    side stream after the compute stream has consumed batch i-1 (stream-ordered, no host sync), so it
+    runs under step i.  No allocator traffic in steady state."""
+
     def __init__(self, loader: Iterable, device, depth: int = 2):
         self.loader = loader
         self.device = torch.device(device)
-        self.depth = max(1, depth)
         self.stream = torch.cuda.Stream(self.device)
+        self._bufs = [None, None]
 
     def __len__(self):
         return len(self.loader)
 
-    def _stage(self, batch) -> Tuple[torch.Tensor, torch.Tensor, torch.cuda.Event]:
-        x, y = batch
-        if not x.is_pinned():
-            x = x.pin_memory()
-        if not y.is_pinned():
-            y = y.pin_memory()
+    def _buffer(self, slot: int, idx: int, like: torch.Tensor) -> torch.Tensor:
+        cur = self._bufs[slot]
+        if cur is None:
+            cur = self._bufs[slot] = {}
+        t = cur.get(idx)
+        if t is None or t.shape != like.shape or t.dtype != like.dtype:
+            t = cur[idx] = torch.empty(like.shape, dtype=like.dtype, device=self.device)
+        return t
+
+    def _stage(self, slot: int, batch):
+        main = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(main)     # the buffer's previous consumer (two steps back) is done by then
+        outs = []
         with torch.cuda.stream(self.stream):
-            xd = x.to(self.device, non_blocking=True)
-            yd = y.to(self.device, non_blocking=True)
+            for idx, t in enumerate(batch):
+                if not t.is_pinned():
+                    t = t.pin_memory()
+                dst = self._buffer(slot, idx, t)
+                dst.copy_(t, non_blocking=True)
+                outs.append(dst)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return xd, yd, ev
+        return outs, ev
 
-    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         it = iter(self.loader)
-        queue = []
         try:
-            for _ in range(self.depth):
-                queue.append(self._stage(next(it)))
+            nxt = self._stage(0, next(it))
         except StopIteration:
-            pass
-        while queue:
-            xd, yd, ev = queue.pop(0)
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
-            xd.record_stream(cur)   # the copies were allocated on the side stream
-            yd.record_stream(cur)
+            return
+        slot = 0
+        while nxt is not None:
+            outs, ev = nxt
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            slot ^= 1
             try:
-                queue.append(self._stage(next(it)))
+                nxt = self._stage(slot, next(it))
             except StopIteration:
-                pass
-            yield xd, yd
+                nxt = None
+            yield tuple(outs)

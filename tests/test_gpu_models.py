@@ -396,9 +396,11 @@ def test_device_prefetcher_yields_the_same_batches_in_order(R):
     from recsys_benchmark_b200.data import DevicePrefetcher
 
     batches = [(torch.randint(0, 100, (64, 5), dtype=torch.int32), torch.rand(64)) for _ in range(7)]
-    got = list(DevicePrefetcher(iter(batches), DEV))
-    assert len(got) == 7
-    for (x, y), (xd, yd) in zip(batches, got):
+    n = 0
+    for (x, y), (xd, yd) in zip(batches, DevicePrefetcher(iter(batches), DEV)):
+        # double-buffered: a yielded batch stays valid until the batch after the next one is staged
         assert xd.is_cuda and yd.is_cuda
         assert torch.equal(xd.cpu(), x) and torch.equal(yd.cpu(), y)
+        n += 1
+    assert n == 7
     assert list(DevicePrefetcher(iter([]), DEV)) == []
