@@ -253,6 +253,27 @@ RSB_API int rsb_colsum(const float* x, int64_t M, int32_t N, int64_t ld, float* 
                        int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * DCN-Mix cross layer glue (src/models/layer_dcn.py:8-24,90-115), identity gate.  With
+ *   P1 = x_l V_cat (GEMM), H1 = tanh(P1), P2 = H1 (x) C (block-diagonal GEMM), T0 = G2 U_cat (GEMM):
+ *  gate_mix_fwd   g[b,e] = x_l[b,:].gates[e,:] ; H2 = tanh(P2) ; G2 = g[b,e] * H2[b,e,:]
+ *  cross_out_fwd  x_next = x_0 * (T0 + bias * sum_e g[b,e]) + x_l
+ *  cross_out_bwd  gT = g_next * x_0 ; gx0 = g_next * (T0 + bias * sg) ; dsg[b] = sum_d gT[b,d] * bias[d]
+ *  gate_mix_bwd   gP2 = gG2 * g * (1 - H2^2) ; dg[b,e] = sum_k gG2*H2 + dsg[b] ; g_xl = g_next + sum_e dg[b,e]*gates[e,:]
+ * x_l, x_0, T0, g_next [B,Dm] ; P2, H2, G2 [B,E*r] ; gates [E,Dm] ; g, dg [B,E] ; bias [Dm].
+ * Dm % 4 == 0, r % 4 == 0, E <= 8, 16-byte aligned rows; else RSB_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------- */
+RSB_API int rsb_dcn_gate_mix_fwd(const float* p2, const float* xl, const float* gates, int64_t B, int32_t Dm,
+                                 int32_t E, int32_t r, float* h2, float* g, float* g2, void* stream);
+RSB_API int rsb_dcn_cross_out_fwd(const float* t0, const float* x0, const float* xl, const float* bias,
+                                  const float* g, int64_t B, int32_t Dm, int32_t E, float* x_next, void* stream);
+RSB_API int rsb_dcn_cross_out_bwd(const float* g_next, const float* x0, const float* t0, const float* bias,
+                                  const float* g, int64_t B, int32_t Dm, int32_t E, float* gT, float* gx0,
+                                  float* dsg, void* stream);
+RSB_API int rsb_dcn_gate_mix_bwd(const float* g_g2, const float* h2, const float* g, const float* dsg,
+                                 const float* gates, const float* g_next, int64_t B, int32_t Dm, int32_t E,
+                                 int32_t r, float* g_p2, float* dg, float* g_xl, void* stream);
+
+/* ------------------------------------------------------------------------
  * Row-sharded tables over the GPUs of one box (no reference
  * counterpart: the reference is single-device).  Rank g owns the rows r of the concatenated
  * table with r % G == g, stored at local row r / G.  Shards live in cudaMalloc'ed buffers

@@ -56,6 +56,10 @@ PROTOTYPES = {
     "rsb_relu_dropout_bwd": (C.c_int, [_p, _p, _i64, _i32, _f, _p, _p, _p, _i64, _p]),
     "rsb_colsum_workspace_bytes": (_i64, [_i64, _i32]),
     "rsb_colsum": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i64, _p]),
+    "rsb_dcn_gate_mix_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
+    "rsb_dcn_cross_out_fwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "rsb_dcn_cross_out_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p]),
+    "rsb_dcn_gate_mix_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),
     "rsb_shared_alloc": (C.c_int, [_i64, C.POINTER(C.c_void_p)]),
     "rsb_shared_free": (C.c_int, [_p]),
     "rsb_ipc_get_handle": (C.c_int, [_p, C.c_char_p]),

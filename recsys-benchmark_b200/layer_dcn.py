@@ -14,6 +14,8 @@ from typing import Optional
 import torch
 from torch import nn
 
+from . import _lib as L
+from . import functional as RF
 from . import linalg as LA
 
 
@@ -33,6 +35,91 @@ def forward_mixture_layer(x0, xl, V, C, U, bias, gates, gate_softmax: bool):
     g2 = (h2.view(bsz, e, r) * g.unsqueeze(2)).reshape(bsz, e * r)
     t = LA.matmul(g2, U.reshape(e * r, dm)) + g.sum(1, keepdim=True) * bias   # sum_e g_e (Eo_e + b)  (:23,102)
     return x0 * t + xl                                     # (:103,113)
+
+
+class _CrossLayer(torch.autograd.Function):
+    """One DCN-Mix cross layer with every element-wise step fused into four custom passes around the
+    three tensor-core GEMMs (csrc/dcn.cu); identity gate."""
+
+    @staticmethod
+    def forward(ctx, x0, xl, V, C, U, bias, gates):
+        lib = L.load()
+        e, dm, r = V.shape
+        bsz = xl.shape[0]
+        er = e * r
+        dev = xl.device
+        x0 = x0.contiguous()
+        xl = xl.contiguous()
+        st = L.stream_ptr(dev)
+        vcat = V.detach().permute(1, 0, 2).reshape(dm, er).contiguous()
+        cc = C.detach().contiguous()
+        ucat = U.detach().reshape(er, dm)
+        g2d = gates.detach().reshape(e, dm)
+        b1d = bias.detach().reshape(dm)
+        h1 = LA.gemm(xl, vcat).tanh_()
+        p2 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
+        LA.gemm_strided(bsz, r, r, e, h1, 0, er, r, cc, 0, r, r * r, p2, 0, er, r)
+        g = torch.empty(bsz, e, dtype=torch.float32, device=dev)
+        g2 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
+        RF._call("dcn_gate_mix_fwd", lib.rsb_dcn_gate_mix_fwd, L.ptr(p2), L.ptr(xl), L.ptr(g2d), bsz, dm, e, r,
+                 L.ptr(p2), L.ptr(g), L.ptr(g2), st, nbytes=bsz * (dm + 3 * er) * 4)     # H2 overwrites P2
+        h2 = p2
+        t0 = LA.gemm(g2, ucat)
+        out = torch.empty(bsz, dm, dtype=torch.float32, device=dev)
+        RF._call("dcn_cross_out_fwd", lib.rsb_dcn_cross_out_fwd, L.ptr(t0), L.ptr(x0), L.ptr(xl), L.ptr(b1d), L.ptr(g),
+                 bsz, dm, e, L.ptr(out), st, nbytes=bsz * dm * 16)
+        ctx.save_for_backward(x0, xl, vcat, cc, ucat, b1d, g2d, h1, h2, g, g2, t0)
+        ctx.dims = (e, dm, r)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_next):
+        lib = L.load()
+        x0, xl, vcat, cc, ucat, b1d, g2d, h1, h2, g, g2, t0 = ctx.saved_tensors
+        e, dm, r = ctx.dims
+        er = e * r
+        bsz = xl.shape[0]
+        dev = xl.device
+        st = L.stream_ptr(dev)
+        g_next = g_next.contiguous()
+        gT = torch.empty(bsz, dm, dtype=torch.float32, device=dev)
+        gx0 = torch.empty(bsz, dm, dtype=torch.float32, device=dev)
+        dsg = torch.empty(bsz, dtype=torch.float32, device=dev)
+        RF._call("dcn_cross_out_bwd", lib.rsb_dcn_cross_out_bwd, L.ptr(g_next), L.ptr(x0), L.ptr(t0), L.ptr(b1d),
+                 L.ptr(g), bsz, dm, e, L.ptr(gT), L.ptr(gx0), L.ptr(dsg), st, nbytes=bsz * dm * 20)
+        d_bias = torch.mv(gT.t(), g.sum(1)).reshape(1, dm)           # sum_b gT[b,:] * sg[b]
+        g_g2 = LA.gemm(gT, ucat, trans_b=True)                        # [B,Dm] @ U_cat^T -> [B,E*r]
+        d_u = LA.gemm(g2, gT, trans_a=True, split_k=LA._split_for(bsz, er, dm)).reshape(e, r, dm)
+        dg = torch.empty(bsz, e, dtype=torch.float32, device=dev)
+        g_xl = torch.empty(bsz, dm, dtype=torch.float32, device=dev)
+        RF._call("dcn_gate_mix_bwd", lib.rsb_dcn_gate_mix_bwd, L.ptr(g_g2), L.ptr(h2), L.ptr(g), L.ptr(dsg), L.ptr(g2d),
+                 L.ptr(g_next), bsz, dm, e, r, L.ptr(g_g2), L.ptr(dg), L.ptr(g_xl), st,
+                 nbytes=bsz * (3 * er + 2 * dm) * 4)                 # gP2 overwrites gG2
+        g_p2 = g_g2
+        d_gates = torch.matmul(dg.t(), xl).reshape(e, dm, 1)
+        # block-diagonal expert GEMM backward (same calls as linalg._ExpertMatMul.backward)
+        g_h1 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
+        LA.gemm_strided(bsz, r, r, e, g_p2, 0, er, r, cc, 0, r, r * r, g_h1, 0, er, r, trans_b=True)
+        split = LA._split_for(bsz, r, r)
+        kc = bsz // split
+        part = torch.empty(e, split, r, r, dtype=torch.float32, device=dev)
+        for ei in range(e):
+            LA.gemm_strided(r, r, kc, split, h1, ei * r, er, kc * er, g_p2, ei * r, er, kc * er, part,
+                            ei * split * r * r, r, r * r, trans_a=True)
+        d_c = part.sum(1)
+        g_p1 = torch.ops.aten.tanh_backward(g_h1, h1)
+        LA.gemm(g_p1, vcat, trans_b=True, beta=1.0, c=g_xl, out=g_xl)   # g_xl += gP1 @ V_cat^T
+        d_vcat = LA.gemm(xl, g_p1, trans_a=True, split_k=LA._split_for(bsz, dm, er))
+        d_v = d_vcat.reshape(dm, e, r).permute(1, 0, 2).contiguous()
+        return gx0, g_xl, d_v, d_c, d_u, d_bias, d_gates
+
+
+def _fused_layer_ok(x0, xl, V, gate_softmax: bool) -> bool:
+    e, dm, r = V.shape
+    bsz = xl.shape[0]
+    return (xl.is_cuda and not gate_softmax and dm % 4 == 0 and r % 4 == 0 and e <= 8 and bsz % 4 == 0
+            and bsz >= 512 and xl.dtype == torch.float32 and LA._split_for(bsz, r, r) >= 1
+            and (bsz // LA._split_for(bsz, r, r)) % 4 == 0)
 
 
 class DCN_MixHead(nn.Module):
@@ -63,6 +150,10 @@ class DCN_MixHead(nn.Module):
     def forward(self, x_0):
         x_l = x_0
         for layer in range(self.num_layers):
-            x_l = forward_mixture_layer(x_0, x_l, self.V[layer], self.C[layer], self.U[layer], self.biases[layer],
-                                        self.gates, self._gate_softmax)
+            if _fused_layer_ok(x_0, x_l, self.V[layer], self._gate_softmax):
+                x_l = _CrossLayer.apply(x_0, x_l, self.V[layer], self.C[layer], self.U[layer], self.biases[layer],
+                                        self.gates)
+            else:
+                x_l = forward_mixture_layer(x_0, x_l, self.V[layer], self.C[layer], self.U[layer],
+                                            self.biases[layer], self.gates, self._gate_softmax)
         return x_l
