@@ -100,13 +100,10 @@ class _CrossLayer(torch.autograd.Function):
         # block-diagonal expert GEMM backward (same calls as linalg._ExpertMatMul.backward)
         g_h1 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
         LA.gemm_strided(bsz, r, r, e, g_p2, 0, er, r, cc, 0, r, r * r, g_h1, 0, er, r, trans_b=True)
-        split = LA._split_for(bsz, r, r)
-        kc = bsz // split
-        part = torch.empty(e, split, r, r, dtype=torch.float32, device=dev)
-        for ei in range(e):
-            LA.gemm_strided(r, r, kc, split, h1, ei * r, er, kc * er, g_p2, ei * r, er, kc * er, part,
-                            ei * split * r * r, r, r * r, trans_a=True)
-        d_c = part.sum(1)
+        # dC[e] = H1[:,e,:]^T @ gP2[:,e,:]: the diagonal r x r blocks of ONE [E*r, E*r] split-K GEMM
+        # (E x the FLOPs of the blocks alone, but a single well-shaped launch instead of E thin ones)
+        full = LA.gemm(h1, g_p2, trans_a=True, split_k=LA._split_for(bsz, er, er))
+        d_c = torch.stack([full[ei * r:(ei + 1) * r, ei * r:(ei + 1) * r] for ei in range(e)])
         g_p1 = torch.ops.aten.tanh_backward(g_h1, h1)
         LA.gemm(g_p1, vcat, trans_b=True, beta=1.0, c=g_xl, out=g_xl)   # g_xl += gP1 @ V_cat^T
         d_vcat = LA.gemm(xl, g_p1, trans_a=True, split_k=LA._split_for(bsz, dm, er))

@@ -121,18 +121,9 @@ class _ExpertMatMul(torch.autograd.Function):
             # gh[:, e, :] = g[:, e, :] @ C[e]^T : B operand "stored [N,K]" = C[e] as is
             gemm_strided(bsz, r, r2, e, g, 0, e * r2, r2, c, 0, r2, r * r2, gh, 0, e * r, r, trans_b=True)
         if ctx.needs_input_grad[1]:
-            split = 1
-            for s in (64, 32, 16, 8, 4, 2):
-                if bsz % s == 0 and (bsz // s) % 4 == 0 and bsz // s >= 256:
-                    split = s
-                    break
-            kc = bsz // split
-            part = torch.empty(e, split, r, r2, dtype=torch.float32, device=h.device)
-            for ei in range(e):
-                # C_grad[e] = h[:, e, :]^T @ g[:, e, :], reduction over the batch split into `split` partial GEMMs
-                gemm_strided(r, r2, kc, split, h, ei * r, e * r, kc * e * r, g, ei * r2, e * r2, kc * e * r2,
-                             part, ei * split * r * r2, r2, r * r2, trans_a=True)
-            gc = part.sum(1)
+            # C_grad[e] = h[:, e, :]^T @ g[:, e, :] = the diagonal blocks of one [E*r, E*r2] split-K GEMM
+            full = gemm(h, g, trans_a=True, split_k=_split_for(bsz, e * r, e * r2))
+            gc = torch.stack([full[ei * r:(ei + 1) * r, ei * r2:(ei + 1) * r2] for ei in range(e)])
         return gh, gc
 
 
