@@ -96,7 +96,11 @@ class _CrossLayer(torch.autograd.Function):
                  L.ptr(g_next), bsz, dm, e, r, L.ptr(g_g2), L.ptr(dg), L.ptr(g_xl), st,
                  nbytes=bsz * (3 * er + 2 * dm) * 4)                 # gP2 overwrites gG2
         g_p2 = g_g2
-        d_gates = torch.matmul(dg.t(), xl).reshape(e, dm, 1)
+        # [E,B] x [B,Dm]: cuBLAS picks a 260 us large-K SGEMM for this shape; the split-K tensor-core GEMM takes it
+        if e % 4 == 0:
+            d_gates = LA.gemm(dg, xl, trans_a=True, split_k=LA._split_for(bsz, e, dm)).reshape(e, dm, 1)
+        else:
+            d_gates = torch.matmul(dg.t(), xl).reshape(e, dm, 1)
         # block-diagonal expert GEMM backward (same calls as linalg._ExpertMatMul.backward)
         g_h1 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
         LA.gemm_strided(bsz, r, r, e, g_p2, 0, er, r, cc, 0, r, r * r, g_h1, 0, er, r, trans_b=True)
