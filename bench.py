@@ -50,6 +50,13 @@ WORKLOADS = {
     # dense Adam on each shard (= configs/deepfm/base_config.yaml semantics), dense MLP grads allreduced
     "deepfm_full_criteo_sharded": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
                                        p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True), sharded=True),
+    # BASELINE.json configs[3]: pruned-mask embeddings on KDD-shaped data (11 fields, 6 M ids, configs/kdd/deepfm)
+    "deepfm_pep_kdd": dict(model="deepfm", dims=KDD_DIMS, emb={"name": "pep", "threshold_type": "feature_dim",
+                                                                 "init_threshold": -150,
+                                                                 "checkpoint_weight_dir": "/tmp/rsb_pep_ckpt"},
+                           use_bn=True, p_dropout=0.2, opt=dict(learning_rate=1e-3, weight_decay=1e-5, fused_adam=True)),
+    "deepfm_optembed_kdd": dict(model="deepfm", dims=KDD_DIMS, emb={"name": "deepfm_optembed"}, use_bn=True,
+                                p_dropout=0.2, opt=dict(learning_rate=3e-5, weight_decay=1e-3, fused_adam=True)),
     "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
 }
