@@ -301,6 +301,11 @@ RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32
                                        const float* row_grads, int32_t E, float* const* grad_shards, int32_t G,
                                        float scale, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* First-order weight gradient of the sharded model: fc_grad_shards[row % G][row / G] += scale * g_yfm[b],
+ * equal rows of 32 consecutive samples merged first (same kernel as the single-GPU fc gradient). */
+RSB_API int rsb_fc_grad_sharded(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F,
+                                float* const* fc_grad_shards, int32_t G, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

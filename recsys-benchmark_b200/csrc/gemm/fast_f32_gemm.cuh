@@ -25,24 +25,30 @@ namespace rsb_gemm {
 
 using namespace cute;
 
-template <class LayoutA, class LayoutB, int TileN>
+// TwoSm = true: a CTA pair (cluster 2x1) works on one 256 x TileN tile with `cta_group::2` MMAs, each
+// CTA staging half of B (measured +5 % on the MLP shapes); TwoSm = false: one CTA per 128 x TileN tile.
+template <class LayoutA, class LayoutB, int TileN, bool TwoSm = false>
 struct FastF32 {
   using Element = float;
   using LayoutC = cutlass::layout::RowMajor;
   static constexpr int Align = 4;  // 16-byte TMA alignment
   using ArchTag = cutlass::arch::Sm100;
   using OpClass = cutlass::arch::OpClassTensorOp;
-  using MmaTileShape = Shape<_128, Int<TileN>, _16>;
-  using ClusterShape = Shape<_1, _1, _1>;
+  using MmaTileShape = Shape<Int<TwoSm ? 256 : 128>, Int<TileN>, _16>;
+  using ClusterShape = Shape<Int<TwoSm ? 2 : 1>, _1, _1>;
   using Fusion = cutlass::epilogue::fusion::LinCombPerColBias<float, float, float>;
+  using EpiSchedule = cute::conditional_t<TwoSm, cutlass::epilogue::TmaWarpSpecialized2Sm,
+                                          cutlass::epilogue::TmaWarpSpecialized1Sm>;
+  using MainSchedule = cute::conditional_t<TwoSm, cutlass::gemm::KernelTmaWarpSpecialized2SmFastFP32Sm100,
+                                           cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>;
   using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
       ArchTag, OpClass, MmaTileShape, ClusterShape, cutlass::epilogue::collective::EpilogueTileAuto, float, float,
-      float, LayoutC, Align, float, LayoutC, Align, cutlass::epilogue::TmaWarpSpecialized1Sm, Fusion>::CollectiveOp;
+      float, LayoutC, Align, float, LayoutC, Align, EpiSchedule, Fusion>::CollectiveOp;
   using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
       ArchTag, OpClass, float, LayoutA, Align, float, LayoutB, Align, float, MmaTileShape, ClusterShape,
       cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(
           sizeof(typename CollectiveEpilogue::SharedStorage))>,
-      cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
+      MainSchedule>::CollectiveOp;
   using GemmKernel =
       cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
   using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;

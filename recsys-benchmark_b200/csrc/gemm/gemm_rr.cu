@@ -4,6 +4,8 @@
 namespace rsb_gemm {
 int64_t gemm_rr(const Problem& p, bool query_ws) {
   if (p.N <= 64) return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::RowMajor, 64>, true, false>(p, query_ws);
+  // large-M problems: CTA pairs on 256-row tiles; small M (weight gradients, split-K) keep 128-row tiles
+  if (p.M >= 2048) return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::RowMajor, 128, true>, true, false>(p, query_ws);
   return run<FastF32<cutlass::layout::RowMajor, cutlass::layout::RowMajor, 128>, true, false>(p, query_ws);
 }
 }  // namespace rsb_gemm

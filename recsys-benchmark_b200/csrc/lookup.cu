@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
 // (Per-lookup atomics serialise ~B updates on each hot row inside L2 and stall the whole gather.)
 __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restrict__ rows,
                                                       const float* __restrict__ g_y, long long B, int F,
-                                                      float* __restrict__ fc_grad) {
+                                                      float* __restrict__ fc_grad, float* const* fc_grad_shards,
+                                                      int G, float scale) {
   extern __shared__ long long tile[];  // [32][F]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long b0 = (long long)blockIdx.x * 32;
@@ -314,7 +315,14 @@ __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restric
         sum += ((peers >> j) & 1u) ? v : 0.f;
       }
     }
-    if (valid && lane == leader) atomicAdd(fc_grad + row, sum);
+    if (valid && lane == leader) {
+      if (fc_grad_shards != nullptr) {   // row-sharded: the owner's accumulator, over NVLink for peers
+        const long long lrow = row / G;
+        atomicAdd(fc_grad_shards[(int)(row - lrow * G)] + lrow, sum * scale);
+      } else {
+        atomicAdd(fc_grad + row, sum);
+      }
+    }
   }
 }
 
@@ -591,11 +599,11 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
 }
 
 static int launch_fc_grad(const long long* rows, const float* g_y, long long B, int F, float* fc_grad,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, float* const* shards = nullptr, int G = 1, float scale = 1.f) {
   const size_t smem = (size_t)32 * F * sizeof(long long);
   if (smem > 200 * 1024) return RSB_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(fc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  fc_grad_kernel<<<(unsigned)((B + 31) / 32), 256, smem, stream>>>(rows, g_y, B, F, fc_grad);
+  fc_grad_kernel<<<(unsigned)((B + 31) / 32), 256, smem, stream>>>(rows, g_y, B, F, fc_grad, shards, G, scale);
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;
@@ -800,4 +808,13 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   a.out_rows = reinterpret_cast<long long*>(out_rows);
   a.err = err_flag;
   return launch_fwd<RSB_KIND_VANILLA>(a, sh, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" RSB_API int rsb_fc_grad_sharded(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F,
+                                           float* const* fc_grad_shards, int32_t G, float scale, void* stream) {
+  if (B < 0 || F <= 0 || G < 1) return RSB_ERR_BAD_ARG;
+  if (B == 0) return RSB_OK;
+  if (!rows || !g_yfm || !fc_grad_shards) return RSB_ERR_BAD_ARG;
+  return launch_fc_grad(reinterpret_cast<const long long*>(rows), g_yfm, B, F, nullptr,
+                        reinterpret_cast<cudaStream_t>(stream), fc_grad_shards, G, scale);
 }

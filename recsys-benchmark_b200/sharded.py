@@ -200,11 +200,8 @@ class _ShardedLookup(torch.autograd.Function):
                  nbytes=n * (8 + 4 * d))
         g_bias = None
         if use_gy:
-            gy_rows = g_y.view(b, 1).expand(b, f).contiguous().view(n, 1)
-            ws1 = RF._ws(lib.rsb_segment_workspace_bytes(n, 1), dev)
-            RF._call("segment_scatter_shards_fc", lib.rsb_segment_scatter_shards, L.ptr(skeys), L.ptr(perm), n,
-                     L.ptr(gy_rows), 1, L.ptr(sg.ptrs["fc_grad"]), sg.world, scale, L.ptr(ws1), ws1.numel(),
-                     L.stream_ptr(dev), nbytes=n * 12)
+            RF._call("fc_grad_sharded", lib.rsb_fc_grad_sharded, L.ptr(rows), L.ptr(g_y), b, f,
+                     L.ptr(sg.ptrs["fc_grad"]), sg.world, scale, L.stream_ptr(dev), nbytes=n * 12)
             g_bias = g_y.sum().reshape(1)
         return None, None, None, g_bias, None
 
