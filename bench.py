@@ -282,7 +282,9 @@ def main_ours(args, wl):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's version / debug banner goes to stdout by default: keep stdout to the ONE JSON line
+        # NCCL_DEBUG=VERSION makes NCCL printf() its version banner to stdout: keep stdout to the ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
