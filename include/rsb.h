@@ -142,6 +142,10 @@ RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, in
                         const float* emb, const float* S, const float* g_yfm, const float* g_deep,
                         float* rg_main, float* rg_aux, float* fc_grad, void* stream);
 
+/* First-order weight gradient alone: fc_grad[row] += g_yfm[b] for every lookup (dense [N,1], pre-zeroed).
+ * rsb_lookup_bwd_rows / rsb_qr_bwd_fused run it too when their fc_grad argument is non-NULL. */
+RSB_API int rsb_fc_grad(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F, float* fc_grad, void* stream);
+
 /* QR (mult / add) variant of stage 1 with the emb1 gradient fused in: emb1 has only `divider`
  * rows (2/5/20 in configs/deepfm/qr_*.yaml), so every lane group keeps one accumulator per emb1
  * row in registers while it streams the lookups; no per-lookup emb1 gradient is written and no

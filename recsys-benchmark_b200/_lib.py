@@ -35,6 +35,7 @@ PROTOTYPES = {
                                  _p, _p, _p, _p, _p, _p, _p, _p]),
     "rsb_lookup_bwd_rows": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p,
                                       _p, _p, _p, _p]),
+    "rsb_fc_grad": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
     "rsb_qr_bwd_fused_workspace_bytes": (_i64, [_i64, _i32]),
     "rsb_qr_bwd_fused": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _i64, _p]),

@@ -12,6 +12,8 @@
 //   retrain masks        pep_embedding.py:215-221, deepfm_opt_embed.py:693-706
 //   OptEmbed supernet    deepfm_opt_embed.py:219-226, optembed_utils.py:25-44,101-104
 //   first order + FM     src/models/deepfm.py:49,91-98
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rsb {
@@ -348,11 +350,11 @@ __global__ void __launch_bounds__(1024) partials_reduce_kernel(const float* __re
   }
 }
 
-template <int K, int V, int LPR, bool TINY = false>
+template <int K, int V, int LPR, bool TINY = false, int KT = 2>
 __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
-  // the register-accumulating QR variant keeps its registers for the emb1 accumulators: no batching there
-  constexpr int KI = TINY ? 2 : kIter;
+  // the register-accumulating QR variant keeps registers for the emb1 accumulators: shallower batching there
+  constexpr int KI = TINY ? KT : kIter;
   FV<V> tacc[TINY ? kTinyRows : 1];
 #pragma unroll
   for (int r = 0; r < (TINY ? kTinyRows : 1); ++r) tacc[r] = FV<V>::zero();
@@ -569,9 +571,14 @@ static long long bwd_blocks(long long B) {
 }
 
 // the register-accumulating QR variant writes one partial table per CTA: a few resident CTAs per SM
+static int tune(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
 static long long tiny_blocks(long long B) {
+  static const int per_sm = tune("RSB_TINY_CTAS_PER_SM", 8);
   long long blocks = bwd_blocks(B);
-  const long long cap = (long long)sm_count() * 8;
+  const long long cap = (long long)sm_count() * per_sm;
   return blocks > cap ? cap : blocks;
 }
 
@@ -582,7 +589,10 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   if constexpr (K == RSB_KIND_QR_MULT || K == RSB_KIND_QR_ADD) {
     if (a.tiny_partials != nullptr) {
       const long long tblocks = tiny_blocks(a.B);
-#define CALLT(VV, LL) lookup_bwd_rows_kernel<K, VV, LL, true><<<(unsigned)tblocks, threads, 0, stream>>>(a)
+      static const int kt = tune("RSB_TINY_KI", 2);
+#define CALLT(VV, LL)                                                                                 \
+  if (kt == 1) lookup_bwd_rows_kernel<K, VV, LL, true, 1><<<(unsigned)tblocks, threads, 0, stream>>>(a); \
+  else lookup_bwd_rows_kernel<K, VV, LL, true, 2><<<(unsigned)tblocks, threads, 0, stream>>>(a)
       RSB_DISPATCH_SHAPE(sh, CALLT);
 #undef CALLT
       RSB_CHECK_LAUNCH();
@@ -817,4 +827,13 @@ extern "C" RSB_API int rsb_fc_grad_sharded(const int64_t* rows, const float* g_y
   if (!rows || !g_yfm || !fc_grad_shards) return RSB_ERR_BAD_ARG;
   return launch_fc_grad(reinterpret_cast<const long long*>(rows), g_yfm, B, F, nullptr,
                         reinterpret_cast<cudaStream_t>(stream), fc_grad_shards, G, scale);
+}
+
+extern "C" RSB_API int rsb_fc_grad(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F, float* fc_grad,
+                                   void* stream) {
+  if (B < 0 || F <= 0) return RSB_ERR_BAD_ARG;
+  if (B == 0) return RSB_OK;
+  if (!rows || !g_yfm || !fc_grad) return RSB_ERR_BAD_ARG;
+  return launch_fc_grad(reinterpret_cast<const long long*>(rows), g_yfm, B, F, fc_grad,
+                        reinterpret_cast<cudaStream_t>(stream));
 }

@@ -252,7 +252,7 @@ class _FusedLookup(torch.autograd.Function):
             nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + f * e * 4 + (e * 4 + 4 + f * 4 if use_gy else 0))
             _call("lookup_bwd_rows", lib.rsb_qr_bwd_fused, kind, L.ptr(rows), b, f, spec.dim, L.ptr(table),
                   table.shape[0], L.ptr(table1), spec.divider, L.ptr(emb), L.ptr(s), L.ptr(g_y) if use_gy else None,
-                  L.ptr(g_emb), L.ptr(rg_main), L.ptr(g_table1_fused), L.ptr(g_fc), L.ptr(ws), ws.numel(),
+                  L.ptr(g_emb), L.ptr(rg_main), L.ptr(g_table1_fused), None, L.ptr(ws), ws.numel(),
                   L.stream_ptr(dev), nbytes=nbytes)
         else:
             rg_main = torch.empty(n, e, dtype=torch.float32, device=dev)
@@ -267,10 +267,14 @@ class _FusedLookup(torch.autograd.Function):
             _call("lookup_bwd_rows", lib.rsb_lookup_bwd_rows,
                   kind, L.ptr(rows), b, f, spec.dim, L.ptr(table), table.shape[0], L.ptr(table1), spec.divider,
                   L.ptr(aux_t), spec.modulus if spec.is_qr else spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
-                  L.ptr(g_y) if use_gy else None, L.ptr(g_emb), L.ptr(rg_main), L.ptr(rg_aux), L.ptr(g_fc),
+                  L.ptr(g_y) if use_gy else None, L.ptr(g_emb), L.ptr(rg_main), L.ptr(rg_aux), None,
                   L.stream_ptr(dev), nbytes=nbytes)
             if kind == L.KIND_QR_ADD:
                 rg_aux = rg_main
+
+        if g_fc is not None:
+            _call("fc_grad", lib.rsb_fc_grad, L.ptr(rows), L.ptr(g_y), b, f, L.ptr(g_fc), L.stream_ptr(dev),
+                  nbytes=n * 12)
 
         # ---- stages 2+3: reduce by target row ---------------------------------
         g_table = g_table1 = g_aux = None
