@@ -589,7 +589,7 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   if constexpr (K == RSB_KIND_QR_MULT || K == RSB_KIND_QR_ADD) {
     if (a.tiny_partials != nullptr) {
       const long long tblocks = tiny_blocks(a.B);
-      static const int kt = tune("RSB_TINY_KI", 2);
+      static const int kt = tune("RSB_TINY_KI", 1);
 #define CALLT(VV, LL)                                                                                 \
   if (kt == 1) lookup_bwd_rows_kernel<K, VV, LL, true, 1><<<(unsigned)tblocks, threads, 0, stream>>>(a); \
   else lookup_bwd_rows_kernel<K, VV, LL, true, 2><<<(unsigned)tblocks, threads, 0, stream>>>(a)
