@@ -32,6 +32,21 @@ constexpr int TM = 256, TN = 128, TK = 32, CM = 2, BANDS = 3; constexpr bool TWO
 constexpr int TM = 128, TN = 128, TK = 32, CM = 1, BANDS = 3; constexpr bool TWO = false;
 #elif VARIANT == 7
 constexpr int TM = 256, TN = 128, TK = 16, CM = 2, BANDS = 4; constexpr bool TWO = true;
+#elif VARIANT == 20
+constexpr int TM = 128, TN = 128, TK = 32, CM = 1, BANDS = 5; constexpr bool TWO = false;
+#define ACCP 2
+#elif VARIANT == 21
+constexpr int TM = 128, TN = 128, TK = 64, CM = 1, BANDS = 5; constexpr bool TWO = false;
+#define ACCP 4
+#elif VARIANT == 22
+constexpr int TM = 256, TN = 128, TK = 32, CM = 2, BANDS = 5; constexpr bool TWO = true;
+#define ACCP 2
+#elif VARIANT == 23
+constexpr int TM = 256, TN = 128, TK = 64, CM = 2, BANDS = 5; constexpr bool TWO = true;
+#define ACCP 4
+#elif VARIANT == 24
+constexpr int TM = 256, TN = 128, TK = 64, CM = 2, BANDS = 3; constexpr bool TWO = true;
+#define ACCP 4
 #elif VARIANT == 8
 constexpr int TM = 128, TN = 80, TK = 16, CM = 1, BANDS = 5; constexpr bool TWO = false;
 #elif VARIANT == 9
@@ -42,6 +57,11 @@ constexpr int TM = 256, TN = 80, TK = 16, CM = 2, BANDS = 5; constexpr bool TWO 
 constexpr int TM = 128, TN = 64, TK = 16, CM = 1, BANDS = 5; constexpr bool TWO = false;
 #endif
 
+#ifdef ACCP
+constexpr int ACCPV = ACCP;
+#else
+constexpr int ACCPV = 1;
+#endif
 using LayoutA = cutlass::layout::RowMajor;
 using LayoutB = cutlass::layout::ColumnMajor;
 using LayoutC = cutlass::layout::RowMajor;
@@ -59,7 +79,7 @@ using Builder = cutlass::gemm::collective::CollectiveBuilder<Arch, Op, float, La
     cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename Epi::SharedStorage))>, MainSched>;
 using Policy = cutlass::gemm::MainloopSm100TmaUmmaWarpSpecializedFastF32<
     Builder::Load2TransformPipelineStageCount, Builder::Transform2MmaPipelineStageCount, Builder::SchedulerPipelineStageCount,
-    Builder::AccumulatorPipelineStageCount, BANDS, Builder::ScalingFactor, Builder::AccPromotionInterval, ClusterS,
+    Builder::AccumulatorPipelineStageCount, BANDS, Builder::ScalingFactor, ACCPV, ClusterS,
     typename Builder::AccumulatorCopyAtom, Arch>;
 using Main = cutlass::gemm::collective::CollectiveMma<Policy, TileS, float, cutlass::gemm::TagToStrideA_t<LayoutA>, float,
     cutlass::gemm::TagToStrideB_t<LayoutB>, typename Builder::TiledMma, typename Builder::GmemTiledCopyA,
@@ -103,8 +123,8 @@ int main(int argc, char** argv) {
     double r = 0; for (int k = 0; k < K; ++k) r += (double)hA[(size_t)i * K + k] * hB[(size_t)j * K + k];
     maxerr = fmax(maxerr, fabs(r - hD[(size_t)i * N + j])); maxref = fmax(maxref, fabs(r));
   }
-  printf("VARIANT %d tile %dx%dx%d cluster %d bands %d stages(l2t %d, t2m %d, acc %d): %.3f ms %.1f TFLOP/s relerr %.2e (%s)\n",
-         VARIANT, TM, TN, TK, CM, BANDS, Builder::Load2TransformPipelineStageCount, Builder::Transform2MmaPipelineStageCount,
+  printf("VARIANT %d accp %d tile %dx%dx%d cluster %d bands %d stages(l2t %d, t2m %d, acc %d): %.3f ms %.1f TFLOP/s relerr %.2e (%s)\n",
+         VARIANT, ACCPV, TM, TN, TK, CM, BANDS, Builder::Load2TransformPipelineStageCount, Builder::Transform2MmaPipelineStageCount,
          Builder::AccumulatorPipelineStageCount, ms, 2.0 * M * N * K / ms / 1e9, maxerr / maxref, cudaGetErrorString(err));
   return 0;
 }
