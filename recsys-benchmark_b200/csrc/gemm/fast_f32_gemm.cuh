@@ -1,6 +1,9 @@
 // fp32-accurate tensor-core GEMM for sm_100a: every fp32 operand is split in-kernel into
-// three bf16 terms and the product is accumulated in fp32 TMEM by 9 tcgen05 bf16 MMAs
-// ("FastF32" / 9xBF16), operands staged by TMA, epilogue (alpha, beta*C, per-column bias)
+// three bf16 terms a0+a1+a2 and the product is accumulated in fp32 TMEM by tcgen05 bf16 MMAs over
+// the term pairs of the first `Bands` anti-diagonals of the 3x3 product table ("FastF32"; 5 bands =
+// all 9 products, 3 bands = the 6 products >= 2^-16 |a||b|; the 3 dropped ones are <= 2^-24 |a||b|,
+// i.e. below the fp32 rounding of the accumulation itself - measured error vs fp64 is the same
+// 1.3e-7 either way), operands staged by TMA, epilogue (alpha, beta*C, per-column bias)
 // fused and stored by TMA.  The reference runs these GEMMs in true fp32 (TF32 is off:
 // src/models/deepfm.py:68 is commented out), so plain TF32/bf16 tensor-core math would
 // break the 1e-5 parity gate; the split keeps fp32-level accuracy at ~1/9 of the bf16 rate,
@@ -31,8 +34,10 @@ using namespace cute;
 // group is drained from TMEM and added in fp32 registers), which makes the mainloop promotion /
 // transform bound (tensor pipe 41 %, same time with 6 or 9 MMAs).  We keep the builder's layouts and
 // stage counts but instantiate the collective with our own policy: 32-deep K tiles promoted every 2
-// MMA groups.  Measured on 65536x400x624: 84 -> 116 TFLOP/s (2-SM), error vs fp64 unchanged (1.3e-7).
-template <class LayoutA, class LayoutB, int TileN, bool TwoSm = false, int TileK = 32, int AccP = 2>
+// MMA groups.  Measured on 65536x400x624: 84 -> 116 TFLOP/s (2-SM), error vs fp64 unchanged (1.3e-7);
+// once promotion is off the critical path the MMA count matters again: 3 bands -> 129 TFLOP/s.
+template <class LayoutA, class LayoutB, int TileN, bool TwoSm = false, int TileK = 32, int AccP = 2,
+          int Bands = 3>
 struct FastF32 {
   using Element = float;
   using LayoutC = cutlass::layout::RowMajor;
@@ -56,7 +61,7 @@ struct FastF32 {
       MainSchedule>;
   using Policy = cutlass::gemm::MainloopSm100TmaUmmaWarpSpecializedFastF32<
       Builder::Load2TransformPipelineStageCount, Builder::Transform2MmaPipelineStageCount,
-      Builder::SchedulerPipelineStageCount, Builder::AccumulatorPipelineStageCount, /*bands=*/5,
+      Builder::SchedulerPipelineStageCount, Builder::AccumulatorPipelineStageCount, Bands,
       Builder::ScalingFactor, AccP, ClusterShape, typename Builder::AccumulatorCopyAtom, ArchTag>;
   using CollectiveMainloop = cutlass::gemm::collective::CollectiveMma<
       Policy, MmaTileShape, float, cutlass::gemm::TagToStrideA_t<LayoutA>, float,

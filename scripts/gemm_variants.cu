@@ -47,6 +47,21 @@ constexpr int TM = 256, TN = 128, TK = 64, CM = 2, BANDS = 5; constexpr bool TWO
 #elif VARIANT == 24
 constexpr int TM = 256, TN = 128, TK = 64, CM = 2, BANDS = 3; constexpr bool TWO = true;
 #define ACCP 4
+#elif VARIANT == 25
+constexpr int TM = 256, TN = 128, TK = 32, CM = 2, BANDS = 3; constexpr bool TWO = true;
+#define ACCP 2
+#elif VARIANT == 26
+constexpr int TM = 256, TN = 128, TK = 64, CM = 2, BANDS = 4; constexpr bool TWO = true;
+#define ACCP 4
+#elif VARIANT == 27
+constexpr int TM = 256, TN = 128, TK = 64, CM = 2, BANDS = 5; constexpr bool TWO = true;
+#define ACCP 2
+#elif VARIANT == 28
+constexpr int TM = 256, TN = 128, TK = 48, CM = 2, BANDS = 5; constexpr bool TWO = true;
+#define ACCP 3
+#elif VARIANT == 29
+constexpr int TM = 128, TN = 128, TK = 32, CM = 1, BANDS = 3; constexpr bool TWO = false;
+#define ACCP 2
 #elif VARIANT == 8
 constexpr int TM = 128, TN = 80, TK = 16, CM = 1, BANDS = 5; constexpr bool TWO = false;
 #elif VARIANT == 9
