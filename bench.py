@@ -35,6 +35,9 @@ CRITEO_DIMS = [49, 101, 126, 45, 223, 118, 84, 76, 95, 9, 30, 40, 75, 1458, 555,
                4, 42646, 5178, 192773, 3175, 27, 11422, 181075, 11, 4654, 2032, 5, 189657, 18, 16, 59697, 86, 45571]
 AVAZU_DIMS = [100000] * 10 + [1000] * 12
 KDD_DIMS = [600000] * 8 + [400000] * 3
+# SURVEY 8(d) "roofline shape": Criteo field structure with every field > 10k ids scaled x16 -> 17.1 M rows,
+# a 1.1 GB fp32 table (>> 126 MB L2), so the gather really runs out of HBM
+ROOFLINE_DIMS = [d * 16 if d > 10000 else d for d in CRITEO_DIMS]
 
 WORKLOADS = {
     # BASELINE.json configs[1] (default)
@@ -46,6 +49,9 @@ WORKLOADS = {
                                opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam=True)),
     "deepfm_full_criteo_dense_adam": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
                                           p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
+    "deepfm_full_roofline": dict(model="deepfm", dims=ROOFLINE_DIMS, emb={"name": "vanilla", "sparse": True}, use_bn=True,
+                                 p_dropout=0.5,
+                                 opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam=True)),
     # BASELINE.json configs[4]: full table row-sharded over the GPUs (NVLink peer gathers + shard atomics),
     # dense Adam on each shard (= configs/deepfm/base_config.yaml semantics), dense MLP grads allreduced
     "deepfm_full_criteo_sharded": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
@@ -70,13 +76,27 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_batches(dims, batch, n, seed, dtype):
+def _zipf_ids(d, batch, g, alpha=1.05):
+    """Zipf(alpha) over the ids of one field, clipped to the field size: id k has weight
+    (k+1)^-alpha, drawn by inverting the CDF with seeded uniforms."""
+    import torch
+
+    w = torch.arange(1, d + 1, dtype=torch.float64).pow_(-alpha)
+    cdf = torch.cumsum(w, 0)
+    u = torch.rand(batch, generator=g, dtype=torch.float64) * cdf[-1]
+    return torch.searchsorted(cdf, u).clamp_(max=d - 1)
+
+
+def make_batches(dims, batch, n, seed, dtype, dist_name="uniform"):
     import torch
 
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n):
-        x = torch.stack([torch.randint(0, d, (batch,), generator=g) for d in dims], 1).to(dtype)
+        if dist_name == "zipf":
+            x = torch.stack([_zipf_ids(d, batch, g) for d in dims], 1).to(dtype)
+        else:
+            x = torch.stack([torch.randint(0, d, (batch,), generator=g) for d in dims], 1).to(dtype)
         y = torch.randint(0, 2, (batch,), generator=g).float()
         out.append((x, y))
     return out
@@ -85,7 +105,7 @@ def make_batches(dims, batch, n, seed, dtype):
 # ------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU PyTorch path
 # ------------------------------------------------------------------------------------
-def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0):
+def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0, ids="uniform"):
     import torch
 
     from oracle import torch_port as TP
@@ -99,7 +119,7 @@ def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0):
     p = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
     opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
     offsets = torch.tensor([0] + dims[:-1]).cumsum(0)[None, :]
-    batches = make_batches(dims, sample_batch, 2, 2023, torch.int64)
+    batches = make_batches(dims, sample_batch, 2, 2023, torch.int64, ids)
     for i in range(warmup):
         TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"])
     times = []
@@ -116,12 +136,41 @@ def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0):
                        f"{cores} threads")
 
 
+def torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, steps):
+    """The reference's own operators (the oracle's functional port of its PyTorch path: F.embedding,
+    embedding_bag, element-wise FM, cuBLAS fp32 Linear, torch Adam) run eagerly on the SAME GPU and the same
+    batches: the 'library kernels to beat' of SURVEY 8(d).  A comparison only - never on the product path."""
+    import torch
+
+    from oracle import torch_port as TP
+
+    emb = dict(wl["emb"])
+    p_cpu = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
+    p = {k: v.detach().to(dev).requires_grad_(True) for k, v in p_cpu.items()}
+    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
+    offsets = torch.tensor([0] + dims[:-1]).cumsum(0)[None, :].to(dev)
+    pool = [(x.long(), y) for x, y in dev_pool[:4]]
+    for i in range(3):
+        TP.train_step(p, opts, *pool[i % len(pool)], offsets, emb, wl["p_dropout"], sync=False)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for i in range(steps):
+        TP.train_step(p, opts, *pool[i % len(pool)], offsets, emb, wl["p_dropout"], sync=False)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / steps
+    return {"ms_per_step": round(ms, 4), "samples_per_s": round(b / ms * 1e3, 1), "batch": b,
+            "note": "oracle/torch_port.py (the reference's torch operators, fp32, TF32 off) eager on this GPU, "
+                    "inputs resident, no loss read-back"}
+
+
 def main_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = min(args.cpu_batch, args.batch)
-    r = run_cpu_port(wl, sample, max(args.steps, 3), max(args.warmup, 1), budget_s=120.0)
+    r = run_cpu_port(wl, sample, max(args.steps, 3), max(args.warmup, 1), budget_s=120.0, ids=args.ids)
     line = {
         "impl": "reference", "metric": "DeepFM train samples/s (Criteo shape)", "value": r["value"],
         "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
@@ -344,7 +393,7 @@ def main_ours(args, wl):
             model.finish_step()
         return loss
 
-    pool = make_batches(dims, b, args.pool, 2023 + rank, torch.int32)
+    pool = make_batches(dims, b, args.pool, 2023 + rank, torch.int32, args.ids)
     dev_pool = [(x.to(dev), y.to(dev)) for x, y in pool]
     host_pool = [(x.pin_memory(), y.pin_memory()) for x, y in pool]
 
@@ -425,6 +474,15 @@ def main_ours(args, wl):
         except Exception as exc:  # noqa: BLE001 - a secondary number must never break the main line
             small = {"batch": args.small_batch, "error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    # ---- the reference's torch operators, eager, on this GPU (comparison only) ----------------------
+    eager = None
+    if world == 1 and not args.no_torch_eager and wl["model"] == "deepfm" and not sharded \
+            and wl["emb"].get("name", "vanilla") in ("vanilla", "qr"):
+        try:
+            eager = torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, max(3, min(args.steps, 10)))
+        except Exception as exc:  # noqa: BLE001
+            eager = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -483,7 +541,7 @@ def main_ours(args, wl):
     # ---- cpu baseline (oracle port of the reference's CPU path), rank 0, N=1 only ----------
     cpu = None
     if world == 1 and not args.no_cpu_baseline and wl["model"] == "deepfm":
-        r = run_cpu_port(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0)
+        r = run_cpu_port(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0, ids=args.ids)
         cpu = {"value": round(r["value"], 1), "unit": "samples/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"]}
 
@@ -494,7 +552,7 @@ def main_ours(args, wl):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": world * b, "batch_per_gpu": b, "fields": len(dims),
                    "rows": sum(dims), "embedding": wl["emb"], "num_factor": 16, "mlp": [400, 400, 400],
-                   "optimizer": wl["opt"], "ids": "int32, uniform per field, seed 2023",
+                   "optimizer": wl["opt"], "ids": f"int32, {'Zipf(1.05) clipped' if args.ids == 'zipf' else 'uniform'} per field, seed 2023",
                    "parallelism": (f"row-sharded tables x{world} (NVLink peer gather / shard atomics) + dp{world} dense"
                                    if sharded else (f"dp{world} (replicated compressed tables, flat grad allreduce)"
                                                     if world > 1 else "single")),
@@ -514,6 +572,7 @@ def main_ours(args, wl):
         "kernels": kernels,
         "cpu_baseline": cpu,
         "small_batch": small,
+        "torch_eager_gpu": eager,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -532,6 +591,9 @@ def main():
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches cycled through")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded sample per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
+                    help="per-field id distribution: uniform, or Zipf(1.05) clipped to the field size")
+    ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager-on-GPU comparison leg")
     ap.add_argument("--small-batch", type=int, default=2048,
                     help="also time this (reference yaml) batch eagerly and as one CUDA graph; 0 = skip")
     args = ap.parse_args()

@@ -217,6 +217,20 @@ RSB_API int rsb_optembed_eval_weight(const float* weight, const float* t_row, co
 RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, int64_t numel, float* out, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Inference gather from a pruned table kept as CSR.  Replaces PrunedEmbedding.forward
+ * and its numba kernel csr_embedding_lookup (src/models/embeddings/pruned_embedding.py:89-173: one thread
+ * per id, zero-fill + scattered stores), fused with DeepFM's offsets add, first order and FM second order
+ * (src/models/deepfm.py:88-98) like rsb_lookup_fwd.
+ *   values [nnz] f32, crow [n_rows+1] (crow_bytes 8 = int64 like torch / the reference, or 4),
+ *   col [nnz] (col_bytes 8, 4 or 1); columns must be sorted and unique inside a row (torch's
+ *   to_sparse_csr() order).  D <= 32.  out_emb [B,F,D]; out_yfm [B] or NULL (then fc/bias unused).
+ *   Out-of-range ids are clamped to row 0 and raise *err_flag like rsb_lookup_fwd. */
+RSB_API int rsb_csr_lookup_fwd(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B, int32_t F,
+                               int32_t D, const float* values, const void* crow, int32_t crow_bytes, const void* col,
+                               int32_t col_bytes, int64_t n_rows, const float* fc, const float* bias, float* out_emb,
+                               float* out_yfm, int32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------
  * fp32-accurate tensor-core GEMM (tcgen05 + TMA; every fp32 operand split into 3 bf16 terms,
  * 9 MMAs accumulated in fp32 TMEM).  Used for the DCN-Mix low-rank expert projections
  * (src/models/layer_dcn.py:20-23: x@V, H@C, H@U, and their backward GEMMs) and for the

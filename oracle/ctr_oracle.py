@@ -551,6 +551,27 @@ def deepfm_logits_eval(state: Dict[str, np.ndarray], emb: np.ndarray, rows: np.n
     return (y_fm + deep)[:, 0]
 
 
+def csr_from_dense(weight: np.ndarray):
+    """Dense [N,D] -> (values, crow_indices, col_indices) in torch.to_sparse_csr() order
+    (PrunedEmbedding.from_weight, pruned_embedding.py:38-49): row-major scan of the non-zeros."""
+    nz = weight != 0
+    crow = np.zeros(weight.shape[0] + 1, dtype=np.int64)
+    np.cumsum(nz.sum(1), out=crow[1:])
+    r, c = np.nonzero(nz)
+    return weight[r, c].astype(np.float32), crow, c.astype(np.int64)
+
+
+def csr_lookup(values: np.ndarray, crow: np.ndarray, col: np.ndarray, ids: np.ndarray, d: int) -> np.ndarray:
+    """PrunedEmbedding.forward (pruned_embedding.py:89-138) / csr_embedding_lookup(_cpu) (:140-173,186-203):
+    out[i, :] = 0; out[i, col[j]] = values[j] for j in [crow[ids[i]], crow[ids[i]+1]).  ids any shape -> [..., d]."""
+    flat = ids.reshape(-1).astype(np.int64)
+    out = np.zeros((flat.shape[0], d), dtype=np.float32)
+    for i, r in enumerate(flat):
+        for j in range(int(crow[r]), int(crow[r + 1])):
+            out[i, int(col[j])] = values[j]
+    return out.reshape(*ids.shape, d)
+
+
 def bce_with_logits_grad(logits: np.ndarray, labels: np.ndarray) -> np.ndarray:
     """d mean-BCEWithLogits / d logits = (sigmoid(z) - y) / B (trainer/deepfm.py:33,51)."""
     return (sigmoid(logits) - labels.astype(logits.dtype)) / logits.dtype.type(logits.shape[0])

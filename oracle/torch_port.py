@@ -119,8 +119,8 @@ def make_optimizers(p: Dict[str, torch.Tensor], cfg: Dict):
     return [torch.optim.Adam(list(p.values()), lr=cfg["learning_rate"], weight_decay=cfg["weight_decay"])]
 
 
-def train_step(p, opts, x, y, offsets, emb_cfg, p_dropout) -> float:
-    """One iteration of src/trainer/deepfm.py:44-62."""
+def train_step(p, opts, x, y, offsets, emb_cfg, p_dropout, sync: bool = True):
+    """One iteration of src/trainer/deepfm.py:44-62 (sync=False skips the loss.item() read-back)."""
     logits = deepfm_forward(p, x, offsets, emb_cfg, p_dropout, training=True)
     loss = F.binary_cross_entropy_with_logits(logits, y.float())
     for o in opts:
@@ -128,4 +128,4 @@ def train_step(p, opts, x, y, offsets, emb_cfg, p_dropout) -> float:
     loss.backward()
     for o in opts:
         o.step()
-    return loss.item()
+    return loss.item() if sync else loss

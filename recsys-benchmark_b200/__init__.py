@@ -55,6 +55,7 @@ from .dcn import DCN_Mix  # noqa: E402
 from .deepfm import DeepFM, get_optimizers, save_model_checkpoint  # noqa: E402
 from .layer_dcn import DCN_MixHead  # noqa: E402
 from .optim import FusedSparseAdam, FusedSparseSGD  # noqa: E402
+from .pruned import PrunedEmbedding  # noqa: E402
 
 
 def get_ctr_model(field_dims, model_config: dict):
@@ -111,3 +112,7 @@ def install_into_reference() -> None:
     deepfm_mod.get_optimizers = get_optimizers
     tr = importlib.import_module("src.trainer.deepfm")
     tr.DeepFM = DeepFM
+    try:    # inference-only CSR table (needs numba on the reference side); scripts import the symbol from here
+        importlib.import_module("src.models.embeddings.pruned_embedding").PrunedEmbedding = PrunedEmbedding
+    except ImportError:
+        pass

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "rsb_pep_dense_bwd": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "rsb_optembed_eval_weight": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "rsb_mask_table": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "rsb_csr_lookup_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p,
+                                     _p, _p]),
     "rsb_gemm_f32_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64]),
     "rsb_gemm_f32": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64,
                                _i64, _p, _f, _f, _p, _i64, _p]),

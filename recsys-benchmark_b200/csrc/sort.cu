@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) sort_rowscan_kernel(unsigned* __restrict_
   if (threadIdx.x == 0) totals[blockIdx.x] = carry_s;
 }
 
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src, long long n, int shift,
+__global__ void __launch_bounds__(kSortThreads, 3) sort_scatter_kernel(SortSrc src, long long n, int shift,
                                                                     int radix_bits, const unsigned* hist_scanned,
                                                                     const unsigned* totals, int nblk,
                                                                     unsigned* out_keys, unsigned* out_vals) {
@@ -112,10 +112,11 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src,
   extern __shared__ unsigned sort_smem[];
   const int radix = 1 << radix_bits;
   unsigned* dbase = sort_smem;                 // [radix] exclusive scan of the digit totals
-  unsigned(*cnt)[kRadixMax] = reinterpret_cast<unsigned(*)[kRadixMax]>(sort_smem + kRadixMax);  // [NW][kRadixMax]
+  unsigned* cnt = sort_smem + radix;           // [NW][radix] per-warp digit counts (sized by the actual radix)
   __shared__ unsigned wtot[NW];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < NW * kRadixMax; i += blockDim.x) (&cnt[0][0])[i] = 0;
+  unsigned* wcnt = cnt + warp * radix;
+  for (int i = threadIdx.x; i < NW * radix; i += blockDim.x) cnt[i] = 0;
   {
     // digit bases: thread t scans its radix/256 consecutive totals, then a 256-wide block scan
     const int per = (radix + kSortThreads - 1) / kSortThreads;
@@ -149,27 +150,29 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src,
   __syncthreads();
 
   const long long base = (long long)blockIdx.x * kSortTile;
-  unsigned key[kSortItems], rank[kSortItems];
-  unsigned short dig[kSortItems];
+  unsigned key[kSortItems], dr[kSortItems];  // dr = digit << 16 | rank within the warp's digit class (< 512)
+  // all loads of the tile are issued before the (serial, shuffle-bound) ranking rounds
 #pragma unroll
   for (int r = 0; r < kSortItems; ++r) {
     long long p = sort_pos(base, warp, r, lane);
-    bool valid = p < n;
-    key[r] = valid ? sort_key_at(src, p) : 0xffffffffu;
+    key[r] = (p < n) ? sort_key_at(src, p) : 0xffffffffu;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const bool valid = sort_pos(base, warp, r, lane) < n;
     unsigned d = valid ? ((key[r] >> shift) & (radix - 1)) : (unsigned)radix;  // invalid: own class
-    dig[r] = (unsigned short)d;
     unsigned peers = __match_any_sync(kFull, d);
     unsigned lower = peers & ((1u << lane) - 1u);
     unsigned pre = 0;
     if (valid) {
       int leader = __ffs(peers) - 1;
       if (lane == leader) {
-        pre = cnt[warp][d];
-        cnt[warp][d] = pre + __popc(peers);
+        pre = wcnt[d];
+        wcnt[d] = pre + __popc(peers);
       }
       pre = __shfl_sync(peers, pre, leader);
     }
-    rank[r] = pre + __popc(lower);
+    dr[r] = (d << 16) | (pre + __popc(lower));
     __syncwarp();
   }
   __syncthreads();
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src,
     unsigned run = dbase[d] + hist_scanned[(long long)d * nblk + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-      unsigned t = cnt[w][d];
-      cnt[w][d] = run;
+      unsigned t = cnt[w * radix + d];
+      cnt[w * radix + d] = run;
       run += t;
     }
   }
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortSrc src,
   for (int r = 0; r < kSortItems; ++r) {
     long long p = sort_pos(base, warp, r, lane);
     if (p < n) {
-      unsigned dst = cnt[warp][dig[r]] + rank[r];
+      unsigned dst = wcnt[dr[r] >> 16] + (dr[r] & 0xffffu);
       out_keys[dst] = key[r];
       out_vals[dst] = src.vals32 ? __ldg(src.vals32 + p) : (unsigned)p;
     }
@@ -251,10 +254,11 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
   if (bits < 1) bits = 1;
   const int passes = (bits + kRadixBitsMax - 1) / kRadixBitsMax;
   const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 11)
-  const size_t scatter_smem = (size_t)(kRadixMax + (kSortThreads / 32) * kRadixMax) * sizeof(unsigned);
+  const size_t scatter_smem_max = (size_t)(kRadixMax + (kSortThreads / 32) * kRadixMax) * sizeof(unsigned);
+  const size_t scatter_smem = ((size_t)(1 << rb) * (1 + kSortThreads / 32)) * sizeof(unsigned);
   static bool attr_set = false;   // one process drives one device
   if (!attr_set) {
-    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem);
+    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_max);
     attr_set = true;
   }
 

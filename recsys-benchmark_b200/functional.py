@@ -328,6 +328,30 @@ def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tens
     return emb, (y if fc is not None else None)
 
 
+def csr_lookup(x: torch.Tensor, offsets: Optional[torch.Tensor], values: torch.Tensor, crow: torch.Tensor,
+               col: torch.Tensor, n_rows: int, d: int, fc: Optional[torch.Tensor] = None,
+               bias: Optional[torch.Tensor] = None, err_flag: Optional[torch.Tensor] = None):
+    """Inference gather from a CSR-pruned table (pruned_embedding.py:89-173) fused with first order + FM.
+    x [B,F] int32/int64 -> (emb [B,F,d], y_fm [B] or None).  No autograd: the reference class is inference-only."""
+    lib = L.load()
+    dev = L.require_cuda(x, values, crow, col, fc, bias, offsets)
+    if x.dim() != 2:
+        raise RuntimeError("rsb: x must be [B, F]")
+    if x.dtype not in (torch.int32, torch.int64):
+        raise RuntimeError(f"rsb: ids must be int32 or int64, got {x.dtype}")
+    x = x.contiguous()
+    b, f = x.shape
+    emb = torch.empty(b, f, d, dtype=torch.float32, device=dev)
+    y = torch.empty(b, dtype=torch.float32, device=dev) if fc is not None else None
+    nnz = values.numel()
+    nbytes = b * f * (x.element_size() + 2 * crow.element_size() + d * 4) + min(nnz, b * f * d) * (
+        4 + col.element_size())
+    _call("csr_lookup_fwd", lib.rsb_csr_lookup_fwd, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, d,
+          L.ptr(values), L.ptr(crow), crow.element_size(), L.ptr(col), col.element_size(), n_rows, L.ptr(fc),
+          L.ptr(bias), L.ptr(emb), L.ptr(y), L.ptr(err_flag), L.stream_ptr(dev), nbytes=nbytes)
+    return emb, y
+
+
 # ----------------------------------------------------------------------------
 # full-table helpers
 # ----------------------------------------------------------------------------

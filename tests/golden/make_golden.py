@@ -301,7 +301,54 @@ def run_embedding_api_case():
     print("wrote embedding_api", len(out), "arrays")
 
 
+def run_pruned_csr_case():
+    """Inference path: the reference's PrunedEmbedding (CSR + numba CPU kernel,
+    src/models/embeddings/pruned_embedding.py) standing in for the embedding of an eval-mode DeepFM, the way
+    scripts/deepfm/infer_deepfm.py:138-153 builds it."""
+    from src.models.embeddings.pruned_embedding import PrunedEmbedding
+
+    torch.manual_seed(21)
+    model = get_ctr_model(list(FIELD_DIMS), dict(num_factor=D, hidden_sizes=[16, 8], p_dropout=0.1, use_batchnorm=True,
+                                                 embedding_config={"name": "vanilla"}))
+    g = torch.Generator().manual_seed(21)
+    w = model.embedding.get_weight().detach().clone()
+    keep = torch.rand(w.shape, generator=g) > 0.8          # ~80 % pruned
+    keep[3] = False                                         # an all-zero row
+    keep[5] = True                                          # a fully dense row
+    keep[len(w) - 1] = False
+    keep[len(w) - 1, D - 1] = True                          # last row: only the last dim
+    w = w * keep
+    with torch.no_grad():
+        model.embedding._emb_module.weight.copy_(w)
+    model.eval()
+    out = {"field_dims": np.asarray(FIELD_DIMS, dtype=np.int64)}
+    _state(model, out)
+    x, _ = _batch(500)
+    x32, _ = _batch(501, dtype=torch.int32)
+    offsets = torch.tensor([0] + FIELD_DIMS[:-1]).cumsum(0)
+    pruned = PrunedEmbedding.from_other_emb(model.embedding)
+    out["csr/values"] = np.asarray(pruned.values).copy()
+    out["csr/crow_indices"] = np.asarray(pruned.crow_indices).copy()
+    out["csr/col_indices"] = np.asarray(pruned.col_indices).copy()
+    out["x"] = _np(x)
+    out["x_int32"] = _np(x32)
+    with torch.no_grad():
+        out["emb"] = _np(pruned(x + offsets))
+        out["emb_1d"] = _np(pruned((x + offsets)[:, 2].contiguous()))
+        out["weight_dense"] = _np(pruned.get_weight())
+        model.embedding = pruned
+        out["logits"] = _np(model(x))
+        out["logits_int32"] = _np(model(x32))
+    np.savez_compressed(os.path.join(HERE, "pruned_csr.npz"), **out)
+    print("wrote pruned_csr", len(out), "arrays")
+
+
 def main():
+    if len(sys.argv) > 1:          # regenerate only the named extra cases
+        for name in sys.argv[1:]:
+            {"pruned_csr": run_pruned_csr_case}[name]()
+        return
+    run_pruned_csr_case()
     adam = dict(learning_rate=1e-2, weight_decay=1e-4)
     sparse_adam = dict(learning_rate=1e-2, weight_decay=1e-4, sparse=True)
     sparse_sgd = dict(learning_rate=1e-1, weight_decay=1e-4, sparse=True, optimizer="sgd")

@@ -404,3 +404,64 @@ def test_device_prefetcher_yields_the_same_batches_in_order(R):
         n += 1
     assert n == 7
     assert list(DevicePrefetcher(iter([]), DEV)) == []
+
+
+# ------------------------------------------------------- pruned CSR inference path (f-4) ---
+def _pruned_model(R, g, compact=False):
+    fd = [int(v) for v in g["field_dims"]]
+    st = sub(g, "state/")
+    model = R.get_ctr_model(fd, dict(num_factor=8, hidden_sizes=[16, 8], p_dropout=0.1, use_batchnorm=True,
+                                     embedding_config={"name": "vanilla"}))
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in st.items()}, strict=True)
+    model.embedding = R.PrunedEmbedding.from_other_emb(model.embedding, compact=compact)
+    return model.to(DEV).eval(), fd
+
+
+@pytest.mark.parametrize("compact", [False, True])
+def test_pruned_csr_matches_reference(R, compact):
+    g = load_golden("pruned_csr")
+    model, fd = _pruned_model(R, g, compact)
+    emb = model.embedding
+    assert emb.is_cuda
+    emb.to_cuda()
+    rows = _t(O.add_offsets(g["x"], O.field_offsets(g["field_dims"])))
+    with torch.no_grad():
+        np.testing.assert_array_equal(emb(rows).cpu().numpy(), g["emb"])                   # bit exact
+        np.testing.assert_array_equal(emb(rows[:, 2].contiguous()).cpu().numpy(), g["emb_1d"])
+        np.testing.assert_array_equal(emb(rows.reshape(2, -1, rows.shape[1])).cpu().numpy(),
+                                      g["emb"].reshape(2, -1, *g["emb"].shape[1:]))
+        np.testing.assert_array_equal(emb.get_weight().cpu().numpy(), g["weight_dense"])
+        assert_close(model(_t(g["x"])).cpu().numpy(), g["logits"], what="logits")
+        assert_close(model(_t(g["x_int32"])).cpu().numpy(), g["logits_int32"], what="logits int32")
+        assert model(_t(g["x"])[:0]).shape == (0,)                                         # empty batch
+
+
+@pytest.mark.parametrize("d,keep", [(16, 0.2), (16, 1.0), (16, 0.0), (32, 0.5), (5, 0.5)])
+def test_pruned_csr_equals_dense_gather_at_criteo_shape(R, d, keep):
+    torch.manual_seed(3)
+    n = sum(CRITEO_DIMS)
+    w = torch.randn(n, d, device=DEV) * (torch.rand(n, d, device=DEV) < keep)
+    emb = R.PrunedEmbedding.from_weight(w, compact=True)
+    van = R.PrunedEmbedding.from_weight(w)
+    x = torch.stack([torch.randint(0, v, (4096,)) for v in CRITEO_DIMS], 1).to(DEV)
+    offsets = torch.tensor([0] + CRITEO_DIMS[:-1]).cumsum(0).to(DEV)
+    fc = torch.randn(n, 1, device=DEV)
+    bias = torch.randn(1, device=DEV)
+    with torch.no_grad():
+        e1, y1 = emb.lookup(x.int(), offsets, fc, bias)
+        e2, y2 = van.lookup(x, offsets, fc, bias)
+    ref = w[x + offsets]
+    assert torch.equal(e1, ref) and torch.equal(e2, ref)
+    assert torch.equal(y1, y2)
+    yref = (fc[x + offsets].sum(1) + bias)[:, 0] + 0.5 * (ref.sum(1).pow(2) - ref.pow(2).sum(1)).sum(1)
+    assert_close(y1.cpu().numpy(), yref.cpu().numpy(), what="y_fm")
+
+
+def test_pruned_csr_out_of_range_and_wide_rows(R):
+    w = torch.randn(10, 8, device=DEV)
+    emb = R.PrunedEmbedding.from_weight(w)
+    emb.validate = True
+    with pytest.raises(IndexError):
+        emb(torch.tensor([[3, 10]], device=DEV))
+    with pytest.raises(RuntimeError):                                   # D > 32 is not supported by this kernel
+        R.PrunedEmbedding.from_weight(torch.randn(10, 64, device=DEV))(torch.tensor([[1]], device=DEV))

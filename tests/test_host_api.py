@@ -150,3 +150,35 @@ def test_dcn_head_torch_math_matches_reference_golden_on_cpu():
             torch.testing.assert_close(getattr(head, n)[l].grad, torch.from_numpy(g[f"grad/cross_head.{n}.{l}"]),
                                        rtol=1e-4, atol=1e-7)
     torch.testing.assert_close(head.gates.grad, torch.from_numpy(g["grad/cross_head.gates"]), rtol=1e-4, atol=1e-7)
+
+
+# ------------------------------------------------------- pruned CSR (f-4) ---
+def test_pruned_embedding_host_side_matches_reference_layout():
+    g = load_golden("pruned_csr")
+    w = torch.from_numpy(np.asarray(g["state/embedding._emb_module.weight"]))
+    emb = R.PrunedEmbedding.from_weight(w)
+    np.testing.assert_array_equal(emb.values.numpy(), g["csr/values"])
+    np.testing.assert_array_equal(emb.crow_indices.numpy(), g["csr/crow_indices"])
+    np.testing.assert_array_equal(emb.col_indices.numpy(), g["csr/col_indices"])
+    np.testing.assert_array_equal(emb.get_weight().numpy(), g["weight_dense"])
+    assert emb.state_dict() == {} and not emb.is_cuda                 # nothing persistent, like the reference
+    assert emb.get_num_params() == int((w != 0).sum())
+    small = R.PrunedEmbedding.from_weight(w, compact=True)
+    assert small.crow_indices.dtype == torch.int32 and small.col_indices.dtype == torch.uint8
+    np.testing.assert_array_equal(small.get_weight().numpy(), g["weight_dense"])
+    van = R.get_embedding({"name": "vanilla"}, [int(v) for v in g["field_dims"]], w.shape[1])
+    with torch.no_grad():
+        van._emb_module.weight.copy_(w)
+    np.testing.assert_array_equal(R.PrunedEmbedding.from_other_emb(van).values.numpy(), g["csr/values"])
+    with pytest.raises(RuntimeError):                                  # no CPU fallback for the gather
+        emb(torch.zeros(2, 3, dtype=torch.int64))
+
+
+def test_pruned_embedding_canonicalises_unsorted_csr():
+    crow = torch.tensor([0, 2, 2, 3])
+    col = torch.tensor([3, 1, 0])                                      # row 0 has its columns out of order
+    val = torch.tensor([1.0, 2.0, 3.0])
+    csr = torch.sparse_csr_tensor(crow, col, val, size=(3, 4))
+    emb = R.PrunedEmbedding.from_weight(csr)
+    assert emb.col_indices.tolist() == [1, 3, 0] and emb.values.tolist() == [2.0, 1.0, 3.0]
+    np.testing.assert_array_equal(emb.get_weight().numpy(), csr.to_dense().numpy())
