@@ -231,6 +231,18 @@ RSB_API int rsb_csr_lookup_fwd(const void* idx, int32_t idx_is_i32, const int64_
                                float* out_yfm, int32_t* err_flag, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Deep hash embedding encoder.  Replaces the cached [N,k] code table of DHEmbedding and its
+ * builders _get_universal_hash / _get_universal_hash_batch / _init_all_hash
+ * (src/models/embeddings/dh_embedding.py:194-236,250-268) and the F.embedding(inp, cache) gather at :312-315:
+ *   out[i,j] = float(((slopes[j]*(ids[i]+prefix+1) + bias[j]) mod primes[j]) mod m) / float(m-1) * 2 - 1
+ * int64 arithmetic with Python's sign convention for mod, bit-exact.  ids [n] int64 or int32; slopes, bias,
+ * primes [k] int64; 2 <= m <= 2^24; out [n,k] fp32.  small_operands != 0 promises |slopes|,|bias| < 2^31,
+ * 2 <= primes < 2^31 and 0 <= ids+prefix+1 < 2^30 (enables the fp64-reciprocal modulo); 0 = generic int64 path. */
+RSB_API int rsb_dhe_encode(const void* ids, int32_t ids_is_i32, int64_t n, int64_t prefix, const int64_t* slopes,
+                           const int64_t* bias, const int64_t* primes, int32_t k, int64_t m, int32_t small_operands,
+                           float* out, void* stream);
+
+/* ------------------------------------------------------------------------
  * fp32-accurate tensor-core GEMM (tcgen05 + TMA; every fp32 operand split into 3 bf16 terms,
  * 9 MMAs accumulated in fp32 TMEM).  Used for the DCN-Mix low-rank expert projections
  * (src/models/layer_dcn.py:20-23: x@V, H@C, H@U, and their backward GEMMs) and for the

@@ -572,6 +572,60 @@ def csr_lookup(values: np.ndarray, crow: np.ndarray, col: np.ndarray, ids: np.nd
     return out.reshape(*ids.shape, d)
 
 
+def dhe_universal_hash(ids: np.ndarray, prefix: int, slopes: np.ndarray, bias: np.ndarray, primes: np.ndarray,
+                       m: int = 1_000_000) -> np.ndarray:
+    """DHEmbedding._get_universal_hash(_batch) (dh_embedding.py:194-236): ids [...] -> codes [..., k] fp32.
+    int64 arithmetic, `%` with the sign of the divisor (numpy == Python == torch.remainder), then the fp32
+    true division by (m - 1) and `* 2 - 1`."""
+    item = ids.astype(np.int64)[..., None] + np.int64(prefix) + np.int64(1)
+    h = (slopes.astype(np.int64) * item + bias.astype(np.int64)) % primes.astype(np.int64) % np.int64(m)
+    enc = h.astype(np.float32) / np.float32(m - 1)
+    return enc * np.float32(2) - np.float32(1)
+
+
+def first_primes_above(lo: int, count: int) -> np.ndarray:
+    """The prime table DHE draws its moduli from: src/assets/large_prime_74518.json is exactly the first
+    74 518 primes above 10^6 (checked against the file in tests/golden/make_golden.py's container)."""
+    hi = int(lo * 2.2) + 1000
+    while True:
+        sieve = np.ones(hi + 1, dtype=bool)
+        sieve[:2] = False
+        for i in range(2, int(hi ** 0.5) + 1):
+            if sieve[i]:
+                sieve[i * i::i] = False
+        pr = np.nonzero(sieve)[0]
+        pr = pr[pr > lo]
+        if len(pr) >= count:
+            return pr[:count].astype(np.int64)
+        hi *= 2
+
+
+def mish(x):
+    """nn.Mish: x * tanh(softplus(x)) (torch thresholds softplus at 20)."""
+    sp = np.where(x > 20, x, np.log1p(np.exp(np.minimum(x, 20))))
+    return x * np.tanh(sp)
+
+
+def dhe_mlp_eval(x: np.ndarray, state: Dict[str, np.ndarray], prefix: str, use_bn: int) -> np.ndarray:
+    """DHEmbedding._seq in eval mode (dh_embedding.py:101-116): per hidden size Linear then
+    use_bn == 1: Mish, BatchNorm1d | use_bn == 2: BatchNorm1d, Mish | else: Mish."""
+    idx = sorted({int(k[len(prefix):].split(".")[0]) for k in state if k.startswith(prefix)})
+    for i in idx:
+        w = state.get(f"{prefix}{i}.weight")
+        if w is None:
+            continue
+        if w.ndim == 2:
+            x = x @ w.T + state[f"{prefix}{i}.bias"]
+            if use_bn != 2:
+                x = mish(x)
+        else:
+            x = (x - state[f"{prefix}{i}.running_mean"]) / np.sqrt(
+                state[f"{prefix}{i}.running_var"] + x.dtype.type(1e-5)) * w + state[f"{prefix}{i}.bias"]
+            if use_bn == 2:
+                x = mish(x)
+    return x
+
+
 def bce_with_logits_grad(logits: np.ndarray, labels: np.ndarray) -> np.ndarray:
     """d mean-BCEWithLogits / d logits = (sigmoid(z) - y) / B (trainer/deepfm.py:33,51)."""
     return (sigmoid(logits) - labels.astype(logits.dtype)) / logits.dtype.type(logits.shape[0])

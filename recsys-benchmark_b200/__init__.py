@@ -56,6 +56,9 @@ from .deepfm import DeepFM, get_optimizers, save_model_checkpoint  # noqa: E402
 from .layer_dcn import DCN_MixHead  # noqa: E402
 from .optim import FusedSparseAdam, FusedSparseSGD  # noqa: E402
 from .pruned import PrunedEmbedding  # noqa: E402
+from .dhe import DHEmbedding  # noqa: E402
+
+NAME_TO_CLS["dhe"] = DHEmbedding
 
 
 def get_ctr_model(field_dims, model_config: dict):

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "rsb_mask_table": (C.c_int, [_p, _p, _i64, _p, _p]),
     "rsb_csr_lookup_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p,
                                      _p, _p]),
+    "rsb_dhe_encode": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _p, _p]),
     "rsb_gemm_f32_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64]),
     "rsb_gemm_f32": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64,
                                _i64, _p, _f, _f, _p, _i64, _p]),

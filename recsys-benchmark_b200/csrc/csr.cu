@@ -6,10 +6,10 @@
 // row, the row expanded to its dense form in registers, and DeepFM's first-order term + FM
 // second order (src/models/deepfm.py:88-98) reduced in the same pass.
 //
-// Expansion without a scatter: the lane group loads the row's (col, value) pairs (lane j takes
-// pair j), ORs the column bits into a presence mask M; dense dim d is present iff bit d of M
-// is set and then its value sits in pair number popc(M & ((1<<d)-1)) (CSR columns are sorted and
-// unique inside a row - the host wrapper guarantees it), fetched with one shuffle.
+// Expansion without a scatter: the lane group loads the row's (col, value) pairs, ORs the column
+// bits into a presence mask M; dense dim d is present iff bit d of M is set and then its value
+// sits in pair number popc(M & ((1<<d)-1)) (CSR columns are sorted and unique inside a row - the
+// host wrapper guarantees it), fetched with a shuffle from the lane that loaded that pair.
 //
 // Index arrays: crow int64 or int32, col int64 / int32 / uint8 (the compact layout the wrapper
 // offers: 5 bytes per kept weight instead of the reference's 12).
@@ -47,29 +47,31 @@ __device__ __forceinline__ unsigned csr_col(const CsrArgs& a, long long i) {
   return (unsigned)__ldg(reinterpret_cast<const unsigned char*>(a.col) + i);
 }
 
-constexpr int kCsrIter = 4;
-
-// G lanes per looked-up row (G = pow2 >= D, D <= 32); lane c of the group owns dense dim c.
-template <int G>
+// G lanes per looked-up row, each lane owning PPL consecutive dense dims (G * PPL >= D) and loading PPL of
+// the row's (col, value) pairs (pair j sits in lane j % G, register j / G).  Fewer lanes per row means more
+// rows in flight per warp: the kernel is bound by the id -> row extent -> pair chain of dependent loads, so
+// the field loop is batched kIter deep like the training gather (lookup.cu).
+template <int G, int PPL, int kIter>
 __global__ void __launch_bounds__(256) csr_lookup_fwd_kernel(CsrArgs a) {
   constexpr int GPW = kWarp / G;
   const int lane = threadIdx.x & 31;
   const int g = lane / G, c = lane % G;
   const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << (g * G));
-  const bool cact = c < a.D;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool fm = a.out_y != nullptr;
+  const bool vec = (PPL == 2) && (a.D % 2 == 0);   // float2 stores need D even (row base stays 8-byte aligned)
 
   for (long long b = warp; b < a.B; b += nwarps) {
-    float S = 0.f, Q = 0.f, first = 0.f;
-    for (int f0 = 0; f0 < a.F; f0 += GPW * kCsrIter) {
-      // batch the dependent loads: ids -> row extents -> (col, value) pairs -> expand / store
-      long long row[kCsrIter], left[kCsrIter];
-      int nnz[kCsrIter];
-      bool act[kCsrIter];
+    float S[PPL], Q[PPL], first = 0.f;
 #pragma unroll
-      for (int it = 0; it < kCsrIter; ++it) {
+    for (int k = 0; k < PPL; ++k) S[k] = Q[k] = 0.f;
+    for (int f0 = 0; f0 < a.F; f0 += GPW * kIter) {
+      long long row[kIter], left[kIter];
+      int nnz[kIter];
+      bool act[kIter];
+#pragma unroll
+      for (int it = 0; it < kIter; ++it) {
         const int f = f0 + it * GPW + g;
         act[it] = f < a.F;
         long long id = 0;
@@ -84,9 +86,9 @@ __global__ void __launch_bounds__(256) csr_lookup_fwd_kernel(CsrArgs a) {
         }
         row[it] = id;
       }
-      float fcv[kCsrIter];
+      float fcv[kIter];
 #pragma unroll
-      for (int it = 0; it < kCsrIter; ++it) {
+      for (int it = 0; it < kIter; ++it) {
         left[it] = 0;
         nnz[it] = 0;
         fcv[it] = 0.f;
@@ -96,39 +98,66 @@ __global__ void __launch_bounds__(256) csr_lookup_fwd_kernel(CsrArgs a) {
           if (c == 0 && a.fc) fcv[it] = __ldg(a.fc + row[it]);
         }
       }
-      unsigned colv[kCsrIter];
-      float valv[kCsrIter];
+      unsigned colv[kIter];
+      float valv[kIter][PPL];
 #pragma unroll
-      for (int it = 0; it < kCsrIter; ++it) {
+      for (int it = 0; it < kIter; ++it) {
         colv[it] = 0;
-        valv[it] = 0.f;
-        if (c < nnz[it]) {
-          colv[it] = 1u << (csr_col(a, left[it] + c) & 31u);
-          valv[it] = __ldg(a.values + left[it] + c);
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int j = c + k * G;
+          valv[it][k] = 0.f;
+          if (j < nnz[it]) {
+            colv[it] |= 1u << (csr_col(a, left[it] + j) & 31u);
+            valv[it][k] = __ldg(a.values + left[it] + j);
+          }
         }
       }
 #pragma unroll
-      for (int it = 0; it < kCsrIter; ++it) {
+      for (int it = 0; it < kIter; ++it) {
         const int f = f0 + it * GPW + g;
         const unsigned M = __reduce_or_sync(gmask, colv[it]);
-        const int src = __popc(M & ((1u << c) - 1u));
-        const float v = __shfl_sync(gmask, valv[it], src, G);
-        const float e = ((M >> c) & 1u) ? v : 0.f;
+        float e[PPL];
+#pragma unroll
+        for (int k = 0; k < PPL; ++k) {
+          const int d = c * PPL + k;
+          const int q = __popc(M & ((1u << d) - 1u));   // pair number holding dim d (if present)
+          float v = __shfl_sync(gmask, valv[it][0], q % G, G);
+          if (PPL == 2) {
+            const float v1 = __shfl_sync(gmask, valv[it][1], q % G, G);
+            v = (q >= G) ? v1 : v;
+          }
+          e[k] = ((M >> d) & 1u) ? v : 0.f;
+        }
         first += fcv[it];
-        if (act[it] && cact) {
-          a.out_emb[(b * a.F + f) * (long long)a.D + c] = e;
-          S += e;
-          Q = fmaf(e, e, Q);
+        if (act[it]) {
+          float* o = a.out_emb + (b * a.F + f) * (long long)a.D + c * PPL;
+          if (vec) {
+            if (c * PPL < a.D) *reinterpret_cast<float2*>(o) = make_float2(e[0], e[PPL - 1]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < PPL; ++k)
+              if (c * PPL + k < a.D) o[k] = e[k];
+          }
+#pragma unroll
+          for (int k = 0; k < PPL; ++k) {   // dims >= D are never present in M: e == 0
+            S[k] += e[k];
+            Q[k] = fmaf(e[k], e[k], Q[k]);
+          }
         }
       }
     }
     if (fm) {
+      float y2 = 0.f;
 #pragma unroll
-      for (int off = G; off < kWarp; off <<= 1) {
-        S += __shfl_xor_sync(kFull, S, off);
-        Q += __shfl_xor_sync(kFull, Q, off);
+      for (int k = 0; k < PPL; ++k) {
+#pragma unroll
+        for (int off = G; off < kWarp; off <<= 1) {
+          S[k] += __shfl_xor_sync(kFull, S[k], off);
+          Q[k] += __shfl_xor_sync(kFull, Q[k], off);
+        }
+        y2 += S[k] * S[k] - Q[k];
       }
-      float y2 = S * S - Q;
 #pragma unroll
       for (int off = 1; off < G; off <<= 1) y2 += __shfl_xor_sync(kFull, y2, off);
 #pragma unroll
@@ -138,7 +167,7 @@ __global__ void __launch_bounds__(256) csr_lookup_fwd_kernel(CsrArgs a) {
   }
 }
 
-template <int G>
+template <int G, int PPL, int kIter>
 static int launch_csr(const CsrArgs& a, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -146,7 +175,7 @@ static int launch_csr(const CsrArgs& a, cudaStream_t s) {
   long long blocks = (a.B + 7) / 8;  // 8 warps (samples) per CTA
   const long long cap = (long long)sms * 8 * 4;
   if (blocks > cap) blocks = cap;
-  csr_lookup_fwd_kernel<G><<<(unsigned)blocks, 256, 0, s>>>(a);
+  csr_lookup_fwd_kernel<G, PPL, kIter><<<(unsigned)blocks, 256, 0, s>>>(a);
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;
@@ -186,8 +215,8 @@ extern "C" RSB_API int rsb_csr_lookup_fwd(const void* idx, int32_t idx_is_i32, c
   a.out_y = out_yfm;
   a.err = err_flag;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (D <= 4) return launch_csr<4>(a, s);
-  if (D <= 8) return launch_csr<8>(a, s);
-  if (D <= 16) return launch_csr<16>(a, s);
-  return launch_csr<32>(a, s);
+  if (D <= 4) return launch_csr<4, 1, 4>(a, s);
+  if (D <= 8) return launch_csr<4, 2, 4>(a, s);
+  if (D <= 16) return launch_csr<8, 2, 5>(a, s);
+  return launch_csr<16, 2, 5>(a, s);
 }

@@ -150,6 +150,13 @@ __global__ void __launch_bounds__(kSortThreads, 3) sort_scatter_kernel(SortSrc s
   __syncthreads();
 
   const long long base = (long long)blockIdx.x * kSortTile;
+  // this CTA's scanned histogram column (a strided, latency-bound read): issued now, consumed after the ranking
+  unsigned hs[kRadixMax / kSortThreads];
+#pragma unroll
+  for (int i = 0; i < kRadixMax / kSortThreads; ++i) {
+    const int d = threadIdx.x + i * kSortThreads;
+    hs[i] = (d < radix) ? __ldg(hist_scanned + (long long)d * nblk + blockIdx.x) : 0u;
+  }
   unsigned key[kSortItems], dr[kSortItems];  // dr = digit << 16 | rank within the warp's digit class (< 512)
   // all loads of the tile are issued before the (serial, shuffle-bound) ranking rounds
 #pragma unroll
@@ -157,33 +164,44 @@ __global__ void __launch_bounds__(kSortThreads, 3) sort_scatter_kernel(SortSrc s
     long long p = sort_pos(base, warp, r, lane);
     key[r] = (p < n) ? sort_key_at(src, p) : 0xffffffffu;
   }
+  // Ranking: lanes holding the same digit are found with one ballot per digit bit (plus one for validity)
+  // instead of match.any, whose cost grows with the number of distinct values in the warp - with 512 digits
+  // nearly all 32 lanes differ, and the kernel was bound by exactly that instruction.
 #pragma unroll
   for (int r = 0; r < kSortItems; ++r) {
     const bool valid = sort_pos(base, warp, r, lane) < n;
-    unsigned d = valid ? ((key[r] >> shift) & (radix - 1)) : (unsigned)radix;  // invalid: own class
-    unsigned peers = __match_any_sync(kFull, d);
-    unsigned lower = peers & ((1u << lane) - 1u);
+    const unsigned d = (key[r] >> shift) & (radix - 1);
+    unsigned peers = __ballot_sync(kFull, valid);
+    for (int bit = 0; bit < radix_bits; ++bit) {
+      const bool one = (d >> bit) & 1u;
+      const unsigned m = __ballot_sync(kFull, one);
+      peers &= one ? m : ~m;
+    }
     unsigned pre = 0;
     if (valid) {
-      int leader = __ffs(peers) - 1;
+      const int leader = __ffs(peers) - 1;
       if (lane == leader) {
         pre = wcnt[d];
         wcnt[d] = pre + __popc(peers);
       }
       pre = __shfl_sync(peers, pre, leader);
     }
-    dr[r] = (d << 16) | (pre + __popc(lower));
+    dr[r] = (d << 16) | (pre + __popc(peers & ((1u << lane) - 1u)));
     __syncwarp();
   }
   __syncthreads();
   // exclusive scan over warps for each digit, plus this CTA's global base
-  for (int d = threadIdx.x; d < radix; d += blockDim.x) {
-    unsigned run = dbase[d] + hist_scanned[(long long)d * nblk + blockIdx.x];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      unsigned t = cnt[w * radix + d];
-      cnt[w * radix + d] = run;
-      run += t;
+  for (int i = 0; i < kRadixMax / kSortThreads; ++i) {
+    const int d = threadIdx.x + i * kSortThreads;
+    if (d < radix) {
+      unsigned run = dbase[d] + hs[i];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        unsigned t = cnt[w * radix + d];
+        cnt[w * radix + d] = run;
+        run += t;
+      }
     }
   }
   __syncthreads();

@@ -352,6 +352,22 @@ def csr_lookup(x: torch.Tensor, offsets: Optional[torch.Tensor], values: torch.T
     return emb, y
 
 
+def dhe_encode(ids: torch.Tensor, prefix: int, slopes: torch.Tensor, bias: torch.Tensor, primes: torch.Tensor,
+               m: int, small_operands: bool) -> torch.Tensor:
+    """Universal-hash codes of `ids` (any shape) -> [*ids.shape, k] fp32 (dh_embedding.py:194-236), no grad."""
+    lib = L.load()
+    dev = L.require_cuda(ids, slopes, bias, primes)
+    if ids.dtype not in (torch.int32, torch.int64):
+        raise RuntimeError(f"rsb: ids must be int32 or int64, got {ids.dtype}")
+    flat = ids.reshape(-1).contiguous()
+    k = slopes.numel()
+    out = torch.empty(flat.numel(), k, dtype=torch.float32, device=dev)
+    _call("dhe_encode", lib.rsb_dhe_encode, L.ptr(flat), int(flat.dtype == torch.int32), flat.numel(), int(prefix),
+          L.ptr(slopes), L.ptr(bias), L.ptr(primes), k, int(m), int(bool(small_operands)), L.ptr(out),
+          L.stream_ptr(dev), nbytes=flat.numel() * (k * 4 + flat.element_size()))
+    return out.reshape(*ids.shape, k)
+
+
 # ----------------------------------------------------------------------------
 # full-table helpers
 # ----------------------------------------------------------------------------

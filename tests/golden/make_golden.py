@@ -56,7 +56,8 @@ def _batch(seed, field_dims=FIELD_DIMS, b=B, dtype=torch.int64):
 
 def _state(model, out, prefix="state/"):
     for k, v in model.state_dict().items():
-        out[prefix + k] = _np(v)
+        if torch.is_tensor(v):            # DHE's `_extra_state` is a dict ({"_prefix": int}); recorded separately
+            out[prefix + k] = _np(v)
 
 
 def _dense(g):
@@ -343,12 +344,40 @@ def run_pruned_csr_case():
     print("wrote pruned_csr", len(out), "arrays")
 
 
+def run_dhe_cases():
+    """Deep hash embedding (src/models/embeddings/dh_embedding.py): universal-hash codes,
+    the cached table, and DeepFM train steps through the hash -> MLP encoder."""
+    from src.models.embeddings.dh_embedding import DHEmbedding
+
+    adam = dict(learning_rate=1e-2, weight_decay=1e-4)
+    for name, cfg, prefix in [
+        ("deepfm_dhe", {"name": "dhe", "inp_size": 32, "hidden_sizes": [16]}, 0),
+        ("deepfm_dhe_v2", {"name": "dhe", "inp_size": 24, "hidden_sizes": [], "use_bn": 1, "compute_v2": True}, 1000),
+        ("deepfm_dhe_nobn", {"name": "dhe", "inp_size": 32, "hidden_sizes": [12, 16], "use_bn": 0}, 37),
+    ]:
+        DHEmbedding.COUNTER = prefix
+
+        def record(model, tag, out, _prefix=prefix):
+            if tag != "eval":
+                return
+            e = model.embedding
+            assert e._prefix == _prefix
+            out["dhe/prefix"] = np.asarray(e._prefix, dtype=np.int64)
+            out["dhe/cache"] = _np(e._cache)
+            ids = torch.tensor([0, 1, 5, len(e._cache) - 1, 123456789, 2 ** 31 + 7])
+            out["dhe/ids"] = _np(ids)
+            out["dhe/hash_batch"] = _np(e._get_universal_hash_batch(ids))
+
+        run_deepfm_case(name, cfg, opt_cfg=adam, steps=2, pre_forward=record)
+
+
 def main():
     if len(sys.argv) > 1:          # regenerate only the named extra cases
         for name in sys.argv[1:]:
-            {"pruned_csr": run_pruned_csr_case}[name]()
+            {"pruned_csr": run_pruned_csr_case, "dhe": run_dhe_cases}[name]()
         return
     run_pruned_csr_case()
+    run_dhe_cases()
     adam = dict(learning_rate=1e-2, weight_decay=1e-4)
     sparse_adam = dict(learning_rate=1e-2, weight_decay=1e-4, sparse=True)
     sparse_sgd = dict(learning_rate=1e-1, weight_decay=1e-4, sparse=True, optimizer="sgd")

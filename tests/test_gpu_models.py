@@ -39,8 +39,12 @@ def _grad_np(p):
 
 def _bias_before_batchnorm(model):
     out = set()
-    for seq_name in ("_deep_branch", "_dnn"):
-        seq = getattr(model, seq_name, None)
+    for seq_name in ("_deep_branch", "_dnn", "embedding._seq"):
+        seq = model
+        for part in seq_name.split("."):
+            seq = getattr(seq, part, None)
+            if seq is None:
+                break
         if seq is None:
             continue
         mods = list(seq)
@@ -50,8 +54,11 @@ def _bias_before_batchnorm(model):
     return out
 
 
-def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, atol_scale=1e-5):
+def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, atol_scale=1e-5, state_extra=None,
+               after_keys=()):
     g, model, state = build_from_golden(name, emb_cfg)
+    if state_extra is not None:
+        state.update(state_extra(g))
     model.load_state_dict(state, strict=True)
     model.to(DEV)
     # eval logits
@@ -97,7 +104,7 @@ def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, a
             for k in ["embedding.p_weight", "embedding.q_weight", "embedding.p_threshold", "embedding.q_threshold",
                       "embedding._emb_module.weight", "embedding.emb1.weight", "embedding.emb2.weight",
                       "embedding.emb.weight", "embedding.s", "embedding._weight",
-                      "embedding._mask_e_module._t_param", "fc.weight", "_bias"]:
+                      "embedding._mask_e_module._t_param", "fc.weight", "_bias", *after_keys]:
                 if k in after:
                     assert_close(cur[k].cpu().numpy(), after[k], what=f"{name} step{s} after {k}", atol_scale=5e-5)
     return g, model
@@ -465,3 +472,50 @@ def test_pruned_csr_out_of_range_and_wide_rows(R):
         emb(torch.tensor([[3, 10]], device=DEV))
     with pytest.raises(RuntimeError):                                   # D > 32 is not supported by this kernel
         R.PrunedEmbedding.from_weight(torch.randn(10, 64, device=DEV))(torch.tensor([[1]], device=DEV))
+
+
+# ------------------------------------------------------- deep hash embedding (f-3) ---
+DHE_CASES = {
+    "deepfm_dhe": {"name": "dhe", "inp_size": 32, "hidden_sizes": [16]},
+    "deepfm_dhe_v2": {"name": "dhe", "inp_size": 24, "hidden_sizes": [], "use_bn": 1, "compute_v2": True},
+    "deepfm_dhe_nobn": {"name": "dhe", "inp_size": 32, "hidden_sizes": [12, 16], "use_bn": 0},
+}
+
+
+def _dhe_extra(g):
+    return {"embedding._extra_state": {"_prefix": int(g["dhe/prefix"])}}
+
+
+@pytest.mark.parametrize("name", sorted(DHE_CASES))
+def test_dhe_codes_are_bit_exact(R, name):
+    g = load_golden(name)
+    fd = [int(v) for v in g["field_dims"]]
+    emb = R.get_embedding(DHE_CASES[name], fd, 8)
+    emb.load_state_dict({**{k[len("embedding."):]: torch.from_numpy(np.asarray(v)) for k, v in sub(g, "state/").items()
+                            if k.startswith("embedding.")}, "_extra_state": {"_prefix": int(g["dhe/prefix"])}})
+    emb.to(DEV)
+    np.testing.assert_array_equal(emb._cache.cpu().numpy(), g["dhe/cache"])            # fast modulo path
+    np.testing.assert_array_equal(emb.encode(_t(g["dhe/ids"])).cpu().numpy(), g["dhe/hash_batch"])  # generic int64
+    ids = torch.arange(len(g["dhe/cache"]), device=DEV)
+    np.testing.assert_array_equal(emb.encode(ids).cpu().numpy(), g["dhe/cache"])       # both paths agree
+    np.testing.assert_array_equal(emb.encode(ids.int(), in_table=True).cpu().numpy(), g["dhe/cache"])
+
+
+@pytest.mark.parametrize("name", sorted(DHE_CASES))
+def test_deepfm_dhe_matches_reference(R, name):
+    g = load_golden(name)
+    keys = [k[len("step0/after/"):] for k in g if k.startswith("step0/after/embedding._seq") and
+            (k.endswith("weight") or k.endswith("bias"))]
+    _run_steps(R, name, DHE_CASES[name], ADAM, 2, state_extra=_dhe_extra, after_keys=keys)
+
+
+def test_dhe_codes_at_scale_match_oracle(R):
+    """k = 1024 codes at the Criteo table size (prefix pushes ids past 2^20): bit-exact against the int64 oracle."""
+    R.DHEmbedding.COUNTER = 123456
+    emb = R.DHEmbedding(CRITEO_DIMS, 16, None, 1024, []).to(DEV)
+    ids = torch.randint(0, sum(CRITEO_DIMS), (4096,), device=DEV)
+    ref = O.dhe_universal_hash(ids.cpu().numpy(), emb._prefix, emb._slopes.cpu().numpy(), emb._bias.cpu().numpy(),
+                               emb._primes_choices.cpu().numpy())
+    np.testing.assert_array_equal(emb.encode(ids, in_table=True).cpu().numpy(), ref)
+    np.testing.assert_array_equal(emb.encode(ids).cpu().numpy(), ref)
+    assert float(ref.min()) >= -1.0 and float(ref.max()) <= 1.0

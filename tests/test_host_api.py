@@ -182,3 +182,29 @@ def test_pruned_embedding_canonicalises_unsorted_csr():
     emb = R.PrunedEmbedding.from_weight(csr)
     assert emb.col_indices.tolist() == [1, 3, 0] and emb.values.tolist() == [2.0, 1.0, 3.0]
     np.testing.assert_array_equal(emb.get_weight().numpy(), csr.to_dense().numpy())
+
+
+# ------------------------------------------------------- deep hash embedding (f-3) ---
+def test_dhe_state_dict_and_counter_semantics():
+    g = load_golden("deepfm_dhe")
+    fd = [int(v) for v in g["field_dims"]]
+    R.DHEmbedding.COUNTER = 0
+    model = R.get_ctr_model(fd, dict(num_factor=8, hidden_sizes=[16, 8], p_dropout=0.0, use_batchnorm=True,
+                                     embedding_config={"name": "dhe", "inp_size": 32, "hidden_sizes": [16]}))
+    ours = model.state_dict()
+    ref = sub(g, "state/")
+    assert sorted(k for k in ours if k != "embedding._extra_state") == sorted(ref.keys())
+    for k, v in ref.items():
+        assert tuple(ours[k].shape) == tuple(v.shape) and ours[k].numpy().dtype == v.dtype, k
+    # same seeded draws as the reference constructor -> identical hash coefficients before any state dict is loaded
+    for k in ("_slopes", "_bias", "_primes_choices"):
+        np.testing.assert_array_equal(ours["embedding." + k].numpy(), ref["embedding." + k])
+    assert ours["embedding._extra_state"] == {"_prefix": 0} and R.DHEmbedding.COUNTER == sum(fd)
+    second = R.DHEmbedding(fd, 8, None, 32, [16])                 # class-level counter keeps tables apart
+    assert second._prefix == sum(fd)
+    hs = [16]
+    R.DHEmbedding(fd, 8, None, 32, hs)
+    with pytest.raises(NotImplementedError):
+        R.DHEmbedding(fd, 8, use_universal_hash=False)
+    with pytest.raises(RuntimeError):
+        model.embedding.encode(torch.zeros(3, dtype=torch.int64))  # CPU tensors: no fallback
