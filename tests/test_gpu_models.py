@@ -506,6 +506,9 @@ def test_deepfm_dhe_matches_reference(R, name):
     g = load_golden(name)
     keys = [k[len("step0/after/"):] for k in g if k.startswith("step0/after/embedding._seq") and
             (k.endswith("weight") or k.endswith("bias"))]
+    if DHE_CASES[name].get("use_bn", 2) == 2:
+        # a Linear bias feeding BatchNorm has a zero gradient by construction; Adam normalises the fp32 noise
+        keys = [k for k in keys if not (k.endswith(".bias") and g["state/" + k[:-4] + "weight"].ndim == 2)]
     _run_steps(R, name, DHE_CASES[name], ADAM, 2, state_extra=_dhe_extra, after_keys=keys)
 
 
