@@ -63,6 +63,11 @@ WORKLOADS = {
                            use_bn=True, p_dropout=0.2, opt=dict(learning_rate=1e-3, weight_decay=1e-5, fused_adam=True)),
     "deepfm_optembed_kdd": dict(model="deepfm", dims=KDD_DIMS, emb={"name": "deepfm_optembed"}, use_bn=True,
                                 p_dropout=0.2, opt=dict(learning_rate=3e-5, weight_decay=1e-3, fused_adam=True)),
+    # deep hash embedding, configs/deepfm/dhe_config-50.yaml (k = 1024 codes generated in-kernel,
+    # 4 x 1536 Mish/BatchNorm encoder, reference batch 2048: 79 872 encoder rows per step, ~4 TFLOP per step)
+    "deepfm_dhe_criteo": dict(model="deepfm", dims=CRITEO_DIMS, batch=2048,
+                              emb={"name": "dhe", "hidden_sizes": [1536, 1536, 1536, 1536], "compute_v2": False},
+                              use_bn=True, p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
     "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
 }
@@ -491,6 +496,13 @@ def main_ours(args, wl):
 
     # ---- roofline of the dominant hand-written kernel ------------------------------------
     peak, peak_src = peaks()
+    unique_rows = None
+    if wl["opt"].get("fused_sparse") and "segment_reduce_apply" in kern and not sharded:
+        # fused SparseAdam: + read/write of w, m, v per UNIQUE row (6*D*4 B); U is counted here, on batch 0,
+        # outside the timed region (the product path never synchronises to learn it)
+        offs = torch.tensor([0] + dims[:-1]).cumsum(0)
+        unique_rows = int(torch.unique(pool[0][0].long() + offs).numel())
+        kern["segment_reduce_apply"]["bytes_avg"] += 6 * 16 * 4 * unique_rows
     kernels = {}
     for name, r in kern.items():
         gbs = (r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9) if r["bytes_avg"] and r["ms_avg"] > 0 else None
@@ -499,7 +511,7 @@ def main_ours(args, wl):
                          "share_of_step": round(r["ms_total"] / ms_total, 4)}
     # roofline of the dominant HOT-PATH kernel (lookup / scatter-add side);
     # the dense-tail glue and the GEMMs are reported in `kernels` / `roofline_gemm`
-    hot = ("lookup_", "segment_", "small_table", "sort_rows")
+    hot = ("lookup_", "segment_", "small_table", "sort_rows", "dhe_encode", "csr_lookup")
     cand = {k: v for k, v in kern.items() if v["bytes_avg"] > 0 and k.startswith(hot)}
     roofline = None
     if cand:
@@ -525,6 +537,11 @@ def main_ours(args, wl):
         if wl["model"] == "dcn_mix":
             dm, e_, r_ = 16 * len(dims), 4, 64
             flops += 3 * 3 * 2.0 * b * e_ * r_ * (2 * dm + r_)
+        if wl["emb"].get("name") == "dhe":
+            enc = [1024] + list(wl["emb"]["hidden_sizes"]) + [16]
+            rows_ = b * len(dims)
+            for i in range(len(enc) - 1):
+                flops += (2 if i == 0 else 3) * 2.0 * rows_ * enc[i] * enc[i + 1]   # no dX for the hash codes
         g = kern["gemm_f32"]
         bf16_peak = 1645.2
         mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -540,7 +557,8 @@ def main_ours(args, wl):
 
     # ---- cpu baseline (oracle port of the reference's CPU path), rank 0, N=1 only ----------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and wl["model"] == "deepfm":
+    if world == 1 and not args.no_cpu_baseline and wl["model"] == "deepfm" and \
+            wl["emb"].get("name", "vanilla") in ("vanilla", "qr"):
         r = run_cpu_port(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0, ids=args.ids)
         cpu = {"value": round(r["value"], 1), "unit": "samples/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"]}
@@ -573,6 +591,7 @@ def main_ours(args, wl):
         "cpu_baseline": cpu,
         "small_batch": small,
         "torch_eager_gpu": eager,
+        "unique_rows_per_step": unique_rows,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -587,7 +606,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="deepfm_qr_criteo", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=65536, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: 65536, or the "
+                                                            "workload's own batch)")
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches cycled through")
     ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded sample per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -599,6 +619,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
+    if args.batch is None:
+        args.batch = int(wl.get("batch", 65536))
     if args.impl == "reference":
         main_reference(args, wl)
     else:
