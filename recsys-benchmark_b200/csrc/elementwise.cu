@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float4* __r
 constexpr int kColsPerThread = 2;  // float4 groups per thread per pass
 
 template <bool MASKED>
-__global__ void __launch_bounds__(256) colsum_slab_kernel(const float* __restrict__ g,
+__global__ void __launch_bounds__(256, 3) colsum_slab_kernel(const float* __restrict__ g,
                                                           const unsigned char* __restrict__ mask, float scale,
                                                           long long M, int N, long long ld, float* __restrict__ gx,
                                                           float* __restrict__ partials, int col0) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
 }
 
 static int slab_blocks(long long M) {
-  long long b = 4ll * sm_count();      // a few resident CTAs per SM; >= 16 rows per CTA
+  long long b = 3ll * sm_count();      // = the resident CTAs (launch bound 3 per SM): one full wave; >= 16 rows per CTA
   if (b > M / 16) b = M / 16;
   if (b < 1) b = 1;
   return (int)b;
@@ -215,9 +215,10 @@ static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t
     if (!workspace || workspace_bytes < rsb_colsum_workspace_bytes(M, N)) return RSB_ERR_WORKSPACE;
     partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   }
-  // thread arrangement: enough column threads for one pass over the row, the rest as row lanes
-  int ctx = 256;
-  while (ctx > 32 && ctx * kColsPerThread / 2 >= N / 4) ctx >>= 1;   // smallest power of two with ctx*kCols >= n4
+  // thread arrangement: exactly enough column threads for one pass over the row (N = 400: 50 threads x 2 float4
+  // groups), the rest of the 256 as row lanes (5) - a power-of-two split left 22 % of the lanes idle there
+  int ctx = (N / 4 + kColsPerThread - 1) / kColsPerThread;
+  if (ctx > 256) ctx = 256;
   const dim3 block(ctx, 256 / ctx);
   const int per_pass = ctx * 4 * kColsPerThread;
   for (int col0 = 0; col0 < N; col0 += per_pass) {

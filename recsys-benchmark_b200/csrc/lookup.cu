@@ -350,14 +350,15 @@ __global__ void __launch_bounds__(1024) partials_reduce_kernel(const float* __re
   }
 }
 
-template <int K, int V, int LPR, bool TINY = false, int KT = 2>
-__global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
+// TR = number of register accumulators of the TINY variant (emb1 rows actually used, rounded up to 5 or 8)
+template <int K, int V, int LPR, bool TINY = false, int KT = 2, int TR = kTinyRows>
+__global__ void __launch_bounds__(256, TINY ? 3 : 1) lookup_bwd_rows_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
   // the register-accumulating QR variant keeps registers for the emb1 accumulators: shallower batching there
   constexpr int KI = TINY ? KT : kIter;
-  FV<V> tacc[TINY ? kTinyRows : 1];
+  FV<V> tacc[TINY ? TR : 1];
 #pragma unroll
-  for (int r = 0; r < (TINY ? kTinyRows : 1); ++r) tacc[r] = FV<V>::zero();
+  for (int r = 0; r < (TINY ? TR : 1); ++r) tacc[r] = FV<V>::zero();
   const int lane = threadIdx.x & 31;
   const int g = lane / LPR, c = lane % LPR;
   const bool cact = c * V < a.E;
@@ -390,12 +391,16 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
         t2v[it] = FV<V>::zero();
         if (act) {
           if (a.g_deep) gdv[it] = ldg<V>(a.g_deep + o);
-          if (a.g_y) eev[it] = ldg<V>(a.emb + o);
+          // QR mult: e = e1 * e2 is recomputed from the two (L2-resident) tables with the forward's own
+          // rounding instead of streaming the saved [B,F,D] output back from HBM (a third of the kernel's traffic)
+          if (a.g_y && K != RSB_KIND_QR_MULT) eev[it] = ldg<V>(a.emb + o);
           if (K == RSB_KIND_QR_MULT) {
             long long i1, i2;
             qr_split(a, rowv[it], i1, i2);
             t1v[it] = ldg<V>(a.table1 + i1 * a.E + d0);
             t2v[it] = ldg<V>(a.table + i2 * a.E + d0);
+#pragma unroll
+            for (int i = 0; i < V; ++i) eev[it].v[i] = __fmul_rn(t1v[it].v[i], t2v[it].v[i]);
           } else if (K == RSB_KIND_PEP || K == RSB_KIND_OPTEMBED) {
             t1v[it] = ldg<V>(a.table + rowv[it] * a.E + d0);
           }
@@ -440,7 +445,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
           if (TINY) {
             const int k1 = (int)i1;
 #pragma unroll
-            for (int r = 0; r < kTinyRows; ++r) {
+            for (int r = 0; r < TR; ++r) {
 #pragma unroll
               for (int i = 0; i < V; ++i) tacc[TINY ? r : 0].v[i] += (k1 == r) ? r1.v[i] : 0.f;
             }
@@ -456,7 +461,7 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
             qr_split(a, row, i1, i2);
             const int k1 = (int)i1;
 #pragma unroll
-            for (int r = 0; r < kTinyRows; ++r) {
+            for (int r = 0; r < TR; ++r) {
 #pragma unroll
               for (int i = 0; i < V; ++i) tacc[TINY ? r : 0].v[i] += (k1 == r) ? go.v[i] : 0.f;
             }
@@ -518,10 +523,10 @@ __global__ void __launch_bounds__(256) lookup_bwd_rows_kernel(LookupArgs a) {
   }
   if constexpr (TINY) {
     // lane groups -> warp (shuffles) -> CTA (shared memory, fixed order) -> one partial table per CTA
-    __shared__ float tred[8][kTinyRows][LPR * V];
+    __shared__ float tred[8][TR][LPR * V];
     const int wib = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < kTinyRows; ++r) {
+    for (int r = 0; r < TR; ++r) {
 #pragma unroll
       for (int off = LPR; off < kWarp; off <<= 1) {
         FV<V> o = shfl_xor<V>(tacc[r], off);
@@ -576,7 +581,7 @@ static int tune(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 static long long tiny_blocks(long long B) {
-  static const int per_sm = tune("RSB_TINY_CTAS_PER_SM", 8);
+  static const int per_sm = tune("RSB_TINY_CTAS_PER_SM", 3);
   long long blocks = bwd_blocks(B);
   const long long cap = (long long)sm_count() * per_sm;
   return blocks > cap ? cap : blocks;
@@ -590,8 +595,11 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
     if (a.tiny_partials != nullptr) {
       const long long tblocks = tiny_blocks(a.B);
       static const int kt = tune("RSB_TINY_KI", 1);
-#define CALLT(VV, LL)                                                                                 \
-  if (kt == 1) lookup_bwd_rows_kernel<K, VV, LL, true, 1><<<(unsigned)tblocks, threads, 0, stream>>>(a); \
+      const bool five = a.modulus <= 5 && a.divider <= 5;   // rows >= modulus are never hit: fewer accumulators, fewer predicated adds
+#define CALLT(VV, LL)                                                                                              \
+  if (five && kt == 1) lookup_bwd_rows_kernel<K, VV, LL, true, 1, 5><<<(unsigned)tblocks, threads, 0, stream>>>(a); \
+  else if (five) lookup_bwd_rows_kernel<K, VV, LL, true, 2, 5><<<(unsigned)tblocks, threads, 0, stream>>>(a);       \
+  else if (kt == 1) lookup_bwd_rows_kernel<K, VV, LL, true, 1><<<(unsigned)tblocks, threads, 0, stream>>>(a);       \
   else lookup_bwd_rows_kernel<K, VV, LL, true, 2><<<(unsigned)tblocks, threads, 0, stream>>>(a)
       RSB_DISPATCH_SHAPE(sh, CALLT);
 #undef CALLT
