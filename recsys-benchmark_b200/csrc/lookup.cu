@@ -190,7 +190,7 @@ __device__ __forceinline__ long long load_id(const LookupArgs& a, long long b, i
 // first-order weights and table rows, then the arithmetic and the stores.  (A plain per-field loop
 // serialises id -> row -> store round trips, because the compiler may not hoist the next id load
 // above the previous emb store; ncu showed the warps stalled on exactly those three loads.)
-constexpr int kIter = 4;
+constexpr int kIter = 5;   // 8 lane groups x 5 = 40 lookups per batch: the 39 Criteo fields in ONE round of dependent loads
 
 template <int K, int V, int LPR>
 __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
