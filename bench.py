@@ -253,7 +253,9 @@ def small_batch_leg(args, wl, dims, cfg, dev, R, crit):
 
     b = args.small_batch
     torch.manual_seed(2023)
-    model = R.get_ctr_model(dims, {k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}).to(dev)
+    cfg = {k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}
+    cfg["embedding_config"].pop("sparse", None)   # dense gradients: the sparse optimizers are not capturable
+    model = R.get_ctr_model(dims, cfg).to(dev)
     model.train()
     opt_cfg = dict(wl["opt"])
     opt_cfg.update(capturable=True, fused_adam=True)

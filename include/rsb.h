@@ -281,6 +281,21 @@ RSB_API int rsb_relu_dropout_bwd(const float* g, const uint8_t* mask, int64_t M,
 RSB_API int64_t rsb_colsum_workspace_bytes(int64_t M, int32_t N);
 RSB_API int rsb_colsum(const float* x, int64_t M, int32_t N, int64_t ld, float* out, void* workspace,
                        int64_t workspace_bytes, void* stream);
+/* The MLPs end in a Linear with ONE output (src/models/deepfm.py:64, src/models/dcn.py:65: Linear(hidden, 1)):
+ * a matrix-vector product whose three passes are folded into the neighbouring glue instead of library GEMV calls.
+ *  rsb_relu_dropout_dot_fwd   y = dropout(relu(x)), mask as rsb_relu_dropout_fwd, and out[r] = y[r,:].w + bias[0]
+ *  rsb_relu_dropout_bwd_rank1 rsb_relu_dropout_bwd with the upstream gradient g[r,c] = g_row[r] * w_col[c] formed
+ *                             on the fly (the Linear's dX is never written)
+ *  rsb_colsum_weighted        out[c] = sum_r row_weight[r] * x[r,c]  (the Linear's weight gradient)
+ * Workspaces as rsb_colsum_workspace_bytes(M, N). */
+RSB_API int rsb_relu_dropout_dot_fwd(const float* x, int64_t M, int32_t N, float p, uint64_t seed, uint64_t offset,
+                                     const uint64_t* offset_dev, const float* w, const float* bias, float* y,
+                                     uint8_t* mask, float* out, void* stream);
+RSB_API int rsb_relu_dropout_bwd_rank1(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M, int32_t N,
+                                       float p, float* gx, float* colsum, void* workspace, int64_t workspace_bytes,
+                                       void* stream);
+RSB_API int rsb_colsum_weighted(const float* x, const float* row_weight, int64_t M, int32_t N, int64_t ld, float* out,
+                                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * DCN-Mix cross layer glue (src/models/layer_dcn.py:8-24,90-115), identity gate.  With

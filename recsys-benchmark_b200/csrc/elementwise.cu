@@ -59,17 +59,86 @@ __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float4* __r
   }
 }
 
+// y = dropout(relu(x)) as above AND out[r] = y[r,:] . w + bias: the last hidden block of the MLP feeds a Linear
+// with ONE output (src/models/deepfm.py:64: Linear(hidden, 1)), a matrix-vector product that would re-read y.
+// One warp per row; same Philox counters as the flat kernel (float4 index r * n4 + c4), so the masks agree.
+__global__ void __launch_bounds__(256) relu_dropout_dot_fwd_kernel(const float* __restrict__ x, long long M, int N,
+                                                                   float p, float scale, unsigned long long seed,
+                                                                   unsigned long long offset,
+                                                                   const unsigned long long* __restrict__ offset_dev,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ bias,
+                                                                   float* __restrict__ y,
+                                                                   unsigned char* __restrict__ mask,
+                                                                   float* __restrict__ out) {
+  Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
+  if (offset_dev) offset += *offset_dev;
+  const unsigned thr = (unsigned)(p * 4294967296.0);
+  const int lane = threadIdx.x & 31;
+  const int n4 = N / 4;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float b0 = bias ? __ldg(bias) : 0.f;
+  for (long long r = warp; r < M; r += nwarps) {
+    float dot = 0.f;
+    for (int c0 = 0; c0 < n4; c0 += 128) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c4 = c0 + u * 32 + lane;
+        v[u] = (c4 < n4) ? __ldg(reinterpret_cast<const float4*>(x + r * (long long)N) + c4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c4 = c0 + u * 32 + lane;
+        if (c4 < n4) {
+          const long long i = r * (long long)n4 + c4;
+          const uint4 q = rng(offset + (unsigned long long)i);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + c4);
+          uchar4 m;
+          m.x = (v[u].x > 0.f) && (q.x >= thr);
+          m.y = (v[u].y > 0.f) && (q.y >= thr);
+          m.z = (v[u].z > 0.f) && (q.z >= thr);
+          m.w = (v[u].w > 0.f) && (q.w >= thr);
+          float4 o;
+          o.x = m.x ? v[u].x * scale : 0.f;
+          o.y = m.y ? v[u].y * scale : 0.f;
+          o.z = m.z ? v[u].z * scale : 0.f;
+          o.w = m.w ? v[u].w * scale : 0.f;
+          reinterpret_cast<float4*>(y)[i] = o;
+          reinterpret_cast<uchar4*>(mask)[i] = m;
+          dot = fmaf(o.x, wv.x, dot);
+          dot = fmaf(o.y, wv.y, dot);
+          dot = fmaf(o.z, wv.z, dot);
+          dot = fmaf(o.w, wv.w, dot);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dot += __shfl_xor_sync(kFull, dot, off);
+    if (lane == 0) out[r] = dot + b0;
+  }
+}
+
 // One CTA owns a slab of rows.  The 256 threads are arranged as (row lane ty) x (column group tx):
 // tx owns the float4 column groups tx, tx+ctx, ... (a row is read with coalesced 128-bit loads), the
 // cty row lanes interleave over the slab's rows; column sums stay in registers, are folded over ty in
 // shared memory (fixed order) and leave the CTA as one partial row.
 constexpr int kColsPerThread = 2;  // float4 groups per thread per pass
 
-template <bool MASKED>
+// MODE 0: column sums of g.  1: gx = g * mask * scale (relu_dropout_bwd) + column sums of gx.
+// 2: as 1 with the rank-1 upstream gradient g[r,c] = rowv[r] * colv[c] formed on the fly (the layer in front of
+//    a Linear with ONE output: its dX = g_logit[r] * w[c] is never materialised).
+// 3: column sums of rowv[r] * g[r,c] (weight gradient of a one-output Linear: sum_r g_logit[r] * y[r,:]).
+template <int MODE>
 __global__ void __launch_bounds__(256, 3) colsum_slab_kernel(const float* __restrict__ g,
                                                           const unsigned char* __restrict__ mask, float scale,
                                                           long long M, int N, long long ld, float* __restrict__ gx,
-                                                          float* __restrict__ partials, int col0) {
+                                                          float* __restrict__ partials, int col0,
+                                                          const float* __restrict__ rowv,
+                                                          const float* __restrict__ colv) {
+  constexpr bool MASKED = (MODE == 1 || MODE == 2);
   __shared__ float4 red[256][kColsPerThread];
   const int ctx = blockDim.x, cty = blockDim.y;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -78,9 +147,14 @@ __global__ void __launch_bounds__(256, 3) colsum_slab_kernel(const float* __rest
   const long long r0 = rows_per * blockIdx.x;
   long long r1 = r0 + rows_per;
   if (r1 > M) r1 = M;
-  float4 acc[kColsPerThread];
+  float4 acc[kColsPerThread], cv[kColsPerThread];
 #pragma unroll
-  for (int j = 0; j < kColsPerThread; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < kColsPerThread; ++j) {
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c4 = col0 / 4 + tx + j * ctx;
+    if (MODE == 2 && c4 < n4) cv[j] = __ldg(reinterpret_cast<const float4*>(colv) + c4);
+  }
   constexpr int RU = 4;  // rows in flight per thread
   for (long long rb = r0 + ty; rb < r1; rb += (long long)cty * RU) {
     float4 v[RU][kColsPerThread];
@@ -94,7 +168,16 @@ __global__ void __launch_bounds__(256, 3) colsum_slab_kernel(const float* __rest
         v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
         m[u][j] = make_uchar4(0, 0, 0, 0);
         if (c4 < n4 && r < r1) {
-          v[u][j] = __ldg(reinterpret_cast<const float4*>(g + r * ld) + c4);
+          if (MODE == 2) {
+            const float rv = __ldg(rowv + r);
+            v[u][j] = make_float4(rv * cv[j].x, rv * cv[j].y, rv * cv[j].z, rv * cv[j].w);
+          } else {
+            v[u][j] = __ldg(reinterpret_cast<const float4*>(g + r * ld) + c4);
+            if (MODE == 3) {
+              const float rv = __ldg(rowv + r);
+              v[u][j].x *= rv; v[u][j].y *= rv; v[u][j].z *= rv; v[u][j].w *= rv;
+            }
+          }
           if (MASKED) m[u][j] = __ldg(reinterpret_cast<const uchar4*>(mask + r * (long long)N) + c4);
         }
       }
@@ -200,14 +283,18 @@ extern "C" RSB_API int64_t rsb_colsum_workspace_bytes(int64_t M, int32_t N) {
 }
 
 static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t M, int32_t N, int64_t ld, float* gx,
-                       float* colsum, void* workspace, int64_t workspace_bytes, cudaStream_t s) {
+                       float* colsum, void* workspace, int64_t workspace_bytes, cudaStream_t s,
+                       const float* rowv = nullptr, const float* colv = nullptr) {
   if (M < 0 || N <= 0) return RSB_ERR_BAD_ARG;
   if (M == 0) {
     if (colsum) cudaMemsetAsync(colsum, 0, (size_t)N * 4, s);
     return RSB_OK;
   }
-  if (!g) return RSB_ERR_BAD_ARG;
-  if (N % 4 || ld % 4 || !aligned16(g) || (gx && !aligned16(gx)) || (mask && (reinterpret_cast<uintptr_t>(mask) & 3u)))
+  const int mode = mask ? (colv ? 2 : 1) : (rowv ? 3 : 0);
+  if (mode != 2 && !g) return RSB_ERR_BAD_ARG;
+  if ((mode == 2 || mode == 3) && !rowv) return RSB_ERR_BAD_ARG;
+  if (colv && !aligned16(colv)) return RSB_ERR_UNSUPPORTED;
+  if (N % 4 || ld % 4 || (g && !aligned16(g)) || (gx && !aligned16(gx)) || (mask && (reinterpret_cast<uintptr_t>(mask) & 3u)))
     return RSB_ERR_UNSUPPORTED;
   float* partials = nullptr;
   const int nblk = slab_blocks(M);
@@ -222,10 +309,15 @@ static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t
   const dim3 block(ctx, 256 / ctx);
   const int per_pass = ctx * 4 * kColsPerThread;
   for (int col0 = 0; col0 < N; col0 += per_pass) {
-    if (mask)
-      colsum_slab_kernel<true><<<nblk, block, 0, s>>>(g, mask, scale, M, N, ld, gx, partials, col0);
+    if (mode == 1)
+      colsum_slab_kernel<1><<<nblk, block, 0, s>>>(g, mask, scale, M, N, ld, gx, partials, col0, nullptr, nullptr);
+    else if (mode == 2)
+      colsum_slab_kernel<2><<<nblk, block, 0, s>>>(nullptr, mask, scale, M, N, ld, gx, partials, col0, rowv, colv);
+    else if (mode == 3)
+      colsum_slab_kernel<3><<<nblk, block, 0, s>>>(g, nullptr, 1.f, M, N, ld, nullptr, partials, col0, rowv, nullptr);
     else
-      colsum_slab_kernel<false><<<nblk, block, 0, s>>>(g, nullptr, 1.f, M, N, ld, nullptr, partials, col0);
+      colsum_slab_kernel<0><<<nblk, block, 0, s>>>(g, nullptr, 1.f, M, N, ld, nullptr, partials, col0, nullptr,
+                                                   nullptr);
     RSB_CHECK_LAUNCH();
     note_launch(1);
   }
@@ -250,4 +342,39 @@ extern "C" RSB_API int rsb_relu_dropout_bwd(const float* g, const uint8_t* mask,
   if (!mask || !gx || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
   return colsum_impl(g, mask, 1.0f / (1.0f - p), M, N, N, gx, colsum, workspace, workspace_bytes,
                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" RSB_API int rsb_colsum_weighted(const float* x, const float* row_weight, int64_t M, int32_t N, int64_t ld,
+                                           float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!out || !row_weight) return RSB_ERR_BAD_ARG;
+  return colsum_impl(x, nullptr, 1.f, M, N, ld, nullptr, out, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream), row_weight, nullptr);
+}
+
+extern "C" RSB_API int rsb_relu_dropout_bwd_rank1(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M,
+                                                  int32_t N, float p, float* gx, float* colsum, void* workspace,
+                                                  int64_t workspace_bytes, void* stream) {
+  if (!g_row || !w_col || !mask || !gx || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  return colsum_impl(nullptr, mask, 1.0f / (1.0f - p), M, N, N, gx, colsum, workspace, workspace_bytes,
+                     reinterpret_cast<cudaStream_t>(stream), g_row, w_col);
+}
+
+extern "C" RSB_API int rsb_relu_dropout_dot_fwd(const float* x, int64_t M, int32_t N, float p, uint64_t seed,
+                                                uint64_t offset, const uint64_t* offset_dev, const float* w,
+                                                const float* bias, float* y, uint8_t* mask, float* out,
+                                                void* stream) {
+  if (M < 0 || N <= 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  if (M == 0) return RSB_OK;
+  if (!x || !y || !mask || !w || !out) return RSB_ERR_BAD_ARG;
+  if (N % 4 || !aligned16(x) || !aligned16(y) || !aligned16(w) || (reinterpret_cast<uintptr_t>(mask) & 3u))
+    return RSB_ERR_UNSUPPORTED;
+  long long blocks = (M + 7) / 8;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  relu_dropout_dot_fwd_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, M, N, p, 1.0f / (1.0f - p), seed, offset, reinterpret_cast<const unsigned long long*>(offset_dev), w, bias, y,
+      mask, out);
+  RSB_CHECK_LAUNCH();
+  note_launch(1);
+  return RSB_OK;
 }

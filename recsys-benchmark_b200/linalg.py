@@ -199,6 +199,44 @@ def _relu_dropout_bwd(g: torch.Tensor, mask: torch.Tensor, p: float, want_colsum
     return gx, cs
 
 
+def _relu_dropout_dot_fwd(x: torch.Tensor, p: float, w: torch.Tensor, bias: Optional[torch.Tensor]):
+    """(y, mask, out) with out[r] = dropout(relu(x))[r,:] . w + bias: the one-output Linear folded into the pass."""
+    lib = L.load()
+    m, n = x.shape
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    out = torch.empty(m, dtype=torch.float32, device=x.device)
+    seed, off = _dropout_stream(x.numel())
+    RF._call("relu_dropout_dot_fwd", lib.rsb_relu_dropout_dot_fwd, L.ptr(x), m, n, float(p), seed, off,
+             L.ptr(_DROPOUT_DEV_COUNTER), L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(mask), L.ptr(out),
+             L.stream_ptr(x.device), nbytes=x.numel() * 9 + m * 4)
+    return y, mask, out
+
+
+def _relu_dropout_bwd_rank1(g_row: torch.Tensor, w_col: torch.Tensor, mask: torch.Tensor, p: float, want_colsum: bool):
+    """relu_dropout_bwd of the upstream gradient g_row[r] * w_col[c] (never materialised)."""
+    lib = L.load()
+    m, n = mask.shape
+    gx = torch.empty(m, n, dtype=torch.float32, device=mask.device)
+    cs = torch.empty(n, dtype=torch.float32, device=mask.device) if want_colsum else None
+    ws = RF._ws(lib.rsb_colsum_workspace_bytes(m, n), mask.device) if want_colsum else None
+    RF._call("relu_dropout_bwd_rank1", lib.rsb_relu_dropout_bwd_rank1, L.ptr(g_row), L.ptr(w_col), L.ptr(mask), m, n,
+             float(p), L.ptr(gx), L.ptr(cs), L.ptr(ws), ws.numel() if ws is not None else 0,
+             L.stream_ptr(mask.device), nbytes=m * n * 5 + m * 4)
+    return gx, cs
+
+
+def _colsum_weighted(x: torch.Tensor, row_weight: torch.Tensor) -> torch.Tensor:
+    """out[c] = sum_r row_weight[r] * x[r,c]."""
+    lib = L.load()
+    m, n = x.shape
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    ws = RF._ws(lib.rsb_colsum_workspace_bytes(m, n), x.device)
+    RF._call("colsum_weighted", lib.rsb_colsum_weighted, L.ptr(x), L.ptr(row_weight), m, n, x.stride(0), L.ptr(out),
+             L.ptr(ws), ws.numel(), L.stream_ptr(x.device), nbytes=m * n * 4 + m * 4)
+    return out
+
+
 def _fusable(x: torch.Tensor) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous() and x.shape[1] % 4 == 0
             and x.shape[1] <= 2048 and x.data_ptr() % 16 == 0)
@@ -248,6 +286,41 @@ class _LinearReluDropout(torch.autograd.Function):
         gw = gemm(gz, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1])) \
             if ctx.needs_input_grad[1] else None
         return gx, gw, gb, None
+
+
+class _HeadBlock(torch.autograd.Function):
+    """The tail of the MLPs, [Linear ->] ReLU -> Dropout -> Linear(hidden, 1) (src/models/deepfm.py:55-66,
+    src/models/dcn.py:56-66), with the one-output Linear folded into the glue passes:
+      fwd  z = x @ W^T + b (tensor-core GEMM, only when W is given), then ONE pass: y = dropout(relu(z)), mask,
+           out = y . w_out + b_out;
+      bwd  dW_out = sum_r g[r] y[r,:] (row-weighted column sum), db_out = sum g, then ONE pass forming
+           g[r] * w_out[c] on the fly -> gz (+ its column sums = db), then the two GEMMs of the Linear.
+    Returns out [M, 1].  With W = None the input is the pre-activation itself (BatchNorm sits in between)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p, w_out, b_out):
+        z = x if weight is None else gemm(x, weight, trans_b=True, bias=bias)
+        y, mask, out = _relu_dropout_dot_fwd(z, p, w_out.reshape(-1), b_out)
+        ctx.save_for_backward(x if weight is not None else None, weight, mask, y, w_out)
+        ctx.p = p
+        ctx.has_bias = bias is not None
+        ctx.has_bout = b_out is not None
+        return out.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        x, weight, mask, y, w_out = ctx.saved_tensors
+        g = g_out.reshape(-1).contiguous()
+        g_wout = _colsum_weighted(y, g).reshape(w_out.shape) if ctx.needs_input_grad[4] else None
+        g_bout = g.sum().reshape(1) if ctx.has_bout and ctx.needs_input_grad[5] else None
+        want_gb = weight is not None and ctx.has_bias and ctx.needs_input_grad[2]
+        gz, gb = _relu_dropout_bwd_rank1(g, w_out.reshape(-1), mask, ctx.p, want_gb)
+        if weight is None:
+            return gz, None, None, None, g_wout, g_bout
+        gx = gemm(gz, weight) if ctx.needs_input_grad[0] else None
+        gw = gemm(gz, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1])) \
+            if ctx.needs_input_grad[1] else None
+        return gx, gw, gb, None, g_wout, g_bout
 
 
 def _split_for(k: int, m: int, n: int, sms: int = 148) -> int:
@@ -330,6 +403,13 @@ def matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.matmul(a, b)
 
 
+def _is_head(mod, width: int) -> bool:
+    """A Linear with ONE output on `width` inputs whose weight the glue kernels can read (fp32, 16-byte aligned)."""
+    return (isinstance(mod, torch.nn.Linear) and mod.weight.shape[0] == 1 and mod.weight.shape[1] == width
+            and width % 4 == 0 and mod.weight.is_cuda and mod.weight.dtype == torch.float32
+            and mod.weight.data_ptr() % 16 == 0)
+
+
 def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
     """nn.Sequential forward of the dense tails with the same parameters / state dict, but
     Linear -> tensor-core GEMM, and (Linear ->) ReLU -> Dropout fused into single passes.
@@ -341,9 +421,14 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < len(mods) else None
         nx2 = mods[i + 2] if i + 2 < len(mods) else None
+        nx3 = mods[i + 3] if i + 3 < len(mods) else None
         if isinstance(m, torch.nn.Linear):
             ok = x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and \
                 _use_kernel(x.shape[0], m.weight.shape[0], m.weight.shape[1], x, m.weight, m.bias)
+            if ok and isinstance(nxt, torch.nn.ReLU) and isinstance(nx2, torch.nn.Dropout) and training and \
+                    0.0 < nx2.p < 1.0 and m.weight.shape[0] <= 2048 and _is_head(nx3, m.weight.shape[0]) and \
+                    i + 4 == len(mods):
+                return _HeadBlock.apply(x, m.weight, m.bias, float(nx2.p), nx3.weight, nx3.bias)
             if ok and isinstance(nxt, torch.nn.ReLU) and isinstance(nx2, torch.nn.Dropout) and training and \
                     0.0 < nx2.p < 1.0 and m.weight.shape[0] <= 2048:
                 x = _LinearReluDropout.apply(x, m.weight, m.bias, float(nx2.p))
@@ -352,6 +437,9 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
             x = linear(x, m.weight, m.bias)
             i += 1
             continue
+        if isinstance(m, torch.nn.ReLU) and isinstance(nxt, torch.nn.Dropout) and training and 0.0 < nxt.p < 1.0 \
+                and i + 3 == len(mods) and _fusable(x) and _is_head(nx2, x.shape[1]) and x.shape[0] >= 256:
+            return _HeadBlock.apply(x, None, None, float(nxt.p), nx2.weight, nx2.bias)
         if isinstance(m, torch.nn.ReLU) and isinstance(nxt, torch.nn.Dropout):
             x = relu_dropout(x, float(nxt.p), training)
             i += 2

@@ -212,3 +212,43 @@ def test_fused_linear_relu_dropout_block_matches_composition(LA):
     assert all(torch.isfinite(g).all() for g in g1)
     seq.eval()
     torch.testing.assert_close(LA.run_sequential(seq, x), seq(x), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("with_bn", [False, True])
+def test_head_block_matches_unfused_path_with_the_same_masks(LA, with_bn, monkeypatch):
+    """[Linear ->] ReLU -> Dropout -> Linear(hidden, 1): the fused head (one-output Linear folded into the glue
+    passes) against the unfused composition, with the Philox stream rewound so both draw identical masks."""
+    torch.manual_seed(5)
+    layers = [torch.nn.Linear(624, 400)]
+    if with_bn:
+        layers.append(torch.nn.BatchNorm1d(400))
+    layers += [torch.nn.ReLU(), torch.nn.Dropout(0.5), torch.nn.Linear(400, 1)]
+    seq = torch.nn.Sequential(*layers).to(DEV).train()
+    x = torch.randn(8192, 624, device=DEV, requires_grad=True)
+    params = [x] + [p for p in seq.parameters()]
+    go = torch.randn(8192, 1, device=DEV)
+
+    calls = LA._DROPOUT_CALLS
+    out_f = LA.run_sequential(seq, x)
+    assert out_f.grad_fn.name().startswith("_HeadBlock")
+    g_f = torch.autograd.grad(out_f, params, go)
+
+    LA._DROPOUT_CALLS = calls                          # same (seed, offset) -> same masks
+    monkeypatch.setattr(LA, "_is_head", lambda mod, width: False)
+    out_u = LA.run_sequential(seq, x)
+    assert not out_u.grad_fn.name().startswith("_HeadBlock")
+    g_u = torch.autograd.grad(out_u, params, go)
+
+    assert _err(out_f, out_u.double()) < 2e-6
+    names = ["x"] + [n for n, _ in seq.named_parameters()]
+    for n, a_, b_ in zip(names, g_f, g_u):
+        if with_bn and n == "0.bias":
+            continue                                   # zero by construction in front of BatchNorm: fp32 noise
+        assert _err(a_, b_.double()) < 5e-6, n
+    # fp64 check of the one-output Linear itself on the activations the kernel produced
+    y, mask, out = LA._relu_dropout_dot_fwd(x.detach()[:, :400].contiguous(), 0.5, seq[-1].weight.reshape(-1),
+                                            seq[-1].bias)
+    ref = y.double() @ seq[-1].weight.double().t() + seq[-1].bias.double()
+    assert _err(out, ref[:, 0]) < 2e-6
+    keep = mask.float().mean().item()
+    assert abs(keep - 0.25) < 0.01                     # P(x > 0) * (1 - p)
