@@ -65,3 +65,35 @@ class DevicePrefetcher:
             except StopIteration:
                 nxt = None
             yield tuple(outs)
+
+
+class DeferredScalar:
+    """Per-step device->host read of a scalar (the loss) that does not drain the launch queue.
+
+    `loss.item()` right after `optimizer.step()` (src/trainer/deepfm.py:62) makes the host wait for the whole
+    step before it can queue the next one, so every step starts with an empty GPU.  `push(loss)` copies the value
+    into a pinned slot asynchronously and returns the value pushed ONE call earlier (None the first time): the
+    D2H read still happens every step, the host just consumes it one step late; `flush()` returns the last one."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self._slots = torch.empty(depth, dtype=torch.float32).pin_memory()
+        self._events = [torch.cuda.Event() for _ in range(depth)]
+        self._n = 0
+
+    def push(self, value: torch.Tensor):
+        k = self._n % len(self._events)
+        prev = None
+        if self._n >= len(self._events) - 1 and self._n > 0:
+            prev = self._read((self._n - 1) % len(self._events))
+        self._slots[k:k + 1].copy_(value.detach().reshape(1), non_blocking=True)
+        self._events[k].record(torch.cuda.current_stream(self.device))
+        self._n += 1
+        return prev
+
+    def _read(self, k: int) -> float:
+        self._events[k].synchronize()
+        return float(self._slots[k])
+
+    def flush(self):
+        return self._read((self._n - 1) % len(self._events)) if self._n else None

@@ -522,3 +522,54 @@ def test_dhe_codes_at_scale_match_oracle(R):
     np.testing.assert_array_equal(emb.encode(ids, in_table=True).cpu().numpy(), ref)
     np.testing.assert_array_equal(emb.encode(ids).cpu().numpy(), ref)
     assert float(ref.min()) >= -1.0 and float(ref.max()) <= 1.0
+
+
+def test_deferred_scalar_returns_each_value_one_push_late(R):
+    from recsys_benchmark_b200.data import DeferredScalar
+
+    r = DeferredScalar(DEV)
+    vals = [torch.tensor(float(i) * 1.5, device=DEV) for i in range(5)]
+    got = [r.push(v) for v in vals]
+    assert got == [None, 0.0, 1.5, 3.0, 4.5] and r.flush() == 6.0
+
+
+def test_graphed_train_step_matches_eager_steps(R):
+    """The whole step replayed from one CUDA graph produces the same losses / weights as eager launches."""
+    from recsys_benchmark_b200.graphed import GraphedTrainStep
+
+    dims = [50, 7, 300, 12, 1000, 4]
+
+    def build():
+        torch.manual_seed(11)
+        m = R.get_ctr_model(dims, dict(num_factor=16, hidden_sizes=[64, 32], p_dropout=0.0, use_batchnorm=False,
+                                       embedding_config={"name": "qr", "divider": 5})).to(DEV).train()
+        return m, R.get_optimizers(m, dict(learning_rate=1e-2, weight_decay=1e-5, fused_adam=True, capturable=True))
+
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.stack([torch.randint(0, d, (512,), generator=g) for d in dims], 1).int(),
+                torch.randint(0, 2, (512,), generator=g).float()) for _ in range(4)]
+    crit = torch.nn.BCEWithLogitsLoss()
+    m1, o1 = build()
+    eager = []
+    for x, y in batches:
+        loss = crit(m1(x.to(DEV)), y.to(DEV))
+        for o in o1:
+            o.zero_grad()
+        loss.backward()
+        for o in o1:
+            o.step()
+        eager.append(float(loss))
+    m2, o2 = build()
+    init = {k: v.clone() for k, v in m2.state_dict().items()}
+    step = GraphedTrainStep(m2, o2, crit, *batches[0])
+    m2.load_state_dict(init)                       # the capture warm-up took real optimizer steps: rewind
+    for o in o2:
+        for st in o.state.values():
+            for k, v in st.items():
+                if torch.is_tensor(v):
+                    v.zero_()
+    graphed = [float(step(x.pin_memory(), y.pin_memory())) for x, y in batches]
+    assert_close(np.asarray(graphed), np.asarray(eager), what="graph-replayed losses", atol_scale=1e-4)
+    for (k, a), (_, b_) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        if a.dtype == torch.float32:
+            assert_close(b_.cpu().numpy(), a.cpu().numpy(), what=f"weights {k}", atol_scale=1e-4)
