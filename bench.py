@@ -110,28 +110,45 @@ def make_batches(dims, batch, n, seed, dtype, dist_name="uniform"):
 # ------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference's CPU PyTorch path
 # ------------------------------------------------------------------------------------
+PORT_EMBEDDINGS = ("vanilla", "qr", "pep")
+
+
+def _port_model(TP, wl, device):
+    """Parameters, optimizers and forward function of oracle/torch_port.py for a workload, on `device`."""
+    dims = wl["dims"]
+    emb = {k: v for k, v in wl["emb"].items() if k != "checkpoint_weight_dir"}
+    if emb.get("name", "vanilla") not in PORT_EMBEDDINGS:
+        raise NotImplementedError(f"torch port: embedding {emb.get('name')}")
+    if wl["model"] == "deepfm":
+        p = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
+        fwd = TP.deepfm_forward
+    else:
+        p = TP.make_dcn_params(dims, 16, [400, 400, 400], emb, seed=0)
+        fwd = TP.dcn_mix_forward
+    if device.type != "cpu":
+        p = {k: v.detach().to(device).requires_grad_(True) for k, v in p.items()}
+    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
+    return p, opts, emb, fwd
+
+
 def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0, ids="uniform"):
     import torch
 
     from oracle import torch_port as TP
 
-    if wl["model"] != "deepfm":
-        raise NotImplementedError("cpu port covers the DeepFM workloads")
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     dims = wl["dims"]
-    emb = {k: v for k, v in wl["emb"].items()}
-    p = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
-    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
+    p, opts, emb, fwd = _port_model(TP, wl, torch.device("cpu"))
     offsets = torch.tensor([0] + dims[:-1]).cumsum(0)[None, :]
     batches = make_batches(dims, sample_batch, 2, 2023, torch.int64, ids)
     for i in range(warmup):
-        TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"])
+        TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"], forward=fwd)
     times = []
     t_all = time.perf_counter()
     for i in range(steps):
         t0 = time.perf_counter()
-        TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"])
+        TP.train_step(p, opts, *batches[i % 2], offsets, emb, wl["p_dropout"], forward=fwd)
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_all > budget_s and len(times) >= 3:
             break
@@ -149,19 +166,16 @@ def torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, steps):
 
     from oracle import torch_port as TP
 
-    emb = dict(wl["emb"])
-    p_cpu = TP.make_deepfm_params(dims, 16, [400, 400, 400], emb, wl["use_bn"], seed=0)
-    p = {k: v.detach().to(dev).requires_grad_(True) for k, v in p_cpu.items()}
-    opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
+    p, opts, emb, fwd = _port_model(TP, wl, dev)
     offsets = torch.tensor([0] + dims[:-1]).cumsum(0)[None, :].to(dev)
     pool = [(x.long(), y) for x, y in dev_pool[:4]]
     for i in range(3):
-        TP.train_step(p, opts, *pool[i % len(pool)], offsets, emb, wl["p_dropout"], sync=False)
+        TP.train_step(p, opts, *pool[i % len(pool)], offsets, emb, wl["p_dropout"], sync=False, forward=fwd)
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for i in range(steps):
-        TP.train_step(p, opts, *pool[i % len(pool)], offsets, emb, wl["p_dropout"], sync=False)
+        TP.train_step(p, opts, *pool[i % len(pool)], offsets, emb, wl["p_dropout"], sync=False, forward=fwd)
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / steps
@@ -177,7 +191,9 @@ def main_reference(args, wl):
     sample = min(args.cpu_batch, args.batch)
     r = run_cpu_port(wl, sample, max(args.steps, 3), max(args.warmup, 1), budget_s=120.0, ids=args.ids)
     line = {
-        "impl": "reference", "metric": "DeepFM train samples/s (Criteo shape)", "value": r["value"],
+        "impl": "reference",
+        "metric": "DeepFM train samples/s (Criteo shape)" if wl["model"] == "deepfm" else "DCN-Mix train samples/s",
+        "value": r["value"],
         "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -520,8 +536,8 @@ def main_ours(args, wl):
 
     # ---- the reference's torch operators, eager, on this GPU (comparison only) ----------------------
     eager = None
-    if world == 1 and not args.no_torch_eager and wl["model"] == "deepfm" and not sharded \
-            and wl["emb"].get("name", "vanilla") in ("vanilla", "qr"):
+    if world == 1 and not args.no_torch_eager and not sharded \
+            and wl["emb"].get("name", "vanilla") in PORT_EMBEDDINGS:
         try:
             eager = torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, max(3, min(args.steps, 10)))
         except Exception as exc:  # noqa: BLE001
@@ -596,8 +612,7 @@ def main_ours(args, wl):
 
     # ---- cpu baseline (oracle port of the reference's CPU path), rank 0, N=1 only ----------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and wl["model"] == "deepfm" and \
-            wl["emb"].get("name", "vanilla") in ("vanilla", "qr"):
+    if world == 1 and not args.no_cpu_baseline and wl["emb"].get("name", "vanilla") in PORT_EMBEDDINGS:
         r = run_cpu_port(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0, ids=args.ids)
         cpu = {"value": round(r["value"], 1), "unit": "samples/s", "cores": r["cores"], "kind": "port",
                "sample": r["sample"]}

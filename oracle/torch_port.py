@@ -36,8 +36,18 @@ def make_deepfm_params(field_dims: List[int], d: int, hidden: List[int], emb_cfg
         alpha = math.sqrt(1 / n)
         p["embedding.emb1.weight"] = torch.empty(div, d).uniform_(alpha, 1, generator=g)
         p["embedding.emb2.weight"] = torch.empty((n - 1) // div + 1, d).uniform_(alpha, 1, generator=g)
+    elif name == "pep":
+        a = math.sqrt(6.0 / (n + d))
+        p["embedding.emb.weight"] = torch.empty(n, d).uniform_(-a, a, generator=g)
+        shape = {"global": (1,), "dimension": (d,), "feature": (n, 1), "feature_dim": (n, d)}[
+            emb_cfg.get("threshold_type", "feature_dim")]
+        p["embedding.s"] = torch.full(shape, float(emb_cfg.get("init_threshold", -150)))
     else:
         raise NotImplementedError(name)
+    if emb_cfg.get("_no_first_order"):
+        for v in p.values():
+            v.requires_grad_(True)
+        return p
     p["fc.weight"] = torch.randn(n, 1, generator=g)
     p["_bias"] = torch.zeros(1)
     inp = d * len(field_dims)
@@ -65,6 +75,9 @@ def embedding_forward(p: Dict[str, torch.Tensor], rows: torch.Tensor, emb_cfg: D
     name = emb_cfg.get("name", "vanilla")
     if name == "vanilla":
         return F.embedding(rows, p["embedding._emb_module.weight"], sparse=bool(emb_cfg.get("sparse", False)))
+    if name == "pep":       # src/models/embeddings/pep_embedding.py:82-92
+        v = p["embedding.emb.weight"]
+        return F.embedding(rows, torch.sign(v) * torch.relu(torch.abs(v) - torch.sigmoid(p["embedding.s"])))
     div = p["embedding.emb1.weight"].shape[0]
     e1 = F.embedding(rows % div, p["embedding.emb1.weight"])
     e2 = F.embedding(rows // div, p["embedding.emb2.weight"])
@@ -108,6 +121,62 @@ def deepfm_forward(p, x, offsets, emb_cfg, p_dropout=0.0, training=True, bn_stat
     return (y_fm + deep).squeeze(-1)
 
 
+def make_dcn_params(field_dims: List[int], d: int, hidden: List[int], emb_cfg: Dict, num_layers: int = 3,
+                    num_experts: int = 4, rank: int = 64, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """DCN_Mix parameters with the reference's shapes / init (src/models/dcn.py:11-74, layer_dcn.py:46-88)."""
+    cfg = dict(emb_cfg)
+    cfg["_no_first_order"] = True
+    p = make_deepfm_params(field_dims, d, [], cfg, False, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    dm = d * len(field_dims)
+
+    def he(*shape):
+        fan_in = shape[1] * (shape[2] if len(shape) > 2 else 1)          # torch's fan_in for a 3-D tensor
+        return torch.randn(*shape, generator=g) * math.sqrt(2.0 / fan_in)
+
+    for l in range(num_layers):
+        p[f"cross_head.U.{l}"] = he(num_experts, rank, dm)
+        p[f"cross_head.C.{l}"] = he(num_experts, rank, rank)
+        p[f"cross_head.V.{l}"] = he(num_experts, dm, rank)
+        p[f"cross_head.biases.{l}"] = torch.zeros(1, dm)
+    p["cross_head.gates"] = he(num_experts, dm, 1)
+    inp, li = dm, 0
+    for h in hidden:
+        k = 1 / math.sqrt(inp)
+        p[f"_dnn.{li}.weight"] = torch.empty(h, inp).uniform_(-k, k, generator=g)
+        p[f"_dnn.{li}.bias"] = torch.empty(h).uniform_(-k, k, generator=g)
+        p[f"_dnn.{li + 1}.weight"] = torch.ones(h)
+        p[f"_dnn.{li + 1}.bias"] = torch.zeros(h)
+        li += 4
+        inp = h
+    k = 1 / math.sqrt(inp)
+    p[f"_dnn.{li}.weight"] = torch.empty(1, inp).uniform_(-k, k, generator=g)
+    p[f"_dnn.{li}.bias"] = torch.empty(1).uniform_(-k, k, generator=g)
+    for v in p.values():
+        v.requires_grad_(True)
+    return p
+
+
+def dcn_mix_forward(p, x, offsets, emb_cfg, p_dropout=0.0, training=True, bn_state=None):
+    """src/models/dcn.py:76-96 + layer_dcn.py:8-24,90-115, the reference's operators in its order
+    (`x @ V`, permute, the two einsums as batched matmuls, tanh always, identity gate)."""
+    rows = x + offsets
+    emb = embedding_forward(p, rows, emb_cfg)
+    x0 = emb.reshape(emb.shape[0], -1)
+    xl = x0
+    x0u = x0.unsqueeze(1)
+    layers = sorted({int(k.split(".")[2]) for k in p if k.startswith("cross_head.U.")})
+    for l in layers:
+        C, U, V, b = (p[f"cross_head.{n}.{l}"] for n in ("C", "U", "V", "biases"))
+        e = torch.tanh(xl @ V).permute(1, 0, 2)                          # [B, E, r]
+        e = torch.tanh(torch.einsum("ber,ers->bes", e, C))
+        e = torch.einsum("ber,erd->bed", e, U)
+        e = x0u * (e + b)
+        gates = (xl @ p["cross_head.gates"]).squeeze(2).permute(1, 0)     # [B, E]
+        xl = torch.einsum("be,bed->bd", gates, e) + xl
+    return mlp_forward(p, xl, "_dnn.", p_dropout, training, bn_state).squeeze(-1)
+
+
 def make_optimizers(p: Dict[str, torch.Tensor], cfg: Dict):
     """src/models/deepfm.py:155-219."""
     sparse = cfg.get("sparse", False)
@@ -119,9 +188,9 @@ def make_optimizers(p: Dict[str, torch.Tensor], cfg: Dict):
     return [torch.optim.Adam(list(p.values()), lr=cfg["learning_rate"], weight_decay=cfg["weight_decay"])]
 
 
-def train_step(p, opts, x, y, offsets, emb_cfg, p_dropout, sync: bool = True):
+def train_step(p, opts, x, y, offsets, emb_cfg, p_dropout, sync: bool = True, forward=None):
     """One iteration of src/trainer/deepfm.py:44-62 (sync=False skips the loss.item() read-back)."""
-    logits = deepfm_forward(p, x, offsets, emb_cfg, p_dropout, training=True)
+    logits = (forward or deepfm_forward)(p, x, offsets, emb_cfg, p_dropout, training=True)
     loss = F.binary_cross_entropy_with_logits(logits, y.float())
     for o in opts:
         o.zero_grad()
