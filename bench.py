@@ -220,7 +220,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -378,7 +378,7 @@ def main_ours(args, wl):
 
         model = ShardedDeepFM(dims, 16, [400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"]).to(dev)
     else:
-        model = R.get_ctr_model(dims, cfg).to(dev)
+        model = R.get_ctr_model(dims, dict(cfg)).to(dev)     # a copy: get_ctr_model pops "name" like the reference
     model.train()
     opts = R.get_optimizers(model, dict(wl["opt"]))
     crit = torch.nn.BCEWithLogitsLoss()
@@ -444,7 +444,6 @@ def main_ours(args, wl):
     l0 = _lib.load().rsb_launch_count()
     ms_total = timed(lambda i: step(*dev_pool[i % len(dev_pool)]), args.steps)
     launches = _lib.load().rsb_launch_count() - l0
-    clocks = sampler.stop() if sampler else None
     # per-kernel CUDA-event timing in a SEPARATE pass of the same steps (an event pair around every C call keeps
     # consecutive kernels from overlapping their launch latency, so it must not sit inside the `value` region)
     timer = RF.KernelTimer()
@@ -518,6 +517,9 @@ def main_ours(args, wl):
         t = torch.tensor([ms_e2e_df], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e_df = float(t.item())
+    # clocks / throttle reasons were sampled (nvidia-smi, every 20 ms) from the start of the `value` region to here:
+    # the timed region itself is ~0.1 s, the e2e legs keep the same step running
+    clocks = sampler.stop() if sampler else None
     h2d = pool[0][0].numel() * pool[0][0].element_size() + pool[0][1].numel() * 4
 
     # ---- reference-yaml batch (2048): launch-bound -> whole step captured in a CUDA graph -------------
