@@ -54,7 +54,8 @@ class DeepFM(nn.Module):
         """x: [B, F] per-field ids (int32 or int64, WITHOUT offsets) -> logits [B]."""
         emb, y_fm = self.embedding.lookup(x, self.offsets, self.fc.weight, self._bias)
         b = emb.shape[0]
-        scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]))
+        scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]),
+                                                       overlap_first_dw=True)
         return scores.squeeze(-1)
 
     def get_ranks(self, x) -> torch.Tensor:

@@ -104,6 +104,67 @@ def sort_rows(rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 
     return skeys, perm
 
 
+# ---- backward stage 2 started early --------------------------------------------------
+# The sort needs only the looked-up row ids, which exist as soon as the forward gather has run, while its
+# consumer (the segmented reduction) runs at the very end of the backward pass.  It is therefore queued on a
+# side stream right after the forward kernel and overlaps the dense tail (GEMMs) of the forward/backward pass;
+# the backward waits on its event.  Set EARLY_SORT = False to sort inside the backward instead.
+EARLY_SORT = True
+_SIDE_STREAMS = {}
+
+
+def side_stream(device) -> torch.cuda.Stream:
+    key = torch.device(device).index
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
+class SortedRows:
+    """(sorted keys, permutation) being produced on the side stream; `get()` makes the current stream wait."""
+
+    def __init__(self, rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 0):
+        lib = L.load()
+        dev = rows.device
+        n = rows.numel()
+        self.key = (int(n_rows), int(key_div), int(key_mod))
+        # buffers come from the CURRENT stream's pool (they are consumed there); the side stream only borrows them
+        self.skeys = torch.empty(n, dtype=torch.int32, device=dev)
+        self.perm = torch.empty(n, dtype=torch.int32, device=dev)
+        self._ws = _ws(lib.rsb_sort_workspace_bytes(n), dev)
+        self._rows = rows
+        main = torch.cuda.current_stream(dev)
+        side = side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _call("sort_rows", lib.rsb_sort_rows, L.ptr(rows), n, int(n_rows), int(key_div), int(key_mod),
+                  L.ptr(self.skeys), L.ptr(self.perm), L.ptr(self._ws), self._ws.numel(), L.stream_ptr(dev))
+            self.event = torch.cuda.Event()
+            self.event.record(side)
+        self._joined = False
+        # Lifetime instead of record_stream (which makes the caching allocator poll events and fall back to
+        # cudaMalloc when the host runs ahead): this object keeps rows / workspace / outputs alive until the
+        # consuming stream has been made to wait for the sort - in get(), or at destruction if never consumed.
+
+    def get(self):
+        torch.cuda.current_stream(self.skeys.device).wait_event(self.event)
+        self._joined = True
+        return self.skeys, self.perm
+
+    def __del__(self):
+        try:
+            if not self._joined:
+                torch.cuda.current_stream(self.skeys.device).wait_event(self.event)
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def early_sort(rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 0) -> Optional[SortedRows]:
+    if not EARLY_SORT or rows.numel() == 0:
+        return None
+    return SortedRows(rows, n_rows, key_div, key_mod)
+
+
 def segment_reduce_apply(apply: int, skeys, perm, row_grads, dst, exp_avg=None, exp_avg_sq=None, lr=0.0,
                          beta1=0.9, beta2=0.999, eps=1e-8, step=1):
     lib = L.load()
@@ -206,6 +267,11 @@ class _FusedLookup(torch.autograd.Function):
         ctx.spec = spec
         ctx.fm = fm
         ctx.shape = (b, f)
+        # the backward's row sort depends only on `rows`: start it now on the side stream (see EARLY_SORT)
+        ctx.presorted = None
+        if torch.is_grad_enabled() and table.requires_grad and not (spec.sparse_grad and getattr(
+                spec.module, "_rsb_fused_opt", None) is None) and spec.kind != L.KIND_QR_CAT:
+            ctx.presorted = early_sort(rows, table.shape[0], key_div=spec.divider if spec.is_qr else 0)
         ctx.save_for_backward(rows, emb, s, mask_d, table, table1, aux, fc)
         ctx.mark_non_differentiable(rows)
         if y is None:
@@ -280,9 +346,11 @@ class _FusedLookup(torch.autograd.Function):
         g_table = g_table1 = g_aux = None
         n_rows = table.shape[0]
         mod = spec.module
+        pre = ctx.presorted.get() if ctx.presorted is not None else None
+        ctx.presorted = None
         if spec.is_qr:
             if need[4]:
-                g_table = dense_row_grad(rows, rg_main, n_rows, key_div=spec.divider)
+                g_table = dense_row_grad(rows, rg_main, n_rows, key_div=spec.divider, sorted_pair=pre)
             if need[5] and g_table1_fused is not None:
                 g_table1 = g_table1_fused
             elif need[5]:
@@ -294,12 +362,12 @@ class _FusedLookup(torch.autograd.Function):
             if need[4]:
                 deferred = getattr(mod, "_rsb_fused_opt", None) if mod is not None else None
                 if deferred is not None:
-                    deferred.stash(table, rows, rg_main)          # consumed by FusedSparse*.step()
+                    deferred.stash(table, rows, rg_main, pre)     # consumed by FusedSparse*.step()
                 elif spec.sparse_grad:
                     # same layout nn.Embedding(sparse=True) produces: uncoalesced COO, nnz = B*F
                     g_table = torch.sparse_coo_tensor(rows.view(1, n), rg_main, (n_rows, e))
                 else:
-                    pair = sort_rows(rows, n_rows)
+                    pair = pre if pre is not None else sort_rows(rows, n_rows)
                     g_table = dense_row_grad(rows, rg_main, n_rows, sorted_pair=pair)
                     if kind == L.KIND_PEP and need[6] and spec.aux_mode == L.PEP_FEATURE_DIM:
                         g_aux = dense_row_grad(rows, rg_aux, n_rows, sorted_pair=pair)

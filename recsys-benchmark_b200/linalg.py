@@ -270,12 +270,13 @@ class _LinearReluDropout(torch.autograd.Function):
     ReLU+dropout pass, and a backward whose single elementwise pass also produces the bias gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, p):
+    def forward(ctx, x, weight, bias, p, side_dw=False):
         z = gemm(x, weight, trans_b=True, bias=bias)
         y, mask = _relu_dropout_fwd(z, p)
         ctx.save_for_backward(x, weight, mask)
         ctx.p = p
         ctx.has_bias = bias is not None
+        ctx.side_dw = side_dw
         return y
 
     @staticmethod
@@ -283,9 +284,31 @@ class _LinearReluDropout(torch.autograd.Function):
         x, weight, mask = ctx.saved_tensors
         gz, gb = _relu_dropout_bwd(gy, mask, ctx.p, ctx.has_bias and ctx.needs_input_grad[2])
         gx = gemm(gz, weight) if ctx.needs_input_grad[0] else None
-        gw = gemm(gz, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1])) \
-            if ctx.needs_input_grad[1] else None
-        return gx, gw, gb, None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            sk = _split_for(x.shape[0], weight.shape[0], weight.shape[1])
+            if ctx.side_dw and gx is not None and not torch.cuda.is_current_stream_capturing():
+                gw = _gemm_on_side_stream(gz, x, sk)
+            else:
+                gw = gemm(gz, x, trans_a=True, split_k=sk)
+        return gx, gw, gb, None, None
+
+
+def _gemm_on_side_stream(gz: torch.Tensor, x: torch.Tensor, split_k: int) -> torch.Tensor:
+    """Weight gradient gz^T @ x of the FIRST dense layer on the side stream: everything queued after it in the
+    backward pass is the embedding side (row gradients, segmented reduction - HBM/latency-bound kernels that
+    leave the tensor pipe idle), so the two overlap.  The main stream re-joins at the end of the backward pass
+    (autograd end-of-pass callback), before any optimizer can read the result."""
+    dev = gz.device
+    main = torch.cuda.current_stream(dev)
+    side = RF.side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        gw = gemm(gz, x, trans_a=True, split_k=split_k)
+    # the callback's closure keeps the main-pool inputs alive until the main stream has re-joined (no
+    # record_stream: it makes the caching allocator poll events and cudaMalloc when the host runs ahead)
+    torch.autograd.Variable._execution_engine.queue_callback(lambda keep=(gz, x): main.wait_stream(side))
+    return gw
 
 
 class _HeadBlock(torch.autograd.Function):
@@ -349,9 +372,10 @@ class _Linear(torch.autograd.Function):
     """y = x @ W^T + b with W [out, in] (nn.Linear layout); all three GEMMs on the tensor-core kernel."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, side_dw=False):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        ctx.side_dw = side_dw
         return gemm(x, weight, trans_b=True, bias=bias)
 
     @staticmethod
@@ -362,17 +386,22 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = gemm(gy, weight)                                   # [B,out] @ [out,in]
         if ctx.needs_input_grad[1]:
-            gw = gemm(gy, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1]))
+            sk = _split_for(x.shape[0], weight.shape[0], weight.shape[1])
+            if ctx.side_dw and gx is not None and not torch.cuda.is_current_stream_capturing():
+                gw = _gemm_on_side_stream(gy, x, sk)
+            else:
+                gw = gemm(gy, x, trans_a=True, split_k=sk)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(gy)
-        return gx, gw, gb
+        return gx, gw, gb, None
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           side_dw: bool = False) -> torch.Tensor:
     """Drop-in for F.linear on 2-D inputs: tensor-core kernel when the shape allows, cuBLAS otherwise."""
     if x.dim() == 2 and _use_kernel(x.shape[0], weight.shape[0], weight.shape[1], x, weight, bias) and \
             x.stride(1) == 1 and x.stride(0) % 4 == 0:
-        return _Linear.apply(x, weight, bias)
+        return _Linear.apply(x, weight, bias, side_dw)
     return torch.nn.functional.linear(x, weight, bias)
 
 
@@ -410,10 +439,11 @@ def _is_head(mod, width: int) -> bool:
             and mod.weight.data_ptr() % 16 == 0)
 
 
-def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: bool = False) -> torch.Tensor:
     """nn.Sequential forward of the dense tails with the same parameters / state dict, but
     Linear -> tensor-core GEMM, and (Linear ->) ReLU -> Dropout fused into single passes.
-    BatchNorm1d (and anything else) runs unchanged."""
+    BatchNorm1d (and anything else) runs unchanged.  overlap_first_dw: the input comes straight from the
+    embedding gather, so the first layer's weight-gradient GEMM may run beside the embedding backward."""
     mods = list(seq)
     i = 0
     training = seq.training
@@ -431,10 +461,10 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor) -> torch.Tensor:
                 return _HeadBlock.apply(x, m.weight, m.bias, float(nx2.p), nx3.weight, nx3.bias)
             if ok and isinstance(nxt, torch.nn.ReLU) and isinstance(nx2, torch.nn.Dropout) and training and \
                     0.0 < nx2.p < 1.0 and m.weight.shape[0] <= 2048:
-                x = _LinearReluDropout.apply(x, m.weight, m.bias, float(nx2.p))
+                x = _LinearReluDropout.apply(x, m.weight, m.bias, float(nx2.p), overlap_first_dw and i == 0)
                 i += 3
                 continue
-            x = linear(x, m.weight, m.bias)
+            x = linear(x, m.weight, m.bias, side_dw=overlap_first_dw and i == 0)
             i += 1
             continue
         if isinstance(m, torch.nn.ReLU) and isinstance(nxt, torch.nn.Dropout) and training and 0.0 < nxt.p < 1.0 \

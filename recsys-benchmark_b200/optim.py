@@ -26,11 +26,11 @@ class _FusedRowOptimizer(torch.optim.Optimizer):
             raise ValueError("fused sparse updates support vanilla / masked single-table embeddings")
         super().__init__([table], defaults)
         self._module = embedding_module
-        self._pending: List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = []
+        self._pending: List[Tuple] = []
         embedding_module._rsb_fused_opt = self
 
-    def stash(self, table, rows, row_grads):
-        self._pending.append((table, rows, row_grads))
+    def stash(self, table, rows, row_grads, sorted_pair=None):
+        self._pending.append((table, rows, row_grads, sorted_pair))
 
     def zero_grad(self, set_to_none: bool = True):
         self._pending.clear()
@@ -50,7 +50,7 @@ class FusedSparseAdam(_FusedRowOptimizer):
         group = self.param_groups[0]
         p = group["params"][0]
         pending, self._pending = self._pending, []
-        for table, rows, rg in pending:
+        for table, rows, rg, pair in pending:
             state = self.state[p]
             if len(state) == 0:
                 state["step"] = 0
@@ -58,7 +58,7 @@ class FusedSparseAdam(_FusedRowOptimizer):
                 state["exp_avg_sq"] = torch.zeros_like(p)
             state["step"] += 1
             b1, b2 = group["betas"]
-            skeys, perm = RF.sort_rows(rows, p.shape[0])
+            skeys, perm = pair if pair is not None else RF.sort_rows(rows, p.shape[0])
             RF.segment_reduce_apply(L.APPLY_SPARSE_ADAM, skeys, perm, rg, p.data, state["exp_avg"],
                                     state["exp_avg_sq"], lr=group["lr"], beta1=b1, beta2=b2, eps=group["eps"],
                                     step=state["step"])
@@ -74,7 +74,7 @@ class FusedSparseSGD(_FusedRowOptimizer):
         group = self.param_groups[0]
         p = group["params"][0]
         pending, self._pending = self._pending, []
-        for table, rows, rg in pending:
-            skeys, perm = RF.sort_rows(rows, p.shape[0])
+        for table, rows, rg, pair in pending:
+            skeys, perm = pair if pair is not None else RF.sort_rows(rows, p.shape[0])
             RF.segment_reduce_apply(L.APPLY_SPARSE_SGD, skeys, perm, rg, p.data, lr=group["lr"])
         return None
