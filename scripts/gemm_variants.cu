@@ -74,6 +74,15 @@ constexpr int TM = 256, TN = 224, TK = 32, CM = 2, BANDS = 3; constexpr bool TWO
 #elif VARIANT == 33
 constexpr int TM = 256, TN = 256, TK = 32, CM = 2, BANDS = 3; constexpr bool TWO = true;
 #define ACCP 2
+#elif VARIANT == 40
+constexpr int TM = 128, TN = 80, TK = 32, CM = 1, BANDS = 3; constexpr bool TWO = false;
+#define ACCP 2
+#elif VARIANT == 41
+constexpr int TM = 256, TN = 96, TK = 32, CM = 2, BANDS = 3; constexpr bool TWO = true;
+#define ACCP 2
+#elif VARIANT == 42
+constexpr int TM = 128, TN = 208, TK = 32, CM = 1, BANDS = 3; constexpr bool TWO = false;
+#define ACCP 2
 #elif VARIANT == 8
 constexpr int TM = 128, TN = 80, TK = 16, CM = 1, BANDS = 5; constexpr bool TWO = false;
 #elif VARIANT == 9
