@@ -177,17 +177,14 @@ __global__ void __launch_bounds__(kSortThreads, 3) sort_scatter_kernel(SortSrc s
       const unsigned m = __ballot_sync(kFull, one);
       peers &= one ? m : ~m;
     }
+    // the class leader reserves the class's ranks with ONE shared-memory atomic whose return value is the
+    // count so far; a warp's shared-memory operations complete in issue order, so the rounds need no barrier
+    // between them and their atomics / shuffles pipeline (the kernel was bound by that round trip)
+    const int leader = valid ? (__ffs(peers) - 1) : lane;
     unsigned pre = 0;
-    if (valid) {
-      const int leader = __ffs(peers) - 1;
-      if (lane == leader) {
-        pre = wcnt[d];
-        wcnt[d] = pre + __popc(peers);
-      }
-      pre = __shfl_sync(peers, pre, leader);
-    }
+    if (valid && lane == leader) pre = atomicAdd(&wcnt[d], (unsigned)__popc(peers));
+    pre = __shfl_sync(kFull, pre, leader);
     dr[r] = (d << 16) | (pre + __popc(peers & ((1u << lane) - 1u)));
-    __syncwarp();
   }
   __syncthreads();
   // exclusive scan over warps for each digit, plus this CTA's global base
