@@ -573,3 +573,38 @@ def test_graphed_train_step_matches_eager_steps(R):
     for (k, a), (_, b_) in zip(m1.state_dict().items(), m2.state_dict().items()):
         if a.dtype == torch.float32:
             assert_close(b_.cpu().numpy(), a.cpu().numpy(), what=f"weights {k}", atol_scale=1e-4)
+
+
+@pytest.mark.parametrize("emb_cfg", [{"name": "qr", "divider": 5}, {"name": "vanilla"}])
+def test_side_stream_overlap_is_bit_identical_to_inline_execution(R, emb_cfg, monkeypatch):
+    """The row sort started on a side stream after the forward gather, and the first layer's weight gradient run
+    beside the embedding backward, must change nothing: same gradients bit for bit as the in-line order."""
+    import recsys_benchmark_b200.functional as RF
+    import recsys_benchmark_b200.linalg as LA
+
+    def grads(early, side_dw):
+        monkeypatch.setattr(RF, "EARLY_SORT", early)
+        if not side_dw:
+            monkeypatch.setattr(LA, "_gemm_on_side_stream",
+                                lambda gz, x, sk: LA.gemm(gz, x, trans_a=True, split_k=sk))
+        torch.manual_seed(9)
+        m = R.get_ctr_model(CRITEO_DIMS, dict(num_factor=16, hidden_sizes=[400, 400], p_dropout=0.0,
+                                              use_batchnorm=False, embedding_config=dict(emb_cfg))).to(DEV).train()
+        g = torch.Generator().manual_seed(3)
+        x = torch.stack([torch.randint(0, d, (4096,), generator=g) for d in CRITEO_DIMS], 1).int().to(DEV)
+        y = torch.randint(0, 2, (4096,), generator=g).float().to(DEV)
+        out = []
+        for _ in range(2):                      # twice: the second pass reuses allocator blocks of the first
+            for p in m.parameters():
+                p.grad = None
+            torch.nn.functional.binary_cross_entropy_with_logits(m(x), y).backward()
+            torch.cuda.synchronize()
+            out.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+        return out
+
+    a = grads(True, True)
+    b = grads(False, False)
+    for ga, gb in zip(a, b):
+        assert ga.keys() == gb.keys()
+        for k in ga:
+            assert torch.equal(ga[k], gb[k]), k
