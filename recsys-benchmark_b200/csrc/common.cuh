@@ -13,6 +13,29 @@
 
 namespace rsb {
 
+// Exact unsigned 32-bit division by a divisor fixed for the whole launch (Granlund & Montgomery, "Division by
+// invariant integers using multiplication", fig. 4.1, N = 32): q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n).
+// Five instructions instead of the ~20 of the emulated 32-bit divide; bit-exact for every n < 2^32, d >= 1.
+struct FastDiv {
+  unsigned d, m, s1, s2;
+};
+inline FastDiv make_fastdiv(unsigned long long d64) {
+  FastDiv f;
+  unsigned d = (unsigned)d64;
+  if (d == 0) d = 1;
+  int L = 0;
+  while ((1ull << L) < d) ++L;                       // ceil(log2 d)
+  f.d = d;
+  f.m = (unsigned)(((1ull << 32) * ((1ull << L) - d)) / d + 1);
+  f.s1 = L < 1 ? L : 1;
+  f.s2 = L > 1 ? L - 1 : 0;
+  return f;
+}
+__device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv& f) {
+  const unsigned t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

@@ -31,6 +31,7 @@ struct LookupArgs {
   long long divider;
   long long modulus;  // i1 = row % modulus (== divider for QR; the CERP bucket size otherwise)
   int small32;
+  FastDiv fd_div, fd_mod, fd_g;   // invariant-divisor division for the small32 paths (divider, modulus, G)
   const void* aux;
   int aux_mode;
   const long long* mask_d;
@@ -63,7 +64,7 @@ constexpr int kTinyRows = 8;
 __device__ __forceinline__ void shard_split(const LookupArgs& a, long long row, int& owner, long long& lrow) {
   if (a.small32) {
     unsigned r = (unsigned)row, g = (unsigned)a.G;
-    unsigned q = r / g;
+    unsigned q = fastdiv(r, a.fd_g);
     lrow = q;
     owner = (int)(r - q * g);
   } else {
@@ -75,9 +76,9 @@ __device__ __forceinline__ void shard_split(const LookupArgs& a, long long row, 
 __device__ __forceinline__ void qr_split(const LookupArgs& a, long long row, long long& i1, long long& i2) {
   if (a.small32) {
     unsigned r = (unsigned)row, d = (unsigned)a.divider;
-    unsigned q = r / d;
+    unsigned q = fastdiv(r, a.fd_div);
     i2 = q;
-    i1 = (a.modulus == a.divider) ? r - q * d : r % (unsigned)a.modulus;
+    i1 = (a.modulus == a.divider) ? r - q * d : r - fastdiv(r, a.fd_mod) * (unsigned)a.modulus;
   } else {
     i2 = row / a.divider;
     i1 = (a.modulus == a.divider) ? row - i2 * a.divider : row % a.modulus;
@@ -655,6 +656,9 @@ static int fill_common(LookupArgs& a, int kind, long long B, int F, int D, const
   a.modulus = divider;
   if (kind >= RSB_KIND_QR_MULT && kind <= RSB_KIND_QR_CAT && aux_mode > 0) a.modulus = aux_mode;
   a.small32 = (n_global < (1ll << 32) && divider < (1ll << 32)) ? 1 : 0;
+  a.fd_div = make_fastdiv((unsigned long long)(divider > 0 ? divider : 1));
+  a.fd_mod = make_fastdiv((unsigned long long)(a.modulus > 0 ? a.modulus : 1));
+  a.fd_g = make_fastdiv(1);
   a.aux = aux;
   a.aux_mode = aux_mode;
   bool al = aligned16(table) && (table1 == nullptr || aligned16(table1)) && extra_aligned;
@@ -815,6 +819,7 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   a.table_shards = table_shards;
   a.fc_shards = fc_shards;
   a.G = G;
+  a.fd_g = make_fastdiv((unsigned long long)G);
   a.small32 = (n_global < (1ll << 32)) ? 1 : 0;
   a.idx = idx;
   a.idx_i32 = idx_is_i32;

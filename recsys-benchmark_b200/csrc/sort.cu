@@ -22,6 +22,7 @@ constexpr int kRadixMax = 1 << kRadixBitsMax;
 struct SortSrc {
   const long long* keys64;  // pass 0 source (or nullptr)
   long long key_div, key_mod;
+  FastDiv fd_div, fd_mod;   // for ids < 2^32 (every table the gather can address today)
   const unsigned* keys32;  // later passes
   const unsigned* vals32;
 };
@@ -29,6 +30,12 @@ struct SortSrc {
 __device__ __forceinline__ unsigned sort_key_at(const SortSrc& s, long long i) {
   if (s.keys64) {
     long long k = __ldg(s.keys64 + i);
+    if (((unsigned long long)k >> 32) == 0 && ((unsigned long long)(s.key_div | s.key_mod) >> 32) == 0) {
+      unsigned r = (unsigned)k;          // exact 32-bit path: a multiply-high instead of an emulated 64-bit divide
+      if (s.key_div > 1) r = fastdiv(r, s.fd_div);
+      if (s.key_mod > 0) r = r - fastdiv(r, s.fd_mod) * (unsigned)s.key_mod;
+      return r;
+    }
     if (s.key_div > 1) k = k / s.key_div;
     if (s.key_mod > 0) k = k % s.key_mod;
     return (unsigned)k;
@@ -281,6 +288,8 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
   src.keys64 = reinterpret_cast<const long long*>(keys);
   src.key_div = key_div;
   src.key_mod = key_mod;
+  src.fd_div = make_fastdiv((unsigned long long)(key_div > 0 ? key_div : 1));
+  src.fd_mod = make_fastdiv((unsigned long long)(key_mod > 0 ? key_mod : 1));
   src.keys32 = nullptr;
   src.vals32 = nullptr;
   for (int p = 0; p < passes; ++p) {

@@ -74,6 +74,28 @@ def test_sort_applies_qr_index_math_bit_exact(RF, div, mod):
     np.testing.assert_array_equal(skeys.cpu().numpy().view(np.uint32).astype(np.int64), keys[order])
 
 
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 7, 20, 64, 65, 1023, 1024, 1025, 65537, 1000003, 2 ** 31 - 1, 2 ** 31,
+                               2 ** 32 - 1])
+def test_invariant_divisor_division_is_exact(RF, d):
+    """The multiply-high division the kernels use for launch-invariant divisors (QR `//`, `%`, shard split) against
+    integer arithmetic, on ids that stress the rounding: multiples of d and their neighbours, 2^k boundaries,
+    the 32-bit limit, plus one id past 2^32 (exercises the 64-bit fallback)."""
+    rng = np.random.default_rng(d % 1000)
+    mult = (rng.integers(0, max(1, (2 ** 32 - 1) // d), 4000) * d).astype(np.int64)
+    ids = np.concatenate([mult, mult + 1, np.maximum(mult - 1, 0), rng.integers(0, 2 ** 32, 4000),
+                          2 ** np.arange(0, 32, dtype=np.int64), 2 ** np.arange(1, 33, dtype=np.int64) - 1,
+                          np.array([0, 2 ** 32 - 1, 2 ** 32 + 12345], dtype=np.int64)])
+    for div, mod in ((d, 0), (0, d)):
+        keys = ids // d if div else ids % d
+        keep = keys < 2 ** 32 - 1                      # the sort's key space (0xffffffff is its sentinel)
+        sub_ids, sub_keys = ids[keep], keys[keep]
+        skeys, perm = RF.sort_rows(torch.from_numpy(sub_ids).to(DEV), int(sub_keys.max()) + 1, key_div=div,
+                                   key_mod=mod)
+        order = np.argsort(sub_keys, kind="stable")
+        np.testing.assert_array_equal(skeys.cpu().numpy().view(np.uint32).astype(np.int64), sub_keys[order])
+        np.testing.assert_array_equal(perm.cpu().numpy().view(np.uint32).astype(np.int64), order)
+
+
 # ------------------------------------------------- segmented reduce/apply ---
 @pytest.mark.parametrize("E", [16, 8, 4, 1, 7, 12, 64, 128, 32])
 @pytest.mark.parametrize("dist", ["uniform", "dup", "zipf", "sorted_runs"])
