@@ -132,7 +132,7 @@ constexpr int kColsPerThread = 2;  // float4 groups per thread per pass
 //    a Linear with ONE output: its dX = g_logit[r] * w[c] is never materialised).
 // 3: column sums of rowv[r] * g[r,c] (weight gradient of a one-output Linear: sum_r g_logit[r] * y[r,:]).
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) colsum_slab_kernel(const float* __restrict__ g,
+__global__ void __launch_bounds__(256, 4) colsum_slab_kernel(const float* __restrict__ g,
                                                           const unsigned char* __restrict__ mask, float scale,
                                                           long long M, int N, long long ld, float* __restrict__ gx,
                                                           float* __restrict__ partials, int col0,
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256, 3) colsum_slab_kernel(const float* __rest
     const int c4 = col0 / 4 + tx + j * ctx;
     if (MODE == 2 && c4 < n4) cv[j] = __ldg(reinterpret_cast<const float4*>(colv) + c4);
   }
-  constexpr int RU = 4;  // rows in flight per thread
+  constexpr int RU = 2;  // rows in flight per thread
   for (long long rb = r0 + ty; rb < r1; rb += (long long)cty * RU) {
     float4 v[RU][kColsPerThread];
     uchar4 m[RU][kColsPerThread];
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
 }
 
 static int slab_blocks(long long M) {
-  long long b = 3ll * sm_count();      // = the resident CTAs (launch bound 3 per SM): one full wave; >= 16 rows per CTA
+  long long b = 4ll * sm_count();      // = the resident CTAs (launch bound 3 per SM): one full wave; >= 16 rows per CTA
   if (b > M / 16) b = M / 16;
   if (b < 1) b = 1;
   return (int)b;
