@@ -132,7 +132,7 @@ constexpr int kColsPerThread = 2;  // float4 groups per thread per pass
 //    a Linear with ONE output: its dX = g_logit[r] * w[c] is never materialised).
 // 3: column sums of rowv[r] * g[r,c] (weight gradient of a one-output Linear: sum_r g_logit[r] * y[r,:]).
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) colsum_slab_kernel(const float* __restrict__ g,
+__global__ void __launch_bounds__(256, MODE == 1 ? 6 : 4) colsum_slab_kernel(const float* __restrict__ g,
                                                           const unsigned char* __restrict__ mask, float scale,
                                                           long long M, int N, long long ld, float* __restrict__ gx,
                                                           float* __restrict__ partials, int col0,
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(256, 4) colsum_slab_kernel(const float* __rest
     const int c4 = col0 / 4 + tx + j * ctx;
     if (MODE == 2 && c4 < n4) cv[j] = __ldg(reinterpret_cast<const float4*>(colv) + c4);
   }
-  constexpr int RU = 2;  // rows in flight per thread
+  // rows in flight per thread / resident CTAs per SM, tuned per mode on the MLP shapes (B = 65536, N = 400)
+  constexpr int RU = (MODE == 1) ? 1 : 2;
   for (long long rb = r0 + ty; rb < r1; rb += (long long)cty * RU) {
     float4 v[RU][kColsPerThread];
     uchar4 m[RU][kColsPerThread];
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
   }
 }
 
-static int slab_blocks(long long M) {
-  long long b = 4ll * sm_count();      // = the resident CTAs (launch bound 3 per SM): one full wave; >= 16 rows per CTA
+static int slab_blocks(long long M, int per_sm = 6) {
+  long long b = (long long)per_sm * sm_count();      // = the resident CTAs (launch bound 3 per SM): one full wave; >= 16 rows per CTA
   if (b > M / 16) b = M / 16;
   if (b < 1) b = 1;
   return (int)b;
@@ -297,7 +298,8 @@ static int colsum_impl(const float* g, const uint8_t* mask, float scale, int64_t
   if (N % 4 || ld % 4 || (g && !aligned16(g)) || (gx && !aligned16(gx)) || (mask && (reinterpret_cast<uintptr_t>(mask) & 3u)))
     return RSB_ERR_UNSUPPORTED;
   float* partials = nullptr;
-  const int nblk = slab_blocks(M);
+  const int mode_ = mask ? (colv ? 2 : 1) : (rowv ? 3 : 0);
+  const int nblk = slab_blocks(M, mode_ == 1 ? 6 : 4);
   if (colsum) {
     if (!workspace || workspace_bytes < rsb_colsum_workspace_bytes(M, N)) return RSB_ERR_WORKSPACE;
     partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
