@@ -308,14 +308,17 @@ __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restric
     const unsigned peers = __match_any_sync(kFull, row);
     const int leader = __ffs(peers) - 1;
     float sum = gy;
-    if (__any_sync(kFull, __popc(peers) > 1)) {
-      // every lane sums its peer set in lane order: 32 INDEPENDENT broadcasts (they pipeline), instead of a
-      // dependent shuffle tree per distinct row
+    // every lane sums its peer set in lane order; the trip count is the size of the LARGEST class in the warp
+    // (a 4-value field: ~12 of 32 samples, a 100-value field: ~3, a big field: 1 = no loop at all)
+    const int maxc = __reduce_max_sync(kFull, __popc(peers));
+    if (maxc > 1) {
       sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = __shfl_sync(kFull, gy, j);
-        sum += ((peers >> j) & 1u) ? v : 0.f;
+      unsigned m = peers;
+      for (int k = 0; k < maxc; ++k) {
+        const int src = m ? (__ffs(m) - 1) : lane;
+        const float v = __shfl_sync(kFull, gy, src);
+        sum += m ? v : 0.f;
+        m &= m - 1;
       }
     }
     if (valid && lane == leader) {
