@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(1024) partials_reduce_kernel(const float* __re
 
 // TR = number of register accumulators of the TINY variant (emb1 rows actually used, rounded up to 5 or 8)
 template <int K, int V, int LPR, bool TINY = false, int KT = 2, int TR = kTinyRows>
-__global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 3) : 1) lookup_bwd_rows_kernel(LookupArgs a) {
+__global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_rows_kernel(LookupArgs a) {
   constexpr int GPW = kWarp / LPR;
   // the register-accumulating QR variant keeps registers for the emb1 accumulators: shallower batching there
   constexpr int KI = TINY ? KT : kIter;
@@ -585,7 +585,7 @@ static int tune(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 static long long tiny_blocks(long long B) {
-  static const int per_sm = tune("RSB_TINY_CTAS_PER_SM", 3);
+  static const int per_sm = tune("RSB_TINY_CTAS_PER_SM", 4);
   long long blocks = bwd_blocks(B);
   const long long cap = (long long)sm_count() * per_sm;
   return blocks > cap ? cap : blocks;
