@@ -307,7 +307,10 @@ def _gemm_on_side_stream(gz: torch.Tensor, x: torch.Tensor, split_k: int) -> tor
         gw = gemm(gz, x, trans_a=True, split_k=split_k)
     # the callback's closure keeps the main-pool inputs alive until the main stream has re-joined (no
     # record_stream: it makes the caching allocator poll events and cudaMalloc when the host runs ahead)
-    torch.autograd.Variable._execution_engine.queue_callback(lambda keep=(gz, x): main.wait_stream(side))
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(lambda keep=(gz, x): main.wait_stream(side))
+    except Exception:  # noqa: BLE001 - not inside an autograd pass (or the hook is gone): join right away
+        main.wait_stream(side)
     return gw
 
 
