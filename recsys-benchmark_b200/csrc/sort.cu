@@ -9,6 +9,8 @@
 // The first pass reads the int64 ids directly and applies the optional QR index
 // transform (key = id / key_div or id % key_mod, qr_embedding.py:96-97, bit exact on
 // non-negative ids), so no separate key-extraction pass is needed.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rsb {
@@ -274,7 +276,12 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
 
   int bits = bit_length((unsigned long long)(n_rows - 1));
   if (bits < 1) bits = 1;
-  const int passes = (bits + kRadixBitsMax - 1) / kRadixBitsMax;
+  static const int max_bits = [] {   // tuning knob: digit width cap (<= kRadixBitsMax)
+    const char* v = getenv("RSB_SORT_MAX_BITS");
+    int m = v ? atoi(v) : kRadixBitsMax;
+    return (m < 4 || m > kRadixBitsMax) ? kRadixBitsMax : m;
+  }();
+  const int passes = (bits + max_bits - 1) / max_bits;
   const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 11)
   const size_t scatter_smem_max = (size_t)(kRadixMax + (kSortThreads / 32) * kRadixMax) * sizeof(unsigned);
   const size_t scatter_smem = ((size_t)(1 << rb) * (1 + kSortThreads / 32)) * sizeof(unsigned);
