@@ -806,7 +806,8 @@ extern "C" RSB_API int rsb_qr_bwd_fused(int32_t kind, const int64_t* rows, int64
 
 extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,
                                               int32_t F, int32_t D, const float* const* table_shards,
-                                              const float* const* fc_shards, int32_t G, int64_t n_global,
+                                              const float* const* fc_shards, const float* fc_replicated,
+                                              int32_t G, int64_t n_global,
                                               const float* bias, float* out_emb, float* out_yfm, float* out_sum,
                                               int64_t* out_rows, int32_t* err_flag, void* stream) {
   LookupArgs a = {};
@@ -820,7 +821,8 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   if (rc) return rc;
   a.table = nullptr;
   a.table_shards = table_shards;
-  a.fc_shards = fc_shards;
+  a.fc_shards = fc_replicated ? nullptr : fc_shards;
+  a.fc = fc_replicated;
   a.G = G;
   a.fd_g = make_fastdiv((unsigned long long)G);
   a.small32 = (n_global < (1ll << 32)) ? 1 : 0;

@@ -111,10 +111,10 @@ def _open(handle: bytes, device) -> int:
 
 
 class ShardGroup:
-    """The per-rank buffers (table / fc shards and their gradient accumulators) and the
-    device-resident pointer tables to every rank's copy."""
+    """The per-rank buffers (table shard and its gradient accumulator) and the device-resident pointer
+    tables to every rank's copy."""
 
-    NAMES = ("table", "fc", "table_grad", "fc_grad")
+    NAMES = ("table", "table_grad")
 
     def __init__(self, num_rows: int, dim: int, device: torch.device, group=None):
         self.group = group
@@ -123,8 +123,8 @@ class ShardGroup:
         self.num_rows, self.dim, self.device = num_rows, dim, device
         self.n_local = shard_rows(num_rows, self.world)
         self.buf: Dict[str, SharedBuffer] = {
-            "table": SharedBuffer((self.n_local, dim), device), "fc": SharedBuffer((self.n_local, 1), device),
-            "table_grad": SharedBuffer((self.n_local, dim), device), "fc_grad": SharedBuffer((self.n_local, 1), device)}
+            "table": SharedBuffer((self.n_local, dim), device),
+            "table_grad": SharedBuffer((self.n_local, dim), device)}
         handles = {k: self.buf[k].handle() for k in self.NAMES}
         if self.world > 1:
             gathered: List[Optional[dict]] = [None] * self.world
@@ -144,16 +144,18 @@ class ShardGroup:
 
     def zero_grads(self):
         self.buf["table_grad"].tensor.zero_()
-        self.buf["fc_grad"].tensor.zero_()
 
 
 # ------------------------------------------------------------------ differentiable op ---
 class _ShardedLookup(torch.autograd.Function):
-    """(x, offsets, bias; shard group) -> emb [B,F,D], y_fm [B].  The shard gradients are not
-    returned to autograd: they are accumulated (pre-scaled by 1/G) in the owners' buffers."""
+    """(x, offsets, fc, bias; shard group) -> emb [B,F,D], y_fm [B].  The table-shard gradients are not
+    returned to autograd: they are accumulated (pre-scaled by 1/G) in the owners' buffers.  The first-order
+    weights `fc` [N,1] are REPLICATED (4 B per row: peer reads / NVLink atomics of that size cost as many
+    transactions as the 64-byte rows - at N=8 the sharded first-order gradient alone took 0.76 ms of a 5.0 ms
+    step); their dense gradient goes back to autograd and is averaged with the other replicated gradients."""
 
     @staticmethod
-    def forward(ctx, sg: ShardGroup, x, offsets, bias, use_fm: bool):
+    def forward(ctx, sg: ShardGroup, x, offsets, fc, bias, use_fm: bool):
         lib = L.load()
         dev = L.require_cuda(x, offsets, bias)
         x = x.contiguous()
@@ -165,10 +167,11 @@ class _ShardedLookup(torch.autograd.Function):
         rows = torch.empty(b, f, dtype=torch.int64, device=dev)
         nbytes = b * (f * x.element_size() + 2 * f * d * 4 + f * 8 + (f * 4 + 4 + d * 4 if use_fm else 0))
         RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded, L.ptr(x), int(x.dtype == torch.int32),
-                 L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(sg.ptrs["fc"]) if use_fm else None,
+                 L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), None, L.ptr(fc) if use_fm else None,
                  sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
                  None, L.stream_ptr(dev), nbytes=nbytes)
         ctx.sg, ctx.use_fm, ctx.shape = sg, use_fm, (b, f)
+        ctx.fc_shape = tuple(fc.shape) if fc is not None else None
         ctx.save_for_backward(rows, emb, s)
         ctx.mark_non_differentiable(rows)
         return emb, (y if use_fm else emb.new_empty(0)), rows
@@ -198,12 +201,14 @@ class _ShardedLookup(torch.autograd.Function):
         RF._call("segment_scatter_shards", lib.rsb_segment_scatter_shards, L.ptr(skeys), L.ptr(perm), n, L.ptr(rg), d,
                  L.ptr(sg.ptrs["table_grad"]), sg.world, scale, L.ptr(ws), ws.numel(), L.stream_ptr(dev),
                  nbytes=n * (8 + 4 * d))
-        g_bias = None
+        g_bias = g_fc = None
         if use_gy:
-            RF._call("fc_grad_sharded", lib.rsb_fc_grad_sharded, L.ptr(rows), L.ptr(g_y), b, f,
-                     L.ptr(sg.ptrs["fc_grad"]), sg.world, scale, L.stream_ptr(dev), nbytes=n * 12)
+            if ctx.needs_input_grad[3]:
+                g_fc = torch.zeros(ctx.fc_shape, dtype=torch.float32, device=dev)
+                RF._call("fc_grad", lib.rsb_fc_grad, L.ptr(rows), L.ptr(g_y), b, f, L.ptr(g_fc), L.stream_ptr(dev),
+                         nbytes=n * 12)
             g_bias = g_y.sum().reshape(1)
-        return None, None, None, g_bias, None
+        return None, None, None, g_fc, g_bias, None
 
 
 # ------------------------------------------------------------------ modules ---
@@ -250,14 +255,15 @@ class ShardedVanillaEmbedding(IEmbedding):
     def lookup(self, x, offsets=None, fc=None, bias=None):
         if offsets is not None:
             offsets = offsets.reshape(-1).long()
-        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, bias, bias is not None)
-        return emb, (y if bias is not None else None)
+        use_fm = fc is not None
+        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm)
+        return emb, (y if use_fm else None)
 
 
 class ShardedDeepFM(DeepFM):
-    """DeepFM (src/models/deepfm.py:11-105) with the embedding table AND the first-order
-    weights `fc` row-sharded; the MLP, `_bias`, BatchNorm are replicated (BatchNorm statistics
-    stay per-rank).  Build it after `dist.init_process_group` with the device current."""
+    """DeepFM (src/models/deepfm.py:11-105) with the embedding table row-sharded; the first-order weights
+    `fc` (4 B per row), the MLP, `_bias` and BatchNorm are replicated (BatchNorm statistics stay per-rank).
+    Build it after `dist.init_process_group` with the device current and the same seed on every rank."""
 
     def __init__(self, field_dims, num_factor, hidden_sizes, p_dropout=0.1, use_batchnorm=False,
                  embedding_config=None, group=None):
@@ -269,22 +275,16 @@ class ShardedDeepFM(DeepFM):
         cfg.pop("name", None)
         cfg.pop("sparse", None)
         self.embedding = ShardedVanillaEmbedding(field_dims, num_factor, group=group, **cfg)
-        sg = self.embedding.shards
-        full_fc = self.fc.weight.detach().clone()   # same init distribution as nn.EmbeddingBag (N(0,1))
-        self.fc = nn.Module()
-        self.fc.weight = nn.Parameter(sg.buf["fc"].tensor)
-        with torch.no_grad():
-            self.fc.weight.copy_(shard_of_full(full_fc.to(sg.device), sg.rank, sg.world))
 
     def shard_params(self):
-        return [self.embedding._emb_module.weight, self.fc.weight]
+        return [self.embedding._emb_module.weight]
 
     def replicated_params(self):
         ids = {id(p) for p in self.shard_params()}
         return [p for p in self.parameters() if id(p) not in ids and p.requires_grad]
 
     def forward(self, x):
-        emb, y_fm = self.embedding.lookup(x, self.offsets, None, self._bias)
+        emb, y_fm = self.embedding.lookup(x, self.offsets, self.fc.weight, self._bias)
         b = emb.shape[0]
         scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]))
         return scores.squeeze(-1)
@@ -297,14 +297,12 @@ class ShardedDeepFM(DeepFM):
         sg = self.embedding.shards
         allreduce_mean_([p.grad for p in self.replicated_params() if p.grad is not None], sg.group)
         self.embedding._emb_module.weight.grad = sg.buf["table_grad"].tensor
-        self.fc.weight.grad = sg.buf["fc_grad"].tensor
 
     def finish_step(self):
         """Call after optimizer.step(): re-zero the shard gradient accumulators and order the
         next step's peer gathers / pushes after every rank's update."""
         sg = self.embedding.shards
         self.embedding._emb_module.weight.grad = None
-        self.fc.weight.grad = None
         sg.zero_grads()
         sg.barrier()
 

@@ -34,11 +34,9 @@ def _sharded_from(R, full, dev, group=None):
 
     m = ShardedDeepFM(DIMS, 16, [32, 16], p_dropout=0.0, use_batchnorm=False, group=group).to(dev)
     sg = m.embedding.shards
-    st = {k: v for k, v in full.state_dict().items() if not k.startswith("embedding.") and k != "fc.weight"}
-    m.load_state_dict(st, strict=False)
+    st = {k: v for k, v in full.state_dict().items() if not k.startswith("embedding.")}
+    m.load_state_dict(st, strict=False)            # fc.weight is replicated: same key / shape as the reference's
     m.embedding.load_full_weight(full.embedding.get_weight().detach())
-    with torch.no_grad():
-        m.fc.weight.copy_(shard_of_full(full.fc.weight.detach(), sg.rank, sg.world))
     return m
 
 
@@ -79,7 +77,8 @@ def test_sharded_world1_matches_unsharded():
         assert_close(b[s].cpu().numpy(), a[s].cpu().numpy(), what=f"logits step {s}", atol_scale=5e-5)
     assert_close(sh.embedding.gather_full_weight().cpu().numpy(),
                  full.embedding.get_weight().detach().cpu().numpy(), what="table after 3 steps", atol_scale=5e-5)
-    assert_close(sh.fc.weight.detach().cpu().numpy()[: sum(DIMS)], full.fc.weight.detach().cpu().numpy(),
+    assert tuple(sh.fc.weight.shape) == tuple(full.fc.weight.shape)
+    assert_close(sh.fc.weight.detach().cpu().numpy(), full.fc.weight.detach().cpu().numpy(),
                  what="fc after 3 steps", atol_scale=5e-5)
 
 
