@@ -333,27 +333,21 @@ RSB_API int rsb_shared_free(void* dev_ptr);
 RSB_API int rsb_ipc_get_handle(const void* dev_ptr, uint8_t* h_handle /* [64] host */);
 RSB_API int rsb_ipc_open_handle(const uint8_t* h_handle /* [64] host */, void** dev_ptr_out /* host */);
 RSB_API int rsb_ipc_close_handle(void* dev_ptr);
-/* rsb_lookup_fwd(kind = VANILLA) over G shards: table_shards / fc_shards are DEVICE arrays of
- * G device pointers (own shard + IPC-mapped peers).  First-order weights: either row-sharded like the table
- * (fc_shards) or one replicated full-length vector (fc_replicated [n_global]; what ShardedDeepFM uses: 4-byte
- * peer reads and 4-byte NVLink atomics are as many transactions as the 64-byte row traffic, for 1/16 of the
- * bytes); both NULL = no FM head. */
+/* rsb_lookup_fwd(kind = VANILLA) over G shards: table_shards is a DEVICE array of G device pointers (own
+ * shard + IPC-mapped peers).  The first-order weights are one REPLICATED full-length vector fc_replicated
+ * [n_global] (NULL = no FM head): 4-byte peer reads / NVLink atomics cost as many transactions as the 64-byte
+ * row traffic for 1/16 of the bytes (measured: a row-sharded first-order gradient took 0.76 ms of a 5.0 ms step
+ * at N=8), so their gradient is rsb_fc_grad into a local dense buffer, allreduced with the other dense grads. */
 RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B, int32_t F,
-                                   int32_t D, const float* const* table_shards, const float* const* fc_shards,
-                                   const float* fc_replicated, int32_t G, int64_t n_global, const float* bias,
-                                   float* out_emb, float* out_yfm, float* out_sum, int64_t* out_rows,
-                                   int32_t* err_flag, void* stream);
+                                   int32_t D, const float* const* table_shards, const float* fc_replicated,
+                                   int32_t G, int64_t n_global, const float* bias, float* out_emb, float* out_yfm,
+                                   float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream);
 /* Backward: segmented reduction of this rank's sorted lookups (rsb_sort_rows on GLOBAL row
  * ids), each locally-unique row's sum * scale added into the owner's dense shard gradient
  * with one 128-bit red.global.add per 4 floats. */
 RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
                                        const float* row_grads, int32_t E, float* const* grad_shards, int32_t G,
                                        float scale, void* workspace, int64_t workspace_bytes, void* stream);
-
-/* First-order weight gradient of the sharded model: fc_grad_shards[row % G][row / G] += scale * g_yfm[b],
- * equal rows of 32 consecutive samples merged first (same kernel as the single-GPU fc gradient). */
-RSB_API int rsb_fc_grad_sharded(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F,
-                                float* const* fc_grad_shards, int32_t G, float scale, void* stream);
 
 #ifdef __cplusplus
 }

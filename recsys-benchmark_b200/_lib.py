@@ -72,9 +72,8 @@ PROTOTYPES = {
     "rsb_ipc_get_handle": (C.c_int, [_p, C.c_char_p]),
     "rsb_ipc_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "rsb_ipc_close_handle": (C.c_int, [_p]),
-    "rsb_lookup_fwd_sharded": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p,
+    "rsb_lookup_fwd_sharded": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p,
                                          _p]),
-    "rsb_fc_grad_sharded": (C.c_int, [_p, _p, _i64, _i32, _p, _i32, _f, _p]),
     "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i64, _p]),
 }
 

@@ -53,7 +53,6 @@ struct LookupArgs {
   float* fc_grad;
   // row-sharded tables (VANILLA only): shard g holds rows r with r % G == g at r / G
   const float* const* table_shards;
-  const float* const* fc_shards;
   int G;
   // QR emb1 gradient accumulated in registers (divider <= kTinyRows): per-CTA partials [grid][kTinyRows][E]
   float* tiny_partials;
@@ -230,12 +229,6 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
           if (c == 0 && vf < a.F) {
             if (a.out_rows) a.out_rows[b * a.F + fv[it]] = rowv[it];
             if (a.fc) fcv[it] = __ldg(a.fc + rowv[it]);
-            if (a.fc_shards) {
-              int owner;
-              long long lrow;
-              shard_split(a, rowv[it], owner, lrow);
-              fcv[it] = __ldg(a.fc_shards[owner] + lrow);
-            }
           }
         }
       }
@@ -293,8 +286,7 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
 // (Per-lookup atomics serialise ~B updates on each hot row inside L2 and stall the whole gather.)
 __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restrict__ rows,
                                                       const float* __restrict__ g_y, long long B, int F,
-                                                      float* __restrict__ fc_grad, float* const* fc_grad_shards,
-                                                      int G, float scale) {
+                                                      float* __restrict__ fc_grad) {
   extern __shared__ long long tile[];  // [32][F]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long b0 = (long long)blockIdx.x * 32;
@@ -321,14 +313,7 @@ __global__ void __launch_bounds__(256) fc_grad_kernel(const long long* __restric
         m &= m - 1;
       }
     }
-    if (valid && lane == leader) {
-      if (fc_grad_shards != nullptr) {   // row-sharded: the owner's accumulator, over NVLink for peers
-        const long long lrow = row / G;
-        atomicAdd(fc_grad_shards[(int)(row - lrow * G)] + lrow, sum * scale);
-      } else {
-        atomicAdd(fc_grad + row, sum);
-      }
-    }
+    if (valid && lane == leader) atomicAdd(fc_grad + row, sum);
   }
 }
 
@@ -621,11 +606,11 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
 }
 
 static int launch_fc_grad(const long long* rows, const float* g_y, long long B, int F, float* fc_grad,
-                          cudaStream_t stream, float* const* shards = nullptr, int G = 1, float scale = 1.f) {
+                          cudaStream_t stream) {
   const size_t smem = (size_t)32 * F * sizeof(long long);
   if (smem > 200 * 1024) return RSB_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) cudaFuncSetAttribute(fc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  fc_grad_kernel<<<(unsigned)((B + 31) / 32), 256, smem, stream>>>(rows, g_y, B, F, fc_grad, shards, G, scale);
+  fc_grad_kernel<<<(unsigned)((B + 31) / 32), 256, smem, stream>>>(rows, g_y, B, F, fc_grad);
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;
@@ -806,8 +791,7 @@ extern "C" RSB_API int rsb_qr_bwd_fused(int32_t kind, const int64_t* rows, int64
 
 extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,
                                               int32_t F, int32_t D, const float* const* table_shards,
-                                              const float* const* fc_shards, const float* fc_replicated,
-                                              int32_t G, int64_t n_global,
+                                              const float* fc_replicated, int32_t G, int64_t n_global,
                                               const float* bias, float* out_emb, float* out_yfm, float* out_sum,
                                               int64_t* out_rows, int32_t* err_flag, void* stream) {
   LookupArgs a = {};
@@ -821,7 +805,6 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   if (rc) return rc;
   a.table = nullptr;
   a.table_shards = table_shards;
-  a.fc_shards = fc_replicated ? nullptr : fc_shards;
   a.fc = fc_replicated;
   a.G = G;
   a.fd_g = make_fastdiv((unsigned long long)G);
@@ -836,15 +819,6 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   a.out_rows = reinterpret_cast<long long*>(out_rows);
   a.err = err_flag;
   return launch_fwd<RSB_KIND_VANILLA>(a, sh, reinterpret_cast<cudaStream_t>(stream));
-}
-
-extern "C" RSB_API int rsb_fc_grad_sharded(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F,
-                                           float* const* fc_grad_shards, int32_t G, float scale, void* stream) {
-  if (B < 0 || F <= 0 || G < 1) return RSB_ERR_BAD_ARG;
-  if (B == 0) return RSB_OK;
-  if (!rows || !g_yfm || !fc_grad_shards) return RSB_ERR_BAD_ARG;
-  return launch_fc_grad(reinterpret_cast<const long long*>(rows), g_yfm, B, F, nullptr,
-                        reinterpret_cast<cudaStream_t>(stream), fc_grad_shards, G, scale);
 }
 
 extern "C" RSB_API int rsb_fc_grad(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F, float* fc_grad,

@@ -167,7 +167,7 @@ class _ShardedLookup(torch.autograd.Function):
         rows = torch.empty(b, f, dtype=torch.int64, device=dev)
         nbytes = b * (f * x.element_size() + 2 * f * d * 4 + f * 8 + (f * 4 + 4 + d * 4 if use_fm else 0))
         RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded, L.ptr(x), int(x.dtype == torch.int32),
-                 L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), None, L.ptr(fc) if use_fm else None,
+                 L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(fc) if use_fm else None,
                  sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
                  None, L.stream_ptr(dev), nbytes=nbytes)
         ctx.sg, ctx.use_fm, ctx.shape = sg, use_fm, (b, f)
