@@ -19,7 +19,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess
@@ -264,8 +263,6 @@ def small_batch_leg(args, wl, dims, cfg, dev, R, crit, batch=None):
     (~70 launches of a few microseconds each), so the same training step is also measured captured in
     ONE CUDA graph (static input buffers, capturable Adam, dropout stream position in device memory)."""
     import torch
-
-    import recsys_benchmark_b200.linalg as LA
 
     b = batch or args.small_batch
     torch.manual_seed(2023)

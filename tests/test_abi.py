@@ -1,6 +1,5 @@
 """CPU-side checks of the C-ABI library: it loads, exports every symbol include/rsb.h
 declares, the ctypes table covers them, and argument validation works without a GPU."""
-import ctypes
 import os
 import re
 

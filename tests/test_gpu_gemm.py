@@ -1,7 +1,6 @@
 """GPU tests of the fp32-accurate tensor-core GEMM (rsb_gemm_f32, tcgen05 9xBF16 split)
 through the C ABI wrappers: every layout, batching, fused epilogue, and fp32-level accuracy
 (error vs an fp64 product must be of the same order as cuBLAS fp32 SGEMM's)."""
-import numpy as np
 import pytest
 import torch
 

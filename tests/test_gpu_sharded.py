@@ -3,7 +3,6 @@ when the box has >= 2 GPUs, world 2 over NCCL + NVLink peer access against the s
 model on the same global batch."""
 import os
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist
@@ -30,7 +29,7 @@ def _batch(b, seed):
 
 
 def _sharded_from(R, full, dev, group=None):
-    from recsys_benchmark_b200.sharded import ShardedDeepFM, shard_of_full
+    from recsys_benchmark_b200.sharded import ShardedDeepFM
 
     m = ShardedDeepFM(DIMS, 16, [32, 16], p_dropout=0.0, use_batchnorm=False, group=group).to(dev)
     sg = m.embedding.shards
