@@ -40,7 +40,9 @@ __global__ void __launch_bounds__(256) dhe_encode_kernel(const void* __restrict_
     for (long long i = blockIdx.x; i < n; i += gridDim.x) {
       const long long id = ids_i32 ? (long long)__ldg(reinterpret_cast<const int*>(ids) + i)
                                    : __ldg(reinterpret_cast<const long long*>(ids) + i);
-      const long long x = a * (id + prefix + 1) + b;
+      // two's-complement wrap-around like torch's int64 arithmetic (signed overflow would be undefined in C++)
+      const long long x = (long long)((unsigned long long)a * (unsigned long long)(id + prefix + 1) +
+                                      (unsigned long long)b);
       long long r;
       if (FAST) {
         const long long q = (long long)((double)x * inv_p);   // |error| < 1: x < 2^62, p >= 2
