@@ -34,6 +34,16 @@ def test_registry_is_rebound_and_reference_yaml_builds_our_model():
             assert isinstance(emb, R.VanillaEmbedding)
             emb = ref_emb.get_embedding({"name": "qr", "divider": 2}, [3, 4], 8)
             assert isinstance(emb, R.QRHashingEmbedding)
+            assert ref_emb.NAME_TO_CLS["dhe"] is R.DHEmbedding and ref_emb.NAME_TO_CLS["cerp"] is R.CerpEmbedding
+            import src.models.embeddings.pruned_embedding as ref_pruned
+
+            assert ref_pruned.PrunedEmbedding is R.PrunedEmbedding
+            # the DHE yaml (k = 1024, 4 x 1536 encoder) builds our plugin; no 4 GB code cache is materialised
+            with open(os.path.join(REF, "configs", "deepfm", "dhe_config-50.yaml")) as fh:
+                dhe_cfg = yaml.safe_load(fh)["model"]
+            dhe_cfg["embedding_config"].pop("cache_path", None)
+            dhe_model = ref_models.get_ctr_model([5, 6, 7], dict(dhe_cfg))
+            assert isinstance(dhe_model.embedding, R.DHEmbedding) and dhe_model.embedding._inp_size == 1024
             for cfg_name in ["base_config.yaml", "qr_80.yaml", "base_config_sparse.yaml"]:
                 with open(os.path.join(REF, "configs", "deepfm", cfg_name)) as fh:
                     cfg = yaml.safe_load(fh)
