@@ -286,6 +286,26 @@ def cerp_backward(p_w, q_w, p_t, q_t, rows, num_item: int, g_out):
     return tuple(res)
 
 
+def cerp_retrain_masks(target: Dict[str, np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """(q_mask, p_mask) = |w| - sigmoid(threshold) > 0 of the searched checkpoint
+    (RetrainCerpEmbedding.load_mask, cerp_embedding.py:302-318)."""
+    return tuple((np.abs(target[w]) - sigmoid(target[t])) > 0
+                 for w, t in (("q_weight", "q_threshold"), ("p_weight", "p_threshold")))
+
+
+def cerp_retrain_forward(p_w, q_w, p_mask, q_mask, rows, num_item: int) -> np.ndarray:
+    """emb = (Q * q_mask)[q_idx] + (P * p_mask)[p_idx] (RetrainCerpEmbedding.forward, cerp_embedding.py:329-349)."""
+    qi, pi = cerp_indices(rows, num_item, p_w.shape[0])
+    return (q_w * q_mask)[qi] + (p_w * p_mask)[pi]
+
+
+def cerp_retrain_backward(p_mask, q_mask, rows, num_item: int, g_out):
+    """Dense (g_p_weight, g_q_weight): scatter-add of g_out by index, times the fixed mask."""
+    qi, pi = cerp_indices(rows, num_item, p_mask.shape[0])
+    n = p_mask.shape[0]
+    return scatter_add_dense(pi, g_out, n) * p_mask, scatter_add_dense(qi, g_out, n) * q_mask
+
+
 def cerp_prune_loss(p_w, q_w, p_t, q_t, K=100):
     """get_prune_loss (cerp_embedding.py:205-207)."""
     emb = pep_soft_threshold(p_w, p_t) + pep_soft_threshold(q_w, q_t)

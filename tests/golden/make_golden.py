@@ -371,13 +371,37 @@ def run_dhe_cases():
         run_deepfm_case(name, cfg, opt_cfg=adam, steps=2, pre_forward=record)
 
 
+def run_cerp_retrain_case():
+    """CERP retrain (cerp_embedding.py:209-378): P, Q re-initialised from `initial.pth`, bool masks from the
+    searched checkpoint `target.pth` (|w| - sigmoid(threshold) > 0), masked tables gathered and added."""
+    bucket = 5
+    g = torch.Generator().manual_seed(31)
+    tgt = {"q_weight": torch.empty(bucket, D).uniform_(-0.6, 0.6, generator=g),
+           "p_weight": torch.empty(bucket, D).uniform_(-0.6, 0.6, generator=g),
+           "q_threshold": -1.2 + torch.randn(bucket, D, generator=g),
+           "p_threshold": -1.2 + torch.randn(bucket, D, generator=g)}
+    init = {"q_weight": torch.empty(bucket, D).uniform_(-0.5, 0.5, generator=g),
+            "p_weight": torch.empty(bucket, D).uniform_(-0.5, 0.5, generator=g)}
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "deepfm"))
+        torch.save(tgt, os.path.join(td, "deepfm", "target.pth"))
+        torch.save(init, os.path.join(td, "deepfm", "initial.pth"))
+        run_deepfm_case("deepfm_cerp_retrain", {"name": "cerp_retrain", "checkpoint_weight_dir": td,
+                                                "bucket_size": bucket},
+                        opt_cfg=dict(learning_rate=1e-2, weight_decay=1e-4), steps=2)
+    np.savez_compressed(os.path.join(HERE, "cerp_retrain_ckpt.npz"),
+                        **{"target/" + k: _np(v) for k, v in tgt.items()},
+                        **{"initial/" + k: _np(v) for k, v in init.items()})
+
+
 def main():
     if len(sys.argv) > 1:          # regenerate only the named extra cases
         for name in sys.argv[1:]:
-            {"pruned_csr": run_pruned_csr_case, "dhe": run_dhe_cases}[name]()
+            {"pruned_csr": run_pruned_csr_case, "dhe": run_dhe_cases, "cerp_retrain": run_cerp_retrain_case}[name]()
         return
     run_pruned_csr_case()
     run_dhe_cases()
+    run_cerp_retrain_case()
     adam = dict(learning_rate=1e-2, weight_decay=1e-4)
     sparse_adam = dict(learning_rate=1e-2, weight_decay=1e-4, sparse=True)
     sparse_sgd = dict(learning_rate=1e-1, weight_decay=1e-4, sparse=True, optimizer="sgd")

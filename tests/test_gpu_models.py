@@ -181,6 +181,15 @@ def test_deepfm_pep_retrain(R, sparse, tmp_path):
     assert model.embedding.emb.weight.grad.is_sparse == sparse
 
 
+def test_deepfm_cerp_retrain(R, tmp_path):
+    from tests.test_host_api import make_cerp_retrain_dir
+
+    g, model = _run_steps(R, "deepfm_cerp_retrain", make_cerp_retrain_dir(tmp_path), ADAM, 2)
+    emb = model.embedding
+    assert emb.get_num_params() == int(g["state/embedding.q_mask"].sum() + g["state/embedding.p_mask"].sum())
+    assert tuple(emb.get_weight().shape) == (int(g["field_dims"].sum()), 8)
+
+
 def test_deepfm_cerp(R):
     g, model = _run_steps(R, "deepfm_cerp", CASES["deepfm_cerp"], ADAM, 2)
     emb = model.embedding

@@ -208,3 +208,26 @@ def test_dhe_state_dict_and_counter_semantics():
         R.DHEmbedding(fd, 8, use_universal_hash=False)
     with pytest.raises(RuntimeError):
         model.embedding.encode(torch.zeros(3, dtype=torch.int64))  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------ CERP retrain (f-1) ---
+def make_cerp_retrain_dir(tmp_path):
+    ck = load_golden("cerp_retrain_ckpt")
+    (tmp_path / "deepfm").mkdir(exist_ok=True)
+    for part in ("target", "initial"):
+        torch.save({k: torch.from_numpy(np.asarray(v)) for k, v in sub(ck, part + "/").items()},
+                   tmp_path / "deepfm" / f"{part}.pth")
+    return {"name": "cerp_retrain", "checkpoint_weight_dir": str(tmp_path), "bucket_size": 5}
+
+
+def test_cerp_retrain_state_dict_and_masks(tmp_path):
+    g, model, state = build_from_golden("deepfm_cerp_retrain", make_cerp_retrain_dir(tmp_path))
+    ours = model.state_dict()
+    assert sorted(ours.keys()) == sorted(state.keys())
+    for k in ("embedding.q_mask", "embedding.p_mask", "embedding.q_weight", "embedding.p_weight"):
+        assert ours[k].dtype == state[k].dtype and torch.equal(ours[k], state[k]), k   # loaded from the checkpoint dir
+    assert not model.embedding.q_mask.requires_grad and model.embedding.q_weight.requires_grad
+    assert model.embedding.get_num_params() == int(state["embedding.q_mask"].sum() + state["embedding.p_mask"].sum())
+    with pytest.raises(AssertionError):
+        R.get_embedding({"name": "cerp_retrain", "checkpoint_weight_dir": str(tmp_path / "nope"), "bucket_size": 5},
+                        [3, 4], 8, field_name="deepfm")
