@@ -231,3 +231,41 @@ def test_cerp_retrain_state_dict_and_masks(tmp_path):
     with pytest.raises(AssertionError):
         R.get_embedding({"name": "cerp_retrain", "checkpoint_weight_dir": str(tmp_path / "nope"), "bucket_size": 5},
                         [3, 4], 8, field_name="deepfm")
+
+
+# ------------------------------------------------------------ checkpoints ---
+def test_checkpoint_round_trip_like_the_reference_scripts(tmp_path):
+    """scripts/deepfm/train_deepfm.py:204-210 writes {"state_dict", "model_config", "field_dims"}; DeepFM.load /
+    DCN_Mix.load / load_ctr_model read it back (src/models/deepfm.py:126-133, src/models/__init__.py:92-131);
+    save_model_checkpoint writes the embedding's own state dict to {dir}/{field}/{name}.pth."""
+    fd = [7, 3, 11]
+    cfg = dict(num_factor=8, hidden_sizes=[16, 8], p_dropout=0.1, use_batchnorm=True,
+               embedding_config={"name": "qr", "divider": 4})
+    torch.manual_seed(0)
+    model = R.get_ctr_model(fd, dict(cfg))
+    ck = {"state_dict": model.state_dict(), "model_config": dict(cfg), "field_dims": fd}
+    path = str(tmp_path / "deepfm_checkpoint.pth")
+    torch.save(ck, path)
+    for loaded in (R.DeepFM.load(path), R.load_ctr_model({"name": "deepfm"}, torch.load(path))):
+        assert isinstance(loaded, R.DeepFM)
+        for k, v in model.state_dict().items():
+            assert torch.equal(loaded.state_dict()[k], v), k
+    bare = R.DeepFM.load(ck, strict=False, empty_embedding=True)      # infer_deepfm.py:150 builds the table itself
+    assert not hasattr(bare, "embedding")
+    R.save_ctr_checkpoint(model, str(tmp_path), "target")
+    saved = torch.load(tmp_path / "deepfm" / "target.pth")
+    assert sorted(saved.keys()) == sorted(model.embedding.state_dict().keys())
+
+    dcfg = dict(num_factor=4, hidden_sizes=[12], num_layers=2, num_experts=3, rank=5, p_dropout=0.0,
+                embedding_config={"name": "vanilla"})
+    dcn = R.get_ctr_model(fd, dict(dcfg, name="dcn_mix", compile_model=True))
+    assert isinstance(dcn, R.DCN_Mix)
+    compiled_keys = {"_orig_mod." + k: v for k, v in dcn.state_dict().items()}   # what a torch.compile'd reference saves
+    back = R.DCN_Mix.load({"state_dict": compiled_keys, "model_config": dict(dcfg, compile_model=True),
+                           "field_dims": fd})
+    for k, v in dcn.state_dict().items():
+        assert torch.equal(back.state_dict()[k], v), k
+    R.save_ctr_checkpoint(dcn, str(tmp_path), "init")
+    assert (tmp_path / "dcn" / "init.pth").exists()
+    with pytest.raises(NotImplementedError):
+        R.save_ctr_checkpoint(torch.nn.Linear(2, 2), str(tmp_path))
