@@ -137,19 +137,21 @@ class DHEmbedding(IEmbedding):
         """Universal-hash codes [*ids.shape, k] of arbitrary ids (`_get_universal_hash_batch`,
         dh_embedding.py:215-236).  in_table=True promises 0 <= ids < num_item (fast modulo)."""
         small = in_table and self._small_operands() and self._num_item + self._prefix + 1 < 2 ** 30
-        return RF.dhe_encode(ids, self._prefix, self._slopes, self._bias, self._primes_choices, self.m, small)
+        dev = ids.device   # the reference moves its coefficients to the ids' device too (dh_embedding.py:217-219)
+        return RF.dhe_encode(ids, self._prefix, self._slopes.to(dev), self._bias.to(dev),
+                             self._primes_choices.to(dev), self.m, small)
 
     _get_universal_hash_batch = encode
 
     @property
     def _cache(self) -> torch.Tensor:
-        """The reference's cached code table [num_item, k] (dh_embedding.py:250-268), built on demand."""
+        """The reference's cached code table [num_item, k] (dh_embedding.py:250-268), built on demand - on "cuda"
+        whenever one is available, like the reference, wherever the module itself lives."""
         dev = self._slopes.device
         if dev.type != "cuda":
             if not torch.cuda.is_available():
                 raise RuntimeError("rsb: DHEmbedding codes are generated on the GPU (no CPU fallback)")
-            self.to("cuda")       # the reference builds its cache on "cuda" whenever one is available
-            dev = self._slopes.device
+            dev = torch.device("cuda", torch.cuda.current_device())
         return self.encode(torch.arange(self._num_item, device=dev), in_table=True)
 
     # ---- forward ----------------------------------------------------------------------------------
