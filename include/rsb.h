@@ -215,6 +215,10 @@ RSB_API int rsb_optembed_eval_weight(const float* weight, const float* t_row, co
                              int64_t n_rows, int32_t D, float* out, int64_t* count, void* stream);
 /* out = weight * mask (uint8) : RetrainPepEmbedding.get_weight / RetrainOptEmbed.get_weight. */
 RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, int64_t numel, float* out, void* stream);
+/* out[i] = sigmoid(s[i]) in the arithmetic every PEP / CERP kernel of this library uses for its thresholds,
+ * 1 / (1 + expf(-s)) - the formula of torch.sigmoid on CUDA (pep_embedding.py:86,91 run on the trainer's device),
+ * so `abs(v) > sigmoid(s)` mask decisions are bit-identical to the reference's GPU path (tested bit-for-bit). */
+RSB_API int rsb_sigmoid(const float* s, int64_t numel, float* out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Inference gather from a pruned table kept as CSR.  Replaces PrunedEmbedding.forward

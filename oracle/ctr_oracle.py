@@ -197,9 +197,14 @@ def sigmoid(s: np.ndarray) -> np.ndarray:
         return one / (one + np.exp(-s))
 
 
-def pep_soft_threshold(v: np.ndarray, s: np.ndarray) -> np.ndarray:
-    """sign(v) * relu(abs(v) - sigmoid(s)) (pep_embedding.py:91-92); s broadcasts."""
-    return np.sign(v) * np.maximum(np.abs(v) - sigmoid(s), v.dtype.type(0))
+def pep_soft_threshold(v: np.ndarray, s: np.ndarray, sig: Optional[np.ndarray] = None) -> np.ndarray:
+    """sign(v) * relu(abs(v) - sigmoid(s)) (pep_embedding.py:91-92); s broadcasts.
+
+    `sig`: sigmoid(s) precomputed by the caller in the arithmetic of the device the reference runs on
+    (torch.sigmoid on CUDA rounds differently from numpy's exp in the last bit); with it every
+    `abs(v) > sigmoid(s)` decision is the reference's own, bit for bit."""
+    sg = sigmoid(s) if sig is None else sig
+    return np.sign(v) * np.maximum(np.abs(v) - sg, v.dtype.type(0))
 
 
 def pep_threshold_shape(threshold_type: str, num_item: int, hidden: int):
@@ -208,19 +213,19 @@ def pep_threshold_shape(threshold_type: str, num_item: int, hidden: int):
             "feature_dim": (num_item, hidden)}[threshold_type]
 
 
-def pep_forward(weight, s, rows) -> np.ndarray:
+def pep_forward(weight, s, rows, sig: Optional[np.ndarray] = None) -> np.ndarray:
     """F.embedding(x, soft_threshold(weight, s)) (pep_embedding.py:82-89)."""
-    return gather_rows(pep_soft_threshold(weight, s), rows)
+    return gather_rows(pep_soft_threshold(weight, s, sig), rows)
 
 
-def pep_backward(weight, s, rows, g_out):
+def pep_backward(weight, s, rows, g_out, sig: Optional[np.ndarray] = None):
     """Dense grads (g_weight[N,D], g_s[shape of s]).
 
     d/dv = 1[abs(v) > sigmoid(s)]; d/ds = -sign(v) 1[...] sigmoid(s)(1-sigmoid(s)),
     reduced to the broadcast shape of `s`."""
     n, d = weight.shape
     g_table = scatter_add_dense(rows, g_out, n)  # grad wrt thresholded table
-    sg = np.broadcast_to(sigmoid(s), weight.shape)
+    sg = np.broadcast_to(sigmoid(s) if sig is None else sig, weight.shape)
     keep = (np.abs(weight) - sg) > 0
     g_w = np.where(keep, np.sign(weight) ** 2 * g_table, 0).astype(weight.dtype)
     g_s_full = np.where(keep, -np.sign(weight) * g_table * sg * (1 - sg), 0).astype(weight.dtype)
@@ -235,14 +240,14 @@ def pep_backward(weight, s, rows, g_out):
     return g_w, g_s.astype(weight.dtype)
 
 
-def pep_count_nonzero(weight, s) -> int:
+def pep_count_nonzero(weight, s, sig: Optional[np.ndarray] = None) -> int:
     """get_num_params: count_nonzero(soft_threshold(weight, s)) (pep_embedding.py:127-130)."""
-    return int(np.count_nonzero(pep_soft_threshold(weight, s)))
+    return int(np.count_nonzero(pep_soft_threshold(weight, s, sig)))
 
 
-def pep_retrain_mask(weight_final, s_final) -> np.ndarray:
+def pep_retrain_mask(weight_final, s_final, sig: Optional[np.ndarray] = None) -> np.ndarray:
     """mask = (abs(w) - sigmoid(s)) > 0 (pep_embedding.py:203)."""
-    return (np.abs(weight_final) - sigmoid(s_final)) > 0
+    return (np.abs(weight_final) - (sigmoid(s_final) if sig is None else sig)) > 0
 
 
 def masked_forward(weight, mask, rows) -> np.ndarray:

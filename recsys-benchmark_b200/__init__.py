@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Union
 
 import torch
 
-from . import _lib
+from . import _lib, embeddings
 from .embeddings import (CerpEmbedding, IEmbedding, OptEmbed, RetrainCerpEmbedding, PepEmbeeding, QRHashingEmbedding, RetrainOptEmbed,
                          RetrainPepEmbedding, VanillaEmbedding)
 
@@ -115,6 +115,20 @@ def install_into_reference() -> None:
     deepfm_mod.get_optimizers = get_optimizers
     tr = importlib.import_module("src.trainer.deepfm")
     tr.DeepFM = DeepFM
+    # scripts import some plugin classes by symbol from their defining modules for isinstance checks
+    # (scripts/deepfm/train_deepfm_optembed.py:13,45 `isinstance(model.embedding, OptEmbed)`): rebind those too
+    for mod_name, names in (("src.models.embeddings.deepfm_opt_embed", ("OptEmbed", "RetrainOptEmbed", "IOptEmbed")),
+                            ("src.models.embeddings.pep_embedding", ("PepEmbeeding", "RetrainPepEmbedding")),
+                            ("src.models.embeddings.qr_embedding", ("QRHashingEmbedding",)),
+                            ("src.models.embeddings.cerp_embedding", ("CerpEmbedding", "RetrainCerpEmbedding")),
+                            ("src.models.embeddings.base", ("VanillaEmbedding",))):
+        try:
+            mod = importlib.import_module(mod_name)
+        except ImportError:
+            continue
+        for n in names:
+            if hasattr(mod, n):
+                setattr(mod, n, globals()[n] if n in globals() else getattr(embeddings, n))
     try:    # inference-only CSR table (needs numba on the reference side); scripts import the symbol from here
         importlib.import_module("src.models.embeddings.pruned_embedding").PrunedEmbedding = PrunedEmbedding
     except ImportError:

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "rsb_pep_dense_bwd": (C.c_int, [_p, _p, _i32, _i64, _i32, _p, _p, _p, _p]),
     "rsb_optembed_eval_weight": (C.c_int, [_p, _p, _p, _i32, _i64, _i32, _p, _p, _p]),
     "rsb_mask_table": (C.c_int, [_p, _p, _i64, _p, _p]),
+    "rsb_sigmoid": (C.c_int, [_p, _i64, _p, _p]),
     "rsb_csr_lookup_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p,
                                      _p, _p]),
     "rsb_dhe_encode": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _p, _p]),

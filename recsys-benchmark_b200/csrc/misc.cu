@@ -179,6 +179,20 @@ extern "C" RSB_API int rsb_optembed_eval_weight(const float* weight, const float
   return RSB_OK;
 }
 
+__global__ void sigmoid_kernel(const float* __restrict__ s, long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = sigmoidf_exact(__ldg(s + i));
+}
+
+extern "C" RSB_API int rsb_sigmoid(const float* s, int64_t numel, float* out, void* stream) {
+  if (!s || !out || numel < 0) return RSB_ERR_BAD_ARG;
+  if (numel == 0) return RSB_OK;
+  sigmoid_kernel<<<grid_for(numel, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(s, numel, out);
+  RSB_CHECK_LAUNCH();
+  note_launch(1);
+  return RSB_OK;
+}
+
 extern "C" RSB_API int rsb_mask_table(const float* weight, const uint8_t* mask, int64_t numel, float* out, void* stream) {
   if (!weight || !mask || !out || numel < 0) return RSB_ERR_BAD_ARG;
   if (numel == 0) return RSB_OK;

@@ -486,6 +486,16 @@ def optembed_eval_weight(weight, t_row, mask_d_row, norm: int, want_out=True, wa
     return out, cnt
 
 
+def sigmoid(s: torch.Tensor) -> torch.Tensor:
+    """sigmoid(s) in the kernels' own arithmetic (the threshold every PEP / CERP kernel compares against)."""
+    lib = L.load()
+    dev = L.require_cuda(s)
+    s = s.contiguous()
+    out = torch.empty_like(s)
+    L.check(lib.rsb_sigmoid(L.ptr(s), s.numel(), L.ptr(out), L.stream_ptr(dev)), "sigmoid")
+    return out
+
+
 def mask_table(weight, mask):
     lib = L.load()
     dev = L.require_cuda(weight, mask)

@@ -67,17 +67,19 @@ def _dense(g):
 
 
 def run_deepfm_case(name, emb_cfg, *, opt_cfg=None, tweak=None, steps=2, use_bn=True,
-                    field_dims=FIELD_DIMS, d=D, int32_input=False, pre_forward=None):
+                    field_dims=FIELD_DIMS, d=D, int32_input=False, pre_forward=None, b=B, hidden=(16, 8)):
     """One golden file: eval logits, train-mode (dropout 0) logits, all grads,
     grad wrt embedding output / deep input, and `steps` optimizer steps."""
     torch.manual_seed(1234)
-    cfg = dict(num_factor=d, hidden_sizes=[16, 8], p_dropout=0.0, use_batchnorm=use_bn,
+    cfg = dict(num_factor=d, hidden_sizes=list(hidden), p_dropout=0.0, use_batchnorm=use_bn,
                embedding_config=copy.deepcopy(emb_cfg))
     model = get_ctr_model(field_dims, cfg)
     if tweak is not None:
         tweak(model)
     out = {}
     out["field_dims"] = np.asarray(field_dims, dtype=np.int64)
+    out["num_factor"] = np.asarray(d, dtype=np.int64)
+    out["hidden_sizes"] = np.asarray(list(hidden), dtype=np.int64)
     _state(model, out)
 
     stash = {}
@@ -95,7 +97,7 @@ def run_deepfm_case(name, emb_cfg, *, opt_cfg=None, tweak=None, steps=2, use_bn=
     h1 = model.embedding.register_forward_hook(emb_hook)
     h2 = model._deep_branch.register_forward_pre_hook(deep_hook)
 
-    x, y = _batch(7, field_dims)
+    x, y = _batch(7, field_dims, b)
     if int32_input:
         x = x.int()
     out["x"], out["y"] = _np(x), _np(y)
@@ -112,7 +114,7 @@ def run_deepfm_case(name, emb_cfg, *, opt_cfg=None, tweak=None, steps=2, use_bn=
     crit = torch.nn.BCEWithLogitsLoss()
     model.train()
     for s in range(steps):
-        xs, ys = _batch(7 + s, field_dims)
+        xs, ys = _batch(7 + s, field_dims, b)
         if int32_input:
             xs = xs.int()
         out[f"step{s}/x"], out[f"step{s}/y"] = _np(xs), _np(ys)
@@ -182,7 +184,7 @@ def optembed_pre_forward(model, tag, out):
         return
     seed = 4242 + int(tag[-1])
     torch.manual_seed(seed)
-    k = torch.randint(0, model.embedding._hidden_size, size=(B, model.embedding._num_field))
+    k = torch.randint(0, model.embedding._hidden_size, size=(out[f"{tag}/x"].shape[0], model.embedding._num_field))
     out[f"{tag}/mask_d_idx"] = _np(k)
     torch.manual_seed(seed)
 
@@ -394,11 +396,33 @@ def run_cerp_retrain_case():
                         **{"initial/" + k: _np(v) for k, v in init.items()})
 
 
+# A second set at the PRODUCTION row width (D = 16, the kernels' <kind, V=4, LPR=4> instantiation) and the Criteo
+# field count (39 small fields): the D = 8 files above exercise <kind, 4, 2> only.
+D16_DIMS = [7, 3, 11, 5, 2, 9, 4, 13, 6, 8, 3, 5, 7, 19, 12, 31, 23, 6, 4, 17, 9, 2, 29, 14, 37, 10, 5, 21, 33, 3, 11,
+            8, 2, 27, 4, 6, 25, 9, 15]
+
+
+def run_d16_cases():
+    kw = dict(field_dims=D16_DIMS, d=16, b=64, hidden=(32, 16))
+    adam = dict(learning_rate=1e-2, weight_decay=1e-4)
+    run_deepfm_case("d16_vanilla_sparse_adam", {"name": "vanilla", "sparse": True},
+                    opt_cfg=dict(learning_rate=1e-2, weight_decay=1e-4, sparse=True), steps=2, **kw)
+    run_deepfm_case("d16_qr_mult", {"name": "qr", "divider": 5}, opt_cfg=adam, use_bn=False, steps=1, **kw)
+    with tempfile.TemporaryDirectory() as td:
+        run_deepfm_case("d16_pep_feature_dim", {"name": "pep", "checkpoint_weight_dir": td,
+                                                "threshold_type": "feature_dim"},
+                        opt_cfg=adam, tweak=tweak_pep(), steps=1, **kw)
+    run_deepfm_case("d16_optembed", {"name": "deepfm_optembed"}, opt_cfg=adam, tweak=tweak_optembed, steps=1,
+                    pre_forward=optembed_pre_forward, **kw)
+
+
 def main():
     if len(sys.argv) > 1:          # regenerate only the named extra cases
         for name in sys.argv[1:]:
-            {"pruned_csr": run_pruned_csr_case, "dhe": run_dhe_cases, "cerp_retrain": run_cerp_retrain_case}[name]()
+            {"pruned_csr": run_pruned_csr_case, "dhe": run_dhe_cases, "cerp_retrain": run_cerp_retrain_case,
+             "d16": run_d16_cases}[name]()
         return
+    run_d16_cases()
     run_pruned_csr_case()
     run_dhe_cases()
     run_cerp_retrain_case()

@@ -620,3 +620,35 @@ def test_side_stream_overlap_is_bit_identical_to_inline_execution(R, emb_cfg, mo
                 assert_close(ga[k].cpu().numpy(), gb[k].cpu().numpy(), what=k)
             else:
                 assert torch.equal(ga[k], gb[k]), k
+
+
+# ---------------- golden files at the production row width (D = 16, 39 fields: kernel templates <kind, 4, 4>) ---
+def test_d16_vanilla_sparse_adam_and_fused_update(R):
+    _run_steps(R, "d16_vanilla_sparse_adam", {"name": "vanilla", "sparse": True}, SPARSE_ADAM, 2)
+    g, model, state = build_from_golden("d16_vanilla_sparse_adam", {"name": "vanilla", "sparse": True})
+    model.load_state_dict(state, strict=True)
+    model.to(DEV).train()
+    opts = R.get_optimizers(model, dict(SPARSE_ADAM, fused_sparse=True))
+    crit = torch.nn.BCEWithLogitsLoss()
+    for s in range(2):
+        loss = crit(model(_t(g[f"step{s}/x"])), _t(g[f"step{s}/y"]).float())
+        for o in opts:
+            o.zero_grad()
+        loss.backward()
+        for o in opts:
+            o.step()
+        assert_close(model.embedding._emb_module.weight.detach().cpu().numpy(),
+                     g[f"step{s}/after/embedding._emb_module.weight"], what=f"d16 fused step {s}", atol_scale=5e-5)
+
+
+def test_d16_qr_mult(R):
+    _run_steps(R, "d16_qr_mult", {"name": "qr", "divider": 5}, ADAM, 1)
+
+
+def test_d16_pep_feature_dim(R, tmp_path):
+    _run_steps(R, "d16_pep_feature_dim", {"name": "pep", "checkpoint_weight_dir": str(tmp_path),
+                                          "threshold_type": "feature_dim"}, ADAM, 1)
+
+
+def test_d16_optembed(R):
+    _run_steps(R, "d16_optembed", {"name": "deepfm_optembed"}, ADAM, 1, pre_step=_optembed_pre)

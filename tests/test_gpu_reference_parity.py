@@ -1,0 +1,280 @@
+"""Parity against the UNMODIFIED reference at the BASELINE.json shapes, on the same GPU.
+
+The reference (staged under baseline/_ref by __graft_entry__.build(), see tests/refimport.py) builds its own
+DeepFM / DCN_Mix with its own embedding plugins and runs them with torch's CUDA operators; our model is built
+from the same config, loads the reference's state dict with strict=True, and must reproduce on identical
+synthetic Criteo- / KDD- / Avazu-shaped batches
+
+  * the plugin output `embedding(rows)`            - bit for bit where the arithmetic is a gather, a single
+                                                     multiply or a threshold (vanilla, QR, PEP, masks),
+  * the logits (eval and train mode)               - fp32 tolerance below,
+  * every parameter gradient (table, QR tables, thresholds, first-order weights, MLP / cross layers),
+  * the weights after one optimizer step of the reference's own `get_optimizers` recipe.
+
+fp32 tolerance: rtol 1e-5 with atol = 1e-5 * max|ref|, OR - for quantities that go through the
+GEMMs, where both sides are a rounding of the exact result - an error against the reference's fp64 twin no larger
+than 4x the error of the reference's own fp32 run against that twin.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from tests import refimport
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not refimport.available(), reason="baseline/_ref not staged")]
+DEV = "cuda:0"
+
+CRITEO_DIMS = [49, 101, 126, 45, 223, 118, 84, 76, 95, 9, 30, 40, 75, 1458, 555, 193949, 138801, 306, 19, 11970, 634,
+               4, 42646, 5178, 192773, 3175, 27, 11422, 181075, 11, 4654, 2032, 5, 189657, 18, 16, 59697, 86, 45571]
+AVAZU_DIMS = [100000] * 10 + [1000] * 12
+KDD_DIMS = [600000] * 8 + [400000] * 3
+
+
+@pytest.fixture(scope="module")
+def R():
+    import __graft_entry__ as G
+
+    G.build()
+    import recsys_benchmark_b200 as r
+
+    return r
+
+
+@pytest.fixture(scope="module")
+def REF():
+    refimport.activate()
+    import src.models as ref_models
+    import src.models.deepfm as ref_deepfm
+
+    # these tests need the reference's OWN classes: fail loudly if another test left the registry rebound
+    assert ref_models.DeepFM.__module__.startswith("src."), "reference registry is rebound to our classes"
+    return ref_models, ref_deepfm
+
+
+def _batch(dims, b, seed, dtype=torch.int64):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.stack([torch.randint(0, d, (b,), generator=g) for d in dims], 1).to(dtype)
+    y = torch.randint(0, 2, (b,), generator=g)
+    return x.to(DEV), y.to(DEV)
+
+
+def _dense(g):
+    return g.to_dense() if g.is_sparse else g
+
+
+def _within(got, ref, rtol=1e-5, atol_scale=1e-5):
+    got, ref = got.double(), ref.double()
+    atol = atol_scale * float(ref.abs().max()) if ref.numel() else 0.0
+    return bool(((got - ref).abs() <= atol + rtol * ref.abs()).all())
+
+
+def assert_parity(got, ref32, ref64, what):
+    """rtol 1e-5 / atol 1e-5*max|ref| against the reference's fp32 result, or no further from the reference's fp64
+    twin than 4x the reference's own fp32 distance to it (both from SURVEY.md 8c)."""
+    assert got.shape == ref32.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref32.shape)}"
+    if _within(got, ref32):
+        return
+    scale = float(ref64.abs().max()) or 1.0
+    e_ours = float((got.double() - ref64).abs().max()) / scale
+    e_ref = float((ref32.double() - ref64).abs().max()) / scale
+    assert e_ours <= 4.0 * e_ref + 1e-7, (f"{what}: max err vs fp64 twin {e_ours:.3e} (relative to max|ref|), "
+                                          f"reference fp32 itself {e_ref:.3e}")
+
+
+def _noise_keys(model):
+    """Linear biases that feed a BatchNorm: their gradient is zero by construction, both sides hold fp32 noise."""
+    out = set()
+    for name in ("_deep_branch", "_dnn"):
+        seq = getattr(model, name, None)
+        if seq is None:
+            continue
+        mods = list(seq)
+        for i, m in enumerate(mods[:-1]):
+            if isinstance(m, torch.nn.Linear) and isinstance(mods[i + 1], torch.nn.BatchNorm1d):
+                out.add(f"{name}.{i}.bias")
+    return out
+
+
+def _tweak(model, kind):
+    """Deterministic non-trivial parameter values for the pruning variants (xavier weights of a 6 M-row table are
+    ~1e-3, far below any threshold: everything would be pruned and the test vacuous)."""
+    g = torch.Generator(device=DEV).manual_seed(99)
+    emb = model.embedding
+    with torch.no_grad():
+        if kind == "pep":
+            emb.emb.weight.uniform_(-0.5, 0.5, generator=g)
+            emb.s.copy_(-0.4 + 0.3 * torch.randn(emb.s.shape, generator=g, device=DEV))    # ~80 % pruned
+        elif kind == "optembed":
+            emb._weight.uniform_(-0.2, 0.2, generator=g)
+            t = emb._mask_e_module._t_param
+            t.copy_(1.2 + 0.8 * torch.rand(t.shape, generator=g, device=DEV))
+        model.fc.weight.uniform_(-0.05, 0.05, generator=g) if hasattr(model, "fc") else None
+
+
+CASES = {
+    # name: (dims, batch, model cfg, optimizer cfg, tweak, exact plugin output?)
+    "criteo_vanilla_adam": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "vanilla"}),
+                            dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+    "criteo_vanilla_sparse_adam": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "vanilla", "sparse": True}),
+                                   dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True), None, True),
+    "criteo_qr2": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 2}),
+                   dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+    "criteo_qr5": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 5}),
+                   dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+    "criteo_qr20": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 20}),
+                    dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+    "criteo_qr_default_add": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "operation": "add"}),
+                              dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+    "criteo_qr5_cat": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 5, "operation": "cat"}),
+                       dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+    "kdd_pep_feature_dim": (KDD_DIMS, 8192, dict(embedding_config={"name": "pep", "threshold_type": "feature_dim"}),
+                            dict(learning_rate=1e-3, weight_decay=1e-5), "pep", True),
+    "kdd_pep_feature": (KDD_DIMS, 8192, dict(embedding_config={"name": "pep", "threshold_type": "feature"}),
+                        dict(learning_rate=1e-3, weight_decay=1e-5), "pep", True),
+    "kdd_optembed": (KDD_DIMS, 8192, dict(embedding_config={"name": "deepfm_optembed"}),
+                     dict(learning_rate=3e-5, weight_decay=1e-3), "optembed", False),
+    "kdd_optembed_d": (KDD_DIMS, 8192, dict(embedding_config={"name": "deepfm_optembed_d"}),
+                       dict(learning_rate=3e-5, weight_decay=1e-3), None, True),
+    "avazu_dcn_mix": (AVAZU_DIMS, 2048, dict(name="dcn_mix", compile_model=False,
+                                             embedding_config={"name": "vanilla"}),
+                      dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+}
+
+
+def _build(mod, dims, cfg, tmp_path):
+    cfg = copy.deepcopy(cfg)
+    cfg.setdefault("num_factor", 16)
+    cfg.setdefault("hidden_sizes", [400, 400, 400])
+    cfg.setdefault("p_dropout", 0.0)           # dropout off: the two sides draw different masks by design
+    if cfg.get("name") != "dcn_mix":
+        cfg.setdefault("use_batchnorm", True)
+    if cfg["embedding_config"]["name"].startswith("pep"):
+        cfg["embedding_config"]["checkpoint_weight_dir"] = str(tmp_path)
+    return mod.get_ctr_model(dims, cfg)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tmp_path):
+    ref_models, ref_deepfm = REF
+    dims, b, cfg, opt_cfg, tweak, exact_emb = CASES[case]
+    torch.manual_seed(2023)
+    ref = _build(ref_models, dims, cfg, tmp_path / "ref").to(DEV)
+    assert type(ref).__module__.startswith("src."), "must be the reference's own class"
+    if tweak:
+        _tweak(ref, tweak)
+    ours = _build(R, dims, cfg, tmp_path / "ours")
+    ours.load_state_dict(ref.state_dict(), strict=True)      # frozen names / shapes / dtypes
+    ours.to(DEV)
+    ref64 = copy.deepcopy(ref).double()
+    is_opt = "optembed" in cfg["embedding_config"]["name"]
+    x, y = _batch(dims, b, 7)
+    rows = x + ref.offsets
+
+    # ---- plugin forward: embedding(rows) ------------------------------------------------------------------
+    for m in (ref, ours, ref64):
+        m.train()
+    outs = []
+    for m in (ref, ours):
+        torch.manual_seed(11)                 # OptEmbed draws its mask-D ids with torch.randint on the device
+        outs.append(m.embedding(rows).detach())
+    assert outs[0].shape == outs[1].shape
+    if exact_emb:
+        assert torch.equal(outs[0], outs[1]), f"{case}: plugin output differs from the reference's"
+    else:
+        # OptEmbed mask-E: ||e||_1 is summed in another order, so a row whose norm is within rounding of its
+        # threshold may flip; everything else is exact
+        diff_rows = (outs[0] != outs[1]).any(-1)
+        if bool(diff_rows.any()):
+            e = torch.nn.functional.embedding(rows, ref.embedding._weight).double()
+            t = ref.embedding._mask_e_module._t_param.double()
+            margin = (e.abs().sum(-1) - t[None, :]).abs()
+            assert float(margin[diff_rows].max()) < 1e-5, "a mask differs away from a rounding tie"
+            assert int(diff_rows.sum()) <= 2
+
+    # ---- eval logits -----------------------------------------------------------------------------------------
+    for m in (ref, ours, ref64):
+        m.eval()
+    with torch.no_grad():
+        if is_opt:
+            for m in (ref, ours, ref64):
+                m.embedding.get_weight()      # fresh OptEmbed in eval mode needs its cache built first
+        assert_parity(ours(x), ref(x), ref64(x), f"{case} eval logits")
+        assert torch.equal(ours(x.int()), ours(x)), "int32 ids must give bit-identical logits"
+
+    # ---- one training step of the reference's recipe -------------------------------------------------------------
+    crit = torch.nn.BCEWithLogitsLoss()
+    models = {"ref": ref, "ours": ours, "ref64": ref64}
+    opts = {"ref": ref_deepfm.get_optimizers(ref, dict(opt_cfg)), "ours": R.get_optimizers(ours, dict(opt_cfg)),
+            "ref64": []}
+    logits, grads = {}, {}
+    for k, m in models.items():
+        m.train()
+        torch.manual_seed(12)
+        out = m(x)
+        loss = crit(out, y.to(out.dtype))
+        for o in opts[k]:
+            o.zero_grad()
+        loss.backward()
+        logits[k] = out.detach()
+        grads[k] = {n: _dense(p.grad).detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert_parity(logits["ours"], logits["ref"], logits["ref64"], f"{case} train logits")
+    noise = _noise_keys(ref)
+    assert set(grads["ours"]) == set(grads["ref"]), "the same parameters must receive gradients"
+    for n in grads["ref"]:
+        if n in noise:
+            assert float(grads["ours"][n].abs().max()) < 1e-5
+            continue
+        assert_parity(grads["ours"][n], grads["ref"][n], grads["ref64"][n], f"{case} grad {n}")
+    if not is_opt:   # untouched rows of the big table have exactly zero gradient on both sides
+        big = max(grads["ref"], key=lambda n: grads["ref"][n].numel())
+        assert torch.equal(grads["ours"][big] == 0, grads["ref"][big] == 0) or "pep" in case
+    for k in ("ref", "ours"):
+        for o in opts[k]:
+            o.step()
+    lr = opt_cfg["learning_rate"]
+    sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+    for n, v in sd_ref.items():
+        if not torch.is_floating_point(v) or n in noise:
+            assert n in noise or torch.equal(v, sd_ours[n]), n
+            continue
+        # Adam's first step moves every weight by <= lr, whatever the gradient's size: the update of an element whose
+        # gradient is at rounding level is noise on both sides, hence the lr-scaled floor
+        d = (v - sd_ours[n]).abs()
+        bound = 1e-5 * float(v.abs().max()) + 1e-5 * v.abs() + 2e-2 * lr
+        assert bool((d <= bound).all()), f"{case} after step {n}: max diff {float(d.max()):.3e}"
+        # ... and only a vanishing share of the elements may need that floor at all
+        tight = 1e-5 * float(v.abs().max()) + 1e-5 * v.abs() + 1e-4 * lr
+        assert float((d > tight).float().mean()) < 1e-3, f"{case} after step {n}: too many loose elements"
+
+
+@pytest.mark.parametrize("fused", ["adam", "sgd"])
+def test_fused_sparse_row_update_matches_the_reference_sparse_optimizers(R, REF, fused, tmp_path):
+    """configs/deepfm/base_config_sparse.yaml recipe: the reference's SparseAdam / sparse SGD on a COO gradient vs our
+    fused segmented-reduce + row update (`fused_sparse: true`), three steps at the Criteo shape."""
+    ref_models, ref_deepfm = REF
+    torch.manual_seed(5)
+    cfg = dict(embedding_config={"name": "vanilla", "sparse": True})
+    ref = _build(ref_models, CRITEO_DIMS, cfg, tmp_path).to(DEV)
+    ours = _build(R, CRITEO_DIMS, cfg, tmp_path)
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.to(DEV)
+    opt_cfg = dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, optimizer=fused)
+    o_ref = ref_deepfm.get_optimizers(ref, dict(opt_cfg))
+    o_ours = R.get_optimizers(ours, dict(opt_cfg, fused_sparse=True))
+    crit = torch.nn.BCEWithLogitsLoss()
+    for step in range(3):
+        x, y = _batch(CRITEO_DIMS, 2048, 100 + step)
+        for m, opts in ((ref, o_ref), (ours, o_ours)):
+            m.train()
+            loss = crit(m(x), y.float())
+            for o in opts:
+                o.zero_grad()
+            loss.backward()
+            for o in opts:
+                o.step()
+        w_ref, w_ours = ref.embedding.get_weight(), ours.embedding.get_weight()
+        d = (w_ref - w_ours).abs()
+        assert float(d.max()) <= 1e-5 * float(w_ref.abs().max()) + 2e-2 * 1e-3, f"step {step}: {float(d.max()):.3e}"
+        assert float((d > 1e-5 * float(w_ref.abs().max()) + 1e-7).float().mean()) < 1e-3

@@ -26,8 +26,9 @@ def build_from_golden(name, emb_cfg, tmp_path=None, **model_kw):
     fd = [int(v) for v in g["field_dims"]]
     st = sub(g, "state/")
     use_bn = any(k.endswith("running_mean") for k in st)
-    d = 8
-    cfg = dict(num_factor=d, hidden_sizes=[16, 8], p_dropout=0.0, use_batchnorm=use_bn,
+    d = int(g["num_factor"]) if "num_factor" in g else 8
+    hidden = [int(v) for v in g["hidden_sizes"]] if "hidden_sizes" in g else [16, 8]
+    cfg = dict(num_factor=d, hidden_sizes=hidden, p_dropout=0.0, use_batchnorm=use_bn,
                embedding_config=dict(emb_cfg))
     cfg.update(model_kw)
     model = R.get_ctr_model(fd, cfg)
