@@ -285,10 +285,15 @@ extern "C" RSB_API int rsb_sort_rows(const int64_t* keys, int64_t n, int64_t n_r
   const int rb = (bits + passes - 1) / passes;  // radix bits per pass (<= 11)
   const size_t scatter_smem_max = (size_t)(kRadixMax + (kSortThreads / 32) * kRadixMax) * sizeof(unsigned);
   const size_t scatter_smem = ((size_t)(1 << rb) * (1 + kSortThreads / 32)) * sizeof(unsigned);
-  static bool attr_set = false;   // one process drives one device
-  if (!attr_set) {
-    cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_max);
-    attr_set = true;
+  {
+    // function attributes are per device: set once for each device this process launches on
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+    if (dev < 0 || !attr_set[dev]) {
+      cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem_max);
+      if (dev >= 0) attr_set[dev] = true;
+    }
   }
 
   SortSrc src;

@@ -52,6 +52,14 @@ class IEmbedding(nn.Module):
     def _mask_d_for(self, b: int, f: int, device) -> Optional[torch.Tensor]:
         return None
 
+    def train(self, mode: bool = True):
+        """Out-of-range ids do not fault inside the gather (they are clamped to row 0 and an error flag is set; the
+        reference's F.embedding raises IndexError / a device assert).  Reading the flag needs a host sync, so it is
+        read where the reference trainer synchronises anyway: on every train() / eval() switch (epoch boundaries,
+        src/trainer/deepfm.py:27,113) - and on every call with `validate = True`."""
+        RF.check_index_errors(self)
+        return super().train(mode)
+
     def lookup(self, x: torch.Tensor, offsets: Optional[torch.Tensor] = None, fc: Optional[torch.Tensor] = None,
                bias: Optional[torch.Tensor] = None):
         """Fused lookup on raw [B,F] ids. Returns (emb [B,VF,E], y_fm [B] or None)."""

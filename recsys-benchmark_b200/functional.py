@@ -123,7 +123,10 @@ def side_stream(device) -> torch.cuda.Stream:
 class SortedRows:
     """(sorted keys, permutation) being produced on the side stream; `get()` makes the current stream wait."""
 
+    constructed = 0   # instances ever made (tests assert that the early sort really runs)
+
     def __init__(self, rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 0):
+        SortedRows.constructed += 1
         lib = L.load()
         dev = rows.device
         n = rows.numel()
@@ -235,7 +238,7 @@ class _FusedLookup(torch.autograd.Function):
     """(spec, x, offsets, mask_d, table, table1, aux, fc, bias) -> (emb [B,VF,E], y_fm [B] or empty)."""
 
     @staticmethod
-    def forward(ctx, spec: LookupSpec, x, offsets, mask_d, table, table1, aux, fc, bias):
+    def forward(ctx, spec: LookupSpec, x, offsets, mask_d, table, table1, aux, fc, bias, presort=False):
         lib = L.load()
         dev = L.require_cuda(x, table, table1, aux, fc, bias, offsets, mask_d)
         if x.dim() != 2:
@@ -268,9 +271,9 @@ class _FusedLookup(torch.autograd.Function):
         ctx.fm = fm
         ctx.shape = (b, f)
         # the backward's row sort depends only on `rows`: start it now on the side stream (see EARLY_SORT)
+        # (grad mode is always off inside Function.forward: the caller decides, see fused_lookup)
         ctx.presorted = None
-        if torch.is_grad_enabled() and table.requires_grad and not (spec.sparse_grad and getattr(
-                spec.module, "_rsb_fused_opt", None) is None) and spec.kind != L.KIND_QR_CAT:
+        if presort:
             ctx.presorted = early_sort(rows, table.shape[0], key_div=spec.divider if spec.is_qr else 0)
         ctx.save_for_backward(rows, emb, s, mask_d, table, table1, aux, fc)
         ctx.mark_non_differentiable(rows)
@@ -294,7 +297,7 @@ class _FusedLookup(torch.autograd.Function):
         if use_gy:
             g_y = g_y.contiguous()
         if g_emb is None and not use_gy:
-            return (None,) * 9
+            return (None,) * 10
 
         g_fc = None
         if ctx.fm and need[7] and use_gy:
@@ -384,7 +387,7 @@ class _FusedLookup(torch.autograd.Function):
                     g_aux = dense_row_grad(rows, rg_aux.sum(dim=1, keepdim=True), n_rows)
             if kind == L.KIND_OPTEMBED and aux is not None and need[6]:
                 g_aux = -rg_aux.sum(dim=0)
-        return None, None, None, None, g_table, g_table1, g_aux, g_fc, g_bias
+        return None, None, None, None, g_table, g_table1, g_aux, g_fc, g_bias, None
 
 
 def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tensor], table: torch.Tensor,
@@ -392,7 +395,12 @@ def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tens
                  mask_d: Optional[torch.Tensor] = None, fc: Optional[torch.Tensor] = None,
                  bias: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Differentiable fused gather.  Returns (emb [B,VF,E], y_fm [B] or None)."""
-    emb, y, _rows = _FusedLookup.apply(spec, x, offsets, mask_d, table, table1, aux, fc, bias)
+    # The backward's row sort depends only on the looked-up rows: when a backward pass that reduces into the big table
+    # will follow (grad mode on HERE, in the caller's context; a COO gradient needs no sort unless the fused row
+    # optimizer consumes it), it is started on the side stream right after the forward gather (see EARLY_SORT).
+    presort = (EARLY_SORT and torch.is_grad_enabled() and table.requires_grad and spec.kind != L.KIND_QR_CAT
+               and not (spec.sparse_grad and getattr(spec.module, "_rsb_fused_opt", None) is None))
+    emb, y, _rows = _FusedLookup.apply(spec, x, offsets, mask_d, table, table1, aux, fc, bias, presort)
     return emb, (y if fc is not None else None)
 
 

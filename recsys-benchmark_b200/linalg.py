@@ -287,11 +287,24 @@ class _LinearReluDropout(torch.autograd.Function):
         gw = None
         if ctx.needs_input_grad[1]:
             sk = _split_for(x.shape[0], weight.shape[0], weight.shape[1])
-            if ctx.side_dw and gx is not None and not torch.cuda.is_current_stream_capturing():
+            if ctx.side_dw and gx is not None and _side_dw_safe(weight):
                 gw = _gemm_on_side_stream(gz, x, sk)
             else:
                 gw = gemm(gz, x, trans_a=True, split_k=sk)
         return gx, gw, gb, None, None
+
+
+def _has_hooks(weight: torch.Tensor) -> bool:
+    return bool(getattr(weight, "_backward_hooks", None)) or bool(getattr(weight, "_post_accumulate_grad_hooks", None))
+
+
+def _side_dw_safe(weight: torch.Tensor) -> bool:
+    """The side-stream weight gradient is handed to autograd while its GEMM is still running; the main stream only
+    re-joins in the end-of-backward callback.  That is safe only if nothing touches the gradient before then:
+    AccumulateGrad must STEAL it (`weight.grad is None`: no `grad += gw` on the main stream - gradient accumulation,
+    zero_grad(set_to_none=False) or a second backward all make .grad non-None) and no tensor / post-accumulate hook
+    may read it.  Otherwise the GEMM runs in line."""
+    return weight.grad is None and not _has_hooks(weight) and not torch.cuda.is_current_stream_capturing()
 
 
 def _gemm_on_side_stream(gz: torch.Tensor, x: torch.Tensor, split_k: int) -> torch.Tensor:
@@ -390,7 +403,7 @@ class _Linear(torch.autograd.Function):
             gx = gemm(gy, weight)                                   # [B,out] @ [out,in]
         if ctx.needs_input_grad[1]:
             sk = _split_for(x.shape[0], weight.shape[0], weight.shape[1])
-            if ctx.side_dw and gx is not None and not torch.cuda.is_current_stream_capturing():
+            if ctx.side_dw and gx is not None and _side_dw_safe(weight):
                 gw = _gemm_on_side_stream(gy, x, sk)
             else:
                 gw = gemm(gy, x, trans_a=True, split_k=sk)
@@ -464,10 +477,11 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: 
                 return _HeadBlock.apply(x, m.weight, m.bias, float(nx2.p), nx3.weight, nx3.bias)
             if ok and isinstance(nxt, torch.nn.ReLU) and isinstance(nx2, torch.nn.Dropout) and training and \
                     0.0 < nx2.p < 1.0 and m.weight.shape[0] <= 2048:
-                x = _LinearReluDropout.apply(x, m.weight, m.bias, float(nx2.p), overlap_first_dw and i == 0)
+                x = _LinearReluDropout.apply(x, m.weight, m.bias, float(nx2.p),
+                                             overlap_first_dw and i == 0 and not _has_hooks(m.weight))
                 i += 3
                 continue
-            x = linear(x, m.weight, m.bias, side_dw=overlap_first_dw and i == 0)
+            x = linear(x, m.weight, m.bias, side_dw=overlap_first_dw and i == 0 and not _has_hooks(m.weight))
             i += 1
             continue
         if isinstance(m, torch.nn.ReLU) and isinstance(nxt, torch.nn.Dropout) and training and 0.0 < nxt.p < 1.0 \

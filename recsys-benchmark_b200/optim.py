@@ -18,7 +18,11 @@ from . import functional as RF
 
 class _FusedRowOptimizer(torch.optim.Optimizer):
     """Owns the embedding module's main table.  While attached, the module's backward
-    stashes (rows, per-lookup grads) here instead of building a gradient tensor."""
+    stashes (rows, per-lookup grads) here instead of building a gradient tensor.
+
+    The table's `.grad` therefore stays None: `clip_grad_norm_(model.parameters())` neither counts nor clips the
+    embedding gradient in this mode.  The reference cannot clip there either (clip_grad_norm_ raises on the COO
+    gradient of `sparse=True`, which is why its sparse configs run with clip_grad = 0, src/trainer/deepfm.py:24,56)."""
 
     def __init__(self, embedding_module, defaults):
         table, table1, _aux = embedding_module._tensors()
@@ -31,6 +35,18 @@ class _FusedRowOptimizer(torch.optim.Optimizer):
 
     def stash(self, table, rows, row_grads, sorted_pair=None):
         self._pending.append((table, rows, row_grads, sorted_pair))
+
+    def _take_pending(self):
+        """All backward passes since the last step as ONE gradient (what torch.optim.SparseAdam / SGD see when
+        several backwards accumulate into one COO .grad: it coalesces and steps once).  A single backward keeps its
+        presorted rows; several are concatenated and sorted together."""
+        pending, self._pending = self._pending, []
+        if len(pending) <= 1:
+            return pending
+        table = pending[0][0]
+        rows = torch.cat([p[1].reshape(-1) for p in pending])
+        rg = torch.cat([p[2].reshape(-1, p[2].shape[-1]) for p in pending])
+        return [(table, rows, rg, None)]
 
     def zero_grad(self, set_to_none: bool = True):
         self._pending.clear()
@@ -49,8 +65,7 @@ class FusedSparseAdam(_FusedRowOptimizer):
     def step(self, closure=None):
         group = self.param_groups[0]
         p = group["params"][0]
-        pending, self._pending = self._pending, []
-        for table, rows, rg, pair in pending:
+        for table, rows, rg, pair in self._take_pending():
             state = self.state[p]
             if len(state) == 0:
                 state["step"] = 0
@@ -73,8 +88,7 @@ class FusedSparseSGD(_FusedRowOptimizer):
     def step(self, closure=None):
         group = self.param_groups[0]
         p = group["params"][0]
-        pending, self._pending = self._pending, []
-        for table, rows, rg, pair in pending:
+        for table, rows, rg, pair in self._take_pending():
             skeys, perm = pair if pair is not None else RF.sort_rows(rows, p.shape[0])
             RF.segment_reduce_apply(L.APPLY_SPARSE_SGD, skeys, perm, rg, p.data, lr=group["lr"])
         return None

@@ -136,6 +136,7 @@ class ShardGroup:
             addr = [self.buf[k].ptr if g == self.rank else _open(gathered[g][k], device) for g in range(self.world)]
             self.ptrs[k] = torch.tensor(addr, dtype=torch.int64, device=device)
         self._tick = torch.zeros(1, device=device)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)   # set by the gather on an out-of-range id
 
     def barrier(self):
         """Stream-ordered cross-rank ordering point (a 1-element allreduce, no host sync)."""
@@ -169,7 +170,7 @@ class _ShardedLookup(torch.autograd.Function):
         RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded, L.ptr(x), int(x.dtype == torch.int32),
                  L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(fc) if use_fm else None,
                  sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
-                 None, L.stream_ptr(dev), nbytes=nbytes)
+                 L.ptr(sg.err_flag), L.stream_ptr(dev), nbytes=nbytes)
         ctx.sg, ctx.use_fm, ctx.shape = sg, use_fm, (b, f)
         ctx.fc_shape = tuple(fc.shape) if fc is not None else None
         ctx.save_for_backward(rows, emb, s)
@@ -228,12 +229,33 @@ class ShardedVanillaEmbedding(IEmbedding):
         self.shards = ShardGroup(self._num_item, hidden_size, device, group)
         self._emb_module = nn.Module()
         self._emb_module.weight = nn.Parameter(self.shards.buf["table"].tensor)
-        with torch.no_grad():
+        self._init_shard(initializer)
+
+    INIT_CHUNK_ROWS = 1 << 20
+
+    @torch.no_grad()
+    def _init_shard(self, initializer: str):
+        """i.i.d. init of the FULL table (base.py:62-67: xavier_uniform_ / normal_(std=0.1)), of which this rank keeps
+        its rows: every rank draws the same global row blocks from the device generator (same seed on every rank, as
+        the replicated parameters already require) and copies out rows r with r % G == rank.  The gathered table is
+        the same for every world size, and no two global rows share values (drawing the local shard directly from
+        the same seed would give rows kG..kG+G-1 identical vectors)."""
+        sg = self.shards
+        n, d, g = self._num_item, self._hidden_size, sg.world
+        a = math.sqrt(6.0 / (n + d))            # xavier_uniform_ bound of the FULL [N, D] table
+        w = self._emb_module.weight
+        w.zero_()
+        for lo in range(0, n, self.INIT_CHUNK_ROWS):
+            hi = min(n, lo + self.INIT_CHUNK_ROWS)
+            blk = torch.empty(hi - lo, d, dtype=torch.float32, device=sg.device)
             if initializer == "xavier":
-                a = math.sqrt(6.0 / (self._num_item + hidden_size))   # xavier_uniform_ bound of the FULL table
-                self._emb_module.weight.uniform_(-a, a)
+                blk.uniform_(-a, a)
             else:
-                self._emb_module.weight.normal_(std=0.1)
+                blk.normal_(std=0.1)
+            first = lo + ((sg.rank - lo) % g)   # first global row >= lo owned by this rank
+            if first < hi:
+                mine = blk[first - lo::g]
+                w[first // g: first // g + mine.shape[0]].copy_(mine)
 
     def get_weight(self):
         return self.gather_full_weight()
@@ -256,7 +278,10 @@ class ShardedVanillaEmbedding(IEmbedding):
         if offsets is not None:
             offsets = offsets.reshape(-1).long()
         use_fm = fc is not None
+        self._rsb_err_flag = self.shards.err_flag     # read by IEmbedding.train() / validate=True like the others
         emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm)
+        if self.validate:
+            RF.check_index_errors(self)
         return emb, (y if use_fm else None)
 
 

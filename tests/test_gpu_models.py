@@ -347,6 +347,48 @@ def test_out_of_range_ids_raise_index_error_when_validating(R):
     assert tuple(emb(torch.tensor([[4, 10]], device=DEV)).shape) == (1, 2, 16)   # max valid ids
 
 
+def test_out_of_range_ids_surface_at_the_next_train_eval_switch_without_validate(R):
+    """Default mode (no per-call sync): the gather flags the bad id, and the next model.eval() / model.train() - the
+    epoch boundaries of the reference trainer - raises the IndexError F.embedding would have raised."""
+    model = R.get_ctr_model([5, 6, 7], dict(num_factor=16, hidden_sizes=[8], p_dropout=0.0)).to(DEV).train()
+    model(torch.tensor([[0, 1, 2]], device=DEV))
+    model.eval()                                            # clean so far
+    model(torch.tensor([[0, 6, 2]], device=DEV))            # field 1 has 6 ids: 6 is out of range... for the table it
+    model.train()                                           # is still a valid global row, like in the reference
+    model(torch.tensor([[0, 1, 7 + 11]], device=DEV))       # global row 29 >= 18: out of range
+    with pytest.raises(IndexError):
+        model.eval()
+    model.train()                                           # the flag was cleared by the raise
+
+
+def test_fused_sparse_adam_accumulates_backwards_like_torch_sparse_adam(R):
+    """Two backward passes before one optimizer step = ONE SparseAdam step on the coalesced sum."""
+    torch.manual_seed(1)
+    dims = [50, 7, 300, 11]
+    ours = R.get_ctr_model(dims, dict(num_factor=16, hidden_sizes=[32], p_dropout=0.0,
+                                      embedding_config={"name": "vanilla", "sparse": True})).to(DEV).train()
+    ref = R.get_ctr_model(dims, dict(num_factor=16, hidden_sizes=[32], p_dropout=0.0,
+                                     embedding_config={"name": "vanilla", "sparse": True})).to(DEV).train()
+    ref.load_state_dict(ours.state_dict())
+    o_ours = R.FusedSparseAdam(ours.embedding, lr=1e-2)
+    o_ref = torch.optim.SparseAdam(list(ref.embedding.parameters()), lr=1e-2)
+    g = torch.Generator().manual_seed(2)
+    for step in range(2):
+        o_ours.zero_grad()
+        o_ref.zero_grad()
+        for micro in range(2):
+            x = torch.stack([torch.randint(0, d, (64,), generator=g) for d in dims], 1).to(DEV)
+            y = torch.randint(0, 2, (64,), generator=g).float().to(DEV)
+            for m in (ours, ref):
+                torch.nn.functional.binary_cross_entropy_with_logits(m(x), y).backward()
+        o_ours.step()
+        o_ref.step()
+        assert o_ours.state[ours.embedding.get_weight()]["step"] == step + 1
+        assert_close(ours.embedding.get_weight().detach().cpu().numpy(),
+                     ref.embedding.get_weight().detach().cpu().numpy(), what=f"step {step}", atol_scale=2e-5)
+    o_ours.detach_from_module()
+
+
 def test_unsupported_row_width_fails_loudly(R):
     emb = R.get_embedding({"name": "vanilla"}, [5, 6], 50).to(DEV)   # 50 % 4 != 0 and > 32
     with pytest.raises(RuntimeError, match="unsupported row width"):
@@ -611,8 +653,12 @@ def test_side_stream_overlap_is_bit_identical_to_inline_execution(R, emb_cfg, mo
             out.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
         return out
 
+    n0 = RF.SortedRows.constructed
     a = grads(True, True)
+    n1 = RF.SortedRows.constructed
     b = grads(False, False)
+    assert n1 - n0 == 2, "the early sort did not run (one SortedRows per training step expected)"
+    assert RF.SortedRows.constructed == n1, "EARLY_SORT = False must sort inside the backward"
     for ga, gb in zip(a, b):
         assert ga.keys() == gb.keys()
         for k in ga:
@@ -652,3 +698,34 @@ def test_d16_pep_feature_dim(R, tmp_path):
 
 def test_d16_optembed(R):
     _run_steps(R, "d16_optembed", {"name": "deepfm_optembed"}, ADAM, 1, pre_step=_optembed_pre)
+
+
+def test_gradient_accumulation_with_side_stream_dw_matches_inline(R, monkeypatch):
+    """Two backward passes into the same .grad (gradient accumulation) and zero_grad(set_to_none=False): the first
+    layer's weight gradient must not race its side-stream GEMM - results equal the in-line execution."""
+    import recsys_benchmark_b200.linalg as LA
+
+    def run(side):
+        if not side:
+            monkeypatch.setattr(LA, "_side_dw_safe", lambda w: False)
+        torch.manual_seed(9)
+        m = R.get_ctr_model(CRITEO_DIMS, dict(num_factor=16, hidden_sizes=[400, 400], p_dropout=0.0,
+                                              use_batchnorm=False, embedding_config={"name": "qr", "divider": 5})
+                            ).to(DEV).train()
+        g = torch.Generator().manual_seed(3)
+        xs = [torch.stack([torch.randint(0, d, (4096,), generator=g) for d in CRITEO_DIMS], 1).int().to(DEV)
+              for _ in range(3)]
+        y = torch.randint(0, 2, (4096,), generator=g).float().to(DEV)
+        for p in m.parameters():
+            p.grad = None
+        for x in xs[:2]:                          # accumulate two micro-batches
+            torch.nn.functional.binary_cross_entropy_with_logits(m(x), y).backward()
+        acc = m._deep_branch[0].weight.grad.clone()
+        m.zero_grad(set_to_none=False)            # .grad stays allocated: the next backward must add in place
+        torch.nn.functional.binary_cross_entropy_with_logits(m(xs[2]), y).backward()
+        torch.cuda.synchronize()
+        return acc, m._deep_branch[0].weight.grad.clone()
+
+    a = run(True)
+    b = run(False)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
