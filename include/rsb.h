@@ -269,6 +269,42 @@ RSB_API int rsb_gemm_f32(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N,
                          void* stream);
 
 /* ------------------------------------------------------------------------
+ * The same fp32-accurate GEMM on PRE-SPLIT operands ("planes"), hand-written TMA + tcgen05 + TMEM kernel
+ * (csrc/gemm/planes_gemm.cu).  An fp32 matrix X is held as three bf16 matrices X0 + X1 + X2 (8 mantissa bits each);
+ * the kernel issues the six plane products >= 2^-16 |a||b| as bf16 tensor-core MMAs, smallest first, and drains the
+ * TMEM accumulator into fp32 registers every 32 k.  Replaces the reference's fp32 cuBLAS GEMMs of nn.Linear
+ * (src/models/deepfm.py:55-66, src/models/dcn.py:56-66) and of the DCN-Mix expert projections
+ * (src/models/layer_dcn.py:20-23); planes are written once by rsb_split_planes (or a producer's epilogue) and reused by
+ * every GEMM that reads the operand (forward + weight gradient share the activation planes).
+ *
+ * rsb_planes_operand: `planes` = bf16 [3][rows][ld] (plane p at planes + p * plane_stride elements), the STORED matrix
+ *   is [rows, cols] row-major.  mn_major = 0: the stored rows are the M (or N) index and the columns the K index
+ *   ("K-major": activations [B, in] for y = x W^T, nn.Linear weights [out, in]); mn_major = 1: the stored rows are K
+ *   and the columns M (or N) (both operands of a weight gradient dW = gz^T x, whose K is the batch).
+ *   batch_row_step / batch_col_step: added to the stored row / column coordinate per batch index (strided batches
+ *   that live inside one matrix, e.g. the E experts of layer_dcn.py:22 as column blocks).
+ * ld, plane_stride multiples of 8 elements; planes 16-byte aligned; N, ldd multiples of 4.
+ * D[l] = alpha * A[l] B[l]^T-or-B[l] + beta * C[l] + bias;  split_k = 0 picks a split that fills the SMs when there
+ * are fewer tiles than SMs (partials in the workspace, summed in fixed order by a second launch).
+ * ---------------------------------------------------------------------- */
+typedef struct {
+  const void* planes;
+  int64_t rows, cols, ld, plane_stride;
+  int32_t mn_major;
+  int64_t batch_row_step, batch_col_step;
+} rsb_planes_operand;
+
+/* fp32 [rows, cols] (ld) -> bf16 planes [3][rows][out_ld] (columns cols..out_ld-1 zero); transpose = 1 writes the
+ * planes of in^T ([cols][out_ld >= rows]) - used once per optimizer step for nn.Linear weights (dX GEMM operand). */
+RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, void* out_planes,
+                             int64_t out_ld, int64_t plane_stride, void* stream);
+RSB_API int64_t rsb_gemm_planes_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int32_t split_k);
+RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operand* B, int64_t M, int64_t N, int64_t K,
+                            int64_t batch, int32_t split_k, const float* C, float* D, int64_t ldd, int64_t d_batch_stride,
+                            const float* bias, float alpha, float beta, void* workspace, int64_t workspace_bytes,
+                            void* stream);
+
+/* ------------------------------------------------------------------------
  * Bandwidth-bound glue of the dense tails (Linear -> [BatchNorm1d] -> ReLU -> Dropout,
  * src/models/deepfm.py:55-66, src/models/dcn.py:56-66), one pass per direction.
  *  rsb_relu_dropout_fwd  y = dropout_p(relu(x)), mask[i] = 1 iff x[i] > 0 and kept (Philox4x32-10 keyed by

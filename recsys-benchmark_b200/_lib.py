@@ -25,6 +25,14 @@ QR_KINDS = {"mult": KIND_QR_MULT, "add": KIND_QR_ADD, "cat": KIND_QR_CAT}
 
 _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
+class PlanesOperand(C.Structure):
+    """rsb_planes_operand of include/rsb.h: an fp32 matrix held as three bf16 planes."""
+
+    _fields_ = [("planes", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("ld", C.c_int64),
+                ("plane_stride", C.c_int64), ("mn_major", C.c_int32), ("batch_row_step", C.c_int64),
+                ("batch_col_step", C.c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/rsb.h declares
 PROTOTYPES = {
     "rsb_version": (C.c_char_p, []),
@@ -57,6 +65,10 @@ PROTOTYPES = {
     "rsb_gemm_f32_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64]),
     "rsb_gemm_f32": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64,
                                _i64, _p, _f, _f, _p, _i64, _p]),
+    "rsb_split_planes": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _i64, _i64, _p]),
+    "rsb_gemm_planes_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i32]),
+    "rsb_gemm_planes": (C.c_int, [C.POINTER(PlanesOperand), C.POINTER(PlanesOperand), _i64, _i64, _i64, _i64, _i32, _p,
+                                  _p, _i64, _i64, _p, _f, _f, _p, _i64, _p]),
     "rsb_relu_dropout_fwd": (C.c_int, [_p, _i64, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p]),
     "rsb_relu_dropout_bwd": (C.c_int, [_p, _p, _i64, _i32, _f, _p, _p, _p, _i64, _p]),
     "rsb_colsum_workspace_bytes": (_i64, [_i64, _i32]),

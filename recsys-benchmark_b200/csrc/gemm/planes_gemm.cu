@@ -1,0 +1,614 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores, hand-written for sm_100a (TMA + tcgen05 + TMEM).
+//
+// What it replaces: the true-fp32 cuBLAS SGEMMs the reference runs for nn.Linear in the dense tails
+// (src/models/deepfm.py:55-66, src/models/dcn.py:56-66) and for the DCN-Mix expert projections
+// (src/models/layer_dcn.py:20-23) - TF32 is off there, so a plain bf16 / TF32 MMA would break the 1e-5 gate.
+//
+// Arithmetic: every fp32 operand x is held as three bf16 "planes" x0 + x1 + x2 (x0 = bf16(x), x1 = bf16(x - x0),
+// x2 = bf16(x - x0 - x1): 3 x 8 mantissa bits).  A product a*b is the sum of the six plane products >= 2^-16 |a||b|
+//      band 3: a0 b2, a1 b1, a2 b0      band 2: a0 b1, a1 b0      band 1: a0 b0
+// (the three dropped ones are <= 2^-24 |a||b|).  bf16 x bf16 products are exact in fp32; what costs accuracy is the
+// accumulation: the tensor core truncates the running fp32 sum once per MMA.  Therefore
+//   * the planes are produced ONCE by whoever writes the operand (the split kernel below, or a producer's epilogue),
+//     not re-split by every CTA for every tile, and arrive by TMA as plain bf16 tiles;
+//   * within a 32-deep K group the 12 MMAs are issued smallest band first into one TMEM accumulator (the small
+//     bands are added while the sum is still small), and after every K group the accumulator is drained into fp32
+//     REGISTERS with round-to-nearest adds by the epilogue warps (two TMEM buffers: the MMAs of group g+1 run
+//     while group g is drained).  Only two truncations of full-size sums per 32 k: error vs fp64 ~1e-7.
+//
+// Kernel: persistent, one CTA per SM, 12 warps:
+//   warp 0      TMA producer (one lane): 3-plane boxes of A and B per stage -> smem ring, mbarrier complete_tx
+//   warp 1      MMA issuer (one lane): tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), tcgen05.commit
+//   warp 2      TMEM allocation
+//   warps 4-11  drain TMEM -> registers every K group (tcgen05.ld 32x32b), final epilogue (alpha, beta*C, bias)
+// Operands may be K-major ([rows, K] row-major: activations for the forward / dX GEMMs, nn.Linear weights) with the
+// 64-byte swizzle, or MN-major ([K, rows] row-major: both operands of a weight-gradient GEMM, whose reduction runs
+// over the batch) with the 128-byte swizzle; the smem / instruction descriptors carry the majorness.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rsb.h"
+
+namespace rsb {
+void note_launch(int n);
+int sm_count();
+}  // namespace rsb
+
+namespace pg {
+
+constexpr int kBlockM = 128;        // rows of D per CTA tile = TMEM lanes
+constexpr int kBlockK = 32;         // K per stage = one drain group (2 MMA K steps of 16)
+constexpr int kThreads = 384;
+constexpr int kEpiWarp0 = 4;        // first epilogue warp
+constexpr int kTmemCols = 512;
+constexpr int kTmemBufStride = 256; // columns between the two accumulator buffers
+constexpr int kMaxStages = 4;
+constexpr uint32_t kSmemLimit = 227 * 1024;
+
+struct Operand {
+  int mn_major;          // 0: K-major [rows, K]; 1: MN-major [K, rows]
+  int batch_row_step;    // added to the ROW coordinate of the stored matrix per batch index
+  int batch_col_step;    // added to the COLUMN coordinate per batch index
+};
+
+struct Params {
+  int M, N, K, batch, splits;
+  int n_tile, m_tiles, n_tiles;
+  int k_blocks;          // ceil(K / 32)
+  int stages;
+  uint32_t a_stage_bytes, b_stage_bytes;
+  Operand a, b;
+  // epilogue
+  float* D;
+  long long ldd, d_batch_stride;
+  const float* C;
+  const float* bias;
+  float alpha, beta;
+  float* partial;        // split-K: [splits][batch][M][N] raw sums (then splitk_reduce_kernel)
+};
+
+// ------------------------------------------------------------------------------------------- PTX wrappers ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"): start address, leading / stride byte
+// offsets (all >> 4), descriptor version 1 (Blackwell) at bit 46, swizzle mode at bits 61-63
+constexpr uint64_t kSwizzle128 = 2, kSwizzle64 = 4;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint64_t swizzle) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (swizzle << 61);
+}
+
+// instruction descriptor for kind::f16: D fp32, A / B bf16, majorness bits, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ kernel ---
+struct Tile {
+  int m_blk, n_blk, batch, split;
+  int kb0, kb1;   // K-block range of this split
+};
+
+__device__ __forceinline__ bool get_tile(const Params& p, int idx, Tile& t) {
+  const int per_split = p.m_tiles * p.n_tiles * p.batch;
+  if (idx >= per_split * p.splits) return false;
+  t.split = idx / per_split;
+  int r = idx - t.split * per_split;
+  // M fastest: CTAs running at the same time share the B (weight) tile, which then stays in L2
+  t.m_blk = r % p.m_tiles;
+  r /= p.m_tiles;
+  t.n_blk = r % p.n_tiles;
+  t.batch = r / p.n_tiles;
+  const int base = p.k_blocks / p.splits, rem = p.k_blocks % p.splits;
+  t.kb0 = t.split * base + (t.split < rem ? t.split : rem);
+  t.kb1 = t.kb0 + base + (t.split < rem ? 1 : 0);
+  return true;
+}
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1)
+planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+  // accumulator columns handled by the two epilogue warps that share a TMEM lane quarter
+  constexpr int kHalf0 = ((N_TILE + 31) / 32) * 16;
+  constexpr int kHalf1 = N_TILE - kHalf0;
+  constexpr int NC = kHalf0;
+  static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "N tile");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 8);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      Tile t;
+      for (int idx = blockIdx.x; get_tile(p, idx, t); idx += gridDim.x) {
+        const int m0 = t.m_blk * kBlockM, n0 = t.n_blk * N_TILE;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + p.a_stage_bytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          const int k0 = kb * kBlockK;
+          if (!p.a.mn_major) {
+            tma_load_3d(&map_a, &full_bar[stage], sa, k0 + t.batch * p.a.batch_col_step,
+                        m0 + t.batch * p.a.batch_row_step, 0);
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < kBlockM / 64; ++j)
+              tma_load_3d(&map_a, &full_bar[stage], sa + j * (3 * kBlockK * 128), m0 + j * 64 + t.batch * p.a.batch_col_step,
+                          k0 + t.batch * p.a.batch_row_step, 0);
+          }
+          if (!p.b.mn_major) {
+            tma_load_3d(&map_b, &full_bar[stage], sb, k0 + t.batch * p.b.batch_col_step,
+                        n0 + t.batch * p.b.batch_row_step, 0);
+          } else {
+#pragma unroll 1
+            for (int j = 0; j < (N_TILE + 63) / 64; ++j)
+              tma_load_3d(&map_b, &full_bar[stage], sb + j * (3 * kBlockK * 128), n0 + j * 64 + t.batch * p.b.batch_col_step,
+                          k0 + t.batch * p.b.batch_row_step, 0);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(N_TILE, p.a.mn_major, p.b.mn_major);
+      // plane strides / descriptor geometry inside a stage
+      const uint32_t a_plane = p.a.mn_major ? kBlockK * 128 : kBlockM * 64;
+      const uint32_t b_plane = p.b.mn_major ? kBlockK * 128 : N_TILE * 64;
+      const uint32_t a_kstep = p.a.mn_major ? 2048 : 32;   // 16 k: two 8-row groups of 1 KiB / 32 bytes in a row
+      const uint32_t b_kstep = p.b.mn_major ? 2048 : 32;
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, tphase[2] = {0, 0};
+      Tile t;
+      for (int idx = blockIdx.x; get_tile(p, idx, t); idx += gridDim.x) {
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&tempty_bar[buf], tphase[buf] ^ 1);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + p.a_stage_bytes;
+          const uint32_t d_tmem = tmem_base + buf * kTmemBufStride;
+          uint64_t da[3], db[3];
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            da[pl] = p.a.mn_major ? make_desc(sa + pl * a_plane, 3 * kBlockK * 128, 1024, kSwizzle128)
+                                  : make_desc(sa + pl * a_plane, 16, 512, kSwizzle64);
+            db[pl] = p.b.mn_major ? make_desc(sb + pl * b_plane, 3 * kBlockK * 128, 1024, kSwizzle128)
+                                  : make_desc(sb + pl * b_plane, 16, 512, kSwizzle64);
+          }
+          // smallest band first; the first MMA of the group overwrites the (drained) accumulator
+          uint32_t acc = 0;
+#define PG_MMA(PA, PB)                                                                                      \
+  _Pragma("unroll") for (int ks = 0; ks < kBlockK / 16; ++ks) {                                             \
+    mma_bf16(d_tmem, da[PA] + (uint64_t)((ks * a_kstep) >> 4), db[PB] + (uint64_t)((ks * b_kstep) >> 4), idesc, acc); \
+    acc = 1;                                                                                                \
+  }
+          PG_MMA(0, 2) PG_MMA(1, 1) PG_MMA(2, 0)   // band 3
+          PG_MMA(0, 1) PG_MMA(1, 0)                // band 2
+          PG_MMA(0, 0)                             // band 1
+#undef PG_MMA
+          mma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs have read it
+          mma_commit(&tfull_bar[buf]);             // accumulator of this K group complete
+          tphase[buf] ^= 1;
+          buf ^= 1;
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ================================ drain + epilogue ================================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;     // which column half of the tile
+    const int col0 = half ? kHalf0 : 0;
+    const int ncols = half ? kHalf1 : kHalf0;     // multiple of 16 (0 possible only if N_TILE == 16)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int buf = 0;
+    uint32_t tphase[2] = {0, 0};
+    Tile t;
+    for (int idx = blockIdx.x; get_tile(p, idx, t); idx += gridDim.x) {
+      float acc[NC];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[i] = 0.f;
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        mbar_wait(&tfull_bar[buf], tphase[buf]);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_addr + buf * kTmemBufStride + col0;
+#pragma unroll
+        for (int c = 0; c < NC; c += 16) {
+          if (c < ncols) {
+            float v[16];
+            tmem_ld16(taddr + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[c + i] += v[i];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        tphase[buf] ^= 1;
+        buf ^= 1;
+      }
+      // ---- epilogue: this thread owns row (m0 + 32 q + lane), columns [n0 + col0, n0 + col0 + ncols) ----
+      const long long row = (long long)t.m_blk * kBlockM + q * 32 + lane;
+      const int n0 = t.n_blk * N_TILE + col0;
+      if (row < p.M) {
+        if (p.partial != nullptr) {
+          float* dst = p.partial + (((long long)t.split * p.batch + t.batch) * p.M + row) * p.N;
+#pragma unroll
+          for (int c = 0; c < NC; c += 4) {
+            if (c < ncols && n0 + c < p.N)
+              *reinterpret_cast<float4*>(dst + n0 + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+          }
+        } else {
+          float* dst = p.D + (long long)t.batch * p.d_batch_stride + row * p.ldd;
+          const float* csrc = p.C ? p.C + (long long)t.batch * p.d_batch_stride + row * p.ldd : nullptr;
+#pragma unroll
+          for (int c = 0; c < NC; c += 4) {
+            if (c < ncols && n0 + c < p.N) {
+              float4 o = make_float4(acc[c] * p.alpha, acc[c + 1] * p.alpha, acc[c + 2] * p.alpha, acc[c + 3] * p.alpha);
+              if (csrc) {
+                const float4 cc = *reinterpret_cast<const float4*>(csrc + n0 + c);
+                o.x = fmaf(p.beta, cc.x, o.x); o.y = fmaf(p.beta, cc.y, o.y);
+                o.z = fmaf(p.beta, cc.z, o.z); o.w = fmaf(p.beta, cc.w, o.w);
+              }
+              if (p.bias) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
+                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+              }
+              *reinterpret_cast<float4*>(dst + n0 + c) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// split-K: D = alpha * sum_s partial[s] + beta * C + bias, fixed summation order
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long batch, long long M, long long N,
+                                     float* __restrict__ D, long long ldd, long long d_batch_stride,
+                                     const float* __restrict__ C, const float* __restrict__ bias, float alpha, float beta) {
+  const long long n4 = N / 4, total = batch * M * n4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c4 = i % n4, r = (i / n4) % M, l = i / (n4 * M);
+    const long long src = (l * M + r) * N + c4 * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < splits; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(partial + (long long)k * batch * M * N + src));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= alpha; s.y *= alpha; s.z *= alpha; s.w *= alpha;
+    const long long o = l * d_batch_stride + r * ldd + c4 * 4;
+    if (C) {
+      const float4 cc = *reinterpret_cast<const float4*>(C + o);
+      s.x = fmaf(beta, cc.x, s.x); s.y = fmaf(beta, cc.y, s.y); s.z = fmaf(beta, cc.z, s.z); s.w = fmaf(beta, cc.w, s.w);
+    }
+    if (bias) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + c4 * 4));
+      s.x += bb.x; s.y += bb.y; s.z += bb.z; s.w += bb.w;
+    }
+    *reinterpret_cast<float4*>(D + o) = s;
+  }
+}
+
+// fp32 [rows, cols] (ld) -> three bf16 planes [3][rows][out_ld]; columns >= cols (up to out_ld) are zero-filled.
+// transpose = 1: out plane [cols][out_ld >= rows] = in^T (small matrices: nn.Linear weights for the dX GEMM).
+__global__ void split_planes_kernel(const float* __restrict__ in, long long rows, long long cols, long long ld,
+                                    __nv_bfloat16* __restrict__ out, long long out_ld, long long plane_stride, int transpose) {
+  const long long orows = transpose ? cols : rows, ocols8 = out_ld / 8;
+  const long long total = orows * ocols8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ocols8, c0 = (i - r * ocols8) * 8;
+    float x[8];
+    const long long icols = transpose ? rows : cols;
+    if (!transpose && c0 + 8 <= icols && (ld & 3) == 0) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(in + r * ld + c0));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * ld + c0 + 4));
+      x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long c = c0 + j;
+        x[j] = (c < icols) ? (transpose ? __ldg(in + c * ld + r) : __ldg(in + r * ld + c)) : 0.f;
+      }
+    }
+    __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[j]);
+      const float r1 = x[j] - __bfloat162float(h0);            // exact in fp32
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+      const float r2 = r1 - __bfloat162float(h1);              // exact
+      p0[j] = h0; p1[j] = h1; p2[j] = __float2bfloat16_rn(r2);
+    }
+    __nv_bfloat16* o = out + r * out_ld + c0;
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p0);
+    *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<const uint4*>(p1);
+    *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<const uint4*>(p2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host ---
+// cuTensorMapEncodeTiled is a DRIVER entry point: resolved at first use through the runtime, so that librsb.so has no
+// link-time dependency on libcuda (the library must load, and its argument checks run, on a box without a driver)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static bool encode_map(CUtensorMap* map, const void* base, long long cols, long long rows, long long ld, long long plane_stride,
+                       int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+  // dims (innermost first): columns, rows, planes
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 3};
+  cuuint32_t estr[3] = {1, 1, 1};
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr) return false;
+  CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
+template <int N_TILE>
+static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, size_t smem, cudaStream_t st) {
+  static bool attr[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(planes_gemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - 2048));   // static: barriers
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) attr[dev] = true;
+  }
+  planes_gemm_kernel<N_TILE><<<grid, kThreads, smem, st>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+static int pick_n_tile(long long N, int* n_tiles) {
+  int nt = (int)((N + 255) / 256);
+  long long per = (N + nt - 1) / nt;
+  int tile = (int)((per + 15) / 16 * 16);
+  *n_tiles = (int)((N + tile - 1) / tile);
+  return tile;
+}
+
+static int default_splits(long long M, long long N, long long K, long long batch) {
+  int n_tiles;
+  const int tile = pick_n_tile(N, &n_tiles);
+  (void)tile;
+  const long long tiles = ((M + kBlockM - 1) / kBlockM) * n_tiles * batch;
+  const long long kb = (K + kBlockK - 1) / kBlockK;
+  const int sms = rsb::sm_count();
+  if (tiles >= sms || kb < 16) return 1;
+  long long s = sms / tiles;                 // fill one wave
+  if (s > kb / 8) s = kb / 8;                // at least 8 K groups (256 k) per split
+  return s < 1 ? 1 : (int)s;
+}
+
+extern "C" RSB_API int64_t rsb_gemm_planes_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int32_t split_k) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return -1;
+  int s = split_k > 0 ? split_k : default_splits(M, N, K, batch);
+  return s > 1 ? (int64_t)s * batch * M * N * 4 + 256 : 256;
+}
+
+extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, void* out_planes,
+                                        int64_t out_ld, int64_t plane_stride, void* stream) {
+  if (!in || !out_planes || rows <= 0 || cols <= 0 || ld < (transpose ? cols : cols)) return RSB_ERR_BAD_ARG;
+  const int64_t ocols = transpose ? rows : cols, orows = transpose ? cols : rows;
+  if (out_ld % 8 || out_ld < ocols || plane_stride < orows * out_ld || plane_stride % 8 ||
+      (reinterpret_cast<uintptr_t>(out_planes) & 15))
+    return RSB_ERR_UNSUPPORTED;
+  const long long total = orows * (out_ld / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)rsb::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  split_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      in, rows, cols, ld, reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride, transpose);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  return RSB_OK;
+}
+
+extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operand* B, int64_t M, int64_t N, int64_t K,
+                                       int64_t batch, int32_t split_k, const float* C, float* D, int64_t ldd,
+                                       int64_t d_batch_stride, const float* bias, float alpha, float beta, void* workspace,
+                                       int64_t workspace_bytes, void* stream) {
+  if (!A || !B || !A->planes || !B->planes || !D || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return RSB_ERR_BAD_ARG;
+  if (beta != 0.f && !C) return RSB_ERR_BAD_ARG;
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff || batch > 65535) return RSB_ERR_BAD_ARG;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+  if (!al16(A->planes) || !al16(B->planes) || !al16(D) || (C && !al16(C)) || (bias && !al16(bias))) return RSB_ERR_UNSUPPORTED;
+  if (N % 4 || ldd % 4 || d_batch_stride % 4 || A->ld % 8 || B->ld % 8 || A->plane_stride % 8 || B->plane_stride % 8)
+    return RSB_ERR_UNSUPPORTED;
+  // a batch that advances along K inside one stored matrix must not let a K tail read its neighbour
+  const bool a_k_step = A->mn_major ? A->batch_row_step != 0 : A->batch_col_step != 0;
+  const bool b_k_step = B->mn_major ? B->batch_row_step != 0 : B->batch_col_step != 0;
+  if (batch > 1 && (a_k_step || b_k_step) && K % kBlockK) return RSB_ERR_UNSUPPORTED;
+  {
+    // cuTensorMapEncodeTiled is a driver call: it needs a context current on this (possibly autograd worker) thread
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return (int)e;
+  }
+  Params p = {};
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
+  p.n_tile = pick_n_tile(N, &p.n_tiles);
+  p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.k_blocks = (int)((K + kBlockK - 1) / kBlockK);
+  p.splits = split_k > 0 ? split_k : default_splits(M, N, K, batch);
+  if (p.splits > p.k_blocks) p.splits = p.k_blocks;
+  p.a.mn_major = A->mn_major; p.a.batch_row_step = (int)A->batch_row_step; p.a.batch_col_step = (int)A->batch_col_step;
+  p.b.mn_major = B->mn_major; p.b.batch_row_step = (int)B->batch_row_step; p.b.batch_col_step = (int)B->batch_col_step;
+  p.a_stage_bytes = 3u * kBlockM * kBlockK * 2;                                           // both majors: 24 KiB
+  p.b_stage_bytes = B->mn_major ? (uint32_t)((p.n_tile + 63) / 64) * 3u * kBlockK * 128 : 3u * p.n_tile * kBlockK * 2;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  p.stages = (int)((kSmemLimit - 4096) / stage_bytes);   // 1 KiB alignment slack + static shared memory
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages < 2) return RSB_ERR_UNSUPPORTED;
+  p.D = D; p.ldd = ldd; p.d_batch_stride = d_batch_stride; p.C = C; p.bias = bias; p.alpha = alpha; p.beta = beta;
+  if (p.splits > 1) {
+    const int64_t need = (int64_t)p.splits * batch * M * N * 4 + 256;
+    if (!workspace || workspace_bytes < need) return RSB_ERR_WORKSPACE;
+    p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  }
+  CUtensorMap ma, mb;
+  bool ok = A->mn_major ? encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
+                        : encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B);
+  ok = ok && (B->mn_major ? encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
+                          : encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, kBlockK, p.n_tile, CU_TENSOR_MAP_SWIZZLE_64B));
+  if (!ok) return RSB_ERR_UNSUPPORTED;
+  const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batch * p.splits;
+  int grid = rsb::sm_count();
+  if (tiles < grid) grid = (int)tiles;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (p.n_tile) {
+#define PG_CASE(NT) case NT: e = launch<NT>(ma, mb, p, grid, smem, st); break;
+    PG_CASE(16) PG_CASE(32) PG_CASE(48) PG_CASE(64) PG_CASE(80) PG_CASE(96) PG_CASE(112) PG_CASE(128)
+    PG_CASE(144) PG_CASE(160) PG_CASE(176) PG_CASE(192) PG_CASE(208) PG_CASE(224) PG_CASE(240) PG_CASE(256)
+#undef PG_CASE
+    default: return RSB_ERR_UNSUPPORTED;
+  }
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  if (p.splits > 1) {
+    const long long total = batch * M * (N / 4);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)rsb::sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, p.splits, batch, M, N, D, ldd, d_batch_stride, C, bias, alpha, beta);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    rsb::note_launch(1);
+  }
+  return RSB_OK;
+}

@@ -14,6 +14,7 @@ import torch
 
 from . import _lib as L
 from . import functional as RF
+from . import planes as P
 
 MIN_FLOPS = 1 << 22   # below this a library call is launch-latency-equivalent
 
@@ -23,107 +24,90 @@ def _aligned(*tensors) -> bool:
 
 
 def gemm_supported(m: int, n: int, k: int, lda: int, ldb: int, ldd: int, trans_a: bool, trans_b: bool) -> bool:
+    """Shapes the tensor-core kernel takes: fp32 results are stored 128 bits at a time (N and the output leading
+    dimension multiples of 4); operands are re-laid out as bf16 planes, so their shapes are free."""
     if trans_a and trans_b:
         return False
-    if min(m, n, k) <= 0 or n % 4 or lda % 4 or ldb % 4 or ldd % 4:
-        return False
-    if (m if trans_a else k) % 4 or (k if trans_b else n) % 4:
-        return False
-    return True
+    return min(m, n, k) > 0 and n % 4 == 0 and ldd % 4 == 0
+
+
+def weight_planes(w: torch.Tensor) -> P.Planes:
+    """Planes of a parameter, rebuilt only when the parameter has changed (in-place updates bump `_version`): ONE
+    split per optimizer step serves the forward GEMM (as the K-major [out, in] operand) and the dX GEMM (the same
+    planes read as the MN-major [K = out, N = in] operand)."""
+    cached = getattr(w, "_rsb_planes", None)
+    key = (w._version, w.data_ptr(), tuple(w.shape))
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    pl = P.split(w.detach().reshape(-1, w.shape[-1]))
+    w._rsb_planes = (key, pl)
+    return pl
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
          bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, alpha: float = 1.0,
-         beta: float = 0.0, c: Optional[torch.Tensor] = None, split_k: int = 1) -> torch.Tensor:
-    """D = alpha * op(a) @ op(b) + beta * c + bias for 2-D fp32 CUDA tensors (contiguous rows).
+         beta: float = 0.0, c: Optional[torch.Tensor] = None, split_k: int = 1,
+         a_planes: Optional[P.Planes] = None, b_planes: Optional[P.Planes] = None) -> torch.Tensor:
+    """D = alpha * op(a) @ op(b) + beta * c + bias for 2-D fp32 CUDA tensors.
 
-    trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K].  split_k > 1 splits the
-    reduction dimension into that many batched partial GEMMs (summed by the caller's dtype,
-    fixed order) — for weight-gradient GEMMs whose K is the batch size."""
-    lib = L.load()
+    trans_a: `a` is stored [K, M]; trans_b: `b` is stored [N, K].  The operands are split into bf16 planes (or taken
+    from `a_planes` / `b_planes` when the caller already holds them) and multiplied by rsb_gemm_planes; no operand is
+    ever transposed in memory - the kernel reads either majorness.  split_k != 1 lets the kernel split the reduction
+    over the SMs (weight-gradient GEMMs whose K is the batch); partials are summed in fixed order."""
     dev = L.require_cuda(a, b, bias, c)
     assert a.dim() == 2 and b.dim() == 2 and a.dtype == torch.float32 and b.dtype == torch.float32
-    a = a if a.stride(1) == 1 else a.contiguous()
-    b = b if b.stride(1) == 1 else b.contiguous()
     k, m = (a.shape if trans_a else a.shape[::-1])
     kb, n = (b.shape[::-1] if trans_b else b.shape)
     assert k == kb, f"inner dimensions differ: {k} vs {kb}"
-    lda, ldb = a.stride(0), b.stride(0)
-    if split_k > 1 and (k % split_k or (k // split_k) % 4 or bias is not None or beta != 0.0):
-        split_k = 1
-    if not gemm_supported(m, n, k, lda, ldb, n if out is None else out.stride(0), trans_a, trans_b) or \
-            not _aligned(a, b, bias, c, out):
-        raise RuntimeError("rsb gemm: shape not supported by the TMA kernel")
-    if split_k > 1:
-        kc = k // split_k
-        part = torch.empty(split_k, m, n, dtype=torch.float32, device=dev)
-        sa = kc * lda if trans_a else kc          # A stored [K,M]: advance rows; A [M,K]: advance columns
-        sb = kc if trans_b else kc * ldb
-        nb = lib.rsb_gemm_f32_workspace_bytes(int(trans_a), int(trans_b), m, n, kc, split_k)
-        ws = RF._ws(nb, dev)
-        RF._call("gemm_f32", lib.rsb_gemm_f32, int(trans_a), int(trans_b), m, n, kc, split_k, L.ptr(a), lda, sa,
-                 L.ptr(b), ldb, sb, None, L.ptr(part), n, m * n, None, alpha, 0.0, L.ptr(ws), ws.numel(),
-                 L.stream_ptr(dev))
-        res = part.sum(0)
-        if out is not None:
-            out.copy_(res)
-            return out
-        return res
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device=dev)
-    nb = lib.rsb_gemm_f32_workspace_bytes(int(trans_a), int(trans_b), m, n, k, 1)
-    ws = RF._ws(nb, dev)
-    RF._call("gemm_f32", lib.rsb_gemm_f32, int(trans_a), int(trans_b), m, n, k, 1, L.ptr(a), lda, 0, L.ptr(b), ldb, 0,
-             L.ptr(c), L.ptr(out), out.stride(0), 0, L.ptr(bias), alpha, beta, L.ptr(ws), ws.numel(),
-             L.stream_ptr(dev))
-    return out
-
-
-def gemm_strided(m, n, k, batch, a, a_off, lda, sa, b, b_off, ldb, sb, out, d_off, ldd, sd, trans_a=False,
-                 trans_b=False, alpha=1.0) -> None:
-    """Raw strided-batched call: element offsets / leading dimensions / batch strides given explicitly
-    (all multiples of 4 floats).  out[d_off + l*sd + i*ldd + j] = alpha * sum_k op(A_l)[i,k] op(B_l)[k,j]."""
-    lib = L.load()
-    dev = a.device
-    nb = lib.rsb_gemm_f32_workspace_bytes(int(trans_a), int(trans_b), m, n, k, batch)
-    ws = RF._ws(nb, dev)
-    RF._call("gemm_f32", lib.rsb_gemm_f32, int(trans_a), int(trans_b), m, n, k, batch, a.data_ptr() + 4 * a_off, lda,
-             sa, b.data_ptr() + 4 * b_off, ldb, sb, None, out.data_ptr() + 4 * d_off, ldd, sd, None, alpha, 0.0,
-             L.ptr(ws), ws.numel(), L.stream_ptr(dev))
+    if not gemm_supported(m, n, k, 0, 0, out.stride(0), trans_a, trans_b) or out.stride(1) != 1 or \
+            not _aligned(bias, c, out):
+        raise RuntimeError("rsb gemm: shape not supported by the tensor-core kernel (N and ldd must be multiples of 4)")
+    pa = a_planes if a_planes is not None else P.split(a)
+    pb = b_planes if b_planes is not None else P.split(b)
+    return P.gemm(pa, pb, m, n, k, a_mn_major=trans_a, b_mn_major=not trans_b, bias=bias, out=out, alpha=alpha,
+                  beta=beta, c=c, split_k=1 if split_k == 1 else 0)
 
 
 class _ExpertMatMul(torch.autograd.Function):
     """Block-diagonal product of the DCN-Mix experts (src/models/layer_dcn.py:22):
     out[b, e, :] = h[b, e, :] @ C[e]   for h [B, E*r] (expert-major columns), C [E, r, r2].
-    One strided-batched tensor-core GEMM (batch = experts) forward and for dh; the weight
-    gradient is one split-K batched GEMM per expert."""
+    Three batched tensor-core GEMMs (batch = experts, addressed as column / row blocks inside the stored matrices):
+    forward, dh, and the split-K weight gradient; h and g are split into planes once each."""
 
     @staticmethod
     def forward(ctx, h, c):
         e, r, r2 = c.shape
         bsz = h.shape[0]
-        h = h.contiguous()
-        c = c.contiguous()
+        hp = P.split(h)
+        cp = weight_planes(c)                                   # stored [E*r, r2]
         out = torch.empty(bsz, e * r2, dtype=torch.float32, device=h.device)
-        gemm_strided(bsz, r2, r, e, h, 0, e * r, r, c, 0, r2, r * r2, out, 0, e * r2, r2)
-        ctx.save_for_backward(h, c)
+        # A = h[:, l*r:(l+1)*r] (K-major, column step r); B = C[l] stored [K = r, N = r2] (MN-major, row step r)
+        P.gemm(hp, cp, bsz, r2, r, a_mn_major=False, b_mn_major=True, out=out, batch=e, a_steps=(0, r),
+               b_steps=(r, 0), d_batch_stride=r2, split_k=1)
+        ctx.hp = hp
+        ctx.save_for_backward(c)
+        ctx.shape = (bsz, e, r, r2)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        h, c = ctx.saved_tensors
-        e, r, r2 = c.shape
-        bsz = h.shape[0]
-        g = g.contiguous()
+        (c,) = ctx.saved_tensors
+        bsz, e, r, r2 = ctx.shape
+        hp, ctx.hp = ctx.hp, None
+        gp = P.split(g)
         gh = gc = None
         if ctx.needs_input_grad[0]:
-            gh = torch.empty(bsz, e * r, dtype=torch.float32, device=h.device)
-            # gh[:, e, :] = g[:, e, :] @ C[e]^T : B operand "stored [N,K]" = C[e] as is
-            gemm_strided(bsz, r, r2, e, g, 0, e * r2, r2, c, 0, r2, r * r2, gh, 0, e * r, r, trans_b=True)
+            gh = torch.empty(bsz, e * r, dtype=torch.float32, device=g.device)
+            # gh[:, l, :] = g[:, l, :] @ C[l]^T : B = C[l] read as stored [N = r, K = r2] (K-major, row step r)
+            P.gemm(gp, weight_planes(c), bsz, r, r2, a_mn_major=False, b_mn_major=False, out=gh, batch=e,
+                   a_steps=(0, r2), b_steps=(r, 0), d_batch_stride=r, split_k=1)
         if ctx.needs_input_grad[1]:
-            # C_grad[e] = h[:, e, :]^T @ g[:, e, :] = the diagonal blocks of one [E*r, E*r2] split-K GEMM
-            full = gemm(h, g, trans_a=True, split_k=_split_for(bsz, e * r, e * r2))
-            gc = torch.stack([full[ei * r:(ei + 1) * r, ei * r2:(ei + 1) * r2] for ei in range(e)])
+            # C_grad[l] = h[:, l, :]^T @ g[:, l, :] : both operands MN-major (K = batch rows), column steps r / r2
+            gc = torch.empty(e, r, r2, dtype=torch.float32, device=g.device)
+            P.gemm(hp, gp, r, r2, bsz, a_mn_major=True, b_mn_major=True, out=gc.view(e * r, r2), batch=e,
+                   a_steps=(0, r), b_steps=(0, r2), d_batch_stride=r * r2, split_k=0)
         return gh, gc
 
 
@@ -131,8 +115,7 @@ def expert_matmul(h: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
     """h [B, E*r] x C [E, r, r2] -> [B, E*r2] (block diagonal)."""
     e, r, r2 = c.shape
     bsz = h.shape[0]
-    if r % 4 == 0 and r2 % 4 == 0 and bsz % 4 == 0 and 2 * bsz * e * r * r2 >= MIN_FLOPS and h.is_cuda and \
-            _aligned(h, c):
+    if r % 32 == 0 and r2 % 4 == 0 and 2 * bsz * e * r * r2 >= MIN_FLOPS and h.is_cuda and h.dtype == torch.float32:
         return _ExpertMatMul.apply(h, c)
     return torch.bmm(h.view(bsz, e, r).transpose(0, 1), c).transpose(0, 1).reshape(bsz, e * r2)
 
