@@ -247,29 +247,7 @@ RSB_API int rsb_dhe_encode(const void* ids, int32_t ids_is_i32, int64_t n, int64
                            float* out, void* stream);
 
 /* ------------------------------------------------------------------------
- * fp32-accurate tensor-core GEMM (tcgen05 + TMA; every fp32 operand split into 3 bf16 terms,
- * 9 MMAs accumulated in fp32 TMEM).  Used for the DCN-Mix low-rank expert projections
- * (src/models/layer_dcn.py:20-23: x@V, H@C, H@U, and their backward GEMMs) and for the
- * dense tails (nn.Linear of the MLPs), which the reference runs as true-fp32 cuBLAS SGEMM
- * (TF32 off), so plain TF32/bf16 MMA would break the 1e-5 parity gate.
- *
- *   D[l] = alpha * op(A[l]) * op(B[l]) + beta * C[l] + bias      l = 0..batch-1, D/C row-major [M,N] (ldd)
- *   trans_a = 0: A is [M,K] row-major (lda)      trans_a = 1: A is stored [K,M] row-major (lda)
- *   trans_b = 0: B is [K,N] row-major (ldb)      trans_b = 1: B is stored [N,K] row-major (ldb)  (nn.Linear weight)
- *   (trans_a = trans_b = 1 is not provided.)  bias: per column [N] or NULL.  C may be NULL when beta == 0.
- * TMA constraints: 16-byte aligned pointers; lda/ldb/ldd/batch strides and the contiguous
- * extents multiples of 4 floats -> otherwise RSB_ERR_UNSUPPORTED (callers use a library GEMM).
- * ---------------------------------------------------------------------- */
-RSB_API int64_t rsb_gemm_f32_workspace_bytes(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N, int64_t K,
-                                             int64_t batch);
-RSB_API int rsb_gemm_f32(int32_t trans_a, int32_t trans_b, int64_t M, int64_t N, int64_t K, int64_t batch,
-                         const float* A, int64_t lda, int64_t stride_a, const float* B, int64_t ldb,
-                         int64_t stride_b, const float* C, float* D, int64_t ldd, int64_t stride_d,
-                         const float* bias, float alpha, float beta, void* workspace, int64_t workspace_bytes,
-                         void* stream);
-
-/* ------------------------------------------------------------------------
- * The same fp32-accurate GEMM on PRE-SPLIT operands ("planes"), hand-written TMA + tcgen05 + TMEM kernel
+ * fp32-accurate tensor-core GEMM on PRE-SPLIT operands ("planes"), hand-written TMA + tcgen05 + TMEM kernel
  * (csrc/gemm/planes_gemm.cu).  An fp32 matrix X is held as three bf16 matrices X0 + X1 + X2 (8 mantissa bits each);
  * the kernel issues the six plane products >= 2^-16 |a||b| as bf16 tensor-core MMAs, smallest first, and drains the
  * TMEM accumulator into fp32 registers every 32 k.  Replaces the reference's fp32 cuBLAS GEMMs of nn.Linear

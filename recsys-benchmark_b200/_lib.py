@@ -62,9 +62,6 @@ PROTOTYPES = {
     "rsb_csr_lookup_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p,
                                      _p, _p]),
     "rsb_dhe_encode": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _p, _p]),
-    "rsb_gemm_f32_workspace_bytes": (_i64, [_i32, _i32, _i64, _i64, _i64, _i64]),
-    "rsb_gemm_f32": (C.c_int, [_i32, _i32, _i64, _i64, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _i64,
-                               _i64, _p, _f, _f, _p, _i64, _p]),
     "rsb_split_planes": (C.c_int, [_p, _i64, _i64, _i64, _i32, _p, _i64, _i64, _p]),
     "rsb_gemm_planes_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i32]),
     "rsb_gemm_planes": (C.c_int, [C.POINTER(PlanesOperand), C.POINTER(PlanesOperand), _i64, _i64, _i64, _i64, _i32, _p,

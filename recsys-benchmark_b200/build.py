@@ -27,21 +27,6 @@ NVCC_FLAGS = [
 ]
 
 
-def cutlass_include_dirs():
-    """CUTLASS/CuTe header trees vendored in the image (used by csrc/gemm only)."""
-    for base in sys.path + [os.path.dirname(os.path.dirname(os.__file__)) + "/site-packages"]:
-        for rel in ("flashinfer/data/cutlass", "tilelang/3rdparty/cutlass"):
-            inc = os.path.join(base, rel, "include")
-            if os.path.isdir(os.path.join(inc, "cutlass")) and os.path.exists(
-                    os.path.join(inc, "cutlass/gemm/collective/sm100_mma_warpspecialized_emulated.hpp")):
-                dirs = [inc]
-                util = os.path.join(base, rel, "tools", "util", "include")
-                if os.path.isdir(util):
-                    dirs.append(util)
-                return dirs
-    return None
-
-
 def sources():
     srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
     srcs += sorted(os.path.join(GEMM, f) for f in os.listdir(GEMM) if f.endswith(".cu"))
@@ -53,7 +38,7 @@ def _deps(src):
     d = os.path.dirname(src)
     deps += sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(".cuh"))
     text = "".join(open(f).read() for f in deps)
-    if "rsb.h" in text:   # the CUTLASS instantiations (gemm_rc/rr/cr.cu) do not see the C header
+    if "rsb.h" in text:
         deps.append(os.path.join(ROOT, "include", "rsb.h"))
     return deps
 
@@ -71,16 +56,13 @@ def _hash(files, extra=""):
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(OBJ, exist_ok=True)
-    cut = cutlass_include_dirs()
-    if cut is None:
-        raise RuntimeError("CUTLASS sm100 headers not found (needed by csrc/gemm)")
     jobs, objs, stamps = [], [], []
     for src in sources():
         is_gemm = os.path.dirname(src) == GEMM
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         inc = ["-I", os.path.join(ROOT, "include"), "-I", CSRC]
         if is_gemm:
-            inc += ["-I", GEMM] + [x for d in cut for x in ("-I", d)]
+            inc += ["-I", GEMM]
         dig = _hash(_deps(src), " ".join(NVCC_FLAGS))
         stamp = obj + ".sha"
         stamps.append(dig)

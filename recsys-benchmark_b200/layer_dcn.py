@@ -17,6 +17,7 @@ from torch import nn
 from . import _lib as L
 from . import functional as RF
 from . import linalg as LA
+from . import planes as P
 
 
 def forward_mixture_layer(x0, xl, V, C, U, bias, gates, gate_softmax: bool):
@@ -39,7 +40,9 @@ def forward_mixture_layer(x0, xl, V, C, U, bias, gates, gate_softmax: bool):
 
 class _CrossLayer(torch.autograd.Function):
     """One DCN-Mix cross layer with every element-wise step fused into four custom passes around the
-    three tensor-core GEMMs (csrc/dcn.cu); identity gate."""
+    three tensor-core GEMMs (csrc/dcn.cu); identity gate.  Every GEMM operand is split into bf16 planes once and
+    the planes are shared by all GEMMs that read it (x_l: forward, d_gates, dV; H1: expert GEMM, dC; G2: mixture
+    GEMM, dU; ...); the experts are a batch addressed as column blocks inside the stored matrices."""
 
     @staticmethod
     def forward(ctx, x0, xl, V, C, U, bias, gates):
@@ -51,31 +54,39 @@ class _CrossLayer(torch.autograd.Function):
         x0 = x0.contiguous()
         xl = xl.contiguous()
         st = L.stream_ptr(dev)
-        vcat = V.detach().permute(1, 0, 2).reshape(dm, er).contiguous()
-        cc = C.detach().contiguous()
-        ucat = U.detach().reshape(er, dm)
+        vcat_p = P.split(V.detach().permute(1, 0, 2).reshape(dm, er).contiguous())   # stored [Dm, E*r]
+        cc_p = P.split(C.detach().reshape(er, r))                                        # stored [E*r, r]
+        ucat_p = P.split(U.detach().reshape(er, dm))                                     # stored [E*r, Dm]
         g2d = gates.detach().reshape(e, dm)
         b1d = bias.detach().reshape(dm)
-        h1 = LA.gemm(xl, vcat).tanh_()
+        xl_p = P.split(xl)
+        h1 = P.gemm(xl_p, vcat_p, bsz, er, dm, b_mn_major=True, split_k=1).tanh_()     # x_l V_cat (layer_dcn.py:20-21)
+        h1_p = P.split(h1)
         p2 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
-        LA.gemm_strided(bsz, r, r, e, h1, 0, er, r, cc, 0, r, r * r, p2, 0, er, r)
+        # P2[:, l, :] = H1[:, l, :] @ C[l]  (:22): A column step r, B = C[l] stored [K = r, N = r] at row l*r
+        P.gemm(h1_p, cc_p, bsz, r, r, b_mn_major=True, out=p2, batch=e, a_steps=(0, r), b_steps=(r, 0),
+               d_batch_stride=r, split_k=1)
         g = torch.empty(bsz, e, dtype=torch.float32, device=dev)
         g2 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
         RF._call("dcn_gate_mix_fwd", lib.rsb_dcn_gate_mix_fwd, L.ptr(p2), L.ptr(xl), L.ptr(g2d), bsz, dm, e, r,
                  L.ptr(p2), L.ptr(g), L.ptr(g2), st, nbytes=bsz * (dm + 3 * er) * 4)     # H2 overwrites P2
         h2 = p2
-        t0 = LA.gemm(g2, ucat)
+        g2_p = P.split(g2)
+        t0 = P.gemm(g2_p, ucat_p, bsz, dm, er, b_mn_major=True, split_k=1)             # G2 U_cat (:23)
         out = torch.empty(bsz, dm, dtype=torch.float32, device=dev)
         RF._call("dcn_cross_out_fwd", lib.rsb_dcn_cross_out_fwd, L.ptr(t0), L.ptr(x0), L.ptr(xl), L.ptr(b1d), L.ptr(g),
                  bsz, dm, e, L.ptr(out), st, nbytes=bsz * dm * 16)
-        ctx.save_for_backward(x0, xl, vcat, cc, ucat, b1d, g2d, h1, h2, g, g2, t0)
+        ctx.save_for_backward(x0, xl, b1d, g2d, h1, h2, g, t0)
+        ctx.planes = (xl_p, h1_p, g2_p, vcat_p, cc_p, ucat_p)
         ctx.dims = (e, dm, r)
         return out
 
     @staticmethod
     def backward(ctx, g_next):
         lib = L.load()
-        x0, xl, vcat, cc, ucat, b1d, g2d, h1, h2, g, g2, t0 = ctx.saved_tensors
+        x0, xl, b1d, g2d, h1, h2, g, t0 = ctx.saved_tensors
+        xl_p, h1_p, g2_p, vcat_p, cc_p, ucat_p = ctx.planes
+        ctx.planes = None
         e, dm, r = ctx.dims
         er = e * r
         bsz = xl.shape[0]
@@ -88,29 +99,31 @@ class _CrossLayer(torch.autograd.Function):
         RF._call("dcn_cross_out_bwd", lib.rsb_dcn_cross_out_bwd, L.ptr(g_next), L.ptr(x0), L.ptr(t0), L.ptr(b1d),
                  L.ptr(g), bsz, dm, e, L.ptr(gT), L.ptr(gx0), L.ptr(dsg), st, nbytes=bsz * dm * 20)
         d_bias = torch.mv(gT.t(), g.sum(1)).reshape(1, dm)           # sum_b gT[b,:] * sg[b]
-        g_g2 = LA.gemm(gT, ucat, trans_b=True)                        # [B,Dm] @ U_cat^T -> [B,E*r]
-        d_u = LA.gemm(g2, gT, trans_a=True, split_k=LA._split_for(bsz, er, dm)).reshape(e, r, dm)
+        gT_p = P.split(gT)
+        g_g2 = P.gemm(gT_p, ucat_p, bsz, er, dm, split_k=1)          # gT @ U_cat^T: U_cat stored [N = E*r, K = Dm]
+        d_u = P.gemm(g2_p, gT_p, er, dm, bsz, a_mn_major=True, b_mn_major=True, split_k=0).reshape(e, r, dm)
         dg = torch.empty(bsz, e, dtype=torch.float32, device=dev)
         g_xl = torch.empty(bsz, dm, dtype=torch.float32, device=dev)
         RF._call("dcn_gate_mix_bwd", lib.rsb_dcn_gate_mix_bwd, L.ptr(g_g2), L.ptr(h2), L.ptr(g), L.ptr(dsg), L.ptr(g2d),
                  L.ptr(g_next), bsz, dm, e, r, L.ptr(g_g2), L.ptr(dg), L.ptr(g_xl), st,
                  nbytes=bsz * (3 * er + 2 * dm) * 4)                 # gP2 overwrites gG2
         g_p2 = g_g2
-        # [E,B] x [B,Dm]: cuBLAS picks a 260 us large-K SGEMM for this shape; the split-K tensor-core GEMM takes it
-        if e % 4 == 0:
-            d_gates = LA.gemm(dg, xl, trans_a=True, split_k=LA._split_for(bsz, e, dm)).reshape(e, dm, 1)
-        else:
-            d_gates = torch.matmul(dg.t(), xl).reshape(e, dm, 1)
-        # block-diagonal expert GEMM backward (same calls as linalg._ExpertMatMul.backward)
+        # [E,B] x [B,Dm] (M = E = 4 rows of one tile): split over the batch
+        d_gates = P.gemm(P.split(dg), xl_p, e, dm, bsz, a_mn_major=True, b_mn_major=True, split_k=0).reshape(e, dm, 1)
+        # block-diagonal expert GEMM backward
+        g_p2_p = P.split(g_p2)
         g_h1 = torch.empty(bsz, er, dtype=torch.float32, device=dev)
-        LA.gemm_strided(bsz, r, r, e, g_p2, 0, er, r, cc, 0, r, r * r, g_h1, 0, er, r, trans_b=True)
-        # dC[e] = H1[:,e,:]^T @ gP2[:,e,:]: the diagonal r x r blocks of ONE [E*r, E*r] split-K GEMM
-        # (E x the FLOPs of the blocks alone, but a single well-shaped launch instead of E thin ones)
-        full = LA.gemm(h1, g_p2, trans_a=True, split_k=LA._split_for(bsz, er, er))
-        d_c = torch.stack([full[ei * r:(ei + 1) * r, ei * r:(ei + 1) * r] for ei in range(e)])
+        # gH1[:, l, :] = gP2[:, l, :] @ C[l]^T : C[l] read as stored [N = r, K = r] at row l*r
+        P.gemm(g_p2_p, cc_p, bsz, r, r, out=g_h1, batch=e, a_steps=(0, r), b_steps=(r, 0), d_batch_stride=r, split_k=1)
+        # dC[l] = H1[:, l, :]^T @ gP2[:, l, :] : batched split-K, both operands MN-major with column step r
+        d_c = torch.empty(e, r, r, dtype=torch.float32, device=dev)
+        P.gemm(h1_p, g_p2_p, r, r, bsz, a_mn_major=True, b_mn_major=True, out=d_c.view(er, r), batch=e,
+               a_steps=(0, r), b_steps=(0, r), d_batch_stride=r * r, split_k=0)
         g_p1 = torch.ops.aten.tanh_backward(g_h1, h1)
-        LA.gemm(g_p1, vcat, trans_b=True, beta=1.0, c=g_xl, out=g_xl)   # g_xl += gP1 @ V_cat^T
-        d_vcat = LA.gemm(xl, g_p1, trans_a=True, split_k=LA._split_for(bsz, dm, er))
+        g_p1_p = P.split(g_p1)
+        # g_xl += gP1 @ V_cat^T : V_cat stored [N = Dm, K = E*r]
+        P.gemm(g_p1_p, vcat_p, bsz, dm, er, beta=1.0, c=g_xl, out=g_xl, split_k=1)
+        d_vcat = P.gemm(xl_p, g_p1_p, dm, er, bsz, a_mn_major=True, b_mn_major=True, split_k=0)
         d_v = d_vcat.reshape(dm, e, r).permute(1, 0, 2).contiguous()
         return gx0, g_xl, d_v, d_c, d_u, d_bias, d_gates
 
@@ -118,9 +131,8 @@ class _CrossLayer(torch.autograd.Function):
 def _fused_layer_ok(x0, xl, V, gate_softmax: bool) -> bool:
     e, dm, r = V.shape
     bsz = xl.shape[0]
-    return (xl.is_cuda and not gate_softmax and dm % 4 == 0 and r % 4 == 0 and e <= 8 and bsz % 4 == 0
-            and bsz >= 512 and xl.dtype == torch.float32 and LA._split_for(bsz, r, r) >= 1
-            and (bsz // LA._split_for(bsz, r, r)) % 4 == 0)
+    return (xl.is_cuda and not gate_softmax and dm % 4 == 0 and r % 32 == 0 and e <= 8 and bsz >= 512
+            and xl.dtype == torch.float32)
 
 
 class DCN_MixHead(nn.Module):

@@ -1,11 +1,10 @@
-"""fp32-accurate tensor-core GEMMs (rsb_gemm_f32: tcgen05 + TMA, 9xBF16 split) behind
-`matmul` / `linear` autograd functions.
+"""fp32-accurate tensor-core GEMMs (rsb_gemm_planes: hand-written TMA + tcgen05 + TMEM kernel on operands held as
+three bf16 planes, see planes.py / csrc/gemm/planes_gemm.cu) behind `matmul` / `linear` autograd functions.
 
-`gemm()` is the raw call (row-major operands with optional "stored transposed" flags,
-batched through strides, fused alpha / beta*C / per-column bias).  Shapes TMA cannot take
-(a leading dimension or contiguous extent not divisible by 4, e.g. the final Linear(400->1)
-or the toy sizes of the unit tests) go to the library GEMM (torch.matmul -> cuBLAS fp32);
-that is a shape dispatch between two fp32 GEMMs, not a CPU fallback."""
+`gemm()` is the raw fp32 call (row-major operands with optional "stored transposed" flags, fused alpha / beta*C /
+per-column bias).  Results narrower than 4 columns or not a multiple of 4 wide (the final Linear(400->1), the toy
+sizes of the unit tests) go to the library GEMM (torch.matmul -> cuBLAS fp32); that is a shape dispatch between two
+fp32 GEMMs, not a CPU fallback."""
 from __future__ import annotations
 
 from typing import Optional
@@ -68,6 +67,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool 
     pb = b_planes if b_planes is not None else P.split(b)
     return P.gemm(pa, pb, m, n, k, a_mn_major=trans_a, b_mn_major=not trans_b, bias=bias, out=out, alpha=alpha,
                   beta=beta, c=c, split_k=1 if split_k == 1 else 0)
+
+
+def _fwd_gemm(xp: P.Planes, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """x W^T + b for W [out, in]: both operands K-major."""
+    n, k = weight.shape
+    return P.gemm(xp, weight_planes(weight), xp.rows, n, k, bias=bias, split_k=1)
+
+
+def _dx_gemm(gp: P.Planes, weight: torch.Tensor) -> torch.Tensor:
+    """g W for W [out, in]: the weight planes read as the MN-major [K = out, N = in] operand (no transposed copy)."""
+    n_out, n_in = weight.shape
+    return P.gemm(gp, weight_planes(weight), gp.rows, n_in, n_out, b_mn_major=True, split_k=1)
+
+
+def _dw_gemm(gp: P.Planes, xp: P.Planes) -> torch.Tensor:
+    """g^T x: the reduction runs over the stored rows (the batch) of both operands; split over the SMs."""
+    return P.gemm(gp, xp, gp.cols, xp.cols, gp.rows, a_mn_major=True, b_mn_major=True, split_k=0)
 
 
 class _ExpertMatMul(torch.autograd.Function):
@@ -250,13 +266,16 @@ def relu_dropout(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
 
 class _LinearReluDropout(torch.autograd.Function):
     """dropout_p(relu(x @ W^T + b)): tensor-core GEMM with the bias in its epilogue, one fused
-    ReLU+dropout pass, and a backward whose single elementwise pass also produces the bias gradient."""
+    ReLU+dropout pass, and a backward whose single elementwise pass also produces the bias gradient.
+    The planes of x are shared by the forward and the weight-gradient GEMM, those of gz by dX and dW."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, p, side_dw=False):
-        z = gemm(x, weight, trans_b=True, bias=bias)
+        xp = P.split(x)
+        z = _fwd_gemm(xp, weight, bias)
         y, mask = _relu_dropout_fwd(z, p)
-        ctx.save_for_backward(x, weight, mask)
+        ctx.xp = xp
+        ctx.save_for_backward(weight, mask)
         ctx.p = p
         ctx.has_bias = bias is not None
         ctx.side_dw = side_dw
@@ -264,16 +283,17 @@ class _LinearReluDropout(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight, mask = ctx.saved_tensors
+        weight, mask = ctx.saved_tensors
+        xp, ctx.xp = ctx.xp, None
         gz, gb = _relu_dropout_bwd(gy, mask, ctx.p, ctx.has_bias and ctx.needs_input_grad[2])
-        gx = gemm(gz, weight) if ctx.needs_input_grad[0] else None
+        gp = P.split(gz)
+        gx = _dx_gemm(gp, weight) if ctx.needs_input_grad[0] else None
         gw = None
         if ctx.needs_input_grad[1]:
-            sk = _split_for(x.shape[0], weight.shape[0], weight.shape[1])
             if ctx.side_dw and gx is not None and _side_dw_safe(weight):
-                gw = _gemm_on_side_stream(gz, x, sk)
+                gw = _dw_on_side_stream(gp, xp)
             else:
-                gw = gemm(gz, x, trans_a=True, split_k=sk)
+                gw = _dw_gemm(gp, xp)
         return gx, gw, gb, None, None
 
 
@@ -290,21 +310,21 @@ def _side_dw_safe(weight: torch.Tensor) -> bool:
     return weight.grad is None and not _has_hooks(weight) and not torch.cuda.is_current_stream_capturing()
 
 
-def _gemm_on_side_stream(gz: torch.Tensor, x: torch.Tensor, split_k: int) -> torch.Tensor:
+def _dw_on_side_stream(gp: P.Planes, xp: P.Planes) -> torch.Tensor:
     """Weight gradient gz^T @ x of the FIRST dense layer on the side stream: everything queued after it in the
     backward pass is the embedding side (row gradients, segmented reduction - HBM/latency-bound kernels that
     leave the tensor pipe idle), so the two overlap.  The main stream re-joins at the end of the backward pass
     (autograd end-of-pass callback), before any optimizer can read the result."""
-    dev = gz.device
+    dev = gp.data.device
     main = torch.cuda.current_stream(dev)
     side = RF.side_stream(dev)
     side.wait_stream(main)
     with torch.cuda.stream(side):
-        gw = gemm(gz, x, trans_a=True, split_k=split_k)
+        gw = _dw_gemm(gp, xp)
     # the callback's closure keeps the main-pool inputs alive until the main stream has re-joined (no
     # record_stream: it makes the caching allocator poll events and cudaMalloc when the host runs ahead)
     try:
-        torch.autograd.Variable._execution_engine.queue_callback(lambda keep=(gz, x): main.wait_stream(side))
+        torch.autograd.Variable._execution_engine.queue_callback(lambda keep=(gp, xp): main.wait_stream(side))
     except Exception:  # noqa: BLE001 - not inside an autograd pass (or the hook is gone): join right away
         main.wait_stream(side)
     return gw
@@ -321,9 +341,14 @@ class _HeadBlock(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, p, w_out, b_out):
-        z = x if weight is None else gemm(x, weight, trans_b=True, bias=bias)
+        ctx.xp = None
+        if weight is None:
+            z = x
+        else:
+            ctx.xp = P.split(x)
+            z = _fwd_gemm(ctx.xp, weight, bias)
         y, mask, out = _relu_dropout_dot_fwd(z, p, w_out.reshape(-1), b_out)
-        ctx.save_for_backward(x if weight is not None else None, weight, mask, y, w_out)
+        ctx.save_for_backward(weight, mask, y, w_out)
         ctx.p = p
         ctx.has_bias = bias is not None
         ctx.has_bout = b_out is not None
@@ -331,7 +356,8 @@ class _HeadBlock(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        x, weight, mask, y, w_out = ctx.saved_tensors
+        weight, mask, y, w_out = ctx.saved_tensors
+        xp, ctx.xp = ctx.xp, None
         g = g_out.reshape(-1).contiguous()
         g_wout = _colsum_weighted(y, g).reshape(w_out.shape) if ctx.needs_input_grad[4] else None
         g_bout = g.sum().reshape(1) if ctx.has_bout and ctx.needs_input_grad[5] else None
@@ -339,31 +365,15 @@ class _HeadBlock(torch.autograd.Function):
         gz, gb = _relu_dropout_bwd_rank1(g, w_out.reshape(-1), mask, ctx.p, want_gb)
         if weight is None:
             return gz, None, None, None, g_wout, g_bout
-        gx = gemm(gz, weight) if ctx.needs_input_grad[0] else None
-        gw = gemm(gz, x, trans_a=True, split_k=_split_for(x.shape[0], weight.shape[0], weight.shape[1])) \
-            if ctx.needs_input_grad[1] else None
+        gp = P.split(gz)
+        gx = _dx_gemm(gp, weight) if ctx.needs_input_grad[0] else None
+        gw = _dw_gemm(gp, xp) if ctx.needs_input_grad[1] else None
         return gx, gw, gb, None, g_wout, g_bout
 
 
-def _split_for(k: int, m: int, n: int, sms: int = 148) -> int:
-    """Split-K factor for a weight-gradient GEMM [m,n] with reduction length k (the batch): the
-    persistent scheduler hands out (128x128 tile, split) units, so pick the split whose unit count
-    fills whole waves of SMs; each split stays >= 256 deep."""
-    tiles = ((m + 127) // 128) * ((n + 127) // 128)
-    best, best_score = 1, -1.0
-    for sp in (1, 2, 4, 8, 16, 32, 64, 128):
-        if k % sp or (k // sp) % 4 or (k // sp < 256 and sp > 1):
-            continue
-        units = tiles * sp
-        eff = units / (((units + sms - 1) // sms) * sms)
-        score = eff - 0.001 * sp
-        if score > best_score:
-            best, best_score = sp, score
-    return best
-
-
 def _use_kernel(m, n, k, *tensors) -> bool:
-    return (2 * m * n * k >= MIN_FLOPS and m % 4 == 0 and n % 4 == 0 and k % 4 == 0 and _aligned(*tensors)
+    """The three GEMMs of a Linear produce [m,n], [m,k] and [n,k] fp32 results: their widths must be multiples of 4."""
+    return (2 * m * n * k >= MIN_FLOPS and n % 4 == 0 and k % 4 == 0 and _aligned(*tensors)
             and all(t is None or (t.is_cuda and t.dtype == torch.float32) for t in tensors))
 
 
@@ -372,24 +382,27 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, side_dw=False):
-        ctx.save_for_backward(x, weight)
+        xp = P.split(x)
+        ctx.xp = xp
+        ctx.save_for_backward(weight)
         ctx.has_bias = bias is not None
         ctx.side_dw = side_dw
-        return gemm(x, weight, trans_b=True, bias=bias)
+        return _fwd_gemm(xp, weight, bias)
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight = ctx.saved_tensors
+        (weight,) = ctx.saved_tensors
+        xp, ctx.xp = ctx.xp, None
         gy = gy.contiguous()
+        gp = P.split(gy)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm(gy, weight)                                   # [B,out] @ [out,in]
+            gx = _dx_gemm(gp, weight)                               # [B,out] @ [out,in]
         if ctx.needs_input_grad[1]:
-            sk = _split_for(x.shape[0], weight.shape[0], weight.shape[1])
             if ctx.side_dw and gx is not None and _side_dw_safe(weight):
-                gw = _gemm_on_side_stream(gy, x, sk)
+                gw = _dw_on_side_stream(gp, xp)
             else:
-                gw = gemm(gy, x, trans_a=True, split_k=sk)
+                gw = _dw_gemm(gp, xp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = colsum(gy)
         return gx, gw, gb, None
@@ -409,18 +422,23 @@ class _MatMul(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, a, b):
-        ctx.save_for_backward(a, b)
-        return gemm(a, b)
+        ap = P.split(a)
+        ctx.ap = ap
+        ctx.save_for_backward(b)
+        m, k = a.shape
+        return P.gemm(ap, weight_planes(b), m, b.shape[1], k, b_mn_major=True, split_k=1)
 
     @staticmethod
     def backward(ctx, gc):
-        a, b = ctx.saved_tensors
-        gc = gc.contiguous()
+        (b,) = ctx.saved_tensors
+        ap, ctx.ap = ctx.ap, None
+        gp = P.split(gc.contiguous())
         ga = gb = None
         if ctx.needs_input_grad[0]:
-            ga = gemm(gc, b, trans_b=True)                          # gc [M,N] @ b^T (b stored [K,N] = "[N',K']" with N'=K)
+            # ga = gc @ b^T: b stored [K, N] read as the K-major "[N' = K, K' = N]" operand
+            ga = P.gemm(gp, weight_planes(b), gp.rows, b.shape[0], b.shape[1], split_k=1)
         if ctx.needs_input_grad[1]:
-            gb = gemm(a, gc, trans_a=True, split_k=_split_for(a.shape[0], a.shape[1], gc.shape[1]))  # a^T @ gc
+            gb = P.gemm(ap, gp, ap.cols, gp.cols, ap.rows, a_mn_major=True, b_mn_major=True, split_k=0)   # a^T @ gc
         return ga, gb
 
 

@@ -1,4 +1,4 @@
-"""The arithmetic argument behind `rsb_gemm_f32`, checked on the CPU: an fp32 number splits exactly enough into
+"""The arithmetic argument behind `rsb_gemm_planes`, checked on the CPU: an fp32 number splits exactly enough into
 three bf16 terms, and the six term products >= 2^-16 (the three "bands" the kernel issues as tensor-core MMAs)
 reproduce the fp32 product to below fp32 rounding - the three dropped products are <= 2^-24 relative.
 (The kernel's own accuracy is measured on the GPU in tests/test_gpu_gemm.py against fp64.)"""

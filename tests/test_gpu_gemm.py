@@ -1,4 +1,4 @@
-"""GPU tests of the fp32-accurate tensor-core GEMM (rsb_gemm_f32, tcgen05 9xBF16 split)
+"""GPU tests of the fp32-accurate tensor-core GEMM (rsb_gemm_planes: hand-written tcgen05 kernel on bf16 planes)
 through the C ABI wrappers: every layout, batching, fused epilogue, and fp32-level accuracy
 (error vs an fp64 product must be of the same order as cuBLAS fp32 SGEMM's)."""
 import pytest
@@ -61,9 +61,11 @@ def test_gemm_split_k_and_strided_batches(LA):
 
 
 def test_unsupported_shapes_fail_loudly_in_raw_call_and_dispatch_in_linear(LA):
-    a, b = torch.randn(64, 30, device=DEV), torch.randn(30, 64, device=DEV)
+    a, b = torch.randn(64, 30, device=DEV), torch.randn(30, 62, device=DEV)   # N = 62: fp32 results are stored 128 bits at a time
     with pytest.raises(RuntimeError):
         LA.gemm(a, b)
+    b = torch.randn(30, 64, device=DEV)                                          # odd K is fine: operands become planes
+    assert _err(LA.gemm(a, b), a.double() @ b.double()) < 2e-6
     w = torch.randn(1, 400, device=DEV)
     x = torch.randn(64, 400, device=DEV)
     torch.testing.assert_close(LA.linear(x, w, None), x @ w.t())   # N = 1 -> library GEMM

@@ -275,20 +275,24 @@ def test_checkpoint_round_trip_like_the_reference_scripts(tmp_path):
 # ------------------------------------------------------------ GEMM host logic ---
 def test_gemm_shape_gate_and_split_k_choice():
     import recsys_benchmark_b200.linalg as LA
+    from recsys_benchmark_b200 import _lib
 
-    # TMA needs 16-byte rows: every extent / leading dimension a multiple of 4 floats; A^T B^T is not provided
+    # fp32 results are stored 128 bits at a time: N and the output leading dimension multiples of 4; operands are
+    # re-laid out as bf16 planes, so K and M are free; A^T B^T is not provided
     assert LA.gemm_supported(65536, 400, 624, 624, 624, 400, False, True)
-    assert not LA.gemm_supported(65536, 400, 622, 622, 622, 400, False, True)
+    assert LA.gemm_supported(65536, 400, 622, 622, 622, 400, False, True)
     assert not LA.gemm_supported(64, 5, 64, 64, 5, 5, False, False)          # the toy DCN rank (r = 5): library GEMM
     assert not LA.gemm_supported(64, 64, 64, 64, 64, 64, True, True)
-    # weight-gradient GEMMs (K = batch): the split fills whole waves of 148 SMs with (tile, split) units,
-    # every split stays >= 256 deep and a multiple of 4
+    # weight-gradient GEMMs (K = batch): the library splits the reduction so that (tile, split) units fill the 148
+    # SMs in one wave, every split at least 256 deep; the workspace query reports the partial buffers it needs
+    lib = _lib.load()
     for m, n in ((400, 624), (400, 400), (256, 352)):
-        sp = LA._split_for(65536, m, n)
-        assert 65536 % sp == 0 and (65536 // sp) % 4 == 0 and 65536 // sp >= 256
-        tiles = -(-m // 128) * -(-n // 128)
-        assert tiles * sp >= 148                                              # at least one full wave
-    assert LA._split_for(512, 400, 400) <= 2                                  # short reductions are not split further
+        ws = lib.rsb_gemm_planes_workspace_bytes(m, n, 65536, 1, 0)
+        splits = (ws - 256) // (m * n * 4)
+        tiles = -(-m // 128) * -(-n // 256)
+        assert 148 // 2 < tiles * splits <= 148 and 65536 // splits >= 256, (m, n, splits)
+    assert lib.rsb_gemm_planes_workspace_bytes(65536, 400, 624, 1, 0) == 256   # enough tiles: no split
+    assert lib.rsb_gemm_planes_workspace_bytes(400, 400, 512, 1, 0) <= 256 + 2 * 400 * 400 * 4   # short reductions
     x = torch.randn(8, 6)
     lin = torch.nn.Linear(6, 3)
     torch.testing.assert_close(LA.linear(x, lin.weight, lin.bias), lin(x))    # off-path CPU tensors: plain F.linear
