@@ -272,15 +272,48 @@ typedef struct {
   int64_t batch_row_step, batch_col_step;
 } rsb_planes_operand;
 
+/* What rsb_gemm_planes does with the accumulator (fused epilogues of the dense tail, src/models/deepfm.py:55-66):
+ *   RSB_EPI_LINEAR               D = alpha * acc + beta * C + bias                                   (fp32)
+ *   RSB_EPI_RELU_DROPOUT_PLANES  y = dropout_p(relu(alpha * acc + bias)) written as bf16 planes (the next layer's GEMM
+ *                                operand) + the 1-byte keep-and-positive mask [M, N]; the forward of Linear -> ReLU ->
+ *                                Dropout in ONE launch.  Same Philox stream as rsb_relu_dropout_fwd (seed, offset,
+ *                                offset_dev), so the mask equals the un-fused pass bit for bit.
+ *   RSB_EPI_MASK_PLANES          g = alpha * acc * mask / (1 - p) written as planes: dX of a hidden layer, i.e. the
+ *                                gradient w.r.t. the previous layer's pre-activation, ready for its dX / dW GEMMs.
+ *   RSB_EPI_MASK_F32             the same as fp32 D (a BatchNorm backward sits in between).
+ * ones_col: the plane writers also store a column of ones right after the (8-padded) data columns; a weight-gradient
+ * GEMM gz^T [x | 1] over such planes yields the bias gradient as its last column, with no extra reduction pass. */
+typedef enum {
+  RSB_EPI_LINEAR = 0,
+  RSB_EPI_RELU_DROPOUT_PLANES = 1,
+  RSB_EPI_MASK_PLANES = 2,
+  RSB_EPI_MASK_F32 = 3
+} rsb_epilogue_mode;
+
+typedef struct {
+  int32_t mode;
+  void* out_planes;            /* bf16 [3][M][out_ld] (modes 1, 2) */
+  int64_t out_ld, out_plane_stride;
+  int32_t ones_col;
+  uint8_t* mask;               /* [M, N]: written by mode 1, read by modes 2, 3 */
+  float p;                     /* dropout probability */
+  uint64_t seed, offset;
+  const uint64_t* offset_dev;  /* optional device-resident stream position (CUDA-graph replays) */
+} rsb_gemm_epilogue;
+
 /* fp32 [rows, cols] (ld) -> bf16 planes [3][rows][out_ld] (columns cols..out_ld-1 zero); transpose = 1 writes the
- * planes of in^T ([cols][out_ld >= rows]) - used once per optimizer step for nn.Linear weights (dX GEMM operand). */
-RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, void* out_planes,
-                             int64_t out_ld, int64_t plane_stride, void* stream);
+ * planes of in^T ([cols][out_ld >= rows]); ones_col = 1 additionally writes 1.0 at column roundup8(cols). */
+RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, int32_t ones_col,
+                             void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream);
+/* gz[r, c] = g_row[r] * w_col[c] * mask[r, c] / (1 - p) written as planes (N, out_ld multiples of 8): the backward of
+ * dropout(relu(.)) for the rank-1 upstream gradient of the MLP's one-output Linear (src/models/deepfm.py:64). */
+RSB_API int rsb_rank1_mask_planes(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M, int32_t N, float p,
+                                  void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream);
 RSB_API int64_t rsb_gemm_planes_workspace_bytes(int64_t M, int64_t N, int64_t K, int64_t batch, int32_t split_k);
 RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operand* B, int64_t M, int64_t N, int64_t K,
                             int64_t batch, int32_t split_k, const float* C, float* D, int64_t ldd, int64_t d_batch_stride,
-                            const float* bias, float alpha, float beta, void* workspace, int64_t workspace_bytes,
-                            void* stream);
+                            const float* bias, float alpha, float beta, const rsb_gemm_epilogue* epilogue /* NULL = linear */,
+                            void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Bandwidth-bound glue of the dense tails (Linear -> [BatchNorm1d] -> ReLU -> Dropout,

@@ -36,6 +36,29 @@ __device__ __forceinline__ unsigned fastdiv(unsigned n, const FastDiv& f) {
   return (t + ((n - t) >> f.s1)) >> f.s2;
 }
 
+// Counter-based Philox4x32-10 stream keyed by (seed, offset): the dropout mask of element group `ctr` (4 consecutive
+// elements of a row-major activation) is a pure function of the counter, so every kernel that needs the mask - the
+// stand-alone ReLU+dropout pass, the row-dot variant, the GEMM epilogue - draws the same one.
+struct Philox {
+  unsigned k0, k1;
+  __device__ __forceinline__ uint4 operator()(unsigned long long ctr) const {
+    unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+    unsigned a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ a;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ b;
+      c3 = lo0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
 

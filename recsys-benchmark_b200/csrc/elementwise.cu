@@ -11,26 +11,6 @@
 
 namespace rsb {
 
-struct Philox {
-  unsigned k0, k1;
-  __device__ __forceinline__ uint4 operator()(unsigned long long ctr) const {
-    unsigned c0 = (unsigned)ctr, c1 = (unsigned)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
-    unsigned a = k0, b = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      c0 = hi1 ^ c1 ^ a;
-      c1 = lo1;
-      c2 = hi0 ^ c3 ^ b;
-      c3 = lo0;
-      a += 0x9E3779B9u;
-      b += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-  }
-};
-
 // numel must be a multiple of 4 and x/y 16-byte aligned (checked by the host function)
 __global__ void __launch_bounds__(256) relu_dropout_fwd_kernel(const float4* __restrict__ x, long long n4,
                                                                float p, float scale, unsigned long long seed,

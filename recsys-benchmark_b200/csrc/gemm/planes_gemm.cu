@@ -28,13 +28,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
-#include "rsb.h"
-
-namespace rsb {
-void note_launch(int n);
-int sm_count();
-}  // namespace rsb
+#include "common.cuh"
 
 namespace pg {
 
@@ -44,7 +40,7 @@ constexpr int kThreads = 384;
 constexpr int kEpiWarp0 = 4;        // first epilogue warp
 constexpr int kTmemCols = 512;
 constexpr int kTmemBufStride = 256; // columns between the two accumulator buffers
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
 struct Operand {
@@ -58,7 +54,9 @@ struct Params {
   int n_tile, m_tiles, n_tiles;
   int k_blocks;          // ceil(K / 32)
   int stages;
-  uint32_t a_stage_bytes, b_stage_bytes;
+  int drain;             // K groups (of 32) accumulated in TMEM between two drains into registers
+  uint32_t a_stage_bytes, b_stage_bytes;   // shared-memory footprint of one stage in one CTA
+  uint32_t tx_bytes;                       // bytes the TMA loads of one CTA deliver per stage
   Operand a, b;
   // epilogue
   float* D;
@@ -67,7 +65,35 @@ struct Params {
   const float* bias;
   float alpha, beta;
   float* partial;        // split-K: [splits][batch][M][N] raw sums (then splitk_reduce_kernel)
+  // fused epilogues (rsb_gemm_epilogue)
+  int epi_mode;
+  __nv_bfloat16* out_planes;
+  long long out_ld, out_plane_stride;
+  int ones_col;
+  unsigned char* mask;
+  float drop_scale;
+  unsigned drop_thr;
+  unsigned long long seed, offset;
+  const unsigned long long* offset_dev;
 };
+
+// x -> (bf16(x), bf16(x - x0), bf16(x - x0 - x1)); both remainders are exact in fp32
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h0, __nv_bfloat16& h1, __nv_bfloat16& h2) {
+  h0 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h0);
+  h1 = __float2bfloat16_rn(r1);
+  h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+}
+
+// 8 consecutive values of one row -> three 16-byte plane stores
+__device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, long long plane_stride, const float* v) {
+  __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split3(v[j], p0[j], p1[j], p2[j]);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(p0);
+  *reinterpret_cast<uint4*>(dst + plane_stride) = *reinterpret_cast<const uint4*>(p1);
+  *reinterpret_cast<uint4*>(dst + 2 * plane_stride) = *reinterpret_cast<const uint4*>(p2);
+}
 
 // ------------------------------------------------------------------------------------------- PTX wrappers ---
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -142,6 +168,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ kernel ---
@@ -155,24 +192,92 @@ __device__ __forceinline__ bool get_tile(const Params& p, int idx, Tile& t) {
   if (idx >= per_split * p.splits) return false;
   t.split = idx / per_split;
   int r = idx - t.split * per_split;
-  // M fastest: CTAs running at the same time share the B (weight) tile, which then stays in L2
-  t.m_blk = r % p.m_tiles;
-  r /= p.m_tiles;
+  // N fastest: the N tiles of one M block run at the same time on neighbouring SMs, so the A block (the big operand:
+  // activations) comes from DRAM once and from L2 for the other N tiles; B (weights) is small and L2-resident anyway.
+  // (M fastest re-read all of A from DRAM once per N tile: 508 MB instead of 245 MB on 65536 x 400 x 624.)
   t.n_blk = r % p.n_tiles;
-  t.batch = r / p.n_tiles;
+  r /= p.n_tiles;
+  t.m_blk = r % p.m_tiles;
+  t.batch = r / p.m_tiles;
   const int base = p.k_blocks / p.splits, rem = p.k_blocks % p.splits;
   t.kb0 = t.split * base + (t.split < rem ? t.split : rem);
   t.kb1 = t.kb0 + base + (t.split < rem ? 1 : 0);
   return true;
 }
 
-template <int N_TILE>
+// ---- cluster helpers (TWO = true: a CTA pair works on one 256-row tile with cta_group::2 MMAs) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool TWO>
+__device__ __forceinline__ void tma_load_3d_to(const CUtensorMap* map, uint32_t bar_addr, void* dst, int c0, int c1, int c2) {
+  if constexpr (TWO) {
+    // cta_group::2: the data lands in THIS CTA's shared memory, the bytes are counted on the leader CTA's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
+}
+template <bool TWO>
+__device__ __forceinline__ void mma_bf16_g(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TWO) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    mma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+  }
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done
+template <bool TWO>
+__device__ __forceinline__ void mma_commit_g(uint64_t* bar) {
+  if constexpr (TWO) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+  } else {
+    mma_commit(bar);
+  }
+}
+
+template <int N_TILE, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
   // accumulator columns handled by the two epilogue warps that share a TMEM lane quarter
   constexpr int kHalf0 = ((N_TILE + 31) / 32) * 16;
   constexpr int kHalf1 = N_TILE - kHalf0;
   constexpr int NC = kHalf0;
+  constexpr int kTileM = TWO ? 2 * kBlockM : kBlockM;      // rows of D per scheduling unit (CTA or CTA pair)
+  constexpr int kBRows = TWO ? N_TILE / 2 : N_TILE;        // rows / columns of the B tile staged by THIS CTA
   static_assert(N_TILE % 16 == 0 && N_TILE >= 16 && N_TILE <= 256, "N tile");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -181,7 +286,11 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const uint32_t cta_rank = TWO ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit0 = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int units = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;   // staged by ONE CTA
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -189,57 +298,69 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);     // the leader's arrive.expect_tx (the TMA bytes of both CTAs are counted on it)
+      mbar_init(&empty_bar[s], 1);    // one tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 8);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[b], TWO ? 16 : 8);   // one arrive per epilogue warp of every CTA that drains this buffer
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Register budget: the producer / MMA / allocator warps need a handful of registers, the drain warps hold up to 128
+  // accumulators + 64 staging registers per thread -> hand the first warpgroup's registers to the other two.
+  // (each setmaxnreg sits at the top of its role's branch so that ptxas allocates that region against the new limit)
+  if (warp >= kEpiWarp0) goto epilogue_role;
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
   if (warp == 0) {
-    // ================================ TMA producer ================================
+    // ================================ TMA producer (every CTA stages its own rows) ================================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       Tile t;
-      for (int idx = blockIdx.x; get_tile(p, idx, t); idx += gridDim.x) {
-        const int m0 = t.m_blk * kBlockM, n0 = t.n_blk * N_TILE;
+      for (int idx = unit0; get_tile(p, idx, t); idx += units) {
+        const int m0 = t.m_blk * kTileM + (int)cta_rank * kBlockM;
+        const int n0 = t.n_blk * N_TILE + (int)cta_rank * (TWO ? kBRows : 0);
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + p.a_stage_bytes;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (leader) mbar_expect_tx(&full_bar[stage], TWO ? 2 * p.tx_bytes : p.tx_bytes);
+          const uint32_t bar = TWO ? map_to_rank(smem_u32(&full_bar[stage]), 0) : smem_u32(&full_bar[stage]);
           const int k0 = kb * kBlockK;
           if (!p.a.mn_major) {
-            tma_load_3d(&map_a, &full_bar[stage], sa, k0 + t.batch * p.a.batch_col_step,
-                        m0 + t.batch * p.a.batch_row_step, 0);
+            tma_load_3d_to<TWO>(&map_a, bar, sa, k0 + t.batch * p.a.batch_col_step, m0 + t.batch * p.a.batch_row_step, 0);
           } else {
 #pragma unroll 1
             for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_3d(&map_a, &full_bar[stage], sa + j * (3 * kBlockK * 128), m0 + j * 64 + t.batch * p.a.batch_col_step,
-                          k0 + t.batch * p.a.batch_row_step, 0);
+              tma_load_3d_to<TWO>(&map_a, bar, sa + j * (3 * kBlockK * 128), m0 + j * 64 + t.batch * p.a.batch_col_step,
+                                  k0 + t.batch * p.a.batch_row_step, 0);
           }
           if (!p.b.mn_major) {
-            tma_load_3d(&map_b, &full_bar[stage], sb, k0 + t.batch * p.b.batch_col_step,
-                        n0 + t.batch * p.b.batch_row_step, 0);
+            tma_load_3d_to<TWO>(&map_b, bar, sb, k0 + t.batch * p.b.batch_col_step, n0 + t.batch * p.b.batch_row_step, 0);
           } else {
 #pragma unroll 1
-            for (int j = 0; j < (N_TILE + 63) / 64; ++j)
-              tma_load_3d(&map_b, &full_bar[stage], sb + j * (3 * kBlockK * 128), n0 + j * 64 + t.batch * p.b.batch_col_step,
-                          k0 + t.batch * p.b.batch_row_step, 0);
+            for (int j = 0; j < (kBRows + 63) / 64; ++j)
+              tma_load_3d_to<TWO>(&map_b, bar, sb + j * (3 * kBlockK * 128), n0 + j * 64 + t.batch * p.b.batch_col_step,
+                                  k0 + t.batch * p.b.batch_row_step, 0);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -249,20 +370,23 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(N_TILE, p.a.mn_major, p.b.mn_major);
+    // ================================ MMA issuer (one lane of the leader CTA) ================================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a.mn_major << 15) | ((uint32_t)p.b.mn_major << 16) |
+                             ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       // plane strides / descriptor geometry inside a stage
       const uint32_t a_plane = p.a.mn_major ? kBlockK * 128 : kBlockM * 64;
-      const uint32_t b_plane = p.b.mn_major ? kBlockK * 128 : N_TILE * 64;
+      const uint32_t b_plane = p.b.mn_major ? kBlockK * 128 : kBRows * 64;
       const uint32_t a_kstep = p.a.mn_major ? 2048 : 32;   // 16 k: two 8-row groups of 1 KiB / 32 bytes in a row
       const uint32_t b_kstep = p.b.mn_major ? 2048 : 32;
       int stage = 0, buf = 0;
       uint32_t phase = 0, tphase[2] = {0, 0};
       Tile t;
-      for (int idx = blockIdx.x; get_tile(p, idx, t); idx += gridDim.x) {
+      for (int idx = unit0; get_tile(p, idx, t); idx += units) {
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(&tempty_bar[buf], tphase[buf] ^ 1);
+          const bool group_start = ((kb - t.kb0) % p.drain) == 0;
+          const bool group_end = ((kb - t.kb0) % p.drain) == p.drain - 1 || kb == t.kb1 - 1;
+          if (group_start) mbar_wait(&tempty_bar[buf], tphase[buf] ^ 1);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -277,20 +401,22 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                                   : make_desc(sb + pl * b_plane, 16, 512, kSwizzle64);
           }
           // smallest band first; the first MMA of the group overwrites the (drained) accumulator
-          uint32_t acc = 0;
-#define PG_MMA(PA, PB)                                                                                      \
-  _Pragma("unroll") for (int ks = 0; ks < kBlockK / 16; ++ks) {                                             \
-    mma_bf16(d_tmem, da[PA] + (uint64_t)((ks * a_kstep) >> 4), db[PB] + (uint64_t)((ks * b_kstep) >> 4), idesc, acc); \
-    acc = 1;                                                                                                \
+          uint32_t acc = group_start ? 0u : 1u;
+#define PG_MMA(PA, PB)                                                                                                \
+  _Pragma("unroll") for (int ks = 0; ks < kBlockK / 16; ++ks) {                                                       \
+    mma_bf16_g<TWO>(d_tmem, da[PA] + (uint64_t)((ks * a_kstep) >> 4), db[PB] + (uint64_t)((ks * b_kstep) >> 4), idesc, acc); \
+    acc = 1;                                                                                                          \
   }
           PG_MMA(0, 2) PG_MMA(1, 1) PG_MMA(2, 0)   // band 3
           PG_MMA(0, 1) PG_MMA(1, 0)                // band 2
           PG_MMA(0, 0)                             // band 1
 #undef PG_MMA
-          mma_commit(&empty_bar[stage]);           // smem stage reusable once these MMAs have read it
-          mma_commit(&tfull_bar[buf]);             // accumulator of this K group complete
-          tphase[buf] ^= 1;
-          buf ^= 1;
+          mma_commit_g<TWO>(&empty_bar[stage]);    // smem stage reusable once these MMAs have read it
+          if (group_end) {
+            mma_commit_g<TWO>(&tfull_bar[buf]);    // accumulator of this drain group complete
+            tphase[buf] ^= 1;
+            buf ^= 1;
+          }
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
@@ -298,42 +424,62 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
     }
-  } else if (warp >= kEpiWarp0) {
-    // ================================ drain + epilogue ================================
+  }
+  goto teardown;
+epilogue_role:
+  {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;" ::: "memory");
+    // ================================ drain + epilogue (every CTA: its own 128 rows) ================================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int half = (warp - kEpiWarp0) >> 2;     // which column half of the tile
     const int col0 = half ? kHalf0 : 0;
     const int ncols = half ? kHalf1 : kHalf0;     // multiple of 16 (0 possible only if N_TILE == 16)
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t tempty_addr[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+      tempty_addr[b] = TWO ? map_to_rank(smem_u32(&tempty_bar[b]), 0) : smem_u32(&tempty_bar[b]);
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     Tile t;
-    for (int idx = blockIdx.x; get_tile(p, idx, t); idx += gridDim.x) {
+    for (int idx = unit0; get_tile(p, idx, t); idx += units) {
       float acc[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) acc[i] = 0.f;
-      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+      for (int kb = t.kb0; kb < t.kb1; kb += p.drain) {
         mbar_wait(&tfull_bar[buf], tphase[buf]);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_addr + buf * kTmemBufStride + col0;
+        // TMEM -> registers in chunks of up to 64 columns: every load of a chunk is issued before the one wait
+        // (a load -> wait -> add chain per 16 columns made this loop, not the MMAs, the pace of the kernel)
 #pragma unroll
-        for (int c = 0; c < NC; c += 16) {
+        for (int c = 0; c < NC; c += 64) {
           if (c < ncols) {
-            float v[16];
-            tmem_ld16(taddr + c, v);
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 64; j += 16) {
+              if (c + j < NC && c + j < ncols) tmem_ld16(taddr + c + j, v + j);
+            }
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[c + i] += v[i];
+            for (int j = 0; j < 64; j += 16) {
+              if (c + j < NC && c + j < ncols) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[c + j + i] += v[j + i];
+              }
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+        if (lane == 0) {
+          if constexpr (TWO) mbar_arrive_cluster(tempty_addr[buf]); else mbar_arrive(&tempty_bar[buf]);
+        }
         tphase[buf] ^= 1;
         buf ^= 1;
       }
       // ---- epilogue: this thread owns row (m0 + 32 q + lane), columns [n0 + col0, n0 + col0 + ncols) ----
-      const long long row = (long long)t.m_blk * kBlockM + q * 32 + lane;
+      const long long row = (long long)t.m_blk * kTileM + (long long)cta_rank * kBlockM + q * 32 + lane;
       const int n0 = t.n_blk * N_TILE + col0;
       if (row < p.M) {
         if (p.partial != nullptr) {
@@ -343,9 +489,10 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (c < ncols && n0 + c < p.N)
               *reinterpret_cast<float4*>(dst + n0 + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
           }
-        } else {
+        } else if (p.epi_mode == RSB_EPI_LINEAR || p.epi_mode == RSB_EPI_MASK_F32) {
           float* dst = p.D + (long long)t.batch * p.d_batch_stride + row * p.ldd;
           const float* csrc = p.C ? p.C + (long long)t.batch * p.d_batch_stride + row * p.ldd : nullptr;
+          const unsigned char* mrow = p.epi_mode == RSB_EPI_MASK_F32 ? p.mask + row * (long long)p.N : nullptr;
 #pragma unroll
           for (int c = 0; c < NC; c += 4) {
             if (c < ncols && n0 + c < p.N) {
@@ -359,19 +506,71 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
                 o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
               }
+              if (mrow) {   // gradient through dropout(relu(.)): keep-and-positive mask of the forward pass
+                const uchar4 m = *reinterpret_cast<const uchar4*>(mrow + n0 + c);
+                o.x = m.x ? o.x * p.drop_scale : 0.f; o.y = m.y ? o.y * p.drop_scale : 0.f;
+                o.z = m.z ? o.z * p.drop_scale : 0.f; o.w = m.w ? o.w * p.drop_scale : 0.f;
+              }
               *reinterpret_cast<float4*>(dst + n0 + c) = o;
             }
+          }
+        } else {
+          // RSB_EPI_RELU_DROPOUT_PLANES: y = dropout(relu(acc + bias)) -> planes + keep mask   (forward of a hidden layer)
+          // RSB_EPI_MASK_PLANES        : g = acc * mask / (1 - p)      -> planes               (dX of a hidden layer)
+          const bool fwd = p.epi_mode == RSB_EPI_RELU_DROPOUT_PLANES;
+          __nv_bfloat16* prow = p.out_planes + row * p.out_ld;
+          unsigned char* mrow = p.mask + row * (long long)p.N;
+          rsb::Philox rng{(unsigned)p.seed, (unsigned)(p.seed >> 32)};
+          const unsigned long long off = p.offset + (p.offset_dev ? *p.offset_dev : 0ull) + (unsigned long long)row * (p.N >> 2);
+#pragma unroll
+          for (int c = 0; c < NC; c += 8) {
+            if (c < ncols && n0 + c < p.N) {
+              float v[8];
+#pragma unroll
+              for (int h = 0; h < 8; h += 4) {
+                const bool valid = n0 + c + h < p.N;      // N is a multiple of 4, not necessarily of 8
+                float4 o = make_float4(acc[c + h] * p.alpha, acc[c + h + 1] * p.alpha, acc[c + h + 2] * p.alpha,
+                                       acc[c + h + 3] * p.alpha);
+                uchar4 m = make_uchar4(0, 0, 0, 0);
+                if (valid) {
+                  if (fwd) {
+                    if (p.bias) {
+                      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h));
+                      o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    }
+                    const uint4 r = rng(off + (unsigned long long)((n0 + c + h) >> 2));
+                    m.x = (o.x > 0.f) && (r.x >= p.drop_thr); m.y = (o.y > 0.f) && (r.y >= p.drop_thr);
+                    m.z = (o.z > 0.f) && (r.z >= p.drop_thr); m.w = (o.w > 0.f) && (r.w >= p.drop_thr);
+                    *reinterpret_cast<uchar4*>(mrow + n0 + c + h) = m;
+                  } else {
+                    m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
+                  }
+                }
+                v[h] = m.x ? o.x * p.drop_scale : 0.f; v[h + 1] = m.y ? o.y * p.drop_scale : 0.f;
+                v[h + 2] = m.z ? o.z * p.drop_scale : 0.f; v[h + 3] = m.w ? o.w * p.drop_scale : 0.f;
+              }
+              store_planes8(prow + n0 + c, p.out_plane_stride, v);
+            }
+          }
+          // "ones" column right after the data: a weight-gradient GEMM over these planes yields the bias gradient
+          if (p.ones_col && t.n_blk == p.n_tiles - 1 && half == 0) {
+            float v[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            store_planes8(prow + ((p.N + 7) & ~7), p.out_plane_stride, v);
           }
         }
       }
     }
   }
+teardown:
   // ---- teardown ----
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (TWO)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -405,8 +604,10 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 // fp32 [rows, cols] (ld) -> three bf16 planes [3][rows][out_ld]; columns >= cols (up to out_ld) are zero-filled.
 // transpose = 1: out plane [cols][out_ld >= rows] = in^T (small matrices: nn.Linear weights for the dX GEMM).
 __global__ void split_planes_kernel(const float* __restrict__ in, long long rows, long long cols, long long ld,
-                                    __nv_bfloat16* __restrict__ out, long long out_ld, long long plane_stride, int transpose) {
+                                    __nv_bfloat16* __restrict__ out, long long out_ld, long long plane_stride, int transpose,
+                                    int ones_col) {
   const long long orows = transpose ? cols : rows, ocols8 = out_ld / 8;
+  const long long ones_at = ones_col ? (((transpose ? rows : cols) + 7) & ~7ll) : -1;   // first column after the padded data
   const long long total = orows * ocols8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / ocols8, c0 = (i - r * ocols8) * 8;
@@ -422,6 +623,7 @@ __global__ void split_planes_kernel(const float* __restrict__ in, long long rows
         const long long c = c0 + j;
         x[j] = (c < icols) ? (transpose ? __ldg(in + c * ld + r) : __ldg(in + r * ld + c)) : 0.f;
       }
+      if (c0 == ones_at) x[0] = 1.f;
     }
     __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
 #pragma unroll
@@ -436,6 +638,30 @@ __global__ void split_planes_kernel(const float* __restrict__ in, long long rows
     *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p0);
     *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<const uint4*>(p1);
     *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<const uint4*>(p2);
+  }
+}
+
+// gz[r, c] = g[r] * w[c] * mask[r, c] / (1 - p) as planes: backward of dropout(relu(.)) for the rank-1 upstream gradient
+// of the MLP's one-output Linear (src/models/deepfm.py:64), written straight in the operand format of the dX / dW GEMMs
+__global__ void rank1_mask_planes_kernel(const float* __restrict__ g_row, const float* __restrict__ w_col,
+                                         const unsigned char* __restrict__ mask, long long M, int N, float scale,
+                                         __nv_bfloat16* __restrict__ out, long long out_ld, long long plane_stride) {
+  const int n8 = N / 8;
+  const long long total = M * n8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n8;
+    const int c0 = (int)(i - r * n8) * 8;
+    const float g = __ldg(g_row + r) * scale;
+    const uint2 m8 = __ldg(reinterpret_cast<const uint2*>(mask + r * (long long)N + c0));
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_col + c0)), w1 = __ldg(reinterpret_cast<const float4*>(w_col + c0 + 4));
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned byte = ((j < 4 ? m8.x : m8.y) >> (8 * (j & 3))) & 0xffu;
+      v[j] = byte ? g * w[j] : 0.f;
+    }
+    store_planes8(out + r * out_ld + c0, plane_stride, v);
   }
 }
 
@@ -472,18 +698,30 @@ static bool encode_map(CUtensorMap* map, const void* base, long long cols, long 
   return rc == CUDA_SUCCESS;
 }
 
-template <int N_TILE>
+template <int N_TILE, bool TWO>
 static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, size_t smem, cudaStream_t st) {
   static bool attr[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(planes_gemm_kernel<N_TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemLimit - 2048));   // static: barriers
+    cudaError_t e = cudaFuncSetAttribute(planes_gemm_kernel<N_TILE, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kSmemLimit - 2048));   // static: barriers
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr[dev] = true;
   }
-  planes_gemm_kernel<N_TILE><<<grid, kThreads, smem, st>>>(ma, mb, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = TWO ? 2 : 1;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, planes_gemm_kernel<N_TILE, TWO>, ma, mb, p);
 }
 
 }  // namespace pg
@@ -498,15 +736,23 @@ static int pick_n_tile(long long N, int* n_tiles) {
   return tile;
 }
 
+// CTA pairs (cta_group::2, 256-row tiles, each CTA stages half of B) whenever there is more than one 128-row block
+static bool use_pairs(long long M) {
+  static const int mode = [] { const char* v = getenv("RSB_GEMM_PAIRS"); return v ? atoi(v) : 0; }();
+  return mode != 0 && M > kBlockM;
+}
+
 static int default_splits(long long M, long long N, long long K, long long batch) {
   int n_tiles;
   const int tile = pick_n_tile(N, &n_tiles);
   (void)tile;
-  const long long tiles = ((M + kBlockM - 1) / kBlockM) * n_tiles * batch;
+  const bool two = use_pairs(M);
+  const int tile_m = two ? 2 * kBlockM : kBlockM;
+  const long long tiles = ((M + tile_m - 1) / tile_m) * n_tiles * batch;
   const long long kb = (K + kBlockK - 1) / kBlockK;
-  const int sms = rsb::sm_count();
-  if (tiles >= sms || kb < 16) return 1;
-  long long s = sms / tiles;                 // fill one wave
+  const int units = two ? rsb::sm_count() / 2 : rsb::sm_count();
+  if (tiles >= units || kb < 16) return 1;
+  long long s = units / tiles;               // fill one wave
   if (s > kb / 8) s = kb / 8;                // at least 8 K groups (256 k) per split
   return s < 1 ? 1 : (int)s;
 }
@@ -517,11 +763,11 @@ extern "C" RSB_API int64_t rsb_gemm_planes_workspace_bytes(int64_t M, int64_t N,
   return s > 1 ? (int64_t)s * batch * M * N * 4 + 256 : 256;
 }
 
-extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, void* out_planes,
-                                        int64_t out_ld, int64_t plane_stride, void* stream) {
+extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, int32_t ones_col,
+                                        void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream) {
   if (!in || !out_planes || rows <= 0 || cols <= 0 || ld < (transpose ? cols : cols)) return RSB_ERR_BAD_ARG;
   const int64_t ocols = transpose ? rows : cols, orows = transpose ? cols : rows;
-  if (out_ld % 8 || out_ld < ocols || plane_stride < orows * out_ld || plane_stride % 8 ||
+  if (out_ld % 8 || out_ld < ocols + (ones_col ? 8 : 0) || plane_stride < orows * out_ld || plane_stride % 8 ||
       (reinterpret_cast<uintptr_t>(out_planes) & 15))
     return RSB_ERR_UNSUPPORTED;
   const long long total = orows * (out_ld / 8);
@@ -529,7 +775,26 @@ extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t c
   const long long cap = (long long)rsb::sm_count() * 16;
   if (blocks > cap) blocks = cap;
   split_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      in, rows, cols, ld, reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride, transpose);
+      in, rows, cols, ld, reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride, transpose, ones_col);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  return RSB_OK;
+}
+
+extern "C" RSB_API int rsb_rank1_mask_planes(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M, int32_t N, float p,
+                                             void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream) {
+  if (!g_row || !w_col || !mask || !out_planes || M < 0 || N <= 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  if (M == 0) return RSB_OK;
+  if (N % 8 || out_ld % 8 || out_ld < N || plane_stride % 8 || (reinterpret_cast<uintptr_t>(out_planes) & 15u) ||
+      (reinterpret_cast<uintptr_t>(mask) & 7u) || (reinterpret_cast<uintptr_t>(w_col) & 15u))
+    return RSB_ERR_UNSUPPORTED;
+  const long long total = M * (N / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)rsb::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  rank1_mask_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      g_row, w_col, mask, M, N, 1.0f / (1.0f - p), reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   rsb::note_launch(1);
@@ -538,13 +803,25 @@ extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t c
 
 extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operand* B, int64_t M, int64_t N, int64_t K,
                                        int64_t batch, int32_t split_k, const float* C, float* D, int64_t ldd,
-                                       int64_t d_batch_stride, const float* bias, float alpha, float beta, void* workspace,
-                                       int64_t workspace_bytes, void* stream) {
-  if (!A || !B || !A->planes || !B->planes || !D || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return RSB_ERR_BAD_ARG;
+                                       int64_t d_batch_stride, const float* bias, float alpha, float beta,
+                                       const rsb_gemm_epilogue* epi, void* workspace, int64_t workspace_bytes, void* stream) {
+  const int mode = epi ? epi->mode : RSB_EPI_LINEAR;
+  const bool to_planes = mode == RSB_EPI_RELU_DROPOUT_PLANES || mode == RSB_EPI_MASK_PLANES;
+  if (!A || !B || !A->planes || !B->planes || (!D && !to_planes) || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return RSB_ERR_BAD_ARG;
+  if (mode < RSB_EPI_LINEAR || mode > RSB_EPI_MASK_F32) return RSB_ERR_BAD_ARG;
+  if (mode != RSB_EPI_LINEAR) {
+    // fused epilogues: one un-batched, un-split GEMM whose output feeds the next GEMM
+    if (batch != 1 || beta != 0.f || !epi->mask || epi->p < 0.f || epi->p >= 1.f) return RSB_ERR_BAD_ARG;
+    if (to_planes && (!epi->out_planes || epi->out_ld % 8 || epi->out_plane_stride % 8 ||
+                      epi->out_ld < ((N + 7) / 8) * 8 + (epi->ones_col ? 8 : 0) ||
+                      (reinterpret_cast<uintptr_t>(epi->out_planes) & 15u) || (reinterpret_cast<uintptr_t>(epi->mask) & 3u)))
+      return RSB_ERR_UNSUPPORTED;
+    split_k = 1;
+  }
   if (beta != 0.f && !C) return RSB_ERR_BAD_ARG;
   if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff || batch > 65535) return RSB_ERR_BAD_ARG;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
-  if (!al16(A->planes) || !al16(B->planes) || !al16(D) || (C && !al16(C)) || (bias && !al16(bias))) return RSB_ERR_UNSUPPORTED;
+  if (!al16(A->planes) || !al16(B->planes) || (D && !al16(D)) || (C && !al16(C)) || (bias && !al16(bias))) return RSB_ERR_UNSUPPORTED;
   if (N % 4 || ldd % 4 || d_batch_stride % 4 || A->ld % 8 || B->ld % 8 || A->plane_stride % 8 || B->plane_stride % 8)
     return RSB_ERR_UNSUPPORTED;
   // a batch that advances along K inside one stored matrix must not let a K tail read its neighbour
@@ -560,19 +837,38 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   }
   Params p = {};
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)batch;
+  const bool two = use_pairs(M);
+  const int tile_m = two ? 2 * kBlockM : kBlockM;
   p.n_tile = pick_n_tile(N, &p.n_tiles);
-  p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.m_tiles = (int)((M + tile_m - 1) / tile_m);
   p.k_blocks = (int)((K + kBlockK - 1) / kBlockK);
   p.splits = split_k > 0 ? split_k : default_splits(M, N, K, batch);
   if (p.splits > p.k_blocks) p.splits = p.k_blocks;
   p.a.mn_major = A->mn_major; p.a.batch_row_step = (int)A->batch_row_step; p.a.batch_col_step = (int)A->batch_col_step;
   p.b.mn_major = B->mn_major; p.b.batch_row_step = (int)B->batch_row_step; p.b.batch_col_step = (int)B->batch_col_step;
   p.a_stage_bytes = 3u * kBlockM * kBlockK * 2;                                           // both majors: 24 KiB
-  p.b_stage_bytes = B->mn_major ? (uint32_t)((p.n_tile + 63) / 64) * 3u * kBlockK * 128 : 3u * p.n_tile * kBlockK * 2;
+  const int b_rows = two ? p.n_tile / 2 : p.n_tile;                                       // staged by one CTA
+  p.b_stage_bytes = B->mn_major ? (uint32_t)((b_rows + 63) / 64) * 3u * kBlockK * 128 : 3u * b_rows * kBlockK * 2;
+  p.tx_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  p.b_stage_bytes = (p.b_stage_bytes + 1023u) & ~1023u;                                   // keep every stage 1 KiB aligned
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   p.stages = (int)((kSmemLimit - 4096) / stage_bytes);   // 1 KiB alignment slack + static shared memory
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return RSB_ERR_UNSUPPORTED;
+  {
+    static const int drain = [] { const char* v = getenv("RSB_GEMM_DRAIN"); int d = v ? atoi(v) : 1; return d < 1 ? 1 : d; }();
+    p.drain = drain;
+  }
+  p.epi_mode = mode;
+  if (epi) {
+    p.out_planes = reinterpret_cast<__nv_bfloat16*>(epi->out_planes);
+    p.out_ld = epi->out_ld; p.out_plane_stride = epi->out_plane_stride; p.ones_col = epi->ones_col;
+    p.mask = epi->mask;
+    p.drop_scale = 1.0f / (1.0f - epi->p);
+    p.drop_thr = (unsigned)(epi->p * 4294967296.0);     // keep iff r >= thr (same rule as rsb_relu_dropout_fwd)
+    p.seed = epi->seed; p.offset = epi->offset;
+    p.offset_dev = reinterpret_cast<const unsigned long long*>(epi->offset_dev);
+  }
   p.D = D; p.ldd = ldd; p.d_batch_stride = d_batch_stride; p.C = C; p.bias = bias; p.alpha = alpha; p.beta = beta;
   if (p.splits > 1) {
     const int64_t need = (int64_t)p.splits * batch * M * N * 4 + 256;
@@ -583,16 +879,17 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   bool ok = A->mn_major ? encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
                         : encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B);
   ok = ok && (B->mn_major ? encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
-                          : encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, kBlockK, p.n_tile, CU_TENSOR_MAP_SWIZZLE_64B));
+                          : encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, kBlockK, b_rows, CU_TENSOR_MAP_SWIZZLE_64B));
   if (!ok) return RSB_ERR_UNSUPPORTED;
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batch * p.splits;
-  int grid = rsb::sm_count();
+  int grid = two ? rsb::sm_count() / 2 : rsb::sm_count();     // scheduling units: CTA pairs or CTAs
   if (tiles < grid) grid = (int)tiles;
+  if (two) grid *= 2;
   const size_t smem = (size_t)p.stages * stage_bytes + 1024;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaErrorInvalidValue;
   switch (p.n_tile) {
-#define PG_CASE(NT) case NT: e = launch<NT>(ma, mb, p, grid, smem, st); break;
+#define PG_CASE(NT) case NT: e = two ? launch<NT, true>(ma, mb, p, grid, smem, st) : launch<NT, false>(ma, mb, p, grid, smem, st); break;
     PG_CASE(16) PG_CASE(32) PG_CASE(48) PG_CASE(64) PG_CASE(80) PG_CASE(96) PG_CASE(112) PG_CASE(128)
     PG_CASE(144) PG_CASE(160) PG_CASE(176) PG_CASE(192) PG_CASE(208) PG_CASE(224) PG_CASE(240) PG_CASE(256)
 #undef PG_CASE

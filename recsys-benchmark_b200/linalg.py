@@ -449,6 +449,112 @@ def matmul(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.matmul(a, b)
 
 
+class _MlpReluDropout(torch.autograd.Function):
+    """The whole dense tail  [Linear -> ReLU -> Dropout] x L  ->  Linear(hidden, 1)  (src/models/deepfm.py:55-66 with
+    use_batchnorm off) as ONE autograd node whose activations live as bf16 planes between the tensor-core GEMMs:
+
+      fwd  layer i < L : ONE launch - GEMM, bias, ReLU, dropout in the epilogue, output written as the next GEMM's planes
+                         (+ the 1-byte mask); no fp32 activation is ever materialised
+           layer L     : GEMM -> fp32, then the pass that applies ReLU + dropout AND the one-output Linear's dot product
+      bwd  head        : dW_out, db_out, and g[r] * w_out[c] * mask as planes (one pass)
+           layer i     : dX GEMM whose epilogue applies the previous layer's mask and writes planes (the operand of that
+                         layer's dX and dW GEMMs); dW GEMM g^T [x | 1] over the planes both directions already hold,
+                         whose extra output column is the bias gradient.  Layer 1's dX is the fp32 gradient handed to the
+                         embedding backward; its dW may run on the side stream beside it."""
+
+    @staticmethod
+    def forward(ctx, x, ps, side_dw, *params):
+        n_layers = (len(params) - 2) // 2
+        ws, bs = params[0:2 * n_layers:2], params[1:2 * n_layers:2]
+        w_out, b_out = params[-2], params[-1]
+        planes = [P.split(x, ones_col=True)]
+        masks = []
+        for i in range(n_layers - 1):
+            seed, off = _dropout_stream(x.shape[0] * ws[i].shape[0])
+            yp, mask = P.linear_relu_dropout(planes[-1], weight_planes(ws[i]), bs[i], ps[i], seed, off,
+                                             _DROPOUT_DEV_COUNTER, ones_col=True)
+            planes.append(yp)
+            masks.append(mask)
+        z = _fwd_gemm(planes[-1], ws[-1], bs[-1])
+        y, mask, out = _relu_dropout_dot_fwd(z, ps[-1], w_out.reshape(-1), b_out)
+        masks.append(mask)
+        ctx.planes, ctx.masks, ctx.ps, ctx.side_dw, ctx.n_layers = planes, masks, ps, side_dw, n_layers
+        ctx.save_for_backward(y, *params)
+        return out.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        y, *params = ctx.saved_tensors
+        n_layers, ps, planes, masks = ctx.n_layers, ctx.ps, ctx.planes, ctx.masks
+        ctx.planes = ctx.masks = None
+        ws, bs = params[0:2 * n_layers:2], params[1:2 * n_layers:2]
+        w_out, b_out = params[-2], params[-1]
+        need = ctx.needs_input_grad                      # (x, ps, side_dw, W1, b1, ..., w_out, b_out)
+        g = g_out.reshape(-1).contiguous()
+        grads = [None] * len(params)
+        if need[3 + 2 * n_layers]:
+            grads[-2] = _colsum_weighted(y, g).reshape(w_out.shape)
+        if b_out is not None and need[4 + 2 * n_layers]:
+            grads[-1] = g.sum().reshape(1)
+        gp = P.rank1_mask_planes(g, w_out.reshape(-1), masks[-1], ps[-1])
+        gx = None
+        for i in reversed(range(n_layers)):
+            gp_prev = None
+            if i > 0:
+                gp_prev = P.dx_masked(gp, weight_planes(ws[i]), masks[i - 1], ps[i - 1])
+            elif need[0]:
+                gx = _dx_gemm(gp, ws[0])
+            want_w, want_b = need[3 + 2 * i], bs[i] is not None and need[4 + 2 * i]
+            if want_w or want_b:
+                if i == 0 and ctx.side_dw and gx is not None and _side_dw_safe(ws[0]) and \
+                        (bs[0] is None or _side_dw_safe(bs[0])):
+                    dw, db = _on_side_stream(lambda gp=gp, xp=planes[0]: P.gemm_dw(gp, xp, want_b), (gp, planes[0]))
+                else:
+                    dw, db = P.gemm_dw(gp, planes[i], want_b)
+                grads[2 * i] = dw if want_w else None
+                grads[2 * i + 1] = db if want_b else None
+            gp = gp_prev
+        return (gx, None, None, *grads)
+
+
+def _on_side_stream(fn, keep):
+    """Run `fn` on the side stream (see _dw_on_side_stream); `keep` = main-pool tensors it reads."""
+    dev = torch.cuda.current_device()
+    main = torch.cuda.current_stream(dev)
+    side = RF.side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        out = fn()
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(lambda keep=keep: main.wait_stream(side))
+    except Exception:  # noqa: BLE001 - not inside an autograd pass: join right away
+        main.wait_stream(side)
+    return out
+
+
+def _mlp_relu_dropout_pattern(mods, x: torch.Tensor):
+    """[Linear, ReLU, Dropout] x L + Linear(h, 1) with widths the plane kernels take (multiples of 8)?  Returns the
+    (linears, dropouts, head) or None."""
+    if (len(mods) - 1) % 3 or len(mods) < 4 or not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+        return None
+    lins, drops = [], []
+    width = x.shape[1]
+    for j in range(0, len(mods) - 1, 3):
+        lin, act, drop = mods[j], mods[j + 1], mods[j + 2]
+        if not (isinstance(lin, torch.nn.Linear) and isinstance(act, torch.nn.ReLU) and isinstance(drop, torch.nn.Dropout)):
+            return None
+        if lin.weight.shape[1] != width or lin.weight.shape[0] % 8 or width % 4 or not 0.0 < drop.p < 1.0 or \
+                lin.weight.dtype != torch.float32 or not lin.weight.is_cuda or lin.weight.shape[0] > 2048:
+            return None
+        width = lin.weight.shape[0]
+        lins.append(lin)
+        drops.append(drop)
+    head = mods[-1]
+    if not _is_head(head, width) or x.shape[0] < 256:
+        return None
+    return lins, drops, head
+
+
 def _is_head(mod, width: int) -> bool:
     """A Linear with ONE output on `width` inputs whose weight the glue kernels can read (fp32, 16-byte aligned)."""
     return (isinstance(mod, torch.nn.Linear) and mod.weight.shape[0] == 1 and mod.weight.shape[1] == width
@@ -464,6 +570,17 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: 
     mods = list(seq)
     i = 0
     training = seq.training
+    if training:
+        pat = _mlp_relu_dropout_pattern(mods, x)
+        if pat is not None:
+            lins, drops, head = pat
+            params = []
+            for lin in lins:
+                params += [lin.weight, lin.bias]
+            side = overlap_first_dw and not _has_hooks(lins[0].weight) and \
+                (lins[0].bias is None or not _has_hooks(lins[0].bias))
+            return _MlpReluDropout.apply(x.contiguous(), tuple(float(d.p) for d in drops), side, *params, head.weight,
+                                         head.bias)
     while i < len(mods):
         m = mods[i]
         nxt = mods[i + 1] if i + 1 < len(mods) else None

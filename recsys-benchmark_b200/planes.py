@@ -27,17 +27,27 @@ class Planes:
     def ld(self) -> int:
         return self.data.shape[2]
 
-    def operand(self, mn_major: bool, row_step: int = 0, col_step: int = 0) -> L.PlanesOperand:
-        return L.PlanesOperand(self.data.data_ptr(), self.rows, self.cols, self.ld, self.data.stride(0), int(mn_major),
-                               row_step, col_step)
+    def operand(self, mn_major: bool, row_step: int = 0, col_step: int = 0, cols: Optional[int] = None) -> L.PlanesOperand:
+        """`cols`: extent of the stored columns the GEMM may read (TMA zero-fills beyond it).  Default: the logical
+        width - a forward GEMM must not reduce over the padding / ones column; a weight-gradient GEMM that wants the
+        bias gradient passes the padded width + 8."""
+        return L.PlanesOperand(self.data.data_ptr(), self.rows, self.cols if cols is None else cols, self.ld,
+                               self.data.stride(0), int(mn_major), row_step, col_step)
 
     def float(self) -> torch.Tensor:
         """The represented fp32 matrix (sum of the planes) - for tests."""
         return self.data.float().sum(0)[:, :self.cols]
 
 
-def split(x: torch.Tensor, transpose: bool = False) -> Planes:
-    """fp32 [rows, cols] (unit column stride) -> Planes of x (or of x^T)."""
+def alloc(rows: int, cols: int, device, ones_col: bool = False) -> Planes:
+    """Uninitialised planes for a [rows, cols] matrix (the writer fills every column up to ld)."""
+    ld = (cols + 7) // 8 * 8 + (8 if ones_col else 0)
+    return Planes(torch.empty(3, rows, ld, dtype=torch.bfloat16, device=device), rows, cols)
+
+
+def split(x: torch.Tensor, transpose: bool = False, ones_col: bool = False) -> Planes:
+    """fp32 [rows, cols] (unit column stride) -> Planes of x (or of x^T).  ones_col: a column of ones after the
+    8-padded data columns (see `gemm_dw`)."""
     lib = L.load()
     dev = L.require_cuda(x)
     assert x.dim() == 2 and x.dtype == torch.float32
@@ -45,31 +55,89 @@ def split(x: torch.Tensor, transpose: bool = False) -> Planes:
         x = x.contiguous()
     rows, cols = x.shape
     orows, ocols = (cols, rows) if transpose else (rows, cols)
-    ld = (ocols + 7) // 8 * 8
-    out = torch.empty(3, orows, ld, dtype=torch.bfloat16, device=dev)
-    RF._call("split_planes", lib.rsb_split_planes, L.ptr(x), rows, cols, x.stride(0), int(transpose), L.ptr(out), ld,
-             out.stride(0), L.stream_ptr(dev), nbytes=rows * cols * 4 + 3 * orows * ld * 2)
-    return Planes(out, orows, ocols)
+    out = alloc(orows, ocols, dev, ones_col)
+    RF._call("split_planes", lib.rsb_split_planes, L.ptr(x), rows, cols, x.stride(0), int(transpose), int(ones_col),
+             L.ptr(out.data), out.ld, out.data.stride(0), L.stream_ptr(dev),
+             nbytes=rows * cols * 4 + 3 * orows * out.ld * 2)
+    return out
+
+
+def _dropout_epilogue(mode: int, out: Optional[Planes], mask: torch.Tensor, p: float, seed: int, offset: int,
+                      offset_dev: Optional[torch.Tensor], ones_col: bool) -> L.GemmEpilogue:
+    return L.GemmEpilogue(mode, out.data.data_ptr() if out is not None else None, out.ld if out is not None else 0,
+                          out.data.stride(0) if out is not None else 0, int(ones_col), mask.data_ptr(), float(p),
+                          seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
+                          offset_dev.data_ptr() if offset_dev is not None else None)
 
 
 def gemm(a: Planes, b: Planes, m: int, n: int, k: int, *, a_mn_major: bool = False, b_mn_major: bool = False,
          bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, alpha: float = 1.0, beta: float = 0.0,
          c: Optional[torch.Tensor] = None, split_k: int = 0, batch: int = 1, a_steps=(0, 0), b_steps=(0, 0),
-         d_batch_stride: int = 0) -> torch.Tensor:
+         d_batch_stride: int = 0, epilogue: Optional[L.GemmEpilogue] = None, want_out: bool = True,
+         b_cols: Optional[int] = None):
     """D [m, n] = alpha * A B^T + beta * C + bias on the tensor cores.
 
     a_mn_major = False: `a` stores [m, k];  True: `a` stores [k, m] (reduction over the stored rows).
     b_mn_major = False: `b` stores [n, k] (nn.Linear weight layout);  True: `b` stores [k, n].
-    batch > 1: operand l starts at stored (row, col) + l * steps; D[l] = out.data + l * d_batch_stride floats."""
+    batch > 1: operand l starts at stored (row, col) + l * steps; D[l] = out.data + l * d_batch_stride floats.
+    epilogue: a fused rsb_gemm_epilogue (see `linear_relu_dropout` / `dx_masked`)."""
     lib = L.load()
     dev = a.data.device
-    if out is None:
+    if out is None and want_out:
         out = torch.empty(m, n, dtype=torch.float32, device=dev)
     nb = lib.rsb_gemm_planes_workspace_bytes(m, n, k, batch, split_k)
     ws = RF._ws(nb, dev)
     oa = a.operand(a_mn_major, *a_steps)
-    ob = b.operand(b_mn_major, *b_steps)
+    ob = b.operand(b_mn_major, *b_steps, cols=b_cols)
     RF._call("gemm_planes", lib.rsb_gemm_planes, C.byref(oa), C.byref(ob), m, n, k, batch, split_k, L.ptr(c), L.ptr(out),
-             out.stride(0), d_batch_stride, L.ptr(bias), alpha, beta, L.ptr(ws), ws.numel(), L.stream_ptr(dev),
-             nbytes=0)
+             out.stride(0) if out is not None else n, d_batch_stride, L.ptr(bias), alpha, beta,
+             C.byref(epilogue) if epilogue is not None else None, L.ptr(ws), ws.numel(), L.stream_ptr(dev),
+             nbytes=2 * m * n * k * batch)       # `bytes` slot of the timer carries the fp32-equivalent FLOPs here
+    return out
+
+
+def linear_relu_dropout(xp: Planes, wp: Planes, bias: Optional[torch.Tensor], p: float, seed: int, offset: int,
+                        offset_dev: Optional[torch.Tensor] = None, ones_col: bool = True):
+    """dropout_p(relu(x W^T + b)) in ONE launch: returns (planes of y [M, N] (+ ones column), keep mask uint8 [M, N])."""
+    m, n, k = xp.rows, wp.rows, wp.cols
+    yp = alloc(m, n, xp.data.device, ones_col)
+    mask = torch.empty(m, n, dtype=torch.uint8, device=xp.data.device)
+    epi = _dropout_epilogue(L.EPI_RELU_DROPOUT_PLANES, yp, mask, p, seed, offset, offset_dev, ones_col)
+    gemm(xp, wp, m, n, k, bias=bias, split_k=1, epilogue=epi, want_out=False)
+    return yp, mask
+
+
+def dx_masked(gp: Planes, wp: Planes, mask: torch.Tensor, p: float, to_planes: bool = True):
+    """(g W) * mask / (1 - p) for W stored [out, in] (read as the MN-major operand): the gradient w.r.t. the previous
+    layer's pre-activation, as planes (next GEMM operand) or as fp32."""
+    m, n, k = gp.rows, wp.cols, wp.rows
+    if to_planes:
+        out = alloc(m, n, gp.data.device)
+        epi = _dropout_epilogue(L.EPI_MASK_PLANES, out, mask, p, 0, 0, None, False)
+        gemm(gp, wp, m, n, k, b_mn_major=True, split_k=1, epilogue=epi, want_out=False)
+        return out
+    epi = _dropout_epilogue(L.EPI_MASK_F32, None, mask, p, 0, 0, None, False)
+    return gemm(gp, wp, m, n, k, b_mn_major=True, split_k=1, epilogue=epi)
+
+
+def gemm_dw(gp: Planes, xp: Planes, want_bias_grad: bool):
+    """Weight gradient g^T x (reduction over the batch rows of both operands, split over the SMs).  When `xp` carries a
+    ones column (split(..., ones_col=True) / the fused forward epilogue) and want_bias_grad is set, the bias gradient
+    sum_r g[r, :] falls out as one more output column: returns (dW [out, in], db [out] or None)."""
+    n_out, n_in, m = gp.cols, xp.cols, gp.rows
+    n_pad = (n_in + 7) // 8 * 8
+    has_ones = xp.ld >= n_pad + 8
+    if want_bias_grad and has_ones:
+        full = gemm(gp, xp, n_out, n_pad + 8, m, a_mn_major=True, b_mn_major=True, split_k=0, b_cols=n_pad + 8)
+        return full[:, :n_in], full[:, n_pad]
+    return gemm(gp, xp, n_out, n_in, m, a_mn_major=True, b_mn_major=True, split_k=0), None
+
+
+def rank1_mask_planes(g_row: torch.Tensor, w_col: torch.Tensor, mask: torch.Tensor, p: float) -> Planes:
+    """Planes of gz[r, c] = g_row[r] * w_col[c] * mask[r, c] / (1 - p)."""
+    lib = L.load()
+    m, n = mask.shape
+    out = alloc(m, n, mask.device)
+    RF._call("rank1_mask_planes", lib.rsb_rank1_mask_planes, L.ptr(g_row), L.ptr(w_col), L.ptr(mask), m, n, float(p),
+             L.ptr(out.data), out.ld, out.data.stride(0), L.stream_ptr(mask.device), nbytes=m * n * 7 + m * 4)
     return out

@@ -137,11 +137,77 @@ def test_dcn_mix_head_avazu_shape_matches_reference_formulation():
         assert _err(a_, b_) < 2e-5, tuple(p.shape)
 
 
+def test_fused_mlp_node_equals_the_unfused_composition(LA, monkeypatch):
+    """[Linear -> ReLU -> Dropout] x 3 -> Linear(400, 1) as one autograd node (GEMM epilogues write the next GEMM's
+    planes, the bias gradient rides the weight-gradient GEMM as a ones column) against the layer-by-layer path: the
+    same Philox stream => the same masks, so the forward must agree bit for bit and the gradients to fp32 rounding;
+    and against plain torch given those masks."""
+    torch.manual_seed(0)
+    seq = torch.nn.Sequential(torch.nn.Linear(624, 400), torch.nn.ReLU(), torch.nn.Dropout(0.5),
+                              torch.nn.Linear(400, 400), torch.nn.ReLU(), torch.nn.Dropout(0.5),
+                              torch.nn.Linear(400, 400), torch.nn.ReLU(), torch.nn.Dropout(0.5),
+                              torch.nn.Linear(400, 1)).to(DEV).train()
+    x = torch.randn(4096, 624, device=DEV, requires_grad=True)
+    gout = torch.randn(4096, 1, device=DEV)
+    params = [x] + list(seq.parameters())
+
+    def run(fused):
+        if not fused:
+            monkeypatch.setattr(LA, "_mlp_relu_dropout_pattern", lambda mods, xx: None)
+        monkeypatch.setattr(LA, "_DROPOUT_CALLS", 0)
+        out = LA.run_sequential(seq, x)
+        return out.detach(), torch.autograd.grad(out, params, gout)
+
+    o1, g1 = run(True)
+    o2, g2 = run(False)
+    assert torch.equal(o1, o2)
+    for a_, b_, p in zip(g1, g2, params):
+        assert a_.shape == p.shape
+        assert _err(a_, b_.double()) < 2e-6, tuple(p.shape)
+
+
+def test_fused_epilogues_match_unfused_kernels(LA):
+    """rsb_gemm_planes epilogue modes against GEMM + stand-alone passes: RELU_DROPOUT_PLANES (planes + mask) and
+    MASK_PLANES / MASK_F32; rank-1 planes; the ones column of a weight-gradient GEMM is the bias gradient."""
+    from recsys_benchmark_b200 import planes as P
+
+    torch.manual_seed(1)
+    m, k, n = 1000, 176, 400
+    x = torch.randn(m, k, device=DEV)
+    w = torch.randn(n, k, device=DEV) * 0.1
+    b = torch.randn(n, device=DEV)
+    xp, wp = P.split(x, ones_col=True), P.split(w)
+    yp, mask = P.linear_relu_dropout(xp, wp, b, 0.3, seed=12345, offset=7 << 32)
+    z = P.gemm(xp, wp, m, n, k, bias=b, split_k=1)
+    lib = LA.L.load()
+    y = torch.empty_like(z)
+    mask2 = torch.empty(m, n, dtype=torch.uint8, device=DEV)
+    LA.L.check(lib.rsb_relu_dropout_fwd(z.data_ptr(), z.numel(), 0.3, 12345, 7 << 32, None, y.data_ptr(), mask2.data_ptr(),
+                                        LA.L.stream_ptr(DEV)))
+    assert torch.equal(mask, mask2)
+    assert torch.equal(yp.float(), P.split(y).float()) and abs(float(mask.float().mean()) - 0.35) < 0.02
+    assert torch.equal(yp.data[0, :, n].float(), torch.ones(m, device=DEV)) and float(yp.data[1:, :, n:].abs().sum()) == 0
+    # dX with the mask of the previous layer
+    g = torch.randn(m, n, device=DEV)
+    gp = P.split(g)
+    mprev = (torch.rand(m, k, device=DEV) > 0.4).to(torch.uint8)
+    ref = (g.double() @ w.double()) * mprev.double() / 0.7
+    assert _err(P.dx_masked(gp, wp, mprev, 0.3, to_planes=False), ref) < 2e-6
+    assert _err(P.dx_masked(gp, wp, mprev, 0.3).float(), ref) < 2e-6
+    # weight gradient + bias gradient from the ones column
+    dw, db = P.gemm_dw(gp, xp, True)
+    assert _err(dw, g.double().t() @ x.double()) < 2e-6 and _err(db, g.double().sum(0)) < 2e-6
+    # rank-1 upstream gradient
+    gr, wc = torch.randn(m, device=DEV), torch.randn(n, device=DEV)
+    r1 = P.rank1_mask_planes(gr, wc, mask, 0.3).float()
+    assert _err(r1, gr.double()[:, None] * wc.double()[None, :] * mask.double() / 0.7) < 1e-6
+
+
 def test_gemm_speed_report(LA, capsys):
     """Not an assertion on speed: prints TFLOP/s of the tensor-core kernel vs cuBLAS fp32 for the MLP shapes."""
     res = []
     for (m, n, k, ta, tb, sk) in [(65536, 400, 624, False, True, 1), (65536, 400, 400, False, True, 1),
-                                  (65536, 624, 400, False, False, 1), (400, 624, 65536, True, False, 32),
+                                  (65536, 624, 400, False, False, 1), (400, 624, 65536, True, False, 0),
                                   (65536, 256, 352, False, False, 1), (65536, 352, 256, False, False, 1)]:
         a = torch.randn((k, m) if ta else (m, k), device=DEV)
         b = torch.randn((n, k) if tb else (k, n), device=DEV)
@@ -231,6 +297,8 @@ def test_head_block_matches_unfused_path_with_the_same_masks(LA, with_bn, monkey
     params = [x] + [p for p in seq.parameters()]
     go = torch.randn(8192, 1, device=DEV)
 
+    # (the no-BatchNorm sequence would be taken whole by the fused MLP node: this test is about the head block)
+    monkeypatch.setattr(LA, "_mlp_relu_dropout_pattern", lambda mods, xx: None)
     calls = LA._DROPOUT_CALLS
     out_f = LA.run_sequential(seq, x)
     assert out_f.grad_fn.name().startswith("_HeadBlock")

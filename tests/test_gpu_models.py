@@ -640,7 +640,7 @@ def test_side_stream_overlap_is_bit_identical_to_inline_execution(R, emb_cfg, mo
     def grads(early, side_dw):
         monkeypatch.setattr(RF, "EARLY_SORT", early)
         if not side_dw:
-            monkeypatch.setattr(LA, "_dw_on_side_stream", LA._dw_gemm)
+            monkeypatch.setattr(LA, "_side_dw_safe", lambda w: False)     # every weight gradient in line
         torch.manual_seed(9)
         m = R.get_ctr_model(CRITEO_DIMS, dict(num_factor=16, hidden_sizes=[400, 400], p_dropout=0.0,
                                               use_batchnorm=False, embedding_config=dict(emb_cfg))).to(DEV).train()
