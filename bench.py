@@ -2,18 +2,24 @@
 """bench.py — DeepFM train samples/s on Criteo-shaped synthetic data (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU PyTorch path (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU PyTorch path (baseline/_ref)
 
 A "step" is one full training iteration of the reference's trainer loop
 (src/trainer/deepfm.py:44-62): forward -> BCEWithLogits -> zero_grad -> backward ->
-optimizer.step, on one batch of synthetic Criteo-shaped ids.  Default workload =
-BASELINE.json configs[1]: DeepFM + QR-hashing embedding (configs/deepfm/qr_80.yaml:
-divider 5, mult, D=16, MLP 400x3, dropout 0.5, dense Adam lr 1e-3 wd 1e-6).
+optimizer.step, on one batch of synthetic Criteo-shaped ids (65 536 per GPU).
 
-Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the same step fed
-from pinned host memory with the loss read back every step; `roofline` = the dominant
-hand-written kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak;
-`cpu_baseline` = the oracle port of the reference's CPU path timed on this box.
+Default workload = BASELINE.json configs[4] / north_star: DeepFM with the FULL Criteo-shaped table
+(configs/deepfm/base_config.yaml: D = 16, MLP 400x3 + BatchNorm, dropout 0.5, Adam lr 1e-3 wd 1e-6) row-sharded
+over the N GPUs of the box - at N = 1 the same model with one shard, so the 1/2/4/8-GPU lines are the same
+experiment.  At N = 1 the line also carries `other_configs`: configs[1] (QR-hashing, qr_80.yaml), configs[0]'s
+shape on one GPU with the fused sparse row update, configs[2] (DCN-Mix, Avazu shape), configs[3] (PEP and OptEmbed,
+KDD shape) and the SURVEY 8(d) roofline shape (17 M rows: a table far larger than L2), each with its own rooflines.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = the reference trainer's loop verbatim fed
+from pinned host memory with loss.item() every step; `roofline` = the kernel with the largest share of the step
+(`roofline_top3`, `roofline_hot_path` list more), measured with CUDA events in a separate pass; `parity_check` = the
+in-run check of the sharded path against the single-GPU model; `cpu_baseline` = the unmodified reference classes
+timed on this box's host cores.
 """
 from __future__ import annotations
 
@@ -37,6 +43,8 @@ KDD_DIMS = [600000] * 8 + [400000] * 3
 # SURVEY 8(d) "roofline shape": Criteo field structure with every field > 10k ids scaled x16 -> 17.1 M rows,
 # a 1.1 GB fp32 table (>> 126 MB L2), so the gather really runs out of HBM
 ROOFLINE_DIMS = [d * 16 if d > 10000 else d for d in CRITEO_DIMS]
+
+METRIC = "DeepFM train samples/s (Criteo shape)"
 
 WORKLOADS = {
     # BASELINE.json configs[1] (default)
@@ -111,9 +119,21 @@ def make_batches(dims, batch, n, seed, dtype, dist_name="uniform"):
 
 
 # ------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU PyTorch path
+# reference arm / cpu baseline
 # ------------------------------------------------------------------------------------
+# `--impl reference` and the `cpu_baseline` leg time the reference's CPU PyTorch path on this box's host cores:
+#   kind "reference": the UNMODIFIED reference classes (src.models.get_ctr_model + src.models.deepfm.get_optimizers,
+#                     the loop of src/trainer/deepfm.py:44-62) imported from baseline/_ref, where
+#                     __graft_entry__.build() stages the pure-Python reference (it travels to the GPU box with the
+#                     snapshot like librsb.so); /root/reference itself is never read here;
+#   kind "port":      oracle/torch_port.py (the functional restatement, pinned against the golden vectors) when
+#                     baseline/_ref is absent.
 PORT_EMBEDDINGS = ("vanilla", "qr", "pep")
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "src", "models"))
 
 
 def _port_model(TP, wl, device):
@@ -132,6 +152,69 @@ def _port_model(TP, wl, device):
         p = {k: v.detach().to(device).requires_grad_(True) for k, v in p.items()}
     opts = TP.make_optimizers(p, {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")})
     return p, opts, emb, fwd
+
+
+def model_config(wl):
+    if wl["model"] == "deepfm":
+        return dict(num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"],
+                    embedding_config=dict(wl["emb"]))
+    return dict(name="dcn_mix", num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"],
+                compile_model=False, embedding_config=dict(wl["emb"]))
+
+
+def run_cpu_reference(wl, sample_batch, steps, warmup, budget_s=25.0, ids="uniform"):
+    """The unmodified reference on the CPU: its own model classes, its own get_optimizers, its trainer's step."""
+    import types
+
+    import torch
+
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    sys.modules.setdefault("lmdb", types.ModuleType("lmdb"))
+    sys.modules.setdefault("optuna", types.ModuleType("optuna"))
+    from loguru import logger
+
+    logger.remove()
+    import src.models as ref_models
+    import src.models.deepfm as ref_deepfm
+
+    if not type(ref_models.DeepFM).__module__ or not ref_models.DeepFM.__module__.startswith("src."):
+        raise RuntimeError("the reference registry is rebound to the B200 classes in this process")
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    torch.manual_seed(2023)
+    cfg = model_config(wl)
+    model = ref_models.get_ctr_model(wl["dims"], cfg)
+    opt_cfg = {k: v for k, v in wl["opt"].items() if k not in ("fused_sparse", "fused_adam")}
+    opts = ref_deepfm.get_optimizers(model, opt_cfg)
+    crit = torch.nn.BCEWithLogitsLoss()
+    model.train()
+    batches = make_batches(wl["dims"], sample_batch, 2, 2023, torch.int32, ids)
+
+    def step(x, y):                       # src/trainer/deepfm.py:44-62
+        out = model(x)
+        loss = crit(out, y.float())
+        for o in opts:
+            o.zero_grad()
+        loss.backward()
+        for o in opts:
+            o.step()
+        return loss.item()
+
+    for i in range(warmup):
+        step(*batches[i % 2])
+    times = []
+    t_all = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step(*batches[i % 2])
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 3:
+            break
+    med = statistics.median(times)
+    return dict(value=sample_batch / med, ms_per_step=med * 1e3, steps=len(times), cores=cores, kind="reference",
+                sample=f"{len(times)} steps of {sample_batch} samples (median step) of the unmodified reference classes "
+                       f"(baseline/_ref), torch {torch.__version__} CPU, {cores} threads")
 
 
 def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0, ids="uniform"):
@@ -156,9 +239,20 @@ def run_cpu_port(wl, sample_batch, steps, warmup, budget_s=25.0, ids="uniform"):
         if time.perf_counter() - t_all > budget_s and len(times) >= 3:
             break
     med = statistics.median(times)
-    return dict(value=sample_batch / med, ms_per_step=med * 1e3, steps=len(times), cores=cores,
-                sample=f"{len(times)} steps of {sample_batch} samples (median step), torch {torch.__version__} CPU, "
-                       f"{cores} threads")
+    return dict(value=sample_batch / med, ms_per_step=med * 1e3, steps=len(times), cores=cores, kind="port",
+                sample=f"{len(times)} steps of {sample_batch} samples (median step), oracle/torch_port.py, "
+                       f"torch {torch.__version__} CPU, {cores} threads")
+
+
+def run_cpu_arm(wl, sample_batch, steps, warmup, budget_s, ids):
+    if _reference_available():
+        try:
+            return run_cpu_reference(wl, sample_batch, steps, warmup, budget_s, ids)
+        except Exception as exc:  # noqa: BLE001 - fall back to the port, say why
+            r = run_cpu_port(wl, sample_batch, steps, warmup, budget_s, ids)
+            r["sample"] += f" (reference classes failed: {type(exc).__name__}: {exc})"[:200]
+            return r
+    return run_cpu_port(wl, sample_batch, steps, warmup, budget_s, ids)
 
 
 def torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, steps):
@@ -191,18 +285,21 @@ def main_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = min(args.cpu_batch, args.batch)
-    r = run_cpu_port(wl, sample, max(args.steps, 3), max(args.warmup, 1), budget_s=120.0, ids=args.ids)
+    # the same workload and the same per-step batch as our arm's per-GPU batch, on this box's host cores
+    sample = args.batch
+    r = run_cpu_arm(wl, sample, max(args.steps, 3), max(args.warmup, 1), budget_s=150.0, ids=args.ids)
     line = {
         "impl": "reference",
-        "metric": "DeepFM train samples/s (Criteo shape)" if wl["model"] == "deepfm" else "DCN-Mix train samples/s",
+        "metric": METRIC if wl["model"] == "deepfm" else "DCN-Mix train samples/s",
         "value": r["value"],
         "unit": "samples/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_step": sample, "fields": len(wl["dims"]),
-                   "rows": sum(wl["dims"]), "embedding": wl["emb"], "device": "cpu"},
-        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                   "rows": sum(wl["dims"]), "embedding": wl["emb"], "device": "cpu",
+                   "note": "single process on the host cores (the reference has no multi-GPU path); same model, "
+                           "optimizer recipe and batch as one GPU of our arm"},
+        "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -335,44 +432,74 @@ def small_batch_leg(args, wl, dims, cfg, dev, R, crit, batch=None):
             "note": "whole step (fwd, BCE, bwd, Adam) captured in one CUDA graph; inputs copied into static buffers"}
 
 
-def main_ours(args, wl):
+def _peaks_all():
+    out = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained"):
+            if d.get(k):
+                out[k] = float(d[k])
+        out["source"] = "measured (MEASURED_PEAKS.json)"
+    except (OSError, ValueError):
+        pass
+    return out
+
+
+NVLINK_GBS = 770.0     # measured peer-copy bandwidth per direction per GPU on this pool (B200_PROFILING.md); nominal 900
+
+
+def kernel_rooflines(kern, ksteps, ms_kpass, world, b, n_fields, traffic_for):
+    """One roofline entry per timed C-ABI call name.  HBM-bound kernels: algorithmic bytes / CUDA-event
+    time vs the measured copy bandwidth.  The GEMM: real bf16 MMA FLOPs (6 plane products per fp32 product, stated
+    separately) vs the measured cuBLAS bf16 throughput sustained inside a long step."""
+    pk = _peaks_all()
+    out = {}
+    for name, r in kern.items():
+        if r["ms_avg"] <= 0:
+            continue
+        share = r["ms_total"] / ms_kpass
+        base = {"calls_per_step": r["calls"] / ksteps, "ms_per_launch": round(r["ms_avg"], 4),
+                "share_of_step": round(share, 4)}
+        if name.startswith("gemm_planes"):
+            flops = r["bytes_avg"]                       # planes.gemm stores 2*M*N*K*batch in the timer's slot
+            tf = flops / (r["ms_avg"] * 1e-3) / 1e12
+            base.update(bound="tensor", achieved=round(6 * tf, 1), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                        frac=round(6 * tf / pk["bf16_tflops_sustained"], 4), fp32_equivalent_tflops=round(tf, 1),
+                        mma_per_fp32_product=6, traffic=None,
+                        note="achieved = bf16 tensor-core FLOPs actually issued (6 plane products per fp32 product); "
+                             "peak = cuBLAS bf16 sustained")
+        elif r["bytes_avg"] > 0:
+            gbs = r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9
+            base.update(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm_gbs"], unit="GB/s",
+                        frac=round(gbs / pk["hbm_gbs"], 4), alg_bytes_per_launch=int(r["bytes_avg"]),
+                        traffic=traffic_for(name))
+            if name == "lookup_fwd_sharded" and world > 1:
+                remote = r["bytes_avg"] and b * n_fields * 64 * (world - 1) / world     # rows fetched from peer shards
+                base["nvlink"] = {"remote_bytes_per_launch": int(remote), "achieved": round(remote / (r["ms_avg"] * 1e-3) / 1e9, 1),
+                                  "peak": NVLINK_GBS, "unit": "GB/s",
+                                  "frac": round(remote / (r["ms_avg"] * 1e-3) / 1e9 / NVLINK_GBS, 4),
+                                  "note": "64-byte rows read from the peers' shards inside the gather kernel"}
+        else:
+            continue
+        base["peak_source"] = pk["source"]
+        out[name] = base
+    return out
+
+
+def run_workload(args, name, wl, dev, rank, world, R, primary):
+    """Build the workload's model and measure it.  primary: every leg; otherwise value + kernel pass + the reference
+    trainer loop only (the extra BASELINE configs reported beside the headline at N = 1)."""
     import torch
     import torch.distributed as dist
 
-    import __graft_entry__ as G
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (our arm) needs a CUDA device: there is no CPU fallback for the hot path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL_DEBUG=VERSION makes NCCL printf() its version banner to stdout: keep stdout to the ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        G.build()
-    if world > 1:
-        dist.barrier()
-    import recsys_benchmark_b200 as R
     import recsys_benchmark_b200.functional as RF
     from recsys_benchmark_b200 import _lib
 
     torch.manual_seed(2023)
     dims = wl["dims"]
-    b = args.batch
-    if wl["model"] == "deepfm":
-        cfg = dict(num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"],
-                   embedding_config=dict(wl["emb"]))
-    else:
-        cfg = dict(name="dcn_mix", num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=wl["p_dropout"],
-                   compile_model=False, embedding_config=dict(wl["emb"]))
+    b = int(wl.get("batch", args.batch)) if not primary else args.batch
+    cfg = model_config(wl)
     sharded = bool(wl.get("sharded", False))
     if sharded:
         from recsys_benchmark_b200.sharded import ShardedDeepFM
@@ -438,25 +565,27 @@ def main_ours(args, wl):
             ms = float(t.item())
         return ms
 
+    steps = args.steps if primary else max(5, min(args.steps, 10))
     # ---- value: inputs resident in HBM -------------------------------------------------
     for i in range(args.warmup):
         step(*dev_pool[i % len(dev_pool)])
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(dev.index) if (rank == 0 and primary) else None
     l0 = _lib.load().rsb_launch_count()
-    ms_total = timed(lambda i: step(*dev_pool[i % len(dev_pool)]), args.steps)
+    ms_total = timed(lambda i: step(*dev_pool[i % len(dev_pool)]), steps)
     launches = _lib.load().rsb_launch_count() - l0
     # per-kernel CUDA-event timing in a SEPARATE pass of the same steps (an event pair around every C call keeps
     # consecutive kernels from overlapping their launch latency, so it must not sit inside the `value` region)
     timer = RF.KernelTimer()
     RF.set_timer(timer)
-    ksteps = max(3, min(args.steps, 10))
+    ksteps = max(3, min(steps, 10))
     ms_kpass = timed(lambda i: step(*dev_pool[i % len(dev_pool)]), ksteps)
     RF.set_timer(None)
     kern = timer.summary()
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     value = world * b / (ms_step * 1e-3)
 
     # ---- e2e: host buffers, H2D inside the timed region, loss read back every step ----------
+    # (1) the reference trainer's loop verbatim (src/trainer/deepfm.py:44-62)
     def e2e_step(i):
         xh, yh = host_pool[i % len(host_pool)]
         loss = step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True))
@@ -464,96 +593,53 @@ def main_ours(args, wl):
 
     for i in range(min(args.warmup, 3)):
         e2e_step(i)
-    ms_e2e = timed(e2e_step, args.steps) / args.steps
-
-    # same, with the library's own input staging (data.DevicePrefetcher: H2D of step i+1 on a side
-    # stream under the compute of step i); still host buffers in, loss read back every step
-    from recsys_benchmark_b200.data import DevicePrefetcher
-
-    class HostCycle:          # a re-iterable "loader" over the pinned host batches
-        n = 0
-
-        def __iter__(self):
-            return (host_pool[i % len(host_pool)] for i in range(self.n))
-
-    loader = HostCycle()
-    prefetcher = DevicePrefetcher(loader, dev)     # ONE object: its side stream and device buffers persist
-
-    def prefetched_run(steps):
-        loader.n = steps
-        for xd, yd in prefetcher:
-            step(xd, yd).item()
-
-    prefetched_run(3)
-    sync_all()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    prefetched_run(args.steps)
-    e_ev.record()
-    sync_all()
-    ms_e2e_pf = s_ev.elapsed_time(e_ev) / args.steps
-    if world > 1:
-        t = torch.tensor([ms_e2e_pf], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e_pf = float(t.item())
-    # ... and with the loss read back one step late (data.DeferredScalar): D2H every step, no queue drain
-    from recsys_benchmark_b200.data import DeferredScalar
-
-    def deferred_run(steps):
-        loader.n = steps
-        reader = DeferredScalar(dev)
-        for xd, yd in prefetcher:
-            reader.push(step(xd, yd))
-        return reader.flush()
-
-    deferred_run(3)
-    sync_all()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    deferred_run(args.steps)
-    e_ev.record()
-    sync_all()
-    ms_e2e_df = s_ev.elapsed_time(e_ev) / args.steps
-    if world > 1:
-        t = torch.tensor([ms_e2e_df], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e_df = float(t.item())
-    # clocks / throttle reasons were sampled (nvidia-smi, every 20 ms) from the start of the `value` region to here:
-    # the timed region itself is ~0.1 s, the e2e legs keep the same step running
-    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(e2e_step, steps) / steps
+    res = {"workload": name, "value": round(value, 1), "ms_per_step": round(ms_step, 4), "batch_per_gpu": b,
+           "gpu_launches": int(launches), "steps": steps,
+           "reference_trainer_loop": {"value": round(world * b / (ms_e2e * 1e-3), 1), "ms_per_step": round(ms_e2e, 4),
+                                      "note": "src/trainer/deepfm.py:44-62 verbatim: blocking inputs.to(device) on the "
+                                              "compute stream, loss.item() right after optimizer.step()"}}
     h2d = pool[0][0].numel() * pool[0][0].element_size() + pool[0][1].numel() * 4
+    res["h2d_bytes_per_step"] = int(h2d)
 
-    # ---- reference-yaml batch (2048): launch-bound -> whole step captured in a CUDA graph -------------
-    small = None
-    big_graph = None
-    if world == 1 and args.small_batch > 0 and not sharded:
-        try:
-            small = small_batch_leg(args, wl, dims, cfg, dev, R, crit)
-        except Exception as exc:  # noqa: BLE001 - a secondary number must never break the main line
-            small = {"batch": args.small_batch, "error": f"{type(exc).__name__}: {exc}"[:300]}
-        if not wl["opt"].get("sparse") and b <= 131072:
-            try:   # the same graph-captured step (recsys_benchmark_b200.graphed.GraphedTrainStep) at the main batch
-                big_graph = small_batch_leg(args, wl, dims, cfg, dev, R, crit, batch=b)
-            except Exception as exc:  # noqa: BLE001
-                big_graph = {"batch": b, "error": f"{type(exc).__name__}: {exc}"[:300]}
+    if primary:
+        # (2) the library's own loop: DevicePrefetcher (H2D of step i+1 on a side stream under step i) and the loss
+        #     copied D2H every step through DeferredScalar, consumed one step late
+        from recsys_benchmark_b200.data import DeferredScalar, DevicePrefetcher
 
-    # ---- the reference's torch operators, eager, on this GPU (comparison only) ----------------------
-    eager = None
-    if world == 1 and not args.no_torch_eager and not sharded \
-            and wl["emb"].get("name", "vanilla") in PORT_EMBEDDINGS:
-        try:
-            eager = torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, max(3, min(args.steps, 10)))
-        except Exception as exc:  # noqa: BLE001
-            eager = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        class HostCycle:          # a re-iterable "loader" over the pinned host batches
+            n = 0
 
-    if rank != 0:
+            def __iter__(self):
+                return (host_pool[i % len(host_pool)] for i in range(self.n))
+
+        loader = HostCycle()
+        prefetcher = DevicePrefetcher(loader, dev)
+
+        def deferred_run(n):
+            loader.n = n
+            reader = DeferredScalar(dev)
+            for xd, yd in prefetcher:
+                reader.push(step(xd, yd))
+            return reader.flush()
+
+        deferred_run(3)
+        sync_all()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        deferred_run(steps)
+        e_ev.record()
+        sync_all()
+        ms_df = s_ev.elapsed_time(e_ev) / steps
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+            t = torch.tensor([ms_df], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_df = float(t.item())
+        res["pipelined_loop"] = {"value": round(world * b / (ms_df * 1e-3), 1), "ms_per_step": round(ms_df, 4),
+                                 "note": "data.DevicePrefetcher + data.DeferredScalar (loss read one step late)"}
+        res["clocks"] = sampler.stop() if sampler else None
 
-    # ---- roofline of the dominant hand-written kernel ------------------------------------
-    peak, peak_src = peaks()
+    # ---- rooflines -----------------------------------------------------------------------------
     unique_rows = None
     if wl["opt"].get("fused_sparse") and "segment_reduce_apply" in kern and not sharded:
         # fused SparseAdam: + read/write of w, m, v per UNIQUE row (6*D*4 B); U is counted here, on batch 0,
@@ -561,108 +647,216 @@ def main_ours(args, wl):
         offs = torch.tensor([0] + dims[:-1]).cumsum(0)
         unique_rows = int(torch.unique(pool[0][0].long() + offs).numel())
         kern["segment_reduce_apply"]["bytes_avg"] += 6 * 16 * 4 * unique_rows
-    kernels = {}
-    for name, r in kern.items():
-        gbs = (r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9) if r["bytes_avg"] and r["ms_avg"] > 0 else None
-        kernels[name] = {"calls_per_step": r["calls"] / ksteps, "ms_avg": round(r["ms_avg"], 4),
-                         "alg_bytes": int(r["bytes_avg"]), "alg_gbs": None if gbs is None else round(gbs, 1),
-                         "share_of_step": round(r["ms_total"] / ms_kpass, 4)}
-    # roofline of the dominant HOT-PATH kernel (lookup / scatter-add side);
-    # the dense-tail glue and the GEMMs are reported in `kernels` / `roofline_gemm`
-    hot = ("lookup_", "segment_", "small_table", "sort_rows", "dhe_encode", "csr_lookup")
-    cand = {k: v for k, v in kern.items() if v["bytes_avg"] > 0 and k.startswith(hot)}
-    roofline = None
-    if cand:
-        top = max(cand, key=lambda k: cand[k]["ms_total"])
-        r = cand[top]
-        ach = r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as fh:
-                traffic = json.load(fh).get(args.workload, {}).get(top)
-        roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": int(r["bytes_avg"]), "ms_per_launch": round(r["ms_avg"], 4)}
+    res["unique_rows_per_step"] = unique_rows
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic_tab = json.load(fh).get(name, {})
+    roofs = kernel_rooflines(kern, ksteps, ms_kpass, world, b, len(dims), lambda k: traffic_tab.get(k))
+    top = sorted(roofs, key=lambda k: -roofs[k]["share_of_step"])
+    res["roofline_top3"] = [dict(kernel=k, **roofs[k]) for k in top[:3]]
+    res["roofline"] = dict(kernel=top[0], **roofs[top[0]]) if top else None
+    hot = [k for k in top if k.startswith(("lookup_", "segment_", "sort_rows", "small_table", "csr_lookup", "dhe_"))]
+    res["roofline_hot_path"] = [dict(kernel=k, **roofs[k]) for k in hot[:4]]
+    res["kernels"] = {k: {"calls_per_step": r["calls"] / ksteps, "ms_avg": round(r["ms_avg"], 4),
+                          "share_of_step": round(r["ms_total"] / ms_kpass, 4)} for k, r in kern.items()}
+    res["_objects"] = (model, opts, crit, cfg, dev_pool, pool)
+    return res
 
-    roofline_gemm = None
-    if "gemm_f32" in kern:
-        # fp32-equivalent FLOPs of the dense-tail GEMMs per step (fwd + dX + dW of every Linear the kernel takes)
-        flops = 0.0
-        widths = [16 * len(dims)] + [400, 400, 400]
-        for i in range(3):
-            flops += 3 * 2.0 * b * widths[i] * widths[i + 1]
-        if wl["model"] == "dcn_mix":
-            dm, e_, r_ = 16 * len(dims), 4, 64
-            flops += 3 * 3 * 2.0 * b * e_ * r_ * (2 * dm + r_)
-        if wl["emb"].get("name") == "dhe":
-            enc = [1024] + list(wl["emb"]["hidden_sizes"]) + [16]
-            rows_ = b * len(dims)
-            for i in range(len(enc) - 1):
-                flops += (2 if i == 0 else 3) * 2.0 * rows_ * enc[i] * enc[i + 1]   # no dX for the hash codes
-        g = kern["gemm_f32"]
-        bf16_peak = 1590.0          # B200_PROFILING.md fallback; MEASURED_PEAKS.json (1645.2 on this pool) wins
-        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+
+def sharded_parity_check(dims, dev, rank, world, R):
+    """In-run parity of the row-sharded path (SURVEY 8e "Parity"): (1) the sharded forward over local + peer shards
+    gives the SAME logits, bit for bit, as the single-GPU gather on this rank's batch; (2) after two data-parallel
+    training steps the gathered table equals the single-GPU model trained on the global batch within 1e-4.
+    Dropout and BatchNorm are off here (dropout draws per-rank masks; BatchNorm statistics are per-rank by design)."""
+    import torch
+    import torch.distributed as dist
+
+    from recsys_benchmark_b200.sharded import ShardedDeepFM
+
+    torch.manual_seed(77)
+    bl = 4096
+    sh = ShardedDeepFM(dims, 16, [400, 400, 400], p_dropout=0.0, use_batchnorm=False).to(dev)
+    full = R.get_ctr_model(dims, dict(num_factor=16, hidden_sizes=[400, 400, 400], p_dropout=0.0, use_batchnorm=False,
+                                      embedding_config={"name": "vanilla"})).to(dev)
+    st = {k: v for k, v in sh.state_dict().items() if not k.startswith("embedding.")}
+    full.load_state_dict(st, strict=False)
+    with torch.no_grad():
+        full.embedding.get_weight().copy_(sh.embedding.gather_full_weight())
+    g = torch.Generator().manual_seed(5)
+    xg = torch.stack([torch.randint(0, d, (bl * world,), generator=g) for d in dims], 1).int()
+    yg = torch.randint(0, 2, (bl * world,), generator=g).float()
+    xl, yl = xg[rank::world].to(dev), yg[rank::world].to(dev)
+    xg, yg = xg.to(dev), yg.to(dev)
+    crit = torch.nn.BCEWithLogitsLoss()
+    o_sh = torch.optim.Adam(sh.parameters(), lr=1e-3)
+    o_full = torch.optim.Adam(full.parameters(), lr=1e-3)
+    out = {"world": world, "local_batch": bl}
+    for s in range(2):
+        lg_sh = sh(xl)
+        lg_full = full(xg)
+        if s == 0:
+            out["logits_bit_identical"] = bool(torch.equal(lg_sh, lg_full[rank::world]))
+        o_sh.zero_grad()
+        crit(lg_sh, yl).backward()
+        sh.sync_gradients()
+        o_sh.step()
+        sh.finish_step()
+        o_full.zero_grad()
+        crit(lg_full, yg).backward()
+        o_full.step()
+    w_sh, w_full = sh.embedding.gather_full_weight(), full.embedding.get_weight().detach()
+    err = float((w_sh - w_full).abs().max() / w_full.abs().max())
+    flags = torch.tensor([float(out["logits_bit_identical"]), err], device=dev)
+    if world > 1:
+        mn = flags.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        mx = flags.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        out["logits_bit_identical"] = bool(mn[0].item() == 1.0)
+        err = float(mx[1].item())
+    out["table_rel_err_after_2_steps"] = err
+    out["ok"] = bool(out["logits_bit_identical"] and err < 1e-4)
+    del sh, full
+    torch.cuda.empty_cache()
+    return out
+
+
+def main_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as G
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL printf() its version banner to stdout: keep stdout to the ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        G.build()
+    if world > 1:
+        dist.barrier()
+    import recsys_benchmark_b200 as R
+
+    sharded = bool(wl.get("sharded", False))
+    parity = None
+    if sharded and not args.no_parity_check:
         try:
-            with open(mp) as fh:
-                bf16_peak = float(json.load(fh).get("bf16_tflops") or bf16_peak)
-        except (OSError, ValueError):
-            pass
-        tf = flops / (g["ms_total"] / ksteps * 1e-3) / 1e12
-        roofline_gemm = {"bound": "tensor", "kernel": "gemm_f32 (tcgen05 3xBF16-split fp32 emulation, 6 MMAs)",
-                         "achieved": round(tf, 1), "peak": bf16_peak, "unit": "TFLOP/s (fp32-equivalent 2MNK)",
-                         "frac": round(tf / bf16_peak, 4), "frac_of_emulation_ceiling": round(tf / (bf16_peak / 6), 4),
-                         "note": "6 bf16 MMAs per fp32 product: ceiling = peak/6; cuBLAS fp32 SGEMM (what the "
-                                 "reference runs) measures 42-57 TFLOP/s on these shapes"}
+            parity = sharded_parity_check(wl["dims"], dev, rank, world, R)
+        except Exception as exc:  # noqa: BLE001 - reported, never hidden
+            parity = {"ok": False, "error": f"{type(exc).__name__}: {exc}"[:300]}
+    res = run_workload(args, args.workload, wl, dev, rank, world, R, primary=True)
+    model, opts, crit, cfg, dev_pool, pool = res.pop("_objects")
+    dims, b = wl["dims"], args.batch
 
-    # ---- cpu baseline (oracle port of the reference's CPU path), rank 0, N=1 only ----------
+    # ---- reference-yaml batch (2048): launch-bound -> whole step captured in a CUDA graph -------------
+    small = None
+    if world == 1 and args.small_batch > 0 and not sharded:
+        try:
+            small = small_batch_leg(args, wl, dims, cfg, dev, R, crit)
+        except Exception as exc:  # noqa: BLE001 - a secondary number must never break the main line
+            small = {"batch": args.small_batch, "error": f"{type(exc).__name__}: {exc}"[:300]}
+    # ---- the reference's torch operators, eager, on this GPU (comparison only) ----------------------
+    eager = None
+    if world == 1 and not args.no_torch_eager and wl["emb"].get("name", "vanilla") in PORT_EMBEDDINGS:
+        try:
+            eager = torch_eager_gpu_leg(wl, dims, b, dev, dev_pool, max(3, min(args.steps, 10)))
+        except Exception as exc:  # noqa: BLE001
+            eager = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    del model, opts, dev_pool
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs, beside the headline (N = 1 only) -----------------------------
+    others = {}
+    if world == 1 and not args.no_other_configs:
+        for other in OTHER_CONFIGS:
+            if other == args.workload:
+                continue
+            try:
+                r = run_workload(args, other, WORKLOADS[other], dev, rank, world, R, primary=False)
+                r.pop("_objects")
+                r.pop("kernels", None)
+                if other == "deepfm_qr_criteo" and args.small_batch > 0:
+                    try:
+                        r["small_batch"] = small_batch_leg(args, WORKLOADS[other], WORKLOADS[other]["dims"],
+                                                           model_config(WORKLOADS[other]), dev, R, crit)
+                    except Exception as exc:  # noqa: BLE001
+                        r["small_batch"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                others[other] = r
+            except Exception as exc:  # noqa: BLE001
+                others[other] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- cpu baseline (the reference's CPU path), rank 0, N=1 only ----------
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and wl["emb"].get("name", "vanilla") in PORT_EMBEDDINGS:
-        r = run_cpu_port(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0, ids=args.ids)
-        cpu = {"value": round(r["value"], 1), "unit": "samples/s", "cores": r["cores"], "kind": "port",
+    if world == 1 and not args.no_cpu_baseline:
+        r = run_cpu_arm(wl, min(args.cpu_batch, b), 6, 1, budget_s=20.0, ids=args.ids)
+        cpu = {"value": round(r["value"], 1), "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
                "sample": r["sample"]}
 
+    e2e_ref = res["reference_trainer_loop"]
     line = {
-        "metric": "DeepFM train samples/s (Criteo shape)" if wl["model"] == "deepfm" else "DCN-Mix train samples/s",
-        "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC if wl["model"] == "deepfm" else "DCN-Mix train samples/s",
+        "value": res["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "global_batch": world * b, "batch_per_gpu": b, "fields": len(dims),
                    "rows": sum(dims), "embedding": wl["emb"], "num_factor": 16, "mlp": [400, 400, 400],
-                   "optimizer": wl["opt"], "ids": f"int32, {'Zipf(1.05) clipped' if args.ids == 'zipf' else 'uniform'} per field, seed 2023",
-                   "parallelism": (f"row-sharded tables x{world} (NVLink peer gather / shard atomics) + dp{world} dense"
-                                   if sharded else (f"dp{world} (replicated compressed tables, flat grad allreduce)"
+                   "use_batchnorm": wl["use_bn"], "optimizer": wl["opt"],
+                   "ids": f"int32, {'Zipf(1.05) clipped' if args.ids == 'zipf' else 'uniform'} per field, seed 2023",
+                   "parallelism": (f"row-sharded table x{world} (rows r % {world} on rank r, forward gather over NVLink "
+                                   f"peer memory, gradients pushed to the owner shard) + dp{world} dense allreduce"
+                                   if sharded else (f"dp{world} (replicated tables, flat grad allreduce)"
                                                     if world > 1 else "single")),
                    "l2": f"{args.pool} distinct batches cycled; per-step traffic "
                          f"{round(b * 13.4e3 / 1e6)} MB vs 126 MB L2 (no flush)"},
-        "clocks": clocks,
-        "e2e": {"value": round(world * b / (ms_e2e_df * 1e-3), 1), "unit": "samples/s",
-                "ms_per_step": round(ms_e2e_df, 4), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                "input_staging": "the library's training loop: pinned host int32 ids -> data.DevicePrefetcher (H2D of "
-                                 "step i+1 on a side stream under step i) -> model step; the loss is copied D2H every "
-                                 "step through data.DeferredScalar and consumed one step late, so the host never "
-                                 "drains the launch queue",
-                "reference_trainer_loop": {
-                    "value": round(world * b / (ms_e2e * 1e-3), 1), "ms_per_step": round(ms_e2e, 4),
-                    "note": "src/trainer/deepfm.py:44-62 verbatim: blocking inputs.to(device) on the compute stream, "
-                            "loss.item() right after optimizer.step()"},
-                "with_device_prefetcher_only": {"value": round(world * b / (ms_e2e_pf * 1e-3), 1),
-                                                "ms_per_step": round(ms_e2e_pf, 4),
-                                                "note": "DevicePrefetcher + loss.item() every step"}},
-        "gpu_launches": int(launches),
-        "roofline": roofline,
-        "roofline_gemm": roofline_gemm,
-        "kernels": kernels,
+        "clocks": res.get("clocks"),
+        # the headline end-to-end number is the reference trainer's own loop (blocking H2D, loss.item() every step);
+        # the library's pipelined loop is reported beside it
+        "e2e": {"value": e2e_ref["value"], "unit": "samples/s", "ms_per_step": e2e_ref["ms_per_step"],
+                "h2d_bytes_per_step": res["h2d_bytes_per_step"], "d2h_bytes_per_step": 4,
+                "loop": e2e_ref["note"], "pipelined_loop": res.get("pipelined_loop")},
+        "reference_trainer_loop": e2e_ref,
+        "gpu_launches": res["gpu_launches"],
+        "roofline": res["roofline"],
+        "roofline_top3": res["roofline_top3"],
+        "roofline_hot_path": res["roofline_hot_path"],
+        "parity_check": parity,
+        "kernels": res["kernels"],
         "cpu_baseline": cpu,
-        "small_batch": small,
-        "cuda_graph_step": big_graph,
+        "small_batch": small if small is not None else others.get("deepfm_qr_criteo", {}).get("small_batch"),
         "torch_eager_gpu": eager,
-        "unique_rows_per_step": unique_rows,
+        "unique_rows_per_step": res["unique_rows_per_step"],
+        "other_configs": others,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# BASELINE.json configs reported beside the headline at N = 1: [1] QR, [0] full table on one GPU (fused SparseAdam),
+# [2] DCN-Mix Avazu, [3] PEP / OptEmbed KDD, and the SURVEY 8(d) roofline shape (17 M rows, table >> L2)
+OTHER_CONFIGS = ["deepfm_qr_criteo", "deepfm_full_criteo", "dcnmix_full_avazu", "deepfm_pep_kdd", "deepfm_optembed_kdd",
+                 "deepfm_full_roofline"]
 
 
 def main():
@@ -671,12 +865,18 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="deepfm_qr_criteo", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="deepfm_full_criteo_sharded", choices=sorted(WORKLOADS),
+                    help="default: BASELINE.json configs[4], the full Criteo-shaped table row-sharded over the N GPUs "
+                         "(N = 1: one shard), so that the 1/2/4/8-GPU lines measure the same model")
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: 65536, or the "
                                                             "workload's own batch)")
     ap.add_argument("--pool", type=int, default=8, help="distinct synthetic batches cycled through")
-    ap.add_argument("--cpu-batch", type=int, default=4096, help="bounded sample per CPU step")
+    ap.add_argument("--cpu-batch", type=int, default=65536, help="samples per CPU step of the cpu_baseline leg "
+                                                                 "(default: the GPU arm's own batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the in-run sharded parity check")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="N = 1: do not also measure the other BASELINE configs (QR, DCN-Mix, PEP, OptEmbed, roofline shape)")
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
                     help="per-field id distribution: uniform, or Zipf(1.05) clipped to the field size")
     ap.add_argument("--no-torch-eager", action="store_true", help="skip the torch-eager-on-GPU comparison leg")

@@ -89,7 +89,11 @@ def gemm(a: Planes, b: Planes, m: int, n: int, k: int, *, a_mn_major: bool = Fal
     ws = RF._ws(nb, dev)
     oa = a.operand(a_mn_major, *a_steps)
     ob = b.operand(b_mn_major, *b_steps, cols=b_cols)
-    RF._call("gemm_planes", lib.rsb_gemm_planes, C.byref(oa), C.byref(ob), m, n, k, batch, split_k, L.ptr(c), L.ptr(out),
+    kind = ("gemm_planes" if epilogue is None else
+            ("gemm_planes_relu_dropout", "gemm_planes_relu_dropout", "gemm_planes_masked", "gemm_planes_masked")[epilogue.mode])
+    if a_mn_major and b_mn_major:
+        kind = "gemm_planes_dw"
+    RF._call(kind, lib.rsb_gemm_planes, C.byref(oa), C.byref(ob), m, n, k, batch, split_k, L.ptr(c), L.ptr(out),
              out.stride(0) if out is not None else n, d_batch_stride, L.ptr(bias), alpha, beta,
              C.byref(epilogue) if epilogue is not None else None, L.ptr(ws), ws.numel(), L.stream_ptr(dev),
              nbytes=2 * m * n * k * batch)       # `bytes` slot of the timer carries the fp32-equivalent FLOPs here

@@ -15,7 +15,7 @@ import bench  # noqa: E402
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2",
-                          "--warmup", "1", "--cpu-batch", "256"], capture_output=True, text=True, timeout=600,
+                          "--warmup", "1", "--batch", "256"], capture_output=True, text=True, timeout=600,
                          cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
@@ -25,9 +25,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
               "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["value"] > 0 and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference classes when baseline/_ref is staged (build container and GPU box), else the oracle port
+    assert d["cpu_baseline"]["kind"] == ("reference" if bench._reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["config"]["batch_per_step"] == 256
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"] == "deepfm_qr_criteo" and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "deepfm_full_criteo_sharded" and d["vs_baseline"] is None
 
 
 def test_reference_arm_is_silent_on_non_zero_ranks():
