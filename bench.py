@@ -693,11 +693,20 @@ def sharded_parity_check(dims, dev, rank, world, R):
     o_sh = torch.optim.Adam(sh.parameters(), lr=1e-3)
     o_full = torch.optim.Adam(full.parameters(), lr=1e-3)
     out = {"world": world, "local_batch": bl}
+    with torch.no_grad():
+        # the sharded gather (local + peer shards over NVLink) against the single-GPU gather: bit for bit
+        e_sh, y_sh = sh.embedding.lookup(xl, sh.offsets, sh.fc.weight, sh._bias)
+        e_full, y_full = full.embedding.lookup(xg, full.offsets, full.fc.weight, full._bias)
+        out["gather_fm_bit_identical"] = bool(torch.equal(e_sh, e_full[rank::world]) and torch.equal(y_sh, y_full[rank::world]))
     for s in range(2):
         lg_sh = sh(xl)
         lg_full = full(xg)
         if s == 0:
-            out["logits_bit_identical"] = bool(torch.equal(lg_sh, lg_full[rank::world]))
+            # (the MLP's one-output Linear is a library GEMV whose kernel choice depends on the batch size: the logits
+            #  of a 4096-row and an 8192-row call agree to fp32 rounding, not necessarily bit for bit)
+            ref = lg_full[rank::world]
+            out["logits_max_rel_err"] = float((lg_sh - ref).abs().max() / ref.abs().max())
+            out["logits_bit_identical"] = bool(torch.equal(lg_sh, ref))
         o_sh.zero_grad()
         crit(lg_sh, yl).backward()
         sh.sync_gradients()
@@ -708,16 +717,16 @@ def sharded_parity_check(dims, dev, rank, world, R):
         o_full.step()
     w_sh, w_full = sh.embedding.gather_full_weight(), full.embedding.get_weight().detach()
     err = float((w_sh - w_full).abs().max() / w_full.abs().max())
-    flags = torch.tensor([float(out["logits_bit_identical"]), err], device=dev)
+    flags = torch.tensor([float(out["gather_fm_bit_identical"]), float(out["logits_bit_identical"]),
+                          -out["logits_max_rel_err"], -err], device=dev)
     if world > 1:
-        mn = flags.clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        mx = flags.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        out["logits_bit_identical"] = bool(mn[0].item() == 1.0)
-        err = float(mx[1].item())
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)          # worst rank
+    out["gather_fm_bit_identical"] = bool(flags[0].item() == 1.0)
+    out["logits_bit_identical"] = bool(flags[1].item() == 1.0)
+    out["logits_max_rel_err"] = float(-flags[2].item())
+    err = float(-flags[3].item())
     out["table_rel_err_after_2_steps"] = err
-    out["ok"] = bool(out["logits_bit_identical"] and err < 1e-4)
+    out["ok"] = bool(out["gather_fm_bit_identical"] and out["logits_max_rel_err"] < 1e-5 and err < 1e-4)
     del sh, full
     torch.cuda.empty_cache()
     return out

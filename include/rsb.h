@@ -275,9 +275,10 @@ typedef struct {
 /* What rsb_gemm_planes does with the accumulator (fused epilogues of the dense tail, src/models/deepfm.py:55-66):
  *   RSB_EPI_LINEAR               D = alpha * acc + beta * C + bias                                   (fp32)
  *   RSB_EPI_RELU_DROPOUT_PLANES  y = dropout_p(relu(alpha * acc + bias)) written as bf16 planes (the next layer's GEMM
- *                                operand) + the 1-byte keep-and-positive mask [M, N]; the forward of Linear -> ReLU ->
- *                                Dropout in ONE launch.  Same Philox stream as rsb_relu_dropout_fwd (seed, offset,
- *                                offset_dev), so the mask equals the un-fused pass bit for bit.
+ *                                operand): the forward of Linear -> ReLU -> Dropout.  `mask` [M, N] holds the dropout
+ *                                keep bits on entry (rsb_dropout_keep_mask: same Philox stream as rsb_relu_dropout_fwd,
+ *                                so the masks equal the un-fused pass bit for bit) and keep && (pre-activation > 0),
+ *                                the mask the backward needs, on exit.
  *   RSB_EPI_MASK_PLANES          g = alpha * acc * mask / (1 - p) written as planes: dX of a hidden layer, i.e. the
  *                                gradient w.r.t. the previous layer's pre-activation, ready for its dX / dW GEMMs.
  *   RSB_EPI_MASK_F32             the same as fp32 D (a BatchNorm backward sits in between).
@@ -295,11 +296,19 @@ typedef struct {
   void* out_planes;            /* bf16 [3][M][out_ld] (modes 1, 2) */
   int64_t out_ld, out_plane_stride;
   int32_t ones_col;
-  uint8_t* mask;               /* [M, N]: written by mode 1, read by modes 2, 3 */
+  uint8_t* mask;               /* [M, N]: updated in place by mode 1, read by modes 2, 3 */
   float p;                     /* dropout probability */
-  uint64_t seed, offset;
-  const uint64_t* offset_dev;  /* optional device-resident stream position (CUDA-graph replays) */
 } rsb_gemm_epilogue;
+
+/* y = dropout_p(relu(x)) of an fp32 [M, N] activation (ldx) written as planes (+ ones column) and the 1-byte
+ * keep-and-positive mask [M, N]: rsb_relu_dropout_fwd + rsb_split_planes in one pass, same Philox stream. */
+RSB_API int rsb_relu_dropout_planes(const float* x, int64_t M, int32_t N, int64_t ldx, float p, uint64_t seed, uint64_t offset,
+                                    const uint64_t* offset_dev, int32_t ones_col, void* out_planes, int64_t out_ld,
+                                    int64_t plane_stride, uint8_t* mask, void* stream);
+/* mask[i] = 1 with probability 1 - p: the dropout keep bits of an activation of `numel` (multiple of 4) elements, drawn
+ * from the Philox stream (seed, offset [+ *offset_dev]) exactly like rsb_relu_dropout_fwd draws them. */
+RSB_API int rsb_dropout_keep_mask(uint8_t* mask, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                                  const uint64_t* offset_dev, void* stream);
 
 /* fp32 [rows, cols] (ld) -> bf16 planes [3][rows][out_ld] (columns cols..out_ld-1 zero); transpose = 1 writes the
  * planes of in^T ([cols][out_ld >= rows]); ones_col = 1 additionally writes 1.0 at column roundup8(cols). */

@@ -37,8 +37,7 @@ class GemmEpilogue(C.Structure):
     """rsb_gemm_epilogue of include/rsb.h."""
 
     _fields_ = [("mode", C.c_int32), ("out_planes", C.c_void_p), ("out_ld", C.c_int64), ("out_plane_stride", C.c_int64),
-                ("ones_col", C.c_int32), ("mask", C.c_void_p), ("p", C.c_float), ("seed", C.c_uint64),
-                ("offset", C.c_uint64), ("offset_dev", C.c_void_p)]
+                ("ones_col", C.c_int32), ("mask", C.c_void_p), ("p", C.c_float)]
 
 
 EPI_LINEAR, EPI_RELU_DROPOUT_PLANES, EPI_MASK_PLANES, EPI_MASK_F32 = range(4)
@@ -73,6 +72,8 @@ PROTOTYPES = {
                                      _p, _p]),
     "rsb_dhe_encode": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _p, _p]),
     "rsb_split_planes": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i64, _p]),
+    "rsb_relu_dropout_planes": (C.c_int, [_p, _i64, _i32, _i64, _f, C.c_uint64, C.c_uint64, _p, _i32, _p, _i64, _i64, _p, _p]),
+    "rsb_dropout_keep_mask": (C.c_int, [_p, _i64, _f, C.c_uint64, C.c_uint64, _p, _p]),
     "rsb_rank1_mask_planes": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _i64, _i64, _p]),
     "rsb_gemm_planes_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64, _i32]),
     "rsb_gemm_planes": (C.c_int, [C.POINTER(PlanesOperand), C.POINTER(PlanesOperand), _i64, _i64, _i64, _i64, _i32, _p,

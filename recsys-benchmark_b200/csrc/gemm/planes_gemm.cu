@@ -72,9 +72,6 @@ struct Params {
   int ones_col;
   unsigned char* mask;
   float drop_scale;
-  unsigned drop_thr;
-  unsigned long long seed, offset;
-  const unsigned long long* offset_dev;
 };
 
 // x -> (bf16(x), bf16(x - x0), bf16(x - x0 - x1)); both remainders are exact in fp32
@@ -515,13 +512,13 @@ epilogue_role:
             }
           }
         } else {
-          // RSB_EPI_RELU_DROPOUT_PLANES: y = dropout(relu(acc + bias)) -> planes + keep mask   (forward of a hidden layer)
+          // RSB_EPI_RELU_DROPOUT_PLANES: y = dropout(relu(acc + bias)) -> planes; `mask` holds the dropout keep bits on
+          //                              entry (rsb_dropout_keep_mask: the Philox draw is NOT part of this exposed
+          //                              epilogue) and keep && (pre-activation > 0) on exit   (forward of a hidden layer)
           // RSB_EPI_MASK_PLANES        : g = acc * mask / (1 - p)      -> planes               (dX of a hidden layer)
           const bool fwd = p.epi_mode == RSB_EPI_RELU_DROPOUT_PLANES;
           __nv_bfloat16* prow = p.out_planes + row * p.out_ld;
           unsigned char* mrow = p.mask + row * (long long)p.N;
-          rsb::Philox rng{(unsigned)p.seed, (unsigned)(p.seed >> 32)};
-          const unsigned long long off = p.offset + (p.offset_dev ? *p.offset_dev : 0ull) + (unsigned long long)row * (p.N >> 2);
 #pragma unroll
           for (int c = 0; c < NC; c += 8) {
             if (c < ncols && n0 + c < p.N) {
@@ -533,17 +530,14 @@ epilogue_role:
                                        acc[c + h + 3] * p.alpha);
                 uchar4 m = make_uchar4(0, 0, 0, 0);
                 if (valid) {
+                  m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
                   if (fwd) {
                     if (p.bias) {
                       const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h));
                       o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                     }
-                    const uint4 r = rng(off + (unsigned long long)((n0 + c + h) >> 2));
-                    m.x = (o.x > 0.f) && (r.x >= p.drop_thr); m.y = (o.y > 0.f) && (r.y >= p.drop_thr);
-                    m.z = (o.z > 0.f) && (r.z >= p.drop_thr); m.w = (o.w > 0.f) && (r.w >= p.drop_thr);
+                    m.x = m.x && (o.x > 0.f); m.y = m.y && (o.y > 0.f); m.z = m.z && (o.z > 0.f); m.w = m.w && (o.w > 0.f);
                     *reinterpret_cast<uchar4*>(mrow + n0 + c + h) = m;
-                  } else {
-                    m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
                   }
                 }
                 v[h] = m.x ? o.x * p.drop_scale : 0.f; v[h + 1] = m.y ? o.y * p.drop_scale : 0.f;
@@ -638,6 +632,55 @@ __global__ void split_planes_kernel(const float* __restrict__ in, long long rows
     *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p0);
     *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<const uint4*>(p1);
     *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<const uint4*>(p2);
+  }
+}
+
+// dropout keep bits of a [.., 4 n4] activation: byte i*4+j = (Philox(offset + i).j >= thr); the same stream position /
+// counter mapping as rsb_relu_dropout_fwd, so fused and un-fused paths draw identical masks
+__global__ void dropout_keep_mask_kernel(uchar4* __restrict__ mask, long long n4, unsigned thr, unsigned long long seed,
+                                         unsigned long long offset, const unsigned long long* __restrict__ offset_dev) {
+  rsb::Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
+  if (offset_dev) offset += *offset_dev;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = rng(offset + (unsigned long long)i);
+    mask[i] = make_uchar4(r.x >= thr, r.y >= thr, r.z >= thr, r.w >= thr);
+  }
+}
+
+// y = dropout_p(relu(x)) of an fp32 [M, N] activation written as planes (+ ones column) and the keep-and-positive mask:
+// rsb_relu_dropout_fwd and rsb_split_planes in one HBM pass (read 4 B, write 6 + 1 B per element), same Philox stream
+__global__ void relu_dropout_planes_kernel(const float* __restrict__ x, long long M, int N, long long ldx, float scale,
+                                           unsigned thr, unsigned long long seed, unsigned long long offset,
+                                           const unsigned long long* __restrict__ offset_dev,
+                                           __nv_bfloat16* __restrict__ out, long long out_ld, long long plane_stride,
+                                           unsigned char* __restrict__ mask, int ones_col) {
+  rsb::Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
+  if (offset_dev) offset += *offset_dev;
+  const int n8 = (N + 7) / 8 + (ones_col ? 1 : 0);
+  const int n4 = N / 4;
+  const long long total = M * n8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / n8;
+    const int c0 = (int)(i - r * n8) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 >= ((N + 7) & ~7)) {
+      v[0] = 1.f;                                     // the ones column
+    } else {
+#pragma unroll
+      for (int h = 0; h < 8; h += 4) {
+        if (c0 + h < N) {
+          const float4 z = __ldg(reinterpret_cast<const float4*>(x + r * ldx + c0 + h));
+          const uint4 q = rng(offset + (unsigned long long)(r * n4 + ((c0 + h) >> 2)));
+          uchar4 m;
+          m.x = (z.x > 0.f) && (q.x >= thr); m.y = (z.y > 0.f) && (q.y >= thr);
+          m.z = (z.z > 0.f) && (q.z >= thr); m.w = (z.w > 0.f) && (q.w >= thr);
+          *reinterpret_cast<uchar4*>(mask + r * (long long)N + c0 + h) = m;
+          v[h] = m.x ? z.x * scale : 0.f; v[h + 1] = m.y ? z.y * scale : 0.f;
+          v[h + 2] = m.z ? z.z * scale : 0.f; v[h + 3] = m.w ? z.w * scale : 0.f;
+        }
+      }
+    }
+    store_planes8(out + r * out_ld + c0, plane_stride, v);
   }
 }
 
@@ -782,6 +825,46 @@ extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t c
   return RSB_OK;
 }
 
+extern "C" RSB_API int rsb_relu_dropout_planes(const float* x, int64_t M, int32_t N, int64_t ldx, float p, uint64_t seed, uint64_t offset,
+                                               const uint64_t* offset_dev, int32_t ones_col, void* out_planes, int64_t out_ld,
+                                               int64_t plane_stride, uint8_t* mask, void* stream) {
+  if (!x || !out_planes || !mask || M < 0 || N <= 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  if (M == 0) return RSB_OK;
+  if (N % 4 || ldx % 4 || out_ld % 8 || plane_stride % 8 || out_ld < ((N + 7) / 8) * 8 + (ones_col ? 8 : 0) ||
+      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(out_planes) & 15u) ||
+      (reinterpret_cast<uintptr_t>(mask) & 3u))
+    return RSB_ERR_UNSUPPORTED;
+  const long long total = M * ((N + 7) / 8 + (ones_col ? 1 : 0));
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)rsb::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  relu_dropout_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, M, N, ldx, 1.0f / (1.0f - p), (unsigned)(p * 4294967296.0), seed, offset,
+      reinterpret_cast<const unsigned long long*>(offset_dev), reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride,
+      mask, ones_col);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  return RSB_OK;
+}
+
+extern "C" RSB_API int rsb_dropout_keep_mask(uint8_t* mask, int64_t numel, float p, uint64_t seed, uint64_t offset,
+                                             const uint64_t* offset_dev, void* stream) {
+  if (!mask || numel < 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+  if (numel == 0) return RSB_OK;
+  if (numel % 4 || (reinterpret_cast<uintptr_t>(mask) & 3u)) return RSB_ERR_UNSUPPORTED;
+  long long blocks = (numel / 4 + 255) / 256;
+  const long long cap = (long long)rsb::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  dropout_keep_mask_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<uchar4*>(mask), numel / 4, (unsigned)(p * 4294967296.0), seed, offset,
+      reinterpret_cast<const unsigned long long*>(offset_dev));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  return RSB_OK;
+}
+
 extern "C" RSB_API int rsb_rank1_mask_planes(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M, int32_t N, float p,
                                              void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream) {
   if (!g_row || !w_col || !mask || !out_planes || M < 0 || N <= 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
@@ -865,9 +948,6 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
     p.out_ld = epi->out_ld; p.out_plane_stride = epi->out_plane_stride; p.ones_col = epi->ones_col;
     p.mask = epi->mask;
     p.drop_scale = 1.0f / (1.0f - epi->p);
-    p.drop_thr = (unsigned)(epi->p * 4294967296.0);     // keep iff r >= thr (same rule as rsb_relu_dropout_fwd)
-    p.seed = epi->seed; p.offset = epi->offset;
-    p.offset_dev = reinterpret_cast<const unsigned long long*>(epi->offset_dev);
   }
   p.D = D; p.ldd = ldd; p.d_batch_stride = d_batch_stride; p.C = C; p.bias = bias; p.alpha = alpha; p.beta = beta;
   if (p.splits > 1) {

@@ -192,33 +192,42 @@ __device__ __forceinline__ long long load_id(const LookupArgs& a, long long b, i
 // above the previous emb store; ncu showed the warps stalled on exactly those three loads.)
 constexpr int kIter = 5;   // 8 lane groups x 5 = 40 lookups per batch: the 39 Criteo fields in ONE round of dependent loads
 
-template <int K, int V, int LPR>
+// W = lanes that share one sample (32, 16 or 8: a warp works on 32 / W samples at once), KI = field iterations whose
+// loads are issued together.  One sample per warp with KI = 5 gives 8 lane groups x 5 = 40 lookup slots - the 39 Criteo
+// fields in one round - but leaves 29 of 40 slots idle on a KDD-shaped batch (11 fields): there two samples share a
+// warp (W = 16) with KI = 3 (12 slots), and the Avazu shape (22 fields) takes W = 32, KI = 3 (24 slots).
+template <int K, int V, int LPR, int W = kWarp, int KI = kIter>
 __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
-  constexpr int GPW = kWarp / LPR;
+  constexpr int GPW = W / LPR;          // lane groups per sample
+  constexpr int SPW = kWarp / W;        // samples per warp
+  static_assert(W >= LPR && GPW >= 1, "a row must fit the lanes of one sample");
   const int lane = threadIdx.x & 31;
-  const int g = lane / LPR, c = lane % LPR;
+  const int sl = lane % W, sw = lane / W;
+  const int g = sl / LPR, c = sl % LPR;
   const bool cact = c * V < a.E;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool fm = a.out_y != nullptr || a.out_sum != nullptr;
 
-  for (long long b = warp; b < a.B; b += nwarps) {
+  for (long long b0 = warp * SPW; b0 < a.B; b0 += nwarps * SPW) {
+    const long long b = b0 + sw;
+    const bool bvalid = b < a.B;      // the lanes of a sample past the end still take part in the shuffles
     FV<V> S = FV<V>::zero(), Q = FV<V>::zero();
     float first = 0.f;
-    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW * kIter) {
-      long long rowv[kIter];
-      int fv[kIter];
-      bool vactv[kIter];
+    for (int vf0 = 0; vf0 < a.VF; vf0 += GPW * KI) {
+      long long rowv[KI];
+      int fv[KI];
+      bool vactv[KI];
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
         const int vf = vf0 + it * GPW + g;
-        vactv[it] = vf < a.VF;
+        vactv[it] = bvalid && vf < a.VF;
         fv[it] = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
         rowv[it] = vactv[it] ? load_id(a, b, fv[it]) : 0;
       }
-      float fcv[kIter];
+      float fcv[KI];
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
         const int vf = vf0 + it * GPW + g;
         fcv[it] = 0.f;
         if (vactv[it]) {
@@ -232,14 +241,14 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
           }
         }
       }
-      FV<V> ev[kIter];
+      FV<V> ev[KI];
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
         const int vf = vf0 + it * GPW + g;
         ev[it] = load_transformed<K, V, LPR>(a, rowv[it], b, fv[it], vf, c, vactv[it] && cact);
       }
 #pragma unroll
-      for (int it = 0; it < kIter; ++it) {
+      for (int it = 0; it < KI; ++it) {
         const int vf = vf0 + it * GPW + g;
         first += fcv[it];
         if (vactv[it] && cact) {
@@ -254,7 +263,7 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
     }
     if (fm) {
 #pragma unroll
-      for (int off = LPR; off < kWarp; off <<= 1) {
+      for (int off = LPR; off < W; off <<= 1) {
         FV<V> s2 = shfl_xor<V>(S, off), q2 = shfl_xor<V>(Q, off);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
@@ -267,9 +276,9 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
       for (int i = 0; i < V; ++i) y2 += S.v[i] * S.v[i] - Q.v[i];
       y2 = group_sum<LPR>(y2);
 #pragma unroll
-      for (int off = 1; off < kWarp; off <<= 1) first += __shfl_xor_sync(kFull, first, off);
-      if (a.out_sum && g == 0 && cact) st<V>(a.out_sum + b * a.E + c * V, S);
-      if (a.out_y && lane == 0) {
+      for (int off = 1; off < W; off <<= 1) first += __shfl_xor_sync(kFull, first, off);
+      if (a.out_sum && bvalid && g == 0 && cact) st<V>(a.out_sum + b * a.E + c * V, S);
+      if (a.out_y && bvalid && sl == 0) {
         float x1 = first + (a.bias ? __ldg(a.bias) : 0.f);
         a.out_y[b] = x1 + 0.5f * y2;
       }
@@ -340,22 +349,27 @@ __global__ void __launch_bounds__(1024) partials_reduce_kernel(const float* __re
 }
 
 // TR = number of register accumulators of the TINY variant (emb1 rows actually used, rounded up to 5 or 8)
-template <int K, int V, int LPR, bool TINY = false, int KT = 2, int TR = kTinyRows>
+// W / KN: lanes per sample and field iterations in flight, as in lookup_fwd_kernel (KN applies to the non-TINY variant)
+template <int K, int V, int LPR, bool TINY = false, int KT = 2, int TR = kTinyRows, int W = kWarp, int KN = kIter>
 __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_rows_kernel(LookupArgs a) {
-  constexpr int GPW = kWarp / LPR;
+  constexpr int GPW = W / LPR;
+  constexpr int SPW = kWarp / W;
   // the register-accumulating QR variant keeps registers for the emb1 accumulators: shallower batching there
-  constexpr int KI = TINY ? KT : kIter;
+  constexpr int KI = TINY ? KT : KN;
   FV<V> tacc[TINY ? TR : 1];
 #pragma unroll
   for (int r = 0; r < (TINY ? TR : 1); ++r) tacc[r] = FV<V>::zero();
   const int lane = threadIdx.x & 31;
-  const int g = lane / LPR, c = lane % LPR;
+  const int sl = lane % W, sw = lane / W;
+  const int g = sl / LPR, c = sl % LPR;
   const bool cact = c * V < a.E;
   const int d0 = c * V;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
 
-  for (long long b = warp; b < a.B; b += nwarps) {
+  for (long long b0 = warp * SPW; b0 < a.B; b0 += nwarps * SPW) {
+    const bool bvalid = b0 + sw < a.B;
+    const long long b = bvalid ? b0 + sw : a.B - 1;     // past-the-end samples: clamp the reads, suppress the writes
     const float gy = a.g_y ? __ldg(a.g_y + b) : 0.f;
     FV<V> S = FV<V>::zero();
     if (a.g_y && cact) S = ldg<V>(a.S + b * a.E + d0);
@@ -367,12 +381,12 @@ __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_
       for (int it = 0; it < KI; ++it) {
         const int vf = vfb + it * GPW + g;
         const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
-        rowv[it] = (vf < a.VF) ? __ldg(a.rows_in + b * a.F + f) : 0;
+        rowv[it] = (bvalid && vf < a.VF) ? __ldg(a.rows_in + b * a.F + f) : 0;
       }
 #pragma unroll
       for (int it = 0; it < KI; ++it) {
         const int vf = vfb + it * GPW + g;
-        const bool act = (vf < a.VF) && cact;
+        const bool act = bvalid && (vf < a.VF) && cact;
         const long long o = (b * a.VF + vf) * (long long)a.E + d0;
         gdv[it] = FV<V>::zero();
         eev[it] = FV<V>::zero();
@@ -399,7 +413,7 @@ __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_
 #pragma unroll
       for (int it = 0; it < KI; ++it) {
       const int vf = vfb + it * GPW + g;
-      const bool vact = vf < a.VF;
+      const bool vact = bvalid && vf < a.VF;
       const bool act = vact && cact;
       const int f = (K == RSB_KIND_QR_CAT && vf >= a.F) ? vf - a.F : vf;
       const long long row = rowv[it];
@@ -540,6 +554,21 @@ __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_
   }
 }
 
+// 0: one sample per warp, 5 iterations in flight (groups x 5 slots: the 39 Criteo fields in one round at D = 16);
+// 1: one sample per warp, 3 iterations (Avazu shape: 22 fields in 24 slots);
+// 2: two samples per warp (16 lanes each), 3 iterations (KDD shape: 11 fields in 12 slots).
+// Picks the mapping with the fewest lane-slots per sample.
+static int pick_mapping(int fields, int groups) {
+  auto cost = [&](int g, int ki, int w) {
+    if (g < 1) return 1 << 30;
+    const int slots = g * ki;
+    return ((fields + slots - 1) / slots) * ki * w;
+  };
+  const int c0 = cost(groups, kIter, 32), c1 = cost(groups, 3, 32), c2 = cost(groups / 2, 3, 16);
+  if (c2 < c0 && c2 < c1) return 2;
+  return c1 < c0 ? 1 : 0;
+}
+
 template <int K>
 static int launch_fwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   const int threads = 256;
@@ -548,7 +577,16 @@ static int launch_fwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
   long long cap = (long long)sm_count() * 32;  // grid-stride beyond this
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-#define CALL(VV, LL) lookup_fwd_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
+  // lanes per sample / iterations in flight for this field count (see lookup_fwd_kernel)
+  const int groups = kWarp / sh.LPR;
+  const int variant = pick_mapping(a.VF, groups);
+  blocks = (warps_needed / (variant == 2 ? 2 : 1) * 32 + threads - 1) / threads;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+#define CALL(VV, LL)                                                                                                  \
+  if (variant == 2 && LL <= 16) lookup_fwd_kernel<K, VV, LL, (LL <= 16 ? 16 : 32), 3><<<(unsigned)blocks, threads, 0, stream>>>(a); \
+  else if (variant == 1) lookup_fwd_kernel<K, VV, LL, 32, 3><<<(unsigned)blocks, threads, 0, stream>>>(a);              \
+  else lookup_fwd_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   RSB_CHECK_LAUNCH();
@@ -597,7 +635,13 @@ static int launch_bwd(const LookupArgs& a, RowShape sh, cudaStream_t stream) {
       return RSB_OK;
     }
   }
-#define CALL(VV, LL) lookup_bwd_rows_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
+  const int variant = pick_mapping(a.VF, kWarp / sh.LPR);
+  long long vblocks = bwd_blocks(variant == 2 ? (a.B + 1) / 2 : a.B);
+#define CALL(VV, LL)                                                                                                       \
+  if (variant == 2 && LL <= 16)                                                                                            \
+    lookup_bwd_rows_kernel<K, VV, LL, false, 2, kTinyRows, (LL <= 16 ? 16 : 32), 3><<<(unsigned)vblocks, threads, 0, stream>>>(a); \
+  else if (variant == 1) lookup_bwd_rows_kernel<K, VV, LL, false, 2, kTinyRows, 32, 3><<<(unsigned)vblocks, threads, 0, stream>>>(a); \
+  else lookup_bwd_rows_kernel<K, VV, LL><<<(unsigned)blocks, threads, 0, stream>>>(a)
   RSB_DISPATCH_SHAPE(sh, CALL);
 #undef CALL
   RSB_CHECK_LAUNCH();

@@ -62,12 +62,19 @@ def split(x: torch.Tensor, transpose: bool = False, ones_col: bool = False) -> P
     return out
 
 
-def _dropout_epilogue(mode: int, out: Optional[Planes], mask: torch.Tensor, p: float, seed: int, offset: int,
-                      offset_dev: Optional[torch.Tensor], ones_col: bool) -> L.GemmEpilogue:
+def _dropout_epilogue(mode: int, out: Optional[Planes], mask: torch.Tensor, p: float, ones_col: bool) -> L.GemmEpilogue:
     return L.GemmEpilogue(mode, out.data.data_ptr() if out is not None else None, out.ld if out is not None else 0,
-                          out.data.stride(0) if out is not None else 0, int(ones_col), mask.data_ptr(), float(p),
-                          seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF,
-                          offset_dev.data_ptr() if offset_dev is not None else None)
+                          out.data.stride(0) if out is not None else 0, int(ones_col), mask.data_ptr(), float(p))
+
+
+def dropout_keep_mask(shape, p: float, seed: int, offset: int, offset_dev: Optional[torch.Tensor], device) -> torch.Tensor:
+    """uint8 keep bits (1 with probability 1 - p) of an activation, from the library's Philox stream."""
+    lib = L.load()
+    mask = torch.empty(shape, dtype=torch.uint8, device=device)
+    RF._call("dropout_keep_mask", lib.rsb_dropout_keep_mask, L.ptr(mask), mask.numel(), float(p),
+             seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, L.ptr(offset_dev), L.stream_ptr(device),
+             nbytes=mask.numel())
+    return mask
 
 
 def gemm(a: Planes, b: Planes, m: int, n: int, k: int, *, a_mn_major: bool = False, b_mn_major: bool = False,
@@ -105,9 +112,22 @@ def linear_relu_dropout(xp: Planes, wp: Planes, bias: Optional[torch.Tensor], p:
     """dropout_p(relu(x W^T + b)) in ONE launch: returns (planes of y [M, N] (+ ones column), keep mask uint8 [M, N])."""
     m, n, k = xp.rows, wp.rows, wp.cols
     yp = alloc(m, n, xp.data.device, ones_col)
-    mask = torch.empty(m, n, dtype=torch.uint8, device=xp.data.device)
-    epi = _dropout_epilogue(L.EPI_RELU_DROPOUT_PLANES, yp, mask, p, seed, offset, offset_dev, ones_col)
+    mask = dropout_keep_mask((m, n), p, seed, offset, offset_dev, xp.data.device)   # the GEMM epilogue ANDs in (z > 0)
+    epi = _dropout_epilogue(L.EPI_RELU_DROPOUT_PLANES, yp, mask, p, ones_col)
     gemm(xp, wp, m, n, k, bias=bias, split_k=1, epilogue=epi, want_out=False)
+    return yp, mask
+
+
+def relu_dropout_planes(z: torch.Tensor, p: float, seed: int, offset: int, offset_dev: Optional[torch.Tensor] = None,
+                        ones_col: bool = True):
+    """dropout_p(relu(z)) of an fp32 activation as (planes (+ ones column), keep-and-positive mask) in one HBM pass."""
+    lib = L.load()
+    m, n = z.shape
+    yp = alloc(m, n, z.device, ones_col)
+    mask = torch.empty(m, n, dtype=torch.uint8, device=z.device)
+    RF._call("relu_dropout_planes", lib.rsb_relu_dropout_planes, L.ptr(z), m, n, z.stride(0), float(p),
+             seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, L.ptr(offset_dev), int(ones_col), L.ptr(yp.data), yp.ld,
+             yp.data.stride(0), L.ptr(mask), L.stream_ptr(z.device), nbytes=m * n * 5 + 3 * m * yp.ld * 2)
     return yp, mask
 
 
@@ -117,10 +137,10 @@ def dx_masked(gp: Planes, wp: Planes, mask: torch.Tensor, p: float, to_planes: b
     m, n, k = gp.rows, wp.cols, wp.rows
     if to_planes:
         out = alloc(m, n, gp.data.device)
-        epi = _dropout_epilogue(L.EPI_MASK_PLANES, out, mask, p, 0, 0, None, False)
+        epi = _dropout_epilogue(L.EPI_MASK_PLANES, out, mask, p, False)
         gemm(gp, wp, m, n, k, b_mn_major=True, split_k=1, epilogue=epi, want_out=False)
         return out
-    epi = _dropout_epilogue(L.EPI_MASK_F32, None, mask, p, 0, 0, None, False)
+    epi = _dropout_epilogue(L.EPI_MASK_F32, None, mask, p, False)
     return gemm(gp, wp, m, n, k, b_mn_major=True, split_k=1, epilogue=epi)
 
 

@@ -185,6 +185,8 @@ def test_fused_epilogues_match_unfused_kernels(LA):
     LA.L.check(lib.rsb_relu_dropout_fwd(z.data_ptr(), z.numel(), 0.3, 12345, 7 << 32, None, y.data_ptr(), mask2.data_ptr(),
                                         LA.L.stream_ptr(DEV)))
     assert torch.equal(mask, mask2)
+    yp2, mask3 = P.relu_dropout_planes(z, 0.3, seed=12345, offset=7 << 32)     # the one-pass un-fused form
+    assert torch.equal(mask3, mask) and torch.equal(yp2.data, yp.data)
     assert torch.equal(yp.float(), P.split(y).float()) and abs(float(mask.float().mean()) - 0.35) < 0.02
     assert torch.equal(yp.data[0, :, n].float(), torch.ones(m, device=DEV)) and float(yp.data[1:, :, n:].abs().sum()) == 0
     # dX with the mask of the previous layer
