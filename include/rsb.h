@@ -325,6 +325,30 @@ RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operan
                             void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
+ * BatchNorm1d in training mode, fused with its neighbours (csrc/batchnorm.cu).  Replaces torch.nn.BatchNorm1d +
+ * ReLU + Dropout of the dense tails (src/models/deepfm.py:57-60, src/models/dcn.py:56-66) forward and backward; torch
+ * semantics: biased batch variance for the normalisation, unbiased for running_var, eps inside the square root,
+ * running = (1 - momentum) * running + momentum * batch.  All reductions are two-stage with a fixed order.
+ *   rsb_bn_train_fwd_stats      z [M,N] (ldz) -> stats [2N] = (mean, rstd), affine [2N] = (gamma * rstd, beta - mean * scale),
+ *                               running_mean / running_var updated in place (NULL: not tracked)
+ *   rsb_bn_relu_dropout_planes  y = dropout_p(relu(z * scale + shift)) as bf16 planes (+ ones column) + the 1-byte
+ *                               keep-and-positive mask; Philox stream as rsb_relu_dropout_fwd; p = 0: no dropout
+ *   rsb_bn_train_bwd_planes     g [M,N] = gradient w.r.t. the BatchNorm output -> sums [2N] = (d beta, d gamma) and
+ *                               gz = gamma * rstd * (g - d beta / M - xhat * d gamma / M) as planes
+ * N, ldz, ldg multiples of 4; workspace from rsb_bn_workspace_bytes.
+ * ---------------------------------------------------------------------- */
+RSB_API int64_t rsb_bn_workspace_bytes(int64_t M, int32_t N);
+RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t N, int64_t ldz, const float* gamma, const float* beta,
+                                   float eps, float momentum, float* running_mean, float* running_var, float* stats,
+                                   float* affine, void* workspace, int64_t workspace_bytes, void* stream);
+RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int32_t N, int64_t ldz, const float* affine, float p,
+                                       uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int32_t ones_col,
+                                       void* out_planes, int64_t out_ld, int64_t plane_stride, uint8_t* mask, void* stream);
+RSB_API int rsb_bn_train_bwd_planes(const float* g, const float* z, int64_t M, int32_t N, int64_t ldg, int64_t ldz,
+                                    const float* stats, const float* gamma, float* sums, void* out_planes, int64_t out_ld,
+                                    int64_t plane_stride, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * Bandwidth-bound glue of the dense tails (Linear -> [BatchNorm1d] -> ReLU -> Dropout,
  * src/models/deepfm.py:55-66, src/models/dcn.py:56-66), one pass per direction.
  *  rsb_relu_dropout_fwd  y = dropout_p(relu(x)), mask[i] = 1 iff x[i] > 0 and kept (Philox4x32-10 keyed by
@@ -343,14 +367,16 @@ RSB_API int rsb_colsum(const float* x, int64_t M, int32_t N, int64_t ld, float* 
                        int64_t workspace_bytes, void* stream);
 /* The MLPs end in a Linear with ONE output (src/models/deepfm.py:64, src/models/dcn.py:65: Linear(hidden, 1)):
  * a matrix-vector product whose three passes are folded into the neighbouring glue instead of library GEMV calls.
- *  rsb_relu_dropout_dot_fwd   y = dropout(relu(x)), mask as rsb_relu_dropout_fwd, and out[r] = y[r,:].w + bias[0]
+ *  rsb_relu_dropout_dot_fwd   y = dropout(relu(x)), mask as rsb_relu_dropout_fwd, and out[r] = y[r,:].w + bias[0];
+ *                             affine [2N] (optional): x is first mapped to x * affine[c] + affine[N + c] (the BatchNorm
+ *                             normalisation of rsb_bn_train_fwd_stats folded into the same pass)
  *  rsb_relu_dropout_bwd_rank1 rsb_relu_dropout_bwd with the upstream gradient g[r,c] = g_row[r] * w_col[c] formed
  *                             on the fly (the Linear's dX is never written)
  *  rsb_colsum_weighted        out[c] = sum_r row_weight[r] * x[r,c]  (the Linear's weight gradient)
  * Workspaces as rsb_colsum_workspace_bytes(M, N). */
 RSB_API int rsb_relu_dropout_dot_fwd(const float* x, int64_t M, int32_t N, float p, uint64_t seed, uint64_t offset,
-                                     const uint64_t* offset_dev, const float* w, const float* bias, float* y,
-                                     uint8_t* mask, float* out, void* stream);
+                                     const uint64_t* offset_dev, const float* w, const float* bias, const float* affine,
+                                     float* y, uint8_t* mask, float* out, void* stream);
 RSB_API int rsb_relu_dropout_bwd_rank1(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M, int32_t N,
                                        float p, float* gx, float* colsum, void* workspace, int64_t workspace_bytes,
                                        void* stream);

@@ -82,7 +82,12 @@ PROTOTYPES = {
     "rsb_relu_dropout_bwd": (C.c_int, [_p, _p, _i64, _i32, _f, _p, _p, _p, _i64, _p]),
     "rsb_colsum_workspace_bytes": (_i64, [_i64, _i32]),
     "rsb_colsum": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i64, _p]),
-    "rsb_relu_dropout_dot_fwd": (C.c_int, [_p, _i64, _i32, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p, _p, _p, _p]),
+    "rsb_relu_dropout_dot_fwd": (C.c_int, [_p, _i64, _i32, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rsb_bn_workspace_bytes": (_i64, [_i64, _i32]),
+    "rsb_bn_train_fwd_stats": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _p]),
+    "rsb_bn_relu_dropout_planes": (C.c_int, [_p, _i64, _i32, _i64, _p, _f, C.c_uint64, C.c_uint64, _p, _i32, _p, _i64, _i64,
+                                             _p, _p]),
+    "rsb_bn_train_bwd_planes": (C.c_int, [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p]),
     "rsb_relu_dropout_bwd_rank1": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _p, _p, _i64, _p]),
     "rsb_colsum_weighted": (C.c_int, [_p, _p, _i64, _i32, _i64, _p, _p, _i64, _p]),
     "rsb_dcn_gate_mix_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(256) relu_dropout_dot_fwd_kernel(const float* 
                                                                    const unsigned long long* __restrict__ offset_dev,
                                                                    const float* __restrict__ w,
                                                                    const float* __restrict__ bias,
+                                                                   const float* __restrict__ affine,
                                                                    float* __restrict__ y,
                                                                    unsigned char* __restrict__ mask,
                                                                    float* __restrict__ out) {
@@ -76,6 +77,12 @@ __global__ void __launch_bounds__(256) relu_dropout_dot_fwd_kernel(const float* 
           const long long i = r * (long long)n4 + c4;
           const uint4 q = rng(offset + (unsigned long long)i);
           const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + c4);
+          if (affine) {     // BatchNorm folded in: x * scale + shift per column
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(affine) + c4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(affine + N) + c4);
+            v[u] = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z),
+                               fmaf(v[u].w, sc.w, sh.w));
+          }
           uchar4 m;
           m.x = (v[u].x > 0.f) && (q.x >= thr);
           m.y = (v[u].y > 0.f) && (q.y >= thr);
@@ -343,19 +350,20 @@ extern "C" RSB_API int rsb_relu_dropout_bwd_rank1(const float* g_row, const floa
 
 extern "C" RSB_API int rsb_relu_dropout_dot_fwd(const float* x, int64_t M, int32_t N, float p, uint64_t seed,
                                                 uint64_t offset, const uint64_t* offset_dev, const float* w,
-                                                const float* bias, float* y, uint8_t* mask, float* out,
-                                                void* stream) {
+                                                const float* bias, const float* affine, float* y, uint8_t* mask,
+                                                float* out, void* stream) {
   if (M < 0 || N <= 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
   if (M == 0) return RSB_OK;
   if (!x || !y || !mask || !w || !out) return RSB_ERR_BAD_ARG;
-  if (N % 4 || !aligned16(x) || !aligned16(y) || !aligned16(w) || (reinterpret_cast<uintptr_t>(mask) & 3u))
+  if (N % 4 || !aligned16(x) || !aligned16(y) || !aligned16(w) || (affine && !aligned16(affine)) ||
+      (reinterpret_cast<uintptr_t>(mask) & 3u))
     return RSB_ERR_UNSUPPORTED;
   long long blocks = (M + 7) / 8;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   relu_dropout_dot_fwd_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, M, N, p, 1.0f / (1.0f - p), seed, offset, reinterpret_cast<const unsigned long long*>(offset_dev), w, bias, y,
-      mask, out);
+      x, M, N, p, 1.0f / (1.0f - p), seed, offset, reinterpret_cast<const unsigned long long*>(offset_dev), w, bias,
+      affine, y, mask, out);
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;

@@ -198,8 +198,10 @@ def _relu_dropout_bwd(g: torch.Tensor, mask: torch.Tensor, p: float, want_colsum
     return gx, cs
 
 
-def _relu_dropout_dot_fwd(x: torch.Tensor, p: float, w: torch.Tensor, bias: Optional[torch.Tensor]):
-    """(y, mask, out) with out[r] = dropout(relu(x))[r,:] . w + bias: the one-output Linear folded into the pass."""
+def _relu_dropout_dot_fwd(x: torch.Tensor, p: float, w: torch.Tensor, bias: Optional[torch.Tensor],
+                          affine: Optional[torch.Tensor] = None):
+    """(y, mask, out) with out[r] = dropout(relu(x))[r,:] . w + bias: the one-output Linear folded into the pass.
+    affine [2N]: x is first normalised as x * affine[:N] + affine[N:] (BatchNorm folded in as well)."""
     lib = L.load()
     m, n = x.shape
     y = torch.empty_like(x)
@@ -207,7 +209,7 @@ def _relu_dropout_dot_fwd(x: torch.Tensor, p: float, w: torch.Tensor, bias: Opti
     out = torch.empty(m, dtype=torch.float32, device=x.device)
     seed, off = _dropout_stream(x.numel())
     RF._call("relu_dropout_dot_fwd", lib.rsb_relu_dropout_dot_fwd, L.ptr(x), m, n, float(p), seed, off,
-             L.ptr(_DROPOUT_DEV_COUNTER), L.ptr(w), L.ptr(bias), L.ptr(y), L.ptr(mask), L.ptr(out),
+             L.ptr(_DROPOUT_DEV_COUNTER), L.ptr(w), L.ptr(bias), L.ptr(affine), L.ptr(y), L.ptr(mask), L.ptr(out),
              L.stream_ptr(x.device), nbytes=x.numel() * 9 + m * 4)
     return y, mask, out
 
@@ -529,6 +531,119 @@ class _MlpReluDropout(torch.autograd.Function):
         return (gx, None, None, *grads)
 
 
+class _MlpBatchNorm(torch.autograd.Function):
+    """The dense tail  [Linear -> BatchNorm1d -> ReLU -> Dropout] x L  ->  Linear(hidden, 1)  in training mode
+    (src/models/deepfm.py:55-66 with use_batchnorm, src/models/dcn.py:56-66) as ONE autograd node:
+
+      fwd  layer i : tensor-core GEMM -> fp32 z; batch statistics (one pass over z, usually still in L2) + running
+                     buffers; then ONE pass  z -> BatchNorm affine -> ReLU -> dropout -> planes of the next GEMM + mask.
+                     Last layer: the same pass also forms the one-output Linear's dot product.
+      bwd  layer i : the gradient w.r.t. the BatchNorm output arrives as fp32 (the next layer's dX GEMM applies the ReLU /
+                     dropout mask in its epilogue; the head forms g[r] * w_out[c] * mask on the fly); one pass for
+                     d gamma, d beta, one pass writes gz as planes; dW (+ bias gradient as its ones column) and dX GEMMs.
+    torch's BatchNorm / threshold / dropout / sum kernels and every fp32 -> planes split of the layer-by-layer path are
+    gone; what is saved for the backward is z (fp32), the planes of each layer's input, the masks and 4 N statistics."""
+
+    @staticmethod
+    def forward(ctx, x, ps, side_dw, bns, *params):
+        n_layers = (len(params) - 2) // 4
+        ws, bs = params[0:4 * n_layers:4], params[1:4 * n_layers:4]
+        gammas, betas = params[2:4 * n_layers:4], params[3:4 * n_layers:4]
+        w_out, b_out = params[-2], params[-1]
+        planes = [P.split(x, ones_col=True)]
+        masks, zs, stats = [], [], []
+        y = out = None
+        for i in range(n_layers):
+            z = _fwd_gemm(planes[-1], ws[i], bs[i])
+            bn = bns[i]
+            st, affine = P.bn_train_stats(z, gammas[i], betas[i], bn.eps, bn.momentum,
+                                          bn.running_mean if bn.track_running_stats else None,
+                                          bn.running_var if bn.track_running_stats else None)
+            if bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+            if i < n_layers - 1:
+                seed, off = _dropout_stream(z.numel())
+                yp, mask = P.bn_relu_dropout_planes(z, affine, ps[i], seed, off, _DROPOUT_DEV_COUNTER, ones_col=True)
+                planes.append(yp)
+            else:
+                y, mask, out = _relu_dropout_dot_fwd(z, ps[i], w_out.reshape(-1), b_out, affine)
+            masks.append(mask)
+            zs.append(z)
+            stats.append(st)
+        ctx.planes, ctx.masks, ctx.ps, ctx.side_dw, ctx.n_layers = planes, masks, ps, side_dw, n_layers
+        ctx.n_z = len(zs)
+        ctx.save_for_backward(y, *zs, *stats, *params)
+        return out.unsqueeze(1)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        n_layers, ps, planes, masks = ctx.n_layers, ctx.ps, ctx.planes, ctx.masks
+        ctx.planes = ctx.masks = None
+        saved = ctx.saved_tensors
+        y, zs, stats, params = saved[0], saved[1:1 + n_layers], saved[1 + n_layers:1 + 2 * n_layers], saved[1 + 2 * n_layers:]
+        ws, bs = params[0:4 * n_layers:4], params[1:4 * n_layers:4]
+        gammas, betas = params[2:4 * n_layers:4], params[3:4 * n_layers:4]
+        w_out, b_out = params[-2], params[-1]
+        need = ctx.needs_input_grad                      # (x, ps, side_dw, bns, W1, b1, gamma1, beta1, ..., w_out, b_out)
+        g = g_out.reshape(-1).contiguous()
+        grads = [None] * len(params)
+        if need[4 + 4 * n_layers]:
+            grads[-2] = _colsum_weighted(y, g).reshape(w_out.shape)
+        if b_out is not None and need[5 + 4 * n_layers]:
+            grads[-1] = g.sum().reshape(1)
+        g_r, _ = _relu_dropout_bwd_rank1(g, w_out.reshape(-1), masks[-1], ps[-1], False)   # fp32 [M, H]
+        gx = None
+        for i in reversed(range(n_layers)):
+            gp, d_beta, d_gamma = P.bn_train_bwd_planes(g_r, zs[i], stats[i], gammas[i])
+            if gammas[i] is not None and need[6 + 4 * i]:
+                grads[4 * i + 2] = d_gamma
+            if betas[i] is not None and need[7 + 4 * i]:
+                grads[4 * i + 3] = d_beta
+            g_prev = None
+            if i > 0:
+                g_prev = P.dx_masked(gp, weight_planes(ws[i]), masks[i - 1], ps[i - 1], to_planes=False)
+            elif need[0]:
+                gx = _dx_gemm(gp, ws[0])
+            want_w, want_b = need[4 + 4 * i], bs[i] is not None and need[5 + 4 * i]
+            if want_w or want_b:
+                if i == 0 and ctx.side_dw and gx is not None and _side_dw_safe(ws[0]) and \
+                        (bs[0] is None or _side_dw_safe(bs[0])):
+                    dw, db = _on_side_stream(lambda gp=gp, xp=planes[0]: P.gemm_dw(gp, xp, want_b), (gp, planes[0]))
+                else:
+                    dw, db = P.gemm_dw(gp, planes[i], want_b)
+                grads[4 * i] = dw if want_w else None
+                grads[4 * i + 1] = db if want_b else None
+            g_r = g_prev
+        return (gx, None, None, None, *grads)
+
+
+def _mlp_batchnorm_pattern(mods, x: torch.Tensor):
+    """[Linear, BatchNorm1d, ReLU, Dropout] x L + Linear(h, 1), training mode, shapes the kernels take?"""
+    if (len(mods) - 1) % 4 or len(mods) < 5 or not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2):
+        return None
+    lins, bns, drops = [], [], []
+    width = x.shape[1]
+    for j in range(0, len(mods) - 1, 4):
+        lin, bn, act, drop = mods[j], mods[j + 1], mods[j + 2], mods[j + 3]
+        if not (isinstance(lin, torch.nn.Linear) and isinstance(bn, torch.nn.BatchNorm1d) and
+                isinstance(act, torch.nn.ReLU) and isinstance(drop, torch.nn.Dropout)):
+            return None
+        h = lin.weight.shape[0]
+        if lin.weight.shape[1] != width or h % 8 or width % 4 or not 0.0 <= drop.p < 1.0 or h > 2048 or \
+                lin.weight.dtype != torch.float32 or not lin.weight.is_cuda or bn.num_features != h or \
+                bn.momentum is None or (bn.weight is None) != (bn.bias is None) or \
+                (bn.weight is not None and bn.weight.dtype != torch.float32):
+            return None
+        width = h
+        lins.append(lin)
+        bns.append(bn)
+        drops.append(drop)
+    head = mods[-1]
+    if not _is_head(head, width) or x.shape[0] < 256:
+        return None
+    return lins, bns, drops, head
+
+
 def _on_side_stream(fn, keep):
     """Run `fn` on the side stream (see _dw_on_side_stream); `keep` = main-pool tensors it reads."""
     dev = torch.cuda.current_device()
@@ -583,6 +698,16 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: 
     i = 0
     training = seq.training
     if training:
+        pat = _mlp_batchnorm_pattern(mods, x)
+        if pat is not None:
+            lins, bns, drops, head = pat
+            params = []
+            for lin, bn in zip(lins, bns):
+                params += [lin.weight, lin.bias, bn.weight, bn.bias]
+            side = overlap_first_dw and not _has_hooks(lins[0].weight) and \
+                (lins[0].bias is None or not _has_hooks(lins[0].bias))
+            return _MlpBatchNorm.apply(x.contiguous(), tuple(float(d.p) for d in drops), side, tuple(bns), *params,
+                                       head.weight, head.bias)
         pat = _mlp_relu_dropout_pattern(mods, x)
         if pat is not None:
             lins, drops, head = pat

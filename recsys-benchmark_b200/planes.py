@@ -165,3 +165,47 @@ def rank1_mask_planes(g_row: torch.Tensor, w_col: torch.Tensor, mask: torch.Tens
     RF._call("rank1_mask_planes", lib.rsb_rank1_mask_planes, L.ptr(g_row), L.ptr(w_col), L.ptr(mask), m, n, float(p),
              L.ptr(out.data), out.ld, out.data.stride(0), L.stream_ptr(mask.device), nbytes=m * n * 7 + m * 4)
     return out
+
+
+# ------------------------------------------------------------------ BatchNorm1d (training mode) around the GEMMs ---
+def bn_train_stats(z: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float,
+                   momentum: float, running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]):
+    """Batch statistics of z [M, N] -> (stats [2N] = mean | rstd, affine [2N] = scale | shift); running buffers are
+    updated in place with torch.nn.BatchNorm1d's rule."""
+    lib = L.load()
+    m, n = z.shape
+    dev = z.device
+    stats = torch.empty(2 * n, dtype=torch.float32, device=dev)
+    affine = torch.empty(2 * n, dtype=torch.float32, device=dev)
+    ws = RF._ws(lib.rsb_bn_workspace_bytes(m, n), dev)
+    RF._call("bn_fwd_stats", lib.rsb_bn_train_fwd_stats, L.ptr(z), m, n, z.stride(0), L.ptr(gamma), L.ptr(beta), float(eps),
+             float(momentum), L.ptr(running_mean), L.ptr(running_var), L.ptr(stats), L.ptr(affine), L.ptr(ws), ws.numel(),
+             L.stream_ptr(dev), nbytes=m * n * 4)
+    return stats, affine
+
+
+def bn_relu_dropout_planes(z: torch.Tensor, affine: torch.Tensor, p: float, seed: int, offset: int,
+                           offset_dev: Optional[torch.Tensor] = None, ones_col: bool = True):
+    """dropout_p(relu(z * scale + shift)) as (planes (+ ones column), keep-and-positive mask)."""
+    lib = L.load()
+    m, n = z.shape
+    yp = alloc(m, n, z.device, ones_col)
+    mask = torch.empty(m, n, dtype=torch.uint8, device=z.device)
+    RF._call("bn_relu_dropout_planes", lib.rsb_bn_relu_dropout_planes, L.ptr(z), m, n, z.stride(0), L.ptr(affine), float(p),
+             seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, L.ptr(offset_dev), int(ones_col), L.ptr(yp.data), yp.ld,
+             yp.data.stride(0), L.ptr(mask), L.stream_ptr(z.device), nbytes=m * n * 5 + 3 * m * yp.ld * 2)
+    return yp, mask
+
+
+def bn_train_bwd_planes(g: torch.Tensor, z: torch.Tensor, stats: torch.Tensor, gamma: Optional[torch.Tensor]):
+    """g = gradient w.r.t. the BatchNorm output -> (planes of the gradient w.r.t. z, d beta [N], d gamma [N])."""
+    lib = L.load()
+    m, n = z.shape
+    dev = z.device
+    sums = torch.empty(2 * n, dtype=torch.float32, device=dev)
+    out = alloc(m, n, dev)
+    ws = RF._ws(lib.rsb_bn_workspace_bytes(m, n), dev)
+    RF._call("bn_bwd_planes", lib.rsb_bn_train_bwd_planes, L.ptr(g), L.ptr(z), m, n, g.stride(0), z.stride(0), L.ptr(stats),
+             L.ptr(gamma), L.ptr(sums), L.ptr(out.data), out.ld, out.data.stride(0), L.ptr(ws), ws.numel(), L.stream_ptr(dev),
+             nbytes=m * n * 16 + 3 * m * out.ld * 2)
+    return out, sums[:n], sums[n:]

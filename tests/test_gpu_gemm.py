@@ -325,3 +325,56 @@ def test_head_block_matches_unfused_path_with_the_same_masks(LA, with_bn, monkey
     assert _err(out, ref[:, 0]) < 2e-6
     keep = mask.float().mean().item()
     assert abs(keep - 0.25) < 0.01                     # P(x > 0) * (1 - p)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.5])
+def test_fused_batchnorm_mlp_node_matches_torch(LA, monkeypatch, p):
+    """[Linear -> BatchNorm1d -> ReLU -> Dropout] x 3 -> Linear(400, 1) as one autograd node (own batch statistics,
+    BatchNorm + ReLU + dropout -> planes passes, BatchNorm backward -> planes) against torch's own modules in fp64
+    driven with the masks the fused node drew; running statistics follow torch's update rule."""
+    import copy
+
+    torch.manual_seed(0)
+    mods = []
+    width = 624
+    for _ in range(3):
+        mods += [torch.nn.Linear(width, 400), torch.nn.BatchNorm1d(400), torch.nn.ReLU(), torch.nn.Dropout(p)]
+        width = 400
+    mods.append(torch.nn.Linear(400, 1))
+    seq = torch.nn.Sequential(*mods).to(DEV).train()
+    with torch.no_grad():
+        for m in seq:
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.normal_(0, 0.2)
+    ref = copy.deepcopy(seq).double()
+    x = torch.randn(4096, 624, device=DEV, requires_grad=True)
+    gout = torch.randn(4096, 1, device=DEV)
+    out = LA.run_sequential(seq, x)
+    assert type(out.grad_fn).__name__ == "_MlpBatchNormBackward"
+    masks = out.grad_fn.masks                      # uint8 keep-and-positive masks, one per layer
+    params = [x] + list(seq.parameters())
+    g1 = torch.autograd.grad(out, params, gout)
+    # fp64 reference with the SAME ReLU + dropout decisions (the keep-and-positive masks of the fused node), so that a
+    # pre-activation within fp32 rounding of zero cannot land on different sides: y = bn(z) * mask / (1 - p)
+    h = x.double()
+    keep_iter = iter(masks)
+    for m in ref:
+        if isinstance(m, torch.nn.ReLU):
+            continue
+        if isinstance(m, torch.nn.Dropout):
+            h = h * next(keep_iter).double() / (1.0 - p)
+        else:
+            h = m(h)
+    g2 = torch.autograd.grad(h, [x] + list(ref.parameters()), gout.double(), allow_unused=True)
+    assert _err(out, h) < 5e-6
+    names = ["x"] + [n for n, _ in seq.named_parameters()]
+    for n, a_, b_ in zip(names, g1, g2):
+        if n.endswith(".bias") and n.split(".")[0] in ("0", "4", "8"):
+            assert float(a_.abs().max()) < 1e-4      # Linear bias in front of BatchNorm: zero by construction
+            continue
+        assert _err(a_, b_) < 2e-5, n
+    for ms, mr in zip(seq, ref):
+        if isinstance(ms, torch.nn.BatchNorm1d):
+            assert _err(ms.running_mean, mr.running_mean) < 1e-5 and _err(ms.running_var, mr.running_var) < 1e-5
+            assert int(ms.num_batches_tracked) == 1
