@@ -99,23 +99,31 @@ __global__ void __launch_bounds__(kBnThreads) bn_slab_sums_kernel(const float* _
   }
 }
 
-// Fold the slab partials in fixed order (fp64 accumulation: nblk ~ 600 terms of very different size) and finish.
+// Fold the slab partials in a fixed order (fp64 accumulation) and finish.
 //   MODE 0: stats[0..N) = mean, stats[N..2N) = rstd, affine[0..N) = gamma * rstd, affine[N..2N) = beta - mean * scale;
 //           running_mean / running_var updated in place (momentum, unbiased variance) when given.
 //   MODE 1: out[0..N) = sum g (d beta), out[N..2N) = sum g * xhat (d gamma).
 template <int MODE>
-__global__ void __launch_bounds__(128) bn_finalize_kernel(const float* __restrict__ partials, int nblk, int N, long long M,
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int nblk, int N, long long M,
                                                           const float* __restrict__ z_row0, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, float momentum,
                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
                                                           float* __restrict__ stats, float* __restrict__ affine) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per column: lane l folds partials l, l + 32, ... (fp64), then a fixed-order xor tree over the lanes
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= N) return;
   double sa = 0.0, sb = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = lane; b < nblk; b += 32) {
     sa += (double)__ldg(partials + ((long long)b * 2) * N + c);
     sb += (double)__ldg(partials + ((long long)b * 2 + 1) * N + c);
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sa += __shfl_xor_sync(kFull, sa, off);
+    sb += __shfl_xor_sync(kFull, sb, off);
+  }
+  if (lane != 0) return;
   if (MODE == 0) {
     const double m = (double)M;
     const double dm = sa / m;                          // mean - k
@@ -237,7 +245,7 @@ extern "C" RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t
   const int nblk = bn_blocks(M);
   bn_slab_sums_kernel<0><<<nblk, kBnThreads, 0, st>>>(z, nullptr, M, N, ldz, 0, nullptr, nullptr, partials);
   RSB_CHECK_LAUNCH();
-  bn_finalize_kernel<0><<<(N + 127) / 128, 128, 0, st>>>(partials, nblk, N, M, z, gamma, beta, eps, momentum, running_mean,
+  bn_finalize_kernel<0><<<(N + 7) / 8, 256, 0, st>>>(partials, nblk, N, M, z, gamma, beta, eps, momentum, running_mean,
                                                          running_var, stats, affine);
   RSB_CHECK_LAUNCH();
   note_launch(2);
@@ -280,7 +288,7 @@ extern "C" RSB_API int rsb_bn_train_bwd_planes(const float* g, const float* z, i
   const int nblk = bn_blocks(M);
   bn_slab_sums_kernel<1><<<nblk, kBnThreads, 0, st>>>(z, g, M, N, ldz, ldg, stats, stats + N, partials);
   RSB_CHECK_LAUNCH();
-  bn_finalize_kernel<1><<<(N + 127) / 128, 128, 0, st>>>(partials, nblk, N, M, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr,
+  bn_finalize_kernel<1><<<(N + 7) / 8, 256, 0, st>>>(partials, nblk, N, M, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr,
                                                          nullptr, sums, nullptr);
   RSB_CHECK_LAUNCH();
   const long long total = M * ((N + 7) / 8 * 2);

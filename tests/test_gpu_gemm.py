@@ -301,6 +301,7 @@ def test_head_block_matches_unfused_path_with_the_same_masks(LA, with_bn, monkey
 
     # (the no-BatchNorm sequence would be taken whole by the fused MLP node: this test is about the head block)
     monkeypatch.setattr(LA, "_mlp_relu_dropout_pattern", lambda mods, xx: None)
+    monkeypatch.setattr(LA, "_mlp_batchnorm_pattern", lambda mods, xx: None)
     calls = LA._DROPOUT_CALLS
     out_f = LA.run_sequential(seq, x)
     assert out_f.grad_fn.name().startswith("_HeadBlock")

@@ -88,12 +88,29 @@ def assert_parity(got, ref32, ref64, what):
         f"ref64 {float(ref64.reshape(-1)[i]):.9e}; {bad}/{got.numel()} elements outside rtol/atol vs ref32")
 
 
+def _find_node(fn, name, seen=None):
+    """Walk the autograd graph from `fn` for the first node whose class name is `name`."""
+    seen = set() if seen is None else seen
+    if fn is None or fn in seen:
+        return None
+    seen.add(fn)
+    if type(fn).__name__ == name:
+        return fn
+    for nxt, _ in fn.next_functions:
+        hit = _find_node(nxt, name, seen)
+        if hit is not None:
+            return hit
+    return None
+
+
 class _ReluTies:
     """ReLU is discontinuous in its gradient: a pre-activation within fp32 rounding of zero can land on either side
     when the Linear before it is computed by two different (equally accurate) GEMMs, and BatchNorm's batch statistics
-    then spread that one decision over every sample's gradient.  The hooks record the sign pattern of every
-    BatchNorm1d output (= ReLU input) on both sides; `flips()` returns how many decisions differ and checks that each
-    of them really is a tie (|pre-activation| < 2e-5 after normalisation)."""
+    then spread that one decision over every sample's gradient.  The reference's BatchNorm1d outputs (= ReLU inputs)
+    are recorded with forward hooks; ours come from the fused dense-tail node (its keep-and-positive masks: dropout is
+    off in these tests, so mask = [pre-activation > 0]) or, on the layer-by-layer path, from the same hooks.
+    `flips()` returns how many decisions differ and checks that each of them really is a tie (|pre-activation| < 2e-5
+    after normalisation)."""
 
     def __init__(self, ref, ours):
         self.pre = {"ref": [], "ours": []}
@@ -102,18 +119,23 @@ class _ReluTies:
             for mod in m.modules():
                 if isinstance(mod, torch.nn.BatchNorm1d):
                     self.handles.append(mod.register_forward_hook(
-                        lambda _m, _i, out, _n=name: self.pre[_n].append(out.detach())))
+                        lambda _m, _i, out, _n=name: self.pre[_n].append(out.detach() > 0)))
+        self.ref_values = []
+        for mod in ref.modules():
+            if isinstance(mod, torch.nn.BatchNorm1d):
+                self.handles.append(mod.register_forward_hook(lambda _m, _i, out: self.ref_values.append(out.detach())))
 
-    def reset(self):
-        self.pre = {"ref": [], "ours": []}
-
-    def flips(self):
+    def flips(self, ours_logits=None):
+        if not self.pre["ours"] and ours_logits is not None:
+            node = _find_node(ours_logits.grad_fn, "_MlpBatchNormBackward")
+            if node is not None:
+                self.pre["ours"] = [m > 0 for m in node.masks]
         n = 0
-        assert len(self.pre["ref"]) == len(self.pre["ours"])
-        for a, b in zip(self.pre["ref"], self.pre["ours"]):
-            diff = (a > 0) != (b > 0)
+        assert len(self.pre["ref"]) == len(self.pre["ours"]), (len(self.pre["ref"]), len(self.pre["ours"]))
+        for a, b, v in zip(self.pre["ref"], self.pre["ours"], self.ref_values):
+            diff = a != b
             if bool(diff.any()):
-                assert float(a[diff].abs().max()) < 2e-5, "a ReLU decision differs away from a rounding tie"
+                assert float(v[diff].abs().max()) < 2e-5, "a ReLU decision differs away from a rounding tie"
                 n += int(diff.sum())
         return n
 
@@ -165,6 +187,8 @@ def _tweak(model, kind):
             emb._weight.uniform_(-0.2, 0.2, generator=g)
             t = emb._mask_e_module._t_param
             t.copy_(1.2 + 0.8 * torch.rand(t.shape, generator=g, device=DEV))
+        elif kind == "optembed_d":
+            emb._weight.uniform_(-0.2, 0.2, generator=g)
         model.fc.weight.uniform_(-0.05, 0.05, generator=g) if hasattr(model, "fc") else None
 
 
@@ -191,7 +215,7 @@ CASES = {
     "kdd_optembed": (KDD_DIMS, 8192, dict(embedding_config={"name": "deepfm_optembed"}),
                      dict(learning_rate=3e-5, weight_decay=1e-3), "optembed", False),
     "kdd_optembed_d": (KDD_DIMS, 8192, dict(embedding_config={"name": "deepfm_optembed_d"}),
-                       dict(learning_rate=3e-5, weight_decay=1e-3), None, True),
+                       dict(learning_rate=3e-5, weight_decay=1e-3), "optembed_d", True),
     "avazu_dcn_mix": (AVAZU_DIMS, 2048, dict(name="dcn_mix", compile_model=False,
                                              embedding_config={"name": "vanilla"}),
                       dict(learning_rate=1e-3, weight_decay=1e-6), None, True),
@@ -264,6 +288,7 @@ def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tm
     opts = {"ref": ref_deepfm.get_optimizers(ref, dict(opt_cfg)), "ours": R.get_optimizers(ours, dict(opt_cfg)),
             "ref64": []}
     logits, grads = {}, {}
+    ours_masks = None
     ties = _ReluTies(ref, ours)
     for k, m in models.items():
         m.train()
@@ -272,9 +297,14 @@ def test_model_matches_the_unmodified_reference_on_the_same_gpu(R, REF, case, tm
         loss = crit(out, y.to(out.dtype))
         for o in opts[k]:
             o.zero_grad()
+        if k == "ours":
+            ours_node = _find_node(out.grad_fn, "_MlpBatchNormBackward")
+            ours_masks = [mm > 0 for mm in ours_node.masks] if ours_node is not None and ours_node.masks else None
         loss.backward()
         logits[k] = out.detach()
         grads[k] = {n: _dense(p.grad).detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    if ours_masks is not None and not ties.pre["ours"]:
+        ties.pre["ours"] = ours_masks
     flips = ties.flips()
     ties.remove()
     assert flips <= 6, f"{flips} ReLU decisions differ"
