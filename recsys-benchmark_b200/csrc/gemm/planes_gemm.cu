@@ -58,6 +58,8 @@ struct Params {
   int drain;             // K groups (of 32) accumulated in TMEM between two drains into registers
   int prefetch;          // A boxes requested into L2 this many K groups ahead of the shared-memory loads (0 = off)
   long long* dbg;        // RSB_GEMM_DEBUG: per-CTA cycle counters (development aid)
+  int tma_store;         // fp32 epilogue through shared memory + TMA stores (map_d); 0: direct stores
+  uint32_t epi_offset;   // byte offset of the epilogue staging buffers in dynamic shared memory
   uint32_t a_stage_bytes, b_stage_bytes;   // shared-memory footprint of one stage in one CTA
   uint32_t tx_bytes;                       // bytes the TMA loads of one CTA deliver per stage
   Operand a, b;
@@ -136,6 +138,13 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
 // TMA prefetch of a box into L2 (no shared memory, no barrier): the later cp.async.bulk.tensor load of the same box hits L2
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// TMA store of a [rows x 16 fp32] box staged in shared memory (64-byte swizzle); rows / columns past the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1)
+               : "memory");
 }
 
 // shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"): start address, leading / stride byte
@@ -276,7 +285,8 @@ __device__ __forceinline__ void mma_commit_g(uint64_t* bar) {
 
 template <int N_TILE, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
-planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Params p) {
+planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_d, const Params p) {
   // accumulator columns handled by the two epilogue warps that share a TMEM lane quarter
   constexpr int kHalf0 = ((N_TILE + 31) / 32) * 16;
   constexpr int kHalf1 = N_TILE - kHalf0;
@@ -476,6 +486,7 @@ epilogue_role:
       tempty_addr[b] = TWO ? map_to_rank(smem_u32(&tempty_bar[b]), 0) : smem_u32(&tempty_bar[b]);
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
+    uint32_t box_seq = 0;          // TMA-store boxes issued by this warp so far (selects the staging buffer)
     Tile t;
     for (int idx = unit0; get_tile(p, idx, t); idx += units) {
       float acc[NC];
@@ -519,7 +530,50 @@ epilogue_role:
       // ---- epilogue: this thread owns row (m0 + 32 q + lane), columns [n0 + col0, n0 + col0 + ncols) ----
       const long long row = (long long)t.m_blk * kTileM + (long long)cta_rank * kBlockM + q * 32 + lane;
       const int n0 = t.n_blk * N_TILE + col0;
-      if (row < p.M) {
+      if (p.tma_store) {
+        // fp32 result through shared memory: a thread owns one ROW of the accumulator, so direct stores write 16-byte
+        // pieces of 32 different rows per instruction (half-used sectors, ~58 clk per store instruction: 6 us per tile
+        // that the next tile's MMAs cannot hide).  Instead each warp stages [32 rows x 16 columns] boxes (64-byte
+        // swizzle: conflict-free 128-bit shared stores) and one lane hands them to the TMA unit, which writes full lines
+        // asynchronously and clips the rows / columns beyond the matrix.
+        uint8_t* stg = smem + p.epi_offset + (warp - kEpiWarp0) * 4096;
+        const int row0 = t.m_blk * kTileM + (int)cta_rank * kBlockM + q * 32;
+        const unsigned char* mrow = (p.epi_mode == RSB_EPI_MASK_F32 && row < p.M) ? p.mask + row * (long long)p.N : nullptr;
+        const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+        for (int c = 0; c < NC; c += 16) {
+          if (c < ncols && n0 + c < p.N) {
+            uint8_t* buf = stg + (box_seq & 1) * 2048;
+            ++box_seq;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store two boxes back has read its buffer
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 16; h += 4) {
+              float4 o = make_float4(acc[c + h] * p.alpha, acc[c + h + 1] * p.alpha, acc[c + h + 2] * p.alpha,
+                                     acc[c + h + 3] * p.alpha);
+              if (n0 + c + h < p.N) {
+                if (p.bias) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h));
+                  o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                }
+                if (p.epi_mode == RSB_EPI_MASK_F32) {
+                  uchar4 m = make_uchar4(0, 0, 0, 0);
+                  if (mrow) m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
+                  o.x = m.x ? o.x * p.drop_scale : 0.f; o.y = m.y ? o.y * p.drop_scale : 0.f;
+                  o.z = m.z ? o.z * p.drop_scale : 0.f; o.w = m.w ? o.w * p.drop_scale : 0.f;
+                }
+              }
+              *reinterpret_cast<float4*>(buf + lane * 64 + ((((uint32_t)h >> 2) ^ sw) << 4)) = o;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_d, buf, n0 + c, row0);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+        }
+      } else if (row < p.M) {
         if (p.partial != nullptr) {
           float* dst = p.partial + (((long long)t.split * p.batch + t.batch) * p.M + row) * p.N;
 #pragma unroll
@@ -595,6 +649,7 @@ epilogue_role:
         }
       }
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staged boxes fully written
   }
 teardown:
   // ---- teardown ----
@@ -783,7 +838,8 @@ static bool encode_map(CUtensorMap* map, const void* base, long long cols, long 
 }
 
 template <int N_TILE, bool TWO>
-static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, int grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& md, const Params& p, int grid, size_t smem,
+                          cudaStream_t st) {
   static bool attr[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -805,7 +861,7 @@ static cudaError_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const Pa
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, planes_gemm_kernel<N_TILE, TWO>, ma, mb, p);
+  return cudaLaunchKernelEx(&cfg, planes_gemm_kernel<N_TILE, TWO>, ma, mb, md, p);
 }
 
 }  // namespace pg
@@ -1013,15 +1069,36 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   ok = ok && (B->mn_major ? encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
                           : encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, kBlockK, b_rows, CU_TENSOR_MAP_SWIZZLE_64B));
   if (!ok) return RSB_ERR_UNSUPPORTED;
+  // fp32 results of the big un-batched, un-split GEMMs leave through shared memory + TMA stores when the staging
+  // buffers (8 warps x 2 x 2 KiB) fit beside the pipeline stages
+  CUtensorMap md = ma;
+  {
+    static const int want = [] { const char* v = getenv("RSB_GEMM_TMA_STORE"); return v ? atoi(v) : 1; }();
+    const uint32_t epi_bytes = 8u * 4096u;
+    const bool f32_out = (mode == RSB_EPI_LINEAR || mode == RSB_EPI_MASK_F32) && p.partial == nullptr && batch == 1 && C == nullptr;
+    if (want && f32_out && (size_t)p.stages * stage_bytes + epi_bytes + 1024 <= kSmemLimit - 2048) {
+      EncodeTiledFn encode = encode_tiled_fn();
+      cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+      cuuint64_t strides[1] = {(cuuint64_t)ldd * 4};
+      cuuint32_t box[2] = {16, 32};
+      cuuint32_t estr[2] = {1, 1};
+      if (encode != nullptr &&
+          encode(&md, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        p.tma_store = 1;
+        p.epi_offset = (uint32_t)((size_t)p.stages * stage_bytes);
+      }
+    }
+  }
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batch * p.splits;
   int grid = two ? rsb::sm_count() / 2 : rsb::sm_count();     // scheduling units: CTA pairs or CTAs
   if (tiles < grid) grid = (int)tiles;
   if (two) grid *= 2;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (p.tma_store ? 8 * 4096 : 0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaErrorInvalidValue;
   switch (p.n_tile) {
-#define PG_CASE(NT) case NT: e = two ? launch<NT, true>(ma, mb, p, grid, smem, st) : launch<NT, false>(ma, mb, p, grid, smem, st); break;
+#define PG_CASE(NT) case NT: e = two ? launch<NT, true>(ma, mb, md, p, grid, smem, st) : launch<NT, false>(ma, mb, md, p, grid, smem, st); break;
     PG_CASE(16) PG_CASE(32) PG_CASE(48) PG_CASE(64) PG_CASE(80) PG_CASE(96) PG_CASE(112) PG_CASE(128)
     PG_CASE(144) PG_CASE(160) PG_CASE(176) PG_CASE(192) PG_CASE(208) PG_CASE(224) PG_CASE(240) PG_CASE(256)
 #undef PG_CASE
