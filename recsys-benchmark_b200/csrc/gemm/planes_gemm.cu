@@ -547,6 +547,10 @@ epilogue_role:
             ++box_seq;
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store two boxes back has read its buffer
             __syncwarp();
+            // the 16 mask bytes of this box in one 128-bit load when the row pitch allows it
+            uint4 m16 = make_uint4(0u, 0u, 0u, 0u);
+            const bool wide_mask = mrow != nullptr && (p.N & 15) == 0;
+            if (wide_mask) m16 = *reinterpret_cast<const uint4*>(mrow + n0 + c);
 #pragma unroll
             for (int h = 0; h < 16; h += 4) {
               float4 o = make_float4(acc[c + h] * p.alpha, acc[c + h + 1] * p.alpha, acc[c + h + 2] * p.alpha,
@@ -558,7 +562,12 @@ epilogue_role:
                 }
                 if (p.epi_mode == RSB_EPI_MASK_F32) {
                   uchar4 m = make_uchar4(0, 0, 0, 0);
-                  if (mrow) m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
+                  if (wide_mask) {
+                    const uint32_t w = h == 0 ? m16.x : (h == 4 ? m16.y : (h == 8 ? m16.z : m16.w));
+                    m = make_uchar4(w & 0xffu, (w >> 8) & 0xffu, (w >> 16) & 0xffu, (w >> 24) & 0xffu);
+                  } else if (mrow) {
+                    m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
+                  }
                   o.x = m.x ? o.x * p.drop_scale : 0.f; o.y = m.y ? o.y * p.drop_scale : 0.f;
                   o.z = m.z ? o.z * p.drop_scale : 0.f; o.w = m.w ? o.w * p.drop_scale : 0.f;
                 }

@@ -30,16 +30,18 @@ def gemm_supported(m: int, n: int, k: int, lda: int, ldb: int, ldd: int, trans_a
     return min(m, n, k) > 0 and n % 4 == 0 and ldd % 4 == 0
 
 
-def weight_planes(w: torch.Tensor) -> P.Planes:
-    """Planes of a parameter, rebuilt only when the parameter has changed (in-place updates bump `_version`): ONE
-    split per optimizer step serves the forward GEMM (as the K-major [out, in] operand) and the dX GEMM (the same
-    planes read as the MN-major [K = out, N = in] operand)."""
-    cached = getattr(w, "_rsb_planes", None)
+def weight_planes(w: torch.Tensor, transpose: bool = False) -> P.Planes:
+    """Planes of a parameter (or of its transpose), rebuilt only when the parameter has changed (in-place updates bump
+    `_version`): one split per optimizer step.  The forward GEMM reads W [out, in] as the K-major operand; the dX GEMM
+    reads the planes of W^T [in, out], K-major as well (the MN-major view of the same planes would also do, but its
+    shared-memory tiles are padded to 64 columns, which costs the room the TMA-store epilogue needs)."""
+    attr = "_rsb_planes_t" if transpose else "_rsb_planes"
+    cached = getattr(w, attr, None)
     key = (w._version, w.data_ptr(), tuple(w.shape))
     if cached is not None and cached[0] == key:
         return cached[1]
-    pl = P.split(w.detach().reshape(-1, w.shape[-1]))
-    w._rsb_planes = (key, pl)
+    pl = P.split(w.detach().reshape(-1, w.shape[-1]), transpose=transpose)
+    setattr(w, attr, (key, pl))
     return pl
 
 
@@ -76,9 +78,9 @@ def _fwd_gemm(xp: P.Planes, weight: torch.Tensor, bias: Optional[torch.Tensor]) 
 
 
 def _dx_gemm(gp: P.Planes, weight: torch.Tensor) -> torch.Tensor:
-    """g W for W [out, in]: the weight planes read as the MN-major [K = out, N = in] operand (no transposed copy)."""
+    """g W for W [out, in]: B = the planes of W^T [in, out], K-major."""
     n_out, n_in = weight.shape
-    return P.gemm(gp, weight_planes(weight), gp.rows, n_in, n_out, b_mn_major=True, split_k=1)
+    return P.gemm(gp, weight_planes(weight, transpose=True), gp.rows, n_in, n_out, split_k=1)
 
 
 def _dw_gemm(gp: P.Planes, xp: P.Planes) -> torch.Tensor:
@@ -515,7 +517,7 @@ class _MlpReluDropout(torch.autograd.Function):
         for i in reversed(range(n_layers)):
             gp_prev = None
             if i > 0:
-                gp_prev = P.dx_masked(gp, weight_planes(ws[i]), masks[i - 1], ps[i - 1])
+                gp_prev = P.dx_masked(gp, weight_planes(ws[i], transpose=True), masks[i - 1], ps[i - 1])
             elif need[0]:
                 gx = _dx_gemm(gp, ws[0])
             want_w, want_b = need[3 + 2 * i], bs[i] is not None and need[4 + 2 * i]
@@ -601,7 +603,7 @@ class _MlpBatchNorm(torch.autograd.Function):
                 grads[4 * i + 3] = d_beta
             g_prev = None
             if i > 0:
-                g_prev = P.dx_masked(gp, weight_planes(ws[i]), masks[i - 1], ps[i - 1], to_planes=False)
+                g_prev = P.dx_masked(gp, weight_planes(ws[i], transpose=True), masks[i - 1], ps[i - 1], to_planes=False)
             elif need[0]:
                 gx = _dx_gemm(gp, ws[0])
             want_w, want_b = need[4 + 4 * i], bs[i] is not None and need[5 + 4 * i]

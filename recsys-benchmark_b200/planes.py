@@ -131,17 +131,17 @@ def relu_dropout_planes(z: torch.Tensor, p: float, seed: int, offset: int, offse
     return yp, mask
 
 
-def dx_masked(gp: Planes, wp: Planes, mask: torch.Tensor, p: float, to_planes: bool = True):
-    """(g W) * mask / (1 - p) for W stored [out, in] (read as the MN-major operand): the gradient w.r.t. the previous
-    layer's pre-activation, as planes (next GEMM operand) or as fp32."""
-    m, n, k = gp.rows, wp.cols, wp.rows
+def dx_masked(gp: Planes, wtp: Planes, mask: torch.Tensor, p: float, to_planes: bool = True):
+    """(g W) * mask / (1 - p) with `wtp` = planes of W^T [in, out] (K-major B): the gradient w.r.t. the previous layer's
+    pre-activation, as planes (next GEMM operand) or as fp32."""
+    m, n, k = gp.rows, wtp.rows, wtp.cols
     if to_planes:
         out = alloc(m, n, gp.data.device)
         epi = _dropout_epilogue(L.EPI_MASK_PLANES, out, mask, p, False)
-        gemm(gp, wp, m, n, k, b_mn_major=True, split_k=1, epilogue=epi, want_out=False)
+        gemm(gp, wtp, m, n, k, split_k=1, epilogue=epi, want_out=False)
         return out
     epi = _dropout_epilogue(L.EPI_MASK_F32, None, mask, p, False)
-    return gemm(gp, wp, m, n, k, b_mn_major=True, split_k=1, epilogue=epi)
+    return gemm(gp, wtp, m, n, k, split_k=1, epilogue=epi)
 
 
 def gemm_dw(gp: Planes, xp: Planes, want_bias_grad: bool):

@@ -194,8 +194,9 @@ def test_fused_epilogues_match_unfused_kernels(LA):
     gp = P.split(g)
     mprev = (torch.rand(m, k, device=DEV) > 0.4).to(torch.uint8)
     ref = (g.double() @ w.double()) * mprev.double() / 0.7
-    assert _err(P.dx_masked(gp, wp, mprev, 0.3, to_planes=False), ref) < 2e-6
-    assert _err(P.dx_masked(gp, wp, mprev, 0.3).float(), ref) < 2e-6
+    wtp = P.split(w, transpose=True)
+    assert _err(P.dx_masked(gp, wtp, mprev, 0.3, to_planes=False), ref) < 2e-6
+    assert _err(P.dx_masked(gp, wtp, mprev, 0.3).float(), ref) < 2e-6
     # weight gradient + bias gradient from the ones column
     dw, db = P.gemm_dw(gp, xp, True)
     assert _err(dw, g.double().t() @ x.double()) < 2e-6 and _err(db, g.double().sum(0)) < 2e-6
