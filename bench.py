@@ -449,7 +449,12 @@ def _peaks_all():
 NVLINK_GBS = 770.0     # measured peer-copy bandwidth per direction per GPU on this pool (B200_PROFILING.md); nominal 900
 
 
-def kernel_rooflines(kern, ksteps, ms_kpass, world, b, n_fields, traffic_for):
+def _hot_rows():
+    from recsys_benchmark_b200.sharded import HOT_FIELD_ROWS
+    return HOT_FIELD_ROWS
+
+
+def kernel_rooflines(kern, ksteps, ms_kpass, world, b, n_fields, traffic_for, n_sharded_fields=None):
     """One roofline entry per timed C-ABI call name.  HBM-bound kernels: algorithmic bytes / CUDA-event
     time vs the measured copy bandwidth.  The GEMM: real bf16 MMA FLOPs (6 plane products per fp32 product, stated
     separately) vs the measured cuBLAS bf16 throughput sustained inside a long step."""
@@ -475,7 +480,10 @@ def kernel_rooflines(kern, ksteps, ms_kpass, world, b, n_fields, traffic_for):
                         frac=round(gbs / pk["hbm_gbs"], 4), alg_bytes_per_launch=int(r["bytes_avg"]),
                         traffic=traffic_for(name))
             if name == "lookup_fwd_sharded" and world > 1:
-                remote = r["bytes_avg"] and b * n_fields * 64 * (world - 1) / world     # rows fetched from peer shards
+                # rows fetched from peer shards: only the SHARDED fields' lookups leave the GPU (small fields are
+                # replicated, sharded.HOT_FIELD_ROWS)
+                nsf = n_fields if n_sharded_fields is None else n_sharded_fields
+                remote = b * nsf * 64 * (world - 1) / world
                 base["nvlink"] = {"remote_bytes_per_launch": int(remote), "achieved": round(remote / (r["ms_avg"] * 1e-3) / 1e9, 1),
                                   "peak": NVLINK_GBS, "unit": "GB/s",
                                   "frac": round(remote / (r["ms_avg"] * 1e-3) / 1e9 / NVLINK_GBS, 4),
@@ -653,7 +661,12 @@ def run_workload(args, name, wl, dev, rank, world, R, primary):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic_tab = json.load(fh).get(name, {})
-    roofs = kernel_rooflines(kern, ksteps, ms_kpass, world, b, len(dims), lambda k: traffic_tab.get(k))
+    n_sharded_fields = None
+    if sharded:
+        from recsys_benchmark_b200.sharded import HOT_FIELD_ROWS
+        n_sharded_fields = sum(1 for d in dims if d > HOT_FIELD_ROWS) if world > 1 else len(dims)
+    roofs = kernel_rooflines(kern, ksteps, ms_kpass, world, b, len(dims), lambda k: traffic_tab.get(k),
+                             n_sharded_fields)
     top = sorted(roofs, key=lambda k: -roofs[k]["share_of_step"])
     res["roofline_top3"] = [dict(kernel=k, **roofs[k]) for k in top[:3]]
     res["roofline"] = dict(kernel=top[0], **roofs[top[0]]) if top else None
@@ -832,7 +845,10 @@ def main_ours(args, wl):
                    "use_batchnorm": wl["use_bn"], "optimizer": wl["opt"],
                    "ids": f"int32, {'Zipf(1.05) clipped' if args.ids == 'zipf' else 'uniform'} per field, seed 2023",
                    "parallelism": (f"row-sharded table x{world} (rows r % {world} on rank r, forward gather over NVLink "
-                                   f"peer memory, gradients pushed to the owner shard) + dp{world} dense allreduce"
+                                   f"peer memory, gradients pushed to the owner shard"
+                                   + (f"; the {sum(1 for d in dims if d <= _hot_rows())} fields of <= {_hot_rows()} ids "
+                                      f"replicated" if world > 1 else "")
+                                   + f") + dp{world} dense allreduce"
                                    if sharded else (f"dp{world} (replicated tables, flat grad allreduce)"
                                                     if world > 1 else "single")),
                    "l2": f"{args.pool} distinct batches cycled; per-step traffic "

@@ -146,6 +146,13 @@ RSB_API int rsb_lookup_bwd_rows(int32_t kind, const int64_t* rows, int64_t B, in
  * rsb_lookup_bwd_rows / rsb_qr_bwd_fused run it too when their fc_grad argument is non-NULL. */
 RSB_API int rsb_fc_grad(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F, float* fc_grad, void* stream);
 
+/* The same gradient from the row-sorted lookups (rsb_sort_rows of the full row ids: sorted_keys[i] is the row of
+ * lookup perm[i] = b * F + f): one writer per touched row, fixed summation order - bit-reproducible where rsb_fc_grad
+ * (float atomics) is not.  fc_grad is the zero-filled dense [N] gradient of FeaturesLinear's nn.Embedding(N, 1)
+ * (src/models/deepfm.py:71-76 / aten embedding_dense_backward).  workspace: rsb_segment_workspace_bytes(n, 1). */
+RSB_API int rsb_fc_grad_sorted(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n, const float* g_yfm, int32_t F,
+                               float* fc_grad, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* QR (mult / add) variant of stage 1 with the emb1 gradient fused in: emb1 has only `divider`
  * rows (2/5/20 in configs/deepfm/qr_*.yaml), so every lane group keeps one accumulator per emb1
  * row in registers while it streams the lookups; no per-lookup emb1 gradient is written and no
@@ -424,16 +431,27 @@ RSB_API int rsb_ipc_close_handle(void* dev_ptr);
  * [n_global] (NULL = no FM head): 4-byte peer reads / NVLink atomics cost as many transactions as the 64-byte
  * row traffic for 1/16 of the bytes (measured: a row-sharded first-order gradient took 0.76 ms of a 5.0 ms step
  * at N=8), so their gradient is rsb_fc_grad into a local dense buffer, allreduced with the other dense grads. */
+/* Small fields may be REPLICATED instead of sharded (the 31 Criteo fields of <= 16 384 ids hold 4 % of the rows but
+ * serve 31 of a sample's 39 lookups; sharded, 7/8 of those cross NVLink at G = 8): hot_map is a device int64 [F, 3]
+ * array, one (lo, hi, delta) per field with lo = the field's offset; a lookup of field f whose global row lies in
+ * [lo, hi) reads hot_table[row + delta] (a local dense [H, D] table, same values on every rank), hi == lo marks a
+ * sharded field.  A row outside [lo, hi) of a replicated field (an id beyond its own field) sets err_flag and takes
+ * the sharded path.  hot_table = hot_map = NULL: everything sharded. */
 RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B, int32_t F,
                                    int32_t D, const float* const* table_shards, const float* fc_replicated,
-                                   int32_t G, int64_t n_global, const float* bias, float* out_emb, float* out_yfm,
+                                   int32_t G, int64_t n_global, const float* bias, const float* hot_table,
+                                   const int64_t* hot_map, float* out_emb, float* out_yfm,
                                    float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream);
 /* Backward: segmented reduction of this rank's sorted lookups (rsb_sort_rows on GLOBAL row
  * ids), each locally-unique row's sum * scale added into the owner's dense shard gradient
- * with one 128-bit red.global.add per 4 floats. */
+ * with one 128-bit red.global.add per 4 floats.  Rows of replicated fields (hot_map [n_fields, 3] as above, the row's
+ * field found by binary search over the offsets) are instead STORED, unscaled, into the zero-filled local dense
+ * gradient hot_grad [H, E] (one writer per row, deterministic); the caller averages it over the ranks with the
+ * other replicated gradients.  hot_map = hot_grad = NULL: everything sharded. */
 RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
                                        const float* row_grads, int32_t E, float* const* grad_shards, int32_t G,
-                                       float scale, void* workspace, int64_t workspace_bytes, void* stream);
+                                       float scale, const int64_t* hot_map, int32_t n_fields, float* hot_grad,
+                                       void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,7 @@ PROTOTYPES = {
     "rsb_lookup_bwd_rows": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p,
                                       _p, _p, _p, _p]),
     "rsb_fc_grad": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
+    "rsb_fc_grad_sorted": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _p, _i64, _p]),
     "rsb_qr_bwd_fused_workspace_bytes": (_i64, [_i64, _i32]),
     "rsb_qr_bwd_fused": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p,
                                    _i64, _p]),
@@ -100,8 +101,8 @@ PROTOTYPES = {
     "rsb_ipc_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "rsb_ipc_close_handle": (C.c_int, [_p]),
     "rsb_lookup_fwd_sharded": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p,
-                                         _p]),
-    "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i64, _p]),
+                                         _p, _p, _p]),
+    "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i32, _p, _p, _i64, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

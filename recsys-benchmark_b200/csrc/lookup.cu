@@ -54,6 +54,10 @@ struct LookupArgs {
   // row-sharded tables (VANILLA only): shard g holds rows r with r % G == g at r / G
   const float* const* table_shards;
   int G;
+  // small fields replicated on every rank instead of sharded: hot_map[f] = (lo, hi, delta) int64 - a row of field f
+  // inside [lo, hi) lives at hot_table[row + delta]; hi == lo for a sharded field
+  const float* hot_table;
+  const long long* hot_map;
   // QR emb1 gradient accumulated in registers (divider <= kTinyRows): per-CTA partials [grid][kTinyRows][E]
   float* tiny_partials;
 };
@@ -119,10 +123,19 @@ __device__ __forceinline__ FV<V> load_transformed(const LookupArgs& a, long long
   if (K == RSB_KIND_VANILLA) {
     if (act) {
       if (a.table_shards != nullptr) {
-        int owner;
-        long long lrow;
-        shard_split(a, row, owner, lrow);
-        e = ldg<V>(a.table_shards[owner] + lrow * a.E + d0);   // peer shard: the load crosses NVLink
+        bool hot = false;
+        if (a.hot_map != nullptr) {
+          const long long lo = __ldg(a.hot_map + 3 * f), hi = __ldg(a.hot_map + 3 * f + 1);
+          hot = row >= lo && row < hi;
+          if (hot) e = ldg<V>(a.hot_table + (row + __ldg(a.hot_map + 3 * f + 2)) * a.E + d0);
+          else if (hi > lo && a.err) *a.err = 1;               // an id outside its own (replicated) field
+        }
+        if (!hot) {
+          int owner;
+          long long lrow;
+          shard_split(a, row, owner, lrow);
+          e = ldg<V>(a.table_shards[owner] + lrow * a.E + d0);   // peer shard: the load crosses NVLink
+        }
       } else {
         e = ldg<V>(a.table + row * a.E + d0);
       }
@@ -836,12 +849,15 @@ extern "C" RSB_API int rsb_qr_bwd_fused(int32_t kind, const int64_t* rows, int64
 extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,
                                               int32_t F, int32_t D, const float* const* table_shards,
                                               const float* fc_replicated, int32_t G, int64_t n_global,
-                                              const float* bias, float* out_emb, float* out_yfm, float* out_sum,
+                                              const float* bias, const float* hot_table, const int64_t* hot_map,
+                                              float* out_emb, float* out_yfm, float* out_sum,
                                               int64_t* out_rows, int32_t* err_flag, void* stream) {
   LookupArgs a = {};
   RowShape sh;
   if (B == 0) return RSB_OK;
   if (idx == nullptr || out_emb == nullptr || table_shards == nullptr || G < 1) return RSB_ERR_BAD_ARG;
+  if ((hot_map != nullptr) != (hot_table != nullptr)) return RSB_ERR_BAD_ARG;
+  if (hot_table != nullptr && !aligned16(hot_table)) return RSB_ERR_UNSUPPORTED;
   bool al = aligned16(out_emb) && (out_sum == nullptr || aligned16(out_sum));
   // shard base pointers come from cudaMalloc (256 B aligned); use a non-null dummy for the common checks
   int rc = fill_common(a, RSB_KIND_VANILLA, B, F, D, reinterpret_cast<const float*>(out_emb), n_global, n_global,
@@ -849,6 +865,8 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   if (rc) return rc;
   a.table = nullptr;
   a.table_shards = table_shards;
+  a.hot_table = hot_table;
+  a.hot_map = reinterpret_cast<const long long*>(hot_map);
   a.fc = fc_replicated;
   a.G = G;
   a.fd_g = make_fastdiv((unsigned long long)G);

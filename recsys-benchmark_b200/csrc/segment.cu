@@ -33,7 +33,20 @@ struct ApplyArgs {
   float* const* shards;
   int G;
   float scale;
+  // source row of sorted position i: perm[i], or perm[i] / src_div when one source row serves src_div consecutive
+  // lookups (the first-order gradient: every lookup of sample b carries g_y[b], rsb_fc_grad_sorted)
+  int use_src_div;
+  FastDiv src_div;
+  // RSB_APPLY_SHARD_ATOMIC with replicated small fields: hot_map[f] = (lo, hi, delta), lo ascending (the field
+  // offsets); a row inside [lo, hi) of its field is stored (unscaled, one writer) at hot_grad[row + delta]
+  const long long* hot_map;
+  int n_fields;
+  float* hot_grad;
 };
+
+// shared-memory slot of sorted position i: one pad word per 32 so that the lane groups of a warp, whose chunks
+// start kChunk = 32 positions apart, read different banks
+__device__ __forceinline__ int pad32(int i) { return i + (i >> 5); }
 
 __device__ __forceinline__ void atomic_add_row(float* p, const FV<4>& g) {
   atomicAdd(reinterpret_cast<float4*>(p), make_float4(g.v[0], g.v[1], g.v[2], g.v[3]));  // red.global.add.v4.f32
@@ -43,6 +56,19 @@ __device__ __forceinline__ void atomic_add_row(float* p, const FV<1>& g) { atomi
 template <int V>
 __device__ __forceinline__ void apply_row(const ApplyArgs& ap, unsigned row, int d0, const FV<V>& g) {
   if (ap.mode == RSB_APPLY_SHARD_ATOMIC) {
+    if (ap.hot_map != nullptr) {
+      // last field whose offset is <= row (39 fields: 6 steps over an L1-resident array, once per unique row)
+      int lo = 0, hi = ap.n_fields;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)row >= __ldg(ap.hot_map + 3 * mid)) lo = mid;
+        else hi = mid;
+      }
+      if ((long long)row < __ldg(ap.hot_map + 3 * lo + 1)) {
+        st<V>(ap.hot_grad + ((long long)row + __ldg(ap.hot_map + 3 * lo + 2)) * ap.E + d0, g);
+        return;
+      }
+    }
     const unsigned q = row / (unsigned)ap.G;
     const unsigned owner = row - q * (unsigned)ap.G;
     FV<V> s;
@@ -88,8 +114,8 @@ __global__ void __launch_bounds__(kSegThreads) seg_chunk_kernel(const unsigned* 
   constexpr int GPW = kWarp / LPR;
   constexpr int WT = GPW * kChunk;  // positions per warp
   constexpr int NW = kSegThreads / 32;
-  __shared__ unsigned s_key[NW][WT + 2];
-  __shared__ unsigned s_perm[NW][WT];
+  __shared__ unsigned s_key[NW][WT + 2 + (WT + 2) / 32 + 1];
+  __shared__ unsigned s_perm[NW][WT + WT / 32 + 1];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane / LPR, c = lane % LPR;
   const int d0 = c * V;
@@ -100,18 +126,20 @@ __global__ void __launch_bounds__(kSegThreads) seg_chunk_kernel(const unsigned* 
 
   for (int i = lane; i < WT + 2; i += 32) {
     long long p = base - 1 + i;
-    s_key[wib][i] = (p >= 0 && p < n) ? __ldg(skeys + p) : kNoKey;
+    s_key[wib][pad32(i)] = (p >= 0 && p < n) ? __ldg(skeys + p) : kNoKey;
   }
   for (int i = lane; i < WT; i += 32) {
     long long p = base + i;
-    s_perm[wib][i] = (p < n) ? __ldg(perm + p) : 0u;
+    unsigned src = (p < n) ? __ldg(perm + p) : 0u;
+    if (ap.use_src_div) src = fastdiv(src, ap.src_div);
+    s_perm[wib][pad32(i)] = src;
   }
   __syncwarp();
 
   const int start = g * kChunk;
   const long long chunk_id = warp * GPW + g;
   if (base + start >= n) return;
-  const unsigned prev_key = s_key[wib][start];  // key just before this chunk (slot 0 == base-1)
+  const unsigned prev_key = s_key[wib][pad32(start)];  // key just before this chunk (slot 0 == base-1)
   unsigned cur = kNoKey;
   bool began0 = false;
   FV<V> acc = FV<V>::zero();
@@ -124,9 +152,9 @@ __global__ void __launch_bounds__(kSegThreads) seg_chunk_kernel(const unsigned* 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = i0 + u;
-      key[u] = s_key[wib][1 + start + i];
+      key[u] = s_key[wib][pad32(1 + start + i)];
       val[u] = FV<V>::zero();
-      if (key[u] != kNoKey && cact) val[u] = ldg<V>(rg + (long long)s_perm[wib][start + i] * ap.E + d0);
+      if (key[u] != kNoKey && cact) val[u] = ldg<V>(rg + (long long)s_perm[wib][pad32(start + i)] * ap.E + d0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -150,7 +178,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_chunk_kernel(const unsigned* 
     }
   }
   if (cur != kNoKey) {
-    const unsigned next_key = s_key[wib][1 + start + kChunk];
+    const unsigned next_key = s_key[wib][pad32(1 + start + kChunk)];
     const bool crosses_start = began0 && prev_key == cur;
     const bool crosses_end = next_key == cur;
     if (cact) {
@@ -283,9 +311,11 @@ static int segment_launch(ApplyArgs ap, RowShape sh, const uint32_t* sorted_keys
 
 extern "C" RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,
                                                   const float* row_grads, int32_t E, float* const* grad_shards,
-                                                  int32_t G, float scale, void* workspace, int64_t workspace_bytes,
+                                                  int32_t G, float scale, const int64_t* hot_map, int32_t n_fields,
+                                                  float* hot_grad, void* workspace, int64_t workspace_bytes,
                                                   void* stream) {
   if (n < 0 || E <= 0 || G < 1) return RSB_ERR_BAD_ARG;
+  if ((hot_map != nullptr) != (hot_grad != nullptr) || (hot_map != nullptr && n_fields < 1)) return RSB_ERR_BAD_ARG;
   if (n == 0) return RSB_OK;
   if (!sorted_keys || !perm || !row_grads || !grad_shards || !workspace) return RSB_ERR_BAD_ARG;
   if (workspace_bytes < rsb_segment_workspace_bytes(n, E)) return RSB_ERR_WORKSPACE;
@@ -297,7 +327,32 @@ extern "C" RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, c
   ap.shards = grad_shards;
   ap.G = G;
   ap.scale = scale;
+  ap.hot_map = reinterpret_cast<const long long*>(hot_map);
+  ap.n_fields = n_fields;
+  ap.hot_grad = hot_grad;
+  if (hot_grad != nullptr && !aligned16(hot_grad)) return RSB_ERR_UNSUPPORTED;
   return segment_launch(ap, sh, sorted_keys, perm, n, row_grads, E, workspace, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// First-order weight gradient fc_grad[row] = sum of g_y[b] over the lookups (b, f) of that row, in sorted order:
+// the same three kernels with a 1-wide "row" whose source is g_y[perm / F].  Every touched row has exactly one
+// writer and a fixed summation order (the atomic rsb_fc_grad is neither).  fc_grad must be zero-filled.
+extern "C" RSB_API int rsb_fc_grad_sorted(const uint32_t* sorted_keys, const uint32_t* perm, int64_t n, const float* g_y,
+                                          int32_t F, float* fc_grad, void* workspace, int64_t workspace_bytes,
+                                          void* stream) {
+  if (n < 0 || F <= 0) return RSB_ERR_BAD_ARG;
+  if (n == 0) return RSB_OK;
+  if (!sorted_keys || !perm || !g_y || !fc_grad || !workspace) return RSB_ERR_BAD_ARG;
+  if (workspace_bytes < rsb_segment_workspace_bytes(n, 1)) return RSB_ERR_WORKSPACE;
+  RowShape sh;
+  sh.V = 1; sh.LPR = 1; sh.ok = true;
+  ApplyArgs ap = {};
+  ap.mode = RSB_APPLY_DENSE;
+  ap.dst = fc_grad;
+  ap.E = 1;
+  ap.use_src_div = 1;
+  ap.src_div = make_fastdiv((unsigned long long)F);
+  return segment_launch(ap, sh, sorted_keys, perm, n, g_y, 1, workspace, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" RSB_API int rsb_segment_reduce_apply(int32_t apply, const uint32_t* sorted_keys, const uint32_t* perm, int64_t n,

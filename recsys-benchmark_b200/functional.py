@@ -211,6 +211,31 @@ def small_table_grad(rows: torch.Tensor, row_grads: torch.Tensor, n_rows: int, k
     return out
 
 
+# The atomic first-order gradient kernel and the shared-memory atomics of the mid-size QR remainder table are the only
+# order-dependent float sums of the backward pass.  The sorted first-order gradient is used whenever the full-row sort
+# exists anyway (vanilla / PEP / OptEmbed / sharded tables); DETERMINISTIC = True also pays an extra sort where it
+# does not (QR keys are sorted by quotient; COO gradients are not sorted at all) and skips the shared-memory path.
+DETERMINISTIC = False
+
+
+def fc_grad(rows: torch.Tensor, g_y: torch.Tensor, b: int, f: int, shape, n_rows: int, sorted_pair=None) -> torch.Tensor:
+    """Dense gradient of the first-order weights fc [N,1] (src/models/deepfm.py:71-76): g_fc[row] = sum of g_y[b]
+    over the lookups of `row`.  With the row-sorted lookups: one writer per row, fixed order (bit-reproducible)."""
+    lib = L.load()
+    dev = rows.device
+    n = b * f
+    g_fc = torch.zeros(shape, dtype=torch.float32, device=dev)
+    if sorted_pair is None and DETERMINISTIC and n > 0:
+        sorted_pair = sort_rows(rows, n_rows)
+    if sorted_pair is not None:
+        ws = _ws(lib.rsb_segment_workspace_bytes(n, 1), dev)
+        _call("fc_grad_sorted", lib.rsb_fc_grad_sorted, L.ptr(sorted_pair[0]), L.ptr(sorted_pair[1]), n, L.ptr(g_y), f,
+              L.ptr(g_fc), L.ptr(ws), ws.numel(), L.stream_ptr(dev), nbytes=n * 12)
+    else:
+        _call("fc_grad", lib.rsb_fc_grad, L.ptr(rows), L.ptr(g_y), b, f, L.ptr(g_fc), L.stream_ptr(dev), nbytes=n * 12)
+    return g_fc
+
+
 def _err_flag(spec: LookupSpec, device) -> Optional[torch.Tensor]:
     mod = spec.module
     if mod is None:
@@ -300,8 +325,7 @@ class _FusedLookup(torch.autograd.Function):
             return (None,) * 10
 
         g_fc = None
-        if ctx.fm and need[7] and use_gy:
-            g_fc = torch.zeros_like(fc)
+        want_fc = ctx.fm and need[7] and use_gy
         g_bias = g_y.sum().reshape(1) if (ctx.fm and need[8] and use_gy) else None
 
         kind = spec.kind
@@ -341,16 +365,19 @@ class _FusedLookup(torch.autograd.Function):
             if kind == L.KIND_QR_ADD:
                 rg_aux = rg_main
 
-        if g_fc is not None:
-            _call("fc_grad", lib.rsb_fc_grad, L.ptr(rows), L.ptr(g_y), b, f, L.ptr(g_fc), L.stream_ptr(dev),
-                  nbytes=n * 12)
-
         # ---- stages 2+3: reduce by target row ---------------------------------
         g_table = g_table1 = g_aux = None
         n_rows = table.shape[0]
         mod = spec.module
         pre = ctx.presorted.get() if ctx.presorted is not None else None
         ctx.presorted = None
+        deferred = getattr(mod, "_rsb_fused_opt", None) if (mod is not None and not spec.is_qr) else None
+        # the lookups sorted by FULL row id (QR sorts by quotient): shared by the table, PEP-threshold and fc gradients
+        full_pair = None if spec.is_qr else pre
+        if full_pair is None and not spec.is_qr and need[4] and n > 0 and (deferred is not None or not spec.sparse_grad):
+            full_pair = sort_rows(rows, n_rows)
+        if want_fc:
+            g_fc = fc_grad(rows, g_y, b, f, fc.shape, fc.shape[0], full_pair)
         if spec.is_qr:
             if need[4]:
                 g_table = dense_row_grad(rows, rg_main, n_rows, key_div=spec.divider, sorted_pair=pre)
@@ -358,19 +385,20 @@ class _FusedLookup(torch.autograd.Function):
                 g_table1 = g_table1_fused
             elif need[5]:
                 kmod = spec.modulus or spec.divider
-                g_table1 = small_table_grad(rows, rg_aux, table1.shape[0], key_mod=kmod)
+                # <= 32 rows: register accumulators, no atomics; larger: float atomics in shared memory
+                g_table1 = (small_table_grad(rows, rg_aux, table1.shape[0], key_mod=kmod)
+                            if (not DETERMINISTIC or table1.shape[0] <= 32) else None)
                 if g_table1 is None:
                     g_table1 = dense_row_grad(rows, rg_aux, table1.shape[0], key_mod=kmod)
         else:
             if need[4]:
-                deferred = getattr(mod, "_rsb_fused_opt", None) if mod is not None else None
                 if deferred is not None:
-                    deferred.stash(table, rows, rg_main, pre)     # consumed by FusedSparse*.step()
+                    deferred.stash(table, rows, rg_main, full_pair)     # consumed by FusedSparse*.step()
                 elif spec.sparse_grad:
                     # same layout nn.Embedding(sparse=True) produces: uncoalesced COO, nnz = B*F
                     g_table = torch.sparse_coo_tensor(rows.view(1, n), rg_main, (n_rows, e))
                 else:
-                    pair = pre if pre is not None else sort_rows(rows, n_rows)
+                    pair = full_pair
                     g_table = dense_row_grad(rows, rg_main, n_rows, sorted_pair=pair)
                     if kind == L.KIND_PEP and need[6] and spec.aux_mode == L.PEP_FEATURE_DIM:
                         g_aux = dense_row_grad(rows, rg_aux, n_rows, sorted_pair=pair)

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -62,6 +63,32 @@ def full_from_shards(shards: List[torch.Tensor], num_rows: int) -> torch.Tensor:
         cnt = len(range(g, num_rows, world))
         out[g::world] = s[:cnt]
     return out
+
+
+# Fields with at most this many ids are replicated on every rank instead of sharded (world > 1).  Criteo shape: 31 of
+# the 39 fields (42 644 of 1 086 810 rows, 2.7 MB) - they serve 31 of a sample's 39 lookups, so the rows crossing NVLink
+# drop from 39 * (G-1)/G to 8 * (G-1)/G per sample; their [H, D] gradient rides the replicated-gradient allreduce.
+HOT_FIELD_ROWS = int(os.environ.get("RSB_HOT_FIELD_ROWS", "16384"))
+
+
+def hot_field_map(field_dims, hot_field_rows: int):
+    """-> (int64 [F, 3] rows (lo, hi, delta), H).  lo = the field's offset in the concatenated table; a replicated
+    ("hot") field has hi = lo + dim and lives at rows [lo + delta, hi + delta) of the [H, D] replica; hi == lo marks
+    a sharded field.  The layout rsb_lookup_fwd_sharded / rsb_segment_scatter_shards take."""
+    rows, off, base = [], 0, 0
+    for d in field_dims:
+        d = int(d)
+        hot = d <= hot_field_rows
+        rows.append((off, off + d if hot else off, base - off if hot else 0))
+        base += d if hot else 0
+        off += d
+    return torch.tensor(rows, dtype=torch.int64).reshape(-1, 3), base
+
+
+def hot_global_rows(hot_map: torch.Tensor) -> torch.Tensor:
+    """Global row ids of the replica's rows, in replica order."""
+    parts = [torch.arange(int(lo), int(hi), dtype=torch.int64) for lo, hi, _ in hot_map.tolist() if hi > lo]
+    return torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64)
 
 
 def allreduce_mean_(grads: List[torch.Tensor], group=None) -> None:
@@ -156,7 +183,8 @@ class _ShardedLookup(torch.autograd.Function):
     step); their dense gradient goes back to autograd and is averaged with the other replicated gradients."""
 
     @staticmethod
-    def forward(ctx, sg: ShardGroup, x, offsets, fc, bias, use_fm: bool):
+    def forward(ctx, sg: ShardGroup, x, offsets, fc, bias, use_fm: bool, presort: bool = False, hot=None,
+                hot_map=None):
         lib = L.load()
         dev = L.require_cuda(x, offsets, bias)
         x = x.contiguous()
@@ -166,13 +194,21 @@ class _ShardedLookup(torch.autograd.Function):
         y = torch.empty(b, dtype=torch.float32, device=dev) if use_fm else None
         s = torch.empty(b, d, dtype=torch.float32, device=dev) if use_fm else None
         rows = torch.empty(b, f, dtype=torch.int64, device=dev)
+        if hot is not None and hot_map.shape[0] != f:
+            raise ValueError(f"replicated small fields need one id column per field: x has {f} columns, the table "
+                             f"{hot_map.shape[0]} fields")
         nbytes = b * (f * x.element_size() + 2 * f * d * 4 + f * 8 + (f * 4 + 4 + d * 4 if use_fm else 0))
         RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded, L.ptr(x), int(x.dtype == torch.int32),
                  L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(fc) if use_fm else None,
-                 sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
+                 sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(hot) if hot is not None else None,
+                 L.ptr(hot_map) if hot is not None else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
                  L.ptr(sg.err_flag), L.stream_ptr(dev), nbytes=nbytes)
         ctx.sg, ctx.use_fm, ctx.shape = sg, use_fm, (b, f)
+        ctx.hot_map = hot_map if hot is not None else None
+        ctx.hot_shape = tuple(hot.shape) if hot is not None else None
         ctx.fc_shape = tuple(fc.shape) if fc is not None else None
+        # the backward's row sort needs only `rows`: queued on the side stream now, consumed at the end of backward
+        ctx.presorted = RF.early_sort(rows, sg.num_rows) if presort else None
         ctx.save_for_backward(rows, emb, s)
         ctx.mark_non_differentiable(rows)
         return emb, (y if use_fm else emb.new_empty(0)), rows
@@ -196,20 +232,24 @@ class _ShardedLookup(torch.autograd.Function):
                      None, None, L.stream_ptr(dev), nbytes=b * (f * 8 + 3 * f * d * 4 + d * 4 + 4))
         else:
             rg = g_emb.view(n, d)
-        skeys, perm = RF.sort_rows(rows, sg.num_rows)
+        pre, ctx.presorted = ctx.presorted, None
+        skeys, perm = pre.get() if pre is not None else RF.sort_rows(rows, sg.num_rows)
         scale = 1.0 / sg.world
         ws = RF._ws(lib.rsb_segment_workspace_bytes(n, d), dev)
+        g_hot = None
+        if ctx.hot_map is not None:
+            # dense local gradient of the replicated rows (averaged over the ranks with the other replicated grads)
+            g_hot = torch.zeros(ctx.hot_shape, dtype=torch.float32, device=dev)
         RF._call("segment_scatter_shards", lib.rsb_segment_scatter_shards, L.ptr(skeys), L.ptr(perm), n, L.ptr(rg), d,
-                 L.ptr(sg.ptrs["table_grad"]), sg.world, scale, L.ptr(ws), ws.numel(), L.stream_ptr(dev),
-                 nbytes=n * (8 + 4 * d))
+                 L.ptr(sg.ptrs["table_grad"]), sg.world, scale,
+                 L.ptr(ctx.hot_map) if g_hot is not None else None, f, L.ptr(g_hot) if g_hot is not None else None,
+                 L.ptr(ws), ws.numel(), L.stream_ptr(dev), nbytes=n * (8 + 4 * d))
         g_bias = g_fc = None
         if use_gy:
             if ctx.needs_input_grad[3]:
-                g_fc = torch.zeros(ctx.fc_shape, dtype=torch.float32, device=dev)
-                RF._call("fc_grad", lib.rsb_fc_grad, L.ptr(rows), L.ptr(g_y), b, f, L.ptr(g_fc), L.stream_ptr(dev),
-                         nbytes=n * 12)
+                g_fc = RF.fc_grad(rows, g_y, b, f, ctx.fc_shape, sg.num_rows, (skeys, perm))
             g_bias = g_y.sum().reshape(1)
-        return None, None, None, g_fc, g_bias, None
+        return None, None, None, g_fc, g_bias, None, None, g_hot, None
 
 
 # ------------------------------------------------------------------ modules ---
@@ -219,7 +259,9 @@ class ShardedVanillaEmbedding(IEmbedding):
     `gather_full_weight` to convert from / to the reference's full-table state dict."""
 
     def __init__(self, field_dims, hidden_size: int, mode=None, initializer="xavier", device=None, group=None,
-                 **kwargs):
+                 hot_field_rows: Optional[int] = None, **kwargs):
+        """hot_field_rows: fields of at most this many ids are replicated (`_emb_module.hot` [H, D], a plain
+        replicated parameter) instead of sharded; default HOT_FIELD_ROWS when world > 1, nothing at world 1."""
         super().__init__()
         assert mode is None, "sharded tables serve the [B,F,D] lookup only"
         field_dims = [field_dims] if isinstance(field_dims, int) else [int(v) for v in field_dims]
@@ -229,6 +271,13 @@ class ShardedVanillaEmbedding(IEmbedding):
         self.shards = ShardGroup(self._num_item, hidden_size, device, group)
         self._emb_module = nn.Module()
         self._emb_module.weight = nn.Parameter(self.shards.buf["table"].tensor)
+        if hot_field_rows is None:
+            hot_field_rows = HOT_FIELD_ROWS if self.shards.world > 1 else 0
+        hot_map, n_hot = hot_field_map(field_dims, int(hot_field_rows))
+        self.hot_map = hot_map.to(device) if n_hot > 0 else None
+        self._hot_rows = hot_global_rows(hot_map).to(device) if n_hot > 0 else None
+        if n_hot > 0:
+            self._emb_module.hot = nn.Parameter(torch.zeros(n_hot, hidden_size, dtype=torch.float32, device=device))
         self._init_shard(initializer)
 
     INIT_CHUNK_ROWS = 1 << 20
@@ -256,6 +305,10 @@ class ShardedVanillaEmbedding(IEmbedding):
             if first < hi:
                 mine = blk[first - lo::g]
                 w[first // g: first // g + mine.shape[0]].copy_(mine)
+            if self._hot_rows is not None:
+                sel = (self._hot_rows >= lo) & (self._hot_rows < hi)
+                if bool(sel.any()):
+                    self._emb_module.hot[sel] = blk[self._hot_rows[sel] - lo]
 
     def get_weight(self):
         return self.gather_full_weight()
@@ -263,23 +316,32 @@ class ShardedVanillaEmbedding(IEmbedding):
     def load_full_weight(self, full: torch.Tensor):
         sg = self.shards
         with torch.no_grad():
-            self._emb_module.weight.copy_(shard_of_full(full.to(sg.device), sg.rank, sg.world))
+            full = full.to(sg.device)
+            self._emb_module.weight.copy_(shard_of_full(full, sg.rank, sg.world))
+            if self._hot_rows is not None:
+                self._emb_module.hot.copy_(full[self._hot_rows])
 
     def gather_full_weight(self) -> torch.Tensor:
         sg = self.shards
         local = self._emb_module.weight.detach()
         if sg.world == 1:
-            return local[: self._num_item].clone()
-        parts = [torch.empty_like(local) for _ in range(sg.world)]
-        dist.all_gather(parts, local.contiguous(), group=sg.group)
-        return full_from_shards(parts, self._num_item)
+            full = local[: self._num_item].clone()
+        else:
+            parts = [torch.empty_like(local) for _ in range(sg.world)]
+            dist.all_gather(parts, local.contiguous(), group=sg.group)
+            full = full_from_shards(parts, self._num_item)
+        if self._hot_rows is not None:
+            full[self._hot_rows] = self._emb_module.hot.detach()   # the owners' copies of replicated rows are stale
+        return full
 
     def lookup(self, x, offsets=None, fc=None, bias=None):
         if offsets is not None:
             offsets = offsets.reshape(-1).long()
         use_fm = fc is not None
         self._rsb_err_flag = self.shards.err_flag     # read by IEmbedding.train() / validate=True like the others
-        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm)
+        presort = RF.EARLY_SORT and torch.is_grad_enabled()
+        hot = getattr(self._emb_module, "hot", None)
+        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm, presort, hot, self.hot_map)
         if self.validate:
             RF.check_index_errors(self)
         return emb, (y if use_fm else None)

@@ -111,6 +111,31 @@ def test_segment_reduce_dense_matches_scatter_add(RF, E, dist):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("b,f", [(1, 1), (33, 3), (1024, 39), (8192, 11), (65536, 39)])
+@pytest.mark.parametrize("dist", ["uniform", "dup", "zipf"])
+def test_sorted_fc_grad_is_the_scatter_add_and_is_bit_reproducible(RF, b, f, dist):
+    """First-order weight gradient from the row-sorted lookups (rsb_fc_grad_sorted): equals the scatter-add of g_y[b]
+    over the lookups of each row (aten embedding_dense_backward of FeaturesLinear, deepfm.py:71-76), untouched rows
+    stay exactly zero, and - unlike the atomic rsb_fc_grad - two runs are bit-identical."""
+    n_rows = max(4, min(200000, b * f // 3))
+    keys = _keys(b * f, n_rows, dist, seed=b + f)
+    gy = np.random.default_rng(b).standard_normal(b).astype(np.float32)
+    rows = torch.from_numpy(keys).to(DEV).view(b, f)
+    g = torch.from_numpy(gy).to(DEV)
+    pair = RF.sort_rows(rows, n_rows)
+    out = RF.fc_grad(rows, g, b, f, (n_rows, 1), n_rows, pair)
+    ref = O.scatter_add_dense(keys, np.repeat(gy.astype(np.float64), f)[:, None], n_rows)
+    assert_close(out.cpu().numpy(), ref, what=f"fc_grad_sorted b={b} f={f} {dist}")
+    untouched = np.ones(n_rows, bool)
+    untouched[keys] = False
+    assert float(out.cpu().numpy()[untouched].__abs__().sum()) == 0.0
+    for _ in range(3):
+        assert torch.equal(out, RF.fc_grad(rows, g, b, f, (n_rows, 1), n_rows, pair))
+    # the atomic kernel agrees to rounding
+    atomic = RF.fc_grad(rows, g, b, f, (n_rows, 1), n_rows, None)
+    assert_close(atomic.cpu().numpy(), ref, what="fc_grad atomic")
+
+
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 255, 256, 257, 1024, 8191])
 def test_segment_reduce_chunk_boundaries(RF, n):
     """Runs that start / end exactly on chunk and warp-tile boundaries, incl. one giant run."""

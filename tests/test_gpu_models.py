@@ -447,6 +447,9 @@ def test_criteo_shape_properties(R, emb_cfg, b):
     g3 = torch.autograd.grad(model(x).square().sum(), params)
     big = max(range(len(params) - 1), key=lambda i: params[i].numel())
     assert torch.equal(g1[big], g3[big])
+    if emb_cfg["name"] == "vanilla":
+        # the whole vanilla backward is order-fixed: fc.weight.grad comes from the sorted lookups too
+        assert torch.equal(g1[-1], g3[-1])
     # (5) untouched rows have exactly zero gradient
     if emb_cfg["name"] == "vanilla":
         touched = torch.zeros(sum(CRITEO_DIMS), dtype=torch.bool, device=DEV)

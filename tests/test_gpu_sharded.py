@@ -28,10 +28,13 @@ def _batch(b, seed):
     return x, y
 
 
-def _sharded_from(R, full, dev, group=None):
+def _sharded_from(R, full, dev, group=None, hot_field_rows=None):
     from recsys_benchmark_b200.sharded import ShardedDeepFM
 
-    m = ShardedDeepFM(DIMS, 16, [32, 16], p_dropout=0.0, use_batchnorm=False, group=group).to(dev)
+    m = ShardedDeepFM(DIMS, 16, [32, 16], p_dropout=0.0, use_batchnorm=False, group=group,
+                      embedding_config={"name": "vanilla", "hot_field_rows": hot_field_rows}).to(dev)
+    hot = getattr(m.embedding._emb_module, "hot", None)
+    assert (hot.shape[0] if hot is not None else 0) == sum(d for d in DIMS if d <= (hot_field_rows or 0))
     sg = m.embedding.shards
     st = {k: v for k, v in full.state_dict().items() if not k.startswith("embedding.")}
     m.load_state_dict(st, strict=False)            # fc.weight is replicated: same key / shape as the reference's
@@ -56,7 +59,10 @@ def _train(model, opt, x, y, steps, sharded):
     return outs
 
 
-def test_sharded_world1_matches_unsharded():
+@pytest.mark.parametrize("hot_field_rows", [None, 0, 11, 300, 10 ** 6])
+def test_sharded_world1_matches_unsharded(hot_field_rows):
+    """hot_field_rows: fields of at most that many ids are served from the replicated [H, D] table instead of the
+    shard (None = the world-1 default: nothing replicated; 10**6: every field)."""
     import __graft_entry__ as G
 
     G.build()
@@ -64,7 +70,7 @@ def test_sharded_world1_matches_unsharded():
 
     dev = torch.device("cuda:0")
     full = _full_model(R, dev)
-    sh = _sharded_from(R, full, dev)
+    sh = _sharded_from(R, full, dev, hot_field_rows=hot_field_rows)
     x, y = _batch(64, 1)
     x, y = x.to(dev), y.to(dev)
     o1 = torch.optim.Adam(full.parameters(), lr=1e-2, weight_decay=1e-4)
@@ -81,7 +87,7 @@ def test_sharded_world1_matches_unsharded():
                  what="fc after 3 steps", atol_scale=5e-5)
 
 
-def _worker2(rank, world, port, ret):
+def _worker2(rank, world, port, ret, hot_field_rows):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -90,7 +96,7 @@ def _worker2(rank, world, port, ret):
         import recsys_benchmark_b200 as R
 
         full = _full_model(R, dev)
-        sh = _sharded_from(R, full, dev)
+        sh = _sharded_from(R, full, dev, hot_field_rows=hot_field_rows)
         x, y = _batch(128, 2)
         xl, yl = x[rank::world].to(dev), y[rank::world].to(dev)
         o1 = torch.optim.Adam(full.parameters(), lr=1e-2, weight_decay=1e-4)
@@ -108,11 +114,14 @@ def _worker2(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_sharded_world2_matches_single_gpu():
+@pytest.mark.parametrize("hot_field_rows", [0, 50])
+def test_sharded_world2_matches_single_gpu(hot_field_rows):
+    """0: every field sharded; 50: the five small fields replicated, the 300- and 1000-id fields sharded."""
     import __graft_entry__ as G
 
     G.build()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker2, args=(2, 29700 + os.getpid() % 1000, ret), nprocs=2, join=True)
+    mp.spawn(_worker2, args=(2, 29700 + os.getpid() % 1000 + hot_field_rows, ret, hot_field_rows), nprocs=2,
+             join=True)
     assert dict(ret) == {0: 1, 1: 1}

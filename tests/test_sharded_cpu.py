@@ -23,6 +23,37 @@ def test_shard_round_trip(n, world):
     assert torch.equal(S.full_from_shards(shards, n), full)
 
 
+def test_hot_field_map_layout():
+    """(lo, hi, delta) per field as the gather / scatter kernels read it: lo = the field offsets (ascending, so the
+    scatter can binary-search a row's field), replicated fields packed in field order, hi == lo for sharded fields."""
+    dims = [50, 7, 300, 11, 5, 1000, 3]
+    m, h = S.hot_field_map(dims, 11)
+    offs = np.concatenate([[0], np.cumsum(dims)[:-1]])
+    assert m.dtype == torch.int64 and tuple(m.shape) == (7, 3) and h == 7 + 11 + 5 + 3
+    np.testing.assert_array_equal(m[:, 0].numpy(), offs)
+    hot = [d <= 11 for d in dims]
+    base = 0
+    for f, d in enumerate(dims):
+        lo, hi, delta = m[f].tolist()
+        assert hi - lo == (d if hot[f] else 0)
+        if hot[f]:
+            assert lo + delta == base
+            base += d
+    rows = S.hot_global_rows(m)
+    assert rows.numel() == h
+    # every replicated row maps to its slot through its own field's delta
+    for slot, row in enumerate(rows.tolist()):
+        f = int(np.searchsorted(offs, row, side="right") - 1)
+        assert hot[f] and row + int(m[f, 2]) == slot
+    m0, h0 = S.hot_field_map(dims, 0)
+    assert h0 == 0 and torch.equal(m0[:, 0], m0[:, 1])
+    mall, hall = S.hot_field_map(dims, 10 ** 9)
+    assert hall == sum(dims) and torch.equal(S.hot_global_rows(mall), torch.arange(sum(dims)))
+    import bench
+    _, hc = S.hot_field_map(bench.CRITEO_DIMS, S.HOT_FIELD_ROWS)
+    assert hc == sum(d for d in bench.CRITEO_DIMS if d <= 16384) and sum(d <= 16384 for d in bench.CRITEO_DIMS) == 31
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
