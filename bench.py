@@ -469,11 +469,12 @@ def kernel_rooflines(kern, ksteps, ms_kpass, world, b, n_fields, traffic_for, n_
         if name.startswith("gemm_planes"):
             flops = r["bytes_avg"]                       # planes.gemm stores 2*M*N*K*batch in the timer's slot
             tf = flops / (r["ms_avg"] * 1e-3) / 1e12
-            base.update(bound="tensor", achieved=round(6 * tf, 1), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
-                        frac=round(6 * tf / pk["bf16_tflops_sustained"], 4), fp32_equivalent_tflops=round(tf, 1),
-                        mma_per_fp32_product=6, traffic=None,
-                        note="achieved = bf16 tensor-core FLOPs actually issued (6 plane products per fp32 product); "
-                             "peak = cuBLAS bf16 sustained")
+            mma = 3 if name.endswith("_h") else 6        # FP16X2 operands: 3 plane products; BF16X3: 6
+            base.update(bound="tensor", achieved=round(mma * tf, 1), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                        frac=round(mma * tf / pk["bf16_tflops_sustained"], 4), fp32_equivalent_tflops=round(tf, 1),
+                        mma_per_fp32_product=mma, traffic=None,
+                        note=f"achieved = 16-bit tensor-core FLOPs actually issued ({mma} plane products per fp32 "
+                             "product); peak = cuBLAS bf16 sustained (fp16 runs at the same rate)")
         elif r["bytes_avg"] > 0:
             gbs = r["bytes_avg"] / (r["ms_avg"] * 1e-3) / 1e9
             base.update(bound="hbm", achieved=round(gbs, 1), peak=pk["hbm_gbs"], unit="GB/s",

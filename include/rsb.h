@@ -272,11 +272,25 @@ RSB_API int rsb_dhe_encode(const void* ids, int32_t ids_is_i32, int64_t n, int64
  * D[l] = alpha * A[l] B[l]^T-or-B[l] + beta * C[l] + bias;  split_k = 0 picks a split that fills the SMs when there
  * are fewer tiles than SMs (partials in the workspace, summed in fixed order by a second launch).
  * ---------------------------------------------------------------------- */
+/* Operand formats.  RSB_PLANES_BF16X3 (default): three bf16 planes, every fp32 value exactly, 6 MMAs per product.
+ * RSB_PLANES_FP16X2: two fp16 planes of X * s, s = the power of two that puts the bound *amax >= max |X| (a DEVICE
+ * scalar, written by whoever knows it: rsb_absmax, the BatchNorm statistics kernels) into [2^13, 2^14), at most
+ * 2^max_scale_exp: 22 bits for the big elements, 2^-38 of the bound for every element, 3 MMAs per product - the
+ * error stays below the fp32 rounding of the sum itself (tests/test_gemm_split_math.py).  Writers and the GEMM derive s
+ * from the same scalar, so no host round trip is involved.  Both operands of one GEMM must use the same format. */
+typedef enum { RSB_PLANES_BF16X3 = 0, RSB_PLANES_FP16X2 = 1 } rsb_planes_format_id;
+typedef struct {
+  int32_t format;          /* rsb_planes_format_id */
+  int32_t max_scale_exp;   /* FP16X2: scale <= 2^max_scale_exp (14 when the planes carry a ones column, which stores s) */
+  float* amax;             /* FP16X2: device scalar bound on |X| (read; written first by rsb_bn_train_bwd_planes) */
+} rsb_planes_format;
+
 typedef struct {
   const void* planes;
   int64_t rows, cols, ld, plane_stride;
   int32_t mn_major;
   int64_t batch_row_step, batch_col_step;
+  rsb_planes_format fmt;   /* zero-initialised = BF16X3 */
 } rsb_planes_operand;
 
 /* What rsb_gemm_planes does with the accumulator (fused epilogues of the dense tail, src/models/deepfm.py:55-66):
@@ -305,6 +319,8 @@ typedef struct {
   int32_t ones_col;
   uint8_t* mask;               /* [M, N]: updated in place by mode 1, read by modes 2, 3 */
   float p;                     /* dropout probability */
+  float* d_amax;               /* modes 0, 3 (fp32 D, no split-K), optional: *d_amax is raised to max |D| - the bound an
+                                  FP16X2 consumer of D needs (rsb_bn_train_bwd_planes), formed in the epilogue for free */
 } rsb_gemm_epilogue;
 
 /* y = dropout_p(relu(x)) of an fp32 [M, N] activation (ldx) written as planes (+ ones column) and the 1-byte
@@ -320,7 +336,14 @@ RSB_API int rsb_dropout_keep_mask(uint8_t* mask, int64_t numel, float p, uint64_
 /* fp32 [rows, cols] (ld) -> bf16 planes [3][rows][out_ld] (columns cols..out_ld-1 zero); transpose = 1 writes the
  * planes of in^T ([cols][out_ld >= rows]); ones_col = 1 additionally writes 1.0 at column roundup8(cols). */
 RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, int32_t ones_col,
-                             void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream);
+                             void* out_planes, int64_t out_ld, int64_t plane_stride, const rsb_planes_format* fmt /* NULL = BF16X3 */,
+                             void* stream);
+/* *amax_out = max(*amax_out, mul * max |g_row| * max |w_col|): bound on the rank-1 head gradient
+ * g_row[r] * w_col[c] * mask / (1 - p) of rsb_relu_dropout_bwd_rank1 (mul = 1 / (1 - p)). */
+RSB_API int rsb_rank1_absmax(const float* g_row, int64_t M, const float* w_col, int64_t N, float mul, float* amax_out,
+                             void* stream);
+/* *amax_out = max(*amax_out, max |in[r, c]|): the bound an FP16X2 split of `in` needs (zero the scalar first). */
+RSB_API int rsb_absmax(const float* in, int64_t rows, int64_t cols, int64_t ld, float* amax_out, void* stream);
 /* gz[r, c] = g_row[r] * w_col[c] * mask[r, c] / (1 - p) written as planes (N, out_ld multiples of 8): the backward of
  * dropout(relu(.)) for the rank-1 upstream gradient of the MLP's one-output Linear (src/models/deepfm.py:64). */
 RSB_API int rsb_rank1_mask_planes(const float* g_row, const float* w_col, const uint8_t* mask, int64_t M, int32_t N, float p,
@@ -337,7 +360,10 @@ RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operan
  * semantics: biased batch variance for the normalisation, unbiased for running_var, eps inside the square root,
  * running = (1 - momentum) * running + momentum * batch.  All reductions are two-stage with a fixed order.
  *   rsb_bn_train_fwd_stats      z [M,N] (ldz) -> stats [2N] = (mean, rstd), affine [2N] = (gamma * rstd, beta - mean * scale),
- *                               running_mean / running_var updated in place (NULL: not tracked)
+ *                               running_mean / running_var updated in place (NULL: not tracked); act_amax (optional,
+ *                               zero on entry) receives bound_mul * max_c (|gamma_c| sqrt(M) + |beta_c|) >= the largest
+ *                               dropout(relu(BN(z))) (|xhat| <= sqrt(M)): the bound an FP16X2 rsb_bn_relu_dropout_planes
+ *                               needs (bound_mul = 1 / (1 - p))
  *   rsb_bn_relu_dropout_planes  y = dropout_p(relu(z * scale + shift)) as bf16 planes (+ ones column) + the 1-byte
  *                               keep-and-positive mask; Philox stream as rsb_relu_dropout_fwd; p = 0: no dropout
  *   rsb_bn_train_bwd_planes     g [M,N] = gradient w.r.t. the BatchNorm output -> sums [2N] = (d beta, d gamma) and
@@ -347,13 +373,18 @@ RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_planes_operan
 RSB_API int64_t rsb_bn_workspace_bytes(int64_t M, int32_t N);
 RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t N, int64_t ldz, const float* gamma, const float* beta,
                                    float eps, float momentum, float* running_mean, float* running_var, float* stats,
-                                   float* affine, void* workspace, int64_t workspace_bytes, void* stream);
+                                   float* affine, float bound_mul, float* act_amax, void* workspace, int64_t workspace_bytes,
+                                   void* stream);
 RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int32_t N, int64_t ldz, const float* affine, float p,
                                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int32_t ones_col,
-                                       void* out_planes, int64_t out_ld, int64_t plane_stride, uint8_t* mask, void* stream);
+                                       void* out_planes, int64_t out_ld, int64_t plane_stride, uint8_t* mask,
+                                       const rsb_planes_format* fmt /* NULL = BF16X3 */, void* stream);
 RSB_API int rsb_bn_train_bwd_planes(const float* g, const float* z, int64_t M, int32_t N, int64_t ldg, int64_t ldz,
                                     const float* stats, const float* gamma, float* sums, void* out_planes, int64_t out_ld,
-                                    int64_t plane_stride, void* workspace, int64_t workspace_bytes, void* stream);
+                                    int64_t plane_stride, const rsb_planes_format* fmt /* NULL = BF16X3; FP16X2: *amax
+                                    (zero on entry) is set to a bound on |gz| before gz is written */,
+                                    const float* g_amax /* FP16X2: device scalar >= max |g| */, void* workspace,
+                                    int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Bandwidth-bound glue of the dense tails (Linear -> [BatchNorm1d] -> ReLU -> Dropout,

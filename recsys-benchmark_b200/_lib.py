@@ -25,19 +25,28 @@ QR_KINDS = {"mult": KIND_QR_MULT, "add": KIND_QR_ADD, "cat": KIND_QR_CAT}
 
 _p, _i32, _i64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
+class PlanesFormat(C.Structure):
+    """rsb_planes_format of include/rsb.h."""
+
+    _fields_ = [("format", C.c_int32), ("max_scale_exp", C.c_int32), ("amax", C.c_void_p)]
+
+
+PLANES_BF16X3, PLANES_FP16X2 = 0, 1
+
+
 class PlanesOperand(C.Structure):
-    """rsb_planes_operand of include/rsb.h: an fp32 matrix held as three bf16 planes."""
+    """rsb_planes_operand of include/rsb.h: an fp32 matrix held as three bf16 planes or two scaled fp16 planes."""
 
     _fields_ = [("planes", C.c_void_p), ("rows", C.c_int64), ("cols", C.c_int64), ("ld", C.c_int64),
                 ("plane_stride", C.c_int64), ("mn_major", C.c_int32), ("batch_row_step", C.c_int64),
-                ("batch_col_step", C.c_int64)]
+                ("batch_col_step", C.c_int64), ("fmt", PlanesFormat)]
 
 
 class GemmEpilogue(C.Structure):
     """rsb_gemm_epilogue of include/rsb.h."""
 
     _fields_ = [("mode", C.c_int32), ("out_planes", C.c_void_p), ("out_ld", C.c_int64), ("out_plane_stride", C.c_int64),
-                ("ones_col", C.c_int32), ("mask", C.c_void_p), ("p", C.c_float)]
+                ("ones_col", C.c_int32), ("mask", C.c_void_p), ("p", C.c_float), ("d_amax", C.c_void_p)]
 
 
 EPI_LINEAR, EPI_RELU_DROPOUT_PLANES, EPI_MASK_PLANES, EPI_MASK_F32 = range(4)
@@ -72,7 +81,9 @@ PROTOTYPES = {
     "rsb_csr_lookup_fwd": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _p, _i32, _i64, _p, _p, _p, _p,
                                      _p, _p]),
     "rsb_dhe_encode": (C.c_int, [_p, _i32, _i64, _i64, _p, _p, _p, _i32, _i64, _i32, _p, _p]),
-    "rsb_split_planes": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i64, _p]),
+    "rsb_split_planes": (C.c_int, [_p, _i64, _i64, _i64, _i32, _i32, _p, _i64, _i64, C.POINTER(PlanesFormat), _p]),
+    "rsb_absmax": (C.c_int, [_p, _i64, _i64, _i64, _p, _p]),
+    "rsb_rank1_absmax": (C.c_int, [_p, _i64, _p, _i64, _f, _p, _p]),
     "rsb_relu_dropout_planes": (C.c_int, [_p, _i64, _i32, _i64, _f, C.c_uint64, C.c_uint64, _p, _i32, _p, _i64, _i64, _p, _p]),
     "rsb_dropout_keep_mask": (C.c_int, [_p, _i64, _f, C.c_uint64, C.c_uint64, _p, _p]),
     "rsb_rank1_mask_planes": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _i64, _i64, _p]),
@@ -85,10 +96,11 @@ PROTOTYPES = {
     "rsb_colsum": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i64, _p]),
     "rsb_relu_dropout_dot_fwd": (C.c_int, [_p, _i64, _i32, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "rsb_bn_workspace_bytes": (_i64, [_i64, _i32]),
-    "rsb_bn_train_fwd_stats": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _p]),
+    "rsb_bn_train_fwd_stats": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _f, _f, _p, _p, _p, _p, _f, _p, _p, _i64, _p]),
     "rsb_bn_relu_dropout_planes": (C.c_int, [_p, _i64, _i32, _i64, _p, _f, C.c_uint64, C.c_uint64, _p, _i32, _p, _i64, _i64,
-                                             _p, _p]),
-    "rsb_bn_train_bwd_planes": (C.c_int, [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _p, _i64, _p]),
+                                             _p, C.POINTER(PlanesFormat), _p]),
+    "rsb_bn_train_bwd_planes": (C.c_int, [_p, _p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _i64, _i64,
+                                          C.POINTER(PlanesFormat), _p, _p, _i64, _p]),
     "rsb_relu_dropout_bwd_rank1": (C.c_int, [_p, _p, _p, _i64, _i32, _f, _p, _p, _p, _i64, _p]),
     "rsb_colsum_weighted": (C.c_int, [_p, _p, _i64, _i32, _i64, _p, _p, _i64, _p]),
     "rsb_dcn_gate_mix_fwd": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _p, _p, _p, _p]),

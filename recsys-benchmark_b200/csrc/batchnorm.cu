@@ -19,23 +19,6 @@ namespace rsb {
 
 constexpr int kBnThreads = 128;   // one float4 column group per thread per pass: 512 columns per pass
 
-__device__ __forceinline__ void bn_split3(float x, __nv_bfloat16& h0, __nv_bfloat16& h1, __nv_bfloat16& h2) {
-  h0 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(h0);
-  h1 = __float2bfloat16_rn(r1);
-  h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
-}
-__device__ __forceinline__ void bn_store_planes4(__nv_bfloat16* dst, long long plane_stride, float4 v) {
-  __align__(8) __nv_bfloat16 p0[4], p1[4], p2[4];
-  bn_split3(v.x, p0[0], p1[0], p2[0]);
-  bn_split3(v.y, p0[1], p1[1], p2[1]);
-  bn_split3(v.z, p0[2], p1[2], p2[2]);
-  bn_split3(v.w, p0[3], p1[3], p2[3]);
-  *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(p0);
-  *reinterpret_cast<uint2*>(dst + plane_stride) = *reinterpret_cast<const uint2*>(p1);
-  *reinterpret_cast<uint2*>(dst + 2 * plane_stride) = *reinterpret_cast<const uint2*>(p2);
-}
-
 // partials[blk][0][c] = sum_r a[r,c] ; partials[blk][1][c] = sum_r b[r,c] over the block's row slab, where
 //   MODE 0 (forward):  a = z - k_c,  b = (z - k_c)^2          (k = z[0, :])
 //   MODE 1 (backward): a = g,        b = g * (z - mean_c) * rstd_c
@@ -60,15 +43,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_slab_sums_kernel(const float* _
     }
     float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
     long long r = r0;
-    for (; r + 4 <= r1; r += 4) {      // four rows in flight
-      float4 zv[4], gv[4];
+    constexpr int U = MODE == 0 ? 8 : 4;   // rows in flight (the backward reads two matrices per row)
+    for (; r + U <= r1; r += U) {
+      float4 zv[U], gv[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         zv[u] = __ldg(reinterpret_cast<const float4*>(z + (r + u) * ldz) + c4);
         if (MODE == 1) gv[u] = __ldg(reinterpret_cast<const float4*>(g + (r + u) * ldg) + c4);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const float4 d = make_float4(zv[u].x - k.x, zv[u].y - k.y, zv[u].z - k.z, zv[u].w - k.w);
         if (MODE == 0) {
           sa.x += d.x; sa.y += d.y; sa.z += d.z; sa.w += d.w;
@@ -103,27 +87,46 @@ __global__ void __launch_bounds__(kBnThreads) bn_slab_sums_kernel(const float* _
 //   MODE 0: stats[0..N) = mean, stats[N..2N) = rstd, affine[0..N) = gamma * rstd, affine[N..2N) = beta - mean * scale;
 //           running_mean / running_var updated in place (momentum, unbiased variance) when given.
 //   MODE 1: out[0..N) = sum g (d beta), out[N..2N) = sum g * xhat (d gamma).
+//   amax != NULL: *amax is raised to a bound on the plane output that follows (the scale of an FP16X2 writer, common.cuh).
+//   A normalised value obeys |xhat| <= sqrt(M) (sum xhat^2 <= M), and mean |xhat| <= 1, hence
+//     MODE 0: |dropout(relu(gamma xhat + beta))| <= bound_mul * (|gamma_c| sqrt(M) + |beta_c|)
+//     MODE 1: |gz| = |gamma rstd (g - mean g - xhat mean(g xhat))| <= |gamma_c rstd_c| * gmax * (2 + sqrt(M)),
+//             gmax = *g_amax >= max |g| (from the producer of g: GEMM epilogue / rank-1 head bound)
+//   The bounds overshoot the true maximum by ~sqrt(M) / 5; the two fp16 planes keep 22 bits for every element down to
+//   2^-27 of the bound, so that costs nothing.
 template <int MODE>
-__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partials, int nblk, int N, long long M,
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partials, int nblk, int N, long long M,
                                                           const float* __restrict__ z_row0, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, float momentum,
                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                          float* __restrict__ stats, float* __restrict__ affine) {
-  // one warp per column: lane l folds partials l, l + 32, ... (fp64), then a fixed-order xor tree over the lanes
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (c >= N) return;
+                                                          float* __restrict__ stats, float* __restrict__ affine,
+                                                          const float* __restrict__ fwd_stats, float bound_mul,
+                                                          const float* __restrict__ g_amax, float* __restrict__ amax) {
+  // 32 columns x 32 partial lanes per CTA: lane (ty) folds partials ty, ty + 32, ... of column tx in fp64 - the loads of
+  // a warp are 32 consecutive columns of one partial row (one line; a warp per column made every load 32 sectors and
+  // the kernel latency-bound at ~20 us) - then a fixed-order fold over ty in shared memory.
+  __shared__ double red_a[32][33], red_b[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   double sa = 0.0, sb = 0.0;
-  for (int b = lane; b < nblk; b += 32) {
-    sa += (double)__ldg(partials + ((long long)b * 2) * N + c);
-    sb += (double)__ldg(partials + ((long long)b * 2 + 1) * N + c);
+  if (c < N) {
+#pragma unroll 4
+    for (int b = ty; b < nblk; b += 32) {
+      sa += (double)__ldg(partials + ((long long)b * 2) * N + c);
+      sb += (double)__ldg(partials + ((long long)b * 2 + 1) * N + c);
+    }
   }
+  red_a[ty][tx] = sa;
+  red_b[ty][tx] = sb;
+  __syncthreads();
+  if (ty != 0 || c >= N) return;
+  sa = 0.0;
+  sb = 0.0;
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    sa += __shfl_xor_sync(kFull, sa, off);
-    sb += __shfl_xor_sync(kFull, sb, off);
+  for (int y = 0; y < 32; ++y) {
+    sa += red_a[y][tx];
+    sb += red_b[y][tx];
   }
-  if (lane != 0) return;
   if (MODE == 0) {
     const double m = (double)M;
     const double dm = sa / m;                          // mean - k
@@ -142,9 +145,18 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
       const float unbiased = (float)(var * (m / (m > 1.0 ? m - 1.0 : 1.0)));
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
     }
+    if (amax) {
+      const float bound = bound_mul * (fabsf(ga) * sqrtf((float)M) * 1.001f + fabsf(be));
+      if (bound > 0.f && bound < 3.0e38f) atomic_max_nonneg(amax, bound);
+    }
   } else {
     stats[c] = (float)sa;
     stats[N + c] = (float)sb;
+    if (amax) {
+      const float rs = __ldg(fwd_stats + N + c), ga = gamma ? __ldg(gamma + c) : 1.f;
+      const float bound = fabsf(ga * rs) * __ldg(g_amax) * (2.f + sqrtf((float)M)) * 1.001f;
+      if (bound > 0.f && bound < 3.0e38f) atomic_max_nonneg(amax, bound);
+    }
   }
 }
 
@@ -153,11 +165,12 @@ __global__ void __launch_bounds__(256) bn_apply_planes_kernel(const float* __res
                                                               const float* __restrict__ affine, float drop_scale,
                                                               unsigned thr, unsigned long long seed, unsigned long long offset,
                                                               const unsigned long long* __restrict__ offset_dev,
-                                                              __nv_bfloat16* __restrict__ out, long long out_ld,
+                                                              uint16_t* __restrict__ out, long long out_ld,
                                                               long long plane_stride, unsigned char* __restrict__ mask,
-                                                              int ones_col) {
+                                                              int ones_col, PlaneFmt fmt) {
   Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
   if (offset_dev) offset += *offset_dev;
+  const float ps = fmt.scale();
   const int n4 = N / 4;
   const int n4o = (N + 7) / 8 * 2 + (ones_col ? 2 : 0);      // 4-column groups written per row (padding + ones column)
   const long long total = M * n4o;
@@ -181,7 +194,8 @@ __global__ void __launch_bounds__(256) bn_apply_planes_kernel(const float* __res
     } else if (ones_col && c4 * 4 == ((N + 7) & ~7)) {
       v.x = 1.f;
     }
-    bn_store_planes4(out + r * out_ld + c4 * 4, plane_stride, v);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    store_planes<4>(out + r * out_ld + c4 * 4, plane_stride, vv, fmt.format, ps);
   }
 }
 
@@ -189,8 +203,9 @@ __global__ void __launch_bounds__(256) bn_apply_planes_kernel(const float* __res
 __global__ void __launch_bounds__(256) bn_bwd_planes_kernel(const float* __restrict__ g, const float* __restrict__ z,
                                                             long long M, int N, long long ldg, long long ldz,
                                                             const float* __restrict__ stats, const float* __restrict__ sums,
-                                                            const float* __restrict__ gamma, __nv_bfloat16* __restrict__ out,
-                                                            long long out_ld, long long plane_stride) {
+                                                            const float* __restrict__ gamma, uint16_t* __restrict__ out,
+                                                            long long out_ld, long long plane_stride, PlaneFmt fmt) {
+  const float ps = fmt.scale();
   const int n4 = N / 4;
   const int n4o = (N + 7) / 8 * 2;
   const float inv_m = 1.0f / (float)M;
@@ -211,7 +226,8 @@ __global__ void __launch_bounds__(256) bn_bwd_planes_kernel(const float* __restr
       v = make_float4(RSB_BN_BWD(x), RSB_BN_BWD(y), RSB_BN_BWD(z), RSB_BN_BWD(w));
 #undef RSB_BN_BWD
     }
-    bn_store_planes4(out + r * out_ld + c4 * 4, plane_stride, v);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    store_planes<4>(out + r * out_ld + c4 * 4, plane_stride, vv, fmt.format, ps);
   }
 }
 
@@ -233,8 +249,8 @@ extern "C" RSB_API int64_t rsb_bn_workspace_bytes(int64_t M, int32_t N) {
 
 extern "C" RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t N, int64_t ldz, const float* gamma,
                                               const float* beta, float eps, float momentum, float* running_mean,
-                                              float* running_var, float* stats, float* affine, void* workspace,
-                                              int64_t workspace_bytes, void* stream) {
+                                              float* running_var, float* stats, float* affine, float bound_mul,
+                                              float* act_amax, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!z || !stats || !affine || M <= 0 || N <= 0) return RSB_ERR_BAD_ARG;
   if (N % 4 || ldz % 4 || !aligned16(z) || !aligned16(stats) || !aligned16(affine) || (gamma && !aligned16(gamma)) ||
       (beta && !aligned16(beta)))
@@ -245,8 +261,8 @@ extern "C" RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t
   const int nblk = bn_blocks(M);
   bn_slab_sums_kernel<0><<<nblk, kBnThreads, 0, st>>>(z, nullptr, M, N, ldz, 0, nullptr, nullptr, partials);
   RSB_CHECK_LAUNCH();
-  bn_finalize_kernel<0><<<(N + 7) / 8, 256, 0, st>>>(partials, nblk, N, M, z, gamma, beta, eps, momentum, running_mean,
-                                                         running_var, stats, affine);
+  bn_finalize_kernel<0><<<(N + 31) / 32, 1024, 0, st>>>(partials, nblk, N, M, z, gamma, beta, eps, momentum, running_mean,
+                                                     running_var, stats, affine, nullptr, bound_mul, nullptr, act_amax);
   RSB_CHECK_LAUNCH();
   note_launch(2);
   return RSB_OK;
@@ -255,8 +271,8 @@ extern "C" RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t
 extern "C" RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int32_t N, int64_t ldz, const float* affine, float p,
                                                   uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int32_t ones_col,
                                                   void* out_planes, int64_t out_ld, int64_t plane_stride, uint8_t* mask,
-                                                  void* stream) {
-  if (!z || !affine || !out_planes || !mask || M < 0 || N <= 0 || p < 0.f || p >= 1.f) return RSB_ERR_BAD_ARG;
+                                                  const rsb_planes_format* fmt, void* stream) {
+  if (!z || !affine || !out_planes || !mask || M < 0 || N <= 0 || p < 0.f || p >= 1.f || !plane_fmt_ok(fmt)) return RSB_ERR_BAD_ARG;
   if (M == 0) return RSB_OK;
   if (N % 4 || ldz % 4 || out_ld % 8 || plane_stride % 8 || out_ld < ((N + 7) / 8) * 8 + (ones_col ? 8 : 0) || !aligned16(z) ||
       !aligned16(affine) || !aligned16(out_planes) || (reinterpret_cast<uintptr_t>(mask) & 3u))
@@ -267,8 +283,8 @@ extern "C" RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int
   if (blocks > cap) blocks = cap;
   bn_apply_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       z, M, N, ldz, affine, 1.0f / (1.0f - p), (unsigned)(p * 4294967296.0), seed, offset,
-      reinterpret_cast<const unsigned long long*>(offset_dev), reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride,
-      mask, ones_col);
+      reinterpret_cast<const unsigned long long*>(offset_dev), reinterpret_cast<uint16_t*>(out_planes), out_ld, plane_stride,
+      mask, ones_col, plane_fmt(fmt));
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;
@@ -276,9 +292,10 @@ extern "C" RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int
 
 extern "C" RSB_API int rsb_bn_train_bwd_planes(const float* g, const float* z, int64_t M, int32_t N, int64_t ldg, int64_t ldz,
                                                const float* stats, const float* gamma, float* sums, void* out_planes,
-                                               int64_t out_ld, int64_t plane_stride, void* workspace, int64_t workspace_bytes,
-                                               void* stream) {
-  if (!g || !z || !stats || !sums || !out_planes || M <= 0 || N <= 0) return RSB_ERR_BAD_ARG;
+                                               int64_t out_ld, int64_t plane_stride, const rsb_planes_format* fmt,
+                                               const float* g_amax, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!g || !z || !stats || !sums || !out_planes || M <= 0 || N <= 0 || !plane_fmt_ok(fmt)) return RSB_ERR_BAD_ARG;
+  if (fmt && fmt->format == kPlanesFp16x2 && !g_amax) return RSB_ERR_BAD_ARG;
   if (N % 4 || ldg % 4 || ldz % 4 || out_ld % 8 || plane_stride % 8 || out_ld < ((N + 7) / 8) * 8 || !aligned16(g) ||
       !aligned16(z) || !aligned16(stats) || !aligned16(sums) || !aligned16(out_planes) || (gamma && !aligned16(gamma)))
     return RSB_ERR_UNSUPPORTED;
@@ -286,17 +303,19 @@ extern "C" RSB_API int rsb_bn_train_bwd_planes(const float* g, const float* z, i
   float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nblk = bn_blocks(M);
+  const bool h = fmt && fmt->format == kPlanesFp16x2;
   bn_slab_sums_kernel<1><<<nblk, kBnThreads, 0, st>>>(z, g, M, N, ldz, ldg, stats, stats + N, partials);
   RSB_CHECK_LAUNCH();
-  bn_finalize_kernel<1><<<(N + 7) / 8, 256, 0, st>>>(partials, nblk, N, M, nullptr, nullptr, nullptr, 0.f, 0.f, nullptr,
-                                                         nullptr, sums, nullptr);
+  bn_finalize_kernel<1><<<(N + 31) / 32, 1024, 0, st>>>(partials, nblk, N, M, nullptr, gamma, nullptr, 0.f, 0.f, nullptr, nullptr,
+                                                     sums, nullptr, stats, 1.f, h ? g_amax : nullptr, h ? fmt->amax : nullptr);
   RSB_CHECK_LAUNCH();
   const long long total = M * ((N + 7) / 8 * 2);
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
   bn_bwd_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, z, M, N, ldg, ldz, stats, sums, gamma,
-                                                         reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride);
+                                                         reinterpret_cast<uint16_t*>(out_planes), out_ld, plane_stride,
+                                                         plane_fmt(fmt));
   RSB_CHECK_LAUNCH();
   note_launch(3);
   return RSB_OK;

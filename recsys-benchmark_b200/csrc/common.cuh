@@ -1,7 +1,12 @@
 // Shared device helpers for librsb (sm_100a).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "rsb.h"
 
@@ -58,6 +63,95 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+
+// ---- operand formats of the tensor-core GEMM (gemm/planes_gemm.cu) ----
+// BF16X3: x = x0 + x1 + x2, three bf16 planes (3 x 8 mantissa bits: every fp32 value exactly), 6 plane products.
+// FP16X2: x * s = h0 + h1, two fp16 planes (2 x 11 bits) of the matrix scaled by a power of two s chosen from a bound
+//         `amax` >= max |x| so that amax * s lies in [2^13, 2^14): the big elements keep 22 bits, every element is
+//         exact to 2^-25 / s (the fp16 subnormal step), i.e. to 2^-38 of the bound; 3 plane products (h1 * h1' <=
+//         2^-22 |a||b| is dropped).  Writer and reader derive s from the same device scalar with plane_scale().
+constexpr int kPlanesBf16x3 = 0, kPlanesFp16x2 = 1;
+constexpr int kPlaneTopExp = 14;
+__host__ __device__ __forceinline__ float plane_scale(float amax, int max_exp) {
+  if (!(amax > 0.f) || amax > 3.0e38f) return 1.f;      // empty / all-zero / non-finite: unscaled
+  int e;
+  frexpf(amax, &e);                                     // amax in [2^(e-1), 2^e)
+  int se = kPlaneTopExp - e;
+  if (se > max_exp) se = max_exp;
+  if (se < -100) se = -100;
+  return ldexpf(1.f, se);
+}
+// non-negative floats order like their bit patterns: a max over a grid is one integer atomic per warp
+__device__ __forceinline__ void atomic_max_nonneg(float* slot, float v) {
+  atomicMax(reinterpret_cast<unsigned*>(slot), __float_as_uint(v));
+}
+
+__device__ __forceinline__ void split3_bf16(float x, __nv_bfloat16& h0, __nv_bfloat16& h1, __nv_bfloat16& h2) {
+  h0 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h0);            // exact in fp32
+  h1 = __float2bfloat16_rn(r1);
+  h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));  // exact
+}
+__device__ __forceinline__ void split2_fp16(float xs, __half& h0, __half& h1) {
+  h0 = __float2half_rn(xs);
+  h1 = __float2half_rn(xs - __half2float(h0));          // the remainder is exact in fp32
+}
+// N (4 or 8) consecutive values of one row -> one 8- or 16-byte store per plane.  `dst` points at plane 0 (16-bit
+// elements of either format), `s` is the FP16X2 scale (ignored for BF16X3).  The 16-bit results are packed into 32-bit
+// words by hand (no local arrays the compiler might leave in local memory).
+template <int N>
+__device__ __forceinline__ void store_planes(void* dst, long long plane_stride, const float* v, int format, float s) {
+  static_assert(N == 4 || N == 8, "4 or 8 values");
+  uint32_t w0[N / 2], w1[N / 2], w2[N / 2];
+  uint16_t* o = reinterpret_cast<uint16_t*>(dst);
+  if (format == kPlanesFp16x2) {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      __half a0, a1, b0, b1;
+      split2_fp16(v[j] * s, a0, a1);
+      split2_fp16(v[j + 1] * s, b0, b1);
+      w0[j / 2] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(b0) << 16);
+      w1[j / 2] = (uint32_t)__half_as_ushort(a1) | ((uint32_t)__half_as_ushort(b1) << 16);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      __nv_bfloat16 a0, a1, a2, b0, b1, b2;
+      split3_bf16(v[j], a0, a1, a2);
+      split3_bf16(v[j + 1], b0, b1, b2);
+      w0[j / 2] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+      w1[j / 2] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+      w2[j / 2] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+    }
+  }
+  if constexpr (N == 8) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+    *reinterpret_cast<uint4*>(o + plane_stride) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+    if (format != kPlanesFp16x2) *reinterpret_cast<uint4*>(o + 2 * plane_stride) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+  } else {
+    *reinterpret_cast<uint2*>(o) = make_uint2(w0[0], w0[1]);
+    *reinterpret_cast<uint2*>(o + plane_stride) = make_uint2(w1[0], w1[1]);
+    if (format != kPlanesFp16x2) *reinterpret_cast<uint2*>(o + 2 * plane_stride) = make_uint2(w2[0], w2[1]);
+  }
+}
+struct PlaneFmt {
+  int format;            // kPlanesBf16x3 / kPlanesFp16x2
+  int max_exp;           // FP16X2: the scale is at most 2^max_exp
+  const float* amax;     // FP16X2: device scalar, bound on |x|
+  __device__ __forceinline__ float scale() const {
+    return format == kPlanesFp16x2 ? plane_scale(amax ? *amax : 0.f, max_exp) : 1.f;
+  }
+};
+inline PlaneFmt plane_fmt(const rsb_planes_format* f) {
+  PlaneFmt r;
+  r.format = f ? f->format : kPlanesBf16x3;
+  r.max_exp = f ? f->max_scale_exp : 0;
+  r.amax = f ? f->amax : nullptr;
+  return r;
+}
+inline bool plane_fmt_ok(const rsb_planes_format* f) {
+  return !f || f->format == kPlanesBf16x3 || (f->format == kPlanesFp16x2 && f->amax != nullptr);
+}
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -60,6 +60,8 @@ struct Params {
   long long* dbg;        // RSB_GEMM_DEBUG: per-CTA cycle counters (development aid)
   int tma_store;         // fp32 epilogue through shared memory + TMA stores (map_d); 0: direct stores
   uint32_t epi_offset;   // byte offset of the epilogue staging buffers in dynamic shared memory
+  int np;                // planes per operand: 3 (bf16) or 2 (fp16, scaled)
+  rsb::PlaneFmt fmt_a, fmt_b;              // FP16X2: the operands hold A * sa, B * sb; the epilogue divides by sa * sb
   uint32_t a_stage_bytes, b_stage_bytes;   // shared-memory footprint of one stage in one CTA
   uint32_t tx_bytes;                       // bytes the TMA loads of one CTA deliver per stage
   Operand a, b;
@@ -77,24 +79,12 @@ struct Params {
   int ones_col;
   unsigned char* mask;
   float drop_scale;
+  float* d_amax;         // fp32 outputs: *d_amax is raised to max |D| (the bound an FP16X2 consumer of D needs)
 };
 
-// x -> (bf16(x), bf16(x - x0), bf16(x - x0 - x1)); both remainders are exact in fp32
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& h0, __nv_bfloat16& h1, __nv_bfloat16& h2) {
-  h0 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(h0);
-  h1 = __float2bfloat16_rn(r1);
-  h2 = __float2bfloat16_rn(r1 - __bfloat162float(h1));
-}
-
-// 8 consecutive values of one row -> three 16-byte plane stores
+// 8 consecutive values of one row -> three 16-byte bf16 plane stores (the fused plane epilogues write BF16X3)
 __device__ __forceinline__ void store_planes8(__nv_bfloat16* dst, long long plane_stride, const float* v) {
-  __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) split3(v[j], p0[j], p1[j], p2[j]);
-  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(p0);
-  *reinterpret_cast<uint4*>(dst + plane_stride) = *reinterpret_cast<const uint4*>(p1);
-  *reinterpret_cast<uint4*>(dst + 2 * plane_stride) = *reinterpret_cast<const uint4*>(p2);
+  rsb::store_planes<8>(dst, plane_stride, v, rsb::kPlanesBf16x3, 1.f);
 }
 
 // ------------------------------------------------------------------------------------------- PTX wrappers ---
@@ -382,7 +372,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           } else {
 #pragma unroll 1
             for (int j = 0; j < kBlockM / 64; ++j)
-              tma_load_3d_to<TWO>(&map_a, bar, sa + j * (3 * kBlockK * 128), m0 + j * 64 + t.batch * p.a.batch_col_step,
+              tma_load_3d_to<TWO>(&map_a, bar, sa + j * (p.np * kBlockK * 128), m0 + j * 64 + t.batch * p.a.batch_col_step,
                                   k0 + t.batch * p.a.batch_row_step, 0);
           }
           if (!p.b.mn_major) {
@@ -390,7 +380,7 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           } else {
 #pragma unroll 1
             for (int j = 0; j < (kBRows + 63) / 64; ++j)
-              tma_load_3d_to<TWO>(&map_b, bar, sb + j * (3 * kBlockK * 128), n0 + j * 64 + t.batch * p.b.batch_col_step,
+              tma_load_3d_to<TWO>(&map_b, bar, sb + j * (p.np * kBlockK * 128), n0 + j * 64 + t.batch * p.b.batch_col_step,
                                   k0 + t.batch * p.b.batch_row_step, 0);
           }
           if (++stage == p.stages) {
@@ -403,8 +393,11 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else if (warp == 1) {
     // ================================ MMA issuer (one lane of the leader CTA) ================================
     if (lane == 0 && leader) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a.mn_major << 15) | ((uint32_t)p.b.mn_major << 16) |
-                             ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      // kind::f16 instruction descriptor: D fp32 (bit 4), A / B format at bits 7 / 10 (1 = bf16, 0 = fp16), majorness,
+      // N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t ab_fmt = p.np == 3 ? 1u : 0u;
+      const uint32_t idesc = (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)p.a.mn_major << 15) |
+                             ((uint32_t)p.b.mn_major << 16) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       // plane strides / descriptor geometry inside a stage
       const uint32_t a_plane = p.a.mn_major ? kBlockK * 128 : kBlockM * 64;
       const uint32_t b_plane = p.b.mn_major ? kBlockK * 128 : kBRows * 64;
@@ -435,9 +428,9 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           uint64_t da[3], db[3];
 #pragma unroll
           for (int pl = 0; pl < 3; ++pl) {
-            da[pl] = p.a.mn_major ? make_desc(sa + pl * a_plane, 3 * kBlockK * 128, 1024, kSwizzle128)
+            da[pl] = p.a.mn_major ? make_desc(sa + pl * a_plane, p.np * kBlockK * 128, 1024, kSwizzle128)
                                   : make_desc(sa + pl * a_plane, 16, 512, kSwizzle64);
-            db[pl] = p.b.mn_major ? make_desc(sb + pl * b_plane, 3 * kBlockK * 128, 1024, kSwizzle128)
+            db[pl] = p.b.mn_major ? make_desc(sb + pl * b_plane, p.np * kBlockK * 128, 1024, kSwizzle128)
                                   : make_desc(sb + pl * b_plane, 16, 512, kSwizzle64);
           }
           // smallest band first; the first MMA of the group overwrites the (drained) accumulator
@@ -447,9 +440,14 @@ planes_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     mma_bf16_g<TWO>(d_tmem, da[PA] + (uint64_t)((ks * a_kstep) >> 4), db[PB] + (uint64_t)((ks * b_kstep) >> 4), idesc, acc); \
     acc = 1;                                                                                                          \
   }
-          PG_MMA(0, 2) PG_MMA(1, 1) PG_MMA(2, 0)   // band 3
-          PG_MMA(0, 1) PG_MMA(1, 0)                // band 2
-          PG_MMA(0, 0)                             // band 1
+          if (p.np == 3) {
+            PG_MMA(0, 2) PG_MMA(1, 1) PG_MMA(2, 0)   // band 3
+            PG_MMA(0, 1) PG_MMA(1, 0)                // band 2
+            PG_MMA(0, 0)                             // band 1
+          } else {
+            PG_MMA(0, 1) PG_MMA(1, 0)                // fp16 planes: h0 h1', h1 h0' (2^-11), then h0 h0'
+            PG_MMA(0, 0)
+          }
 #undef PG_MMA
           mma_commit_g<TWO>(&empty_bar[stage]);    // smem stage reusable once these MMAs have read it
           if (group_end) {
@@ -487,6 +485,8 @@ epilogue_role:
     int buf = 0;
     uint32_t tphase[2] = {0, 0};
     uint32_t box_seq = 0;          // TMA-store boxes issued by this warp so far (selects the staging buffer)
+    // FP16X2 operands hold A * sa and B * sb (powers of two): undo both with the caller's alpha
+    const float alpha = p.alpha / (p.fmt_a.scale() * p.fmt_b.scale());
     Tile t;
     for (int idx = unit0; get_tile(p, idx, t); idx += units) {
       float acc[NC];
@@ -540,6 +540,7 @@ epilogue_role:
         const int row0 = t.m_blk * kTileM + (int)cta_rank * kBlockM + q * 32;
         const unsigned char* mrow = (p.epi_mode == RSB_EPI_MASK_F32 && row < p.M) ? p.mask + row * (long long)p.N : nullptr;
         const uint32_t sw = (uint32_t)(lane >> 1) & 3u;
+        float omax = 0.f;
 #pragma unroll
         for (int c = 0; c < NC; c += 16) {
           if (c < ncols && n0 + c < p.N) {
@@ -553,8 +554,8 @@ epilogue_role:
             if (wide_mask) m16 = *reinterpret_cast<const uint4*>(mrow + n0 + c);
 #pragma unroll
             for (int h = 0; h < 16; h += 4) {
-              float4 o = make_float4(acc[c + h] * p.alpha, acc[c + h + 1] * p.alpha, acc[c + h + 2] * p.alpha,
-                                     acc[c + h + 3] * p.alpha);
+              float4 o = make_float4(acc[c + h] * alpha, acc[c + h + 1] * alpha, acc[c + h + 2] * alpha,
+                                     acc[c + h + 3] * alpha);
               if (n0 + c + h < p.N) {
                 if (p.bias) {
                   const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + h));
@@ -571,6 +572,7 @@ epilogue_role:
                   o.x = m.x ? o.x * p.drop_scale : 0.f; o.y = m.y ? o.y * p.drop_scale : 0.f;
                   o.z = m.z ? o.z * p.drop_scale : 0.f; o.w = m.w ? o.w * p.drop_scale : 0.f;
                 }
+                omax = fmaxf(fmaxf(omax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
               }
               *reinterpret_cast<float4*>(buf + lane * 64 + ((((uint32_t)h >> 2) ^ sw) << 4)) = o;
             }
@@ -581,6 +583,11 @@ epilogue_role:
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
+        }
+        if (p.d_amax) {                      // one atomic per warp and tile (rows past M hold alpha * 0 + bias: harmless)
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) omax = fmaxf(omax, __shfl_xor_sync(0xffffffffu, omax, off));
+          if (lane == 0 && omax > 0.f && omax < 3.0e38f) rsb::atomic_max_nonneg(p.d_amax, omax);
         }
       } else if (row < p.M) {
         if (p.partial != nullptr) {
@@ -594,10 +601,11 @@ epilogue_role:
           float* dst = p.D + (long long)t.batch * p.d_batch_stride + row * p.ldd;
           const float* csrc = p.C ? p.C + (long long)t.batch * p.d_batch_stride + row * p.ldd : nullptr;
           const unsigned char* mrow = p.epi_mode == RSB_EPI_MASK_F32 ? p.mask + row * (long long)p.N : nullptr;
+          float omax = 0.f;
 #pragma unroll
           for (int c = 0; c < NC; c += 4) {
             if (c < ncols && n0 + c < p.N) {
-              float4 o = make_float4(acc[c] * p.alpha, acc[c + 1] * p.alpha, acc[c + 2] * p.alpha, acc[c + 3] * p.alpha);
+              float4 o = make_float4(acc[c] * alpha, acc[c + 1] * alpha, acc[c + 2] * alpha, acc[c + 3] * alpha);
               if (csrc) {
                 const float4 cc = *reinterpret_cast<const float4*>(csrc + n0 + c);
                 o.x = fmaf(p.beta, cc.x, o.x); o.y = fmaf(p.beta, cc.y, o.y);
@@ -612,9 +620,11 @@ epilogue_role:
                 o.x = m.x ? o.x * p.drop_scale : 0.f; o.y = m.y ? o.y * p.drop_scale : 0.f;
                 o.z = m.z ? o.z * p.drop_scale : 0.f; o.w = m.w ? o.w * p.drop_scale : 0.f;
               }
+              omax = fmaxf(fmaxf(omax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
               *reinterpret_cast<float4*>(dst + n0 + c) = o;
             }
           }
+          if (p.d_amax && omax > 0.f && omax < 3.0e38f) rsb::atomic_max_nonneg(p.d_amax, omax);   // (rows diverge here: per thread)
         } else {
           // RSB_EPI_RELU_DROPOUT_PLANES: y = dropout(relu(acc + bias)) -> planes; `mask` holds the dropout keep bits on
           //                              entry (rsb_dropout_keep_mask: the Philox draw is NOT part of this exposed
@@ -630,8 +640,8 @@ epilogue_role:
 #pragma unroll
               for (int h = 0; h < 8; h += 4) {
                 const bool valid = n0 + c + h < p.N;      // N is a multiple of 4, not necessarily of 8
-                float4 o = make_float4(acc[c + h] * p.alpha, acc[c + h + 1] * p.alpha, acc[c + h + 2] * p.alpha,
-                                       acc[c + h + 3] * p.alpha);
+                float4 o = make_float4(acc[c + h] * alpha, acc[c + h + 1] * alpha, acc[c + h + 2] * alpha,
+                                       acc[c + h + 3] * alpha);
                 uchar4 m = make_uchar4(0, 0, 0, 0);
                 if (valid) {
                   m = *reinterpret_cast<const uchar4*>(mrow + n0 + c + h);
@@ -676,7 +686,9 @@ teardown:
 // split-K: D = alpha * sum_s partial[s] + beta * C + bias, fixed summation order
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long batch, long long M, long long N,
                                      float* __restrict__ D, long long ldd, long long d_batch_stride,
-                                     const float* __restrict__ C, const float* __restrict__ bias, float alpha, float beta) {
+                                     const float* __restrict__ C, const float* __restrict__ bias, float alpha, float beta,
+                                     rsb::PlaneFmt fmt_a, rsb::PlaneFmt fmt_b) {
+  alpha /= fmt_a.scale() * fmt_b.scale();
   const long long n4 = N / 4, total = batch * M * n4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long c4 = i % n4, r = (i / n4) % M, l = i / (n4 * M);
@@ -703,8 +715,9 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 // fp32 [rows, cols] (ld) -> three bf16 planes [3][rows][out_ld]; columns >= cols (up to out_ld) are zero-filled.
 // transpose = 1: out plane [cols][out_ld >= rows] = in^T (small matrices: nn.Linear weights for the dX GEMM).
 __global__ void split_planes_kernel(const float* __restrict__ in, long long rows, long long cols, long long ld,
-                                    __nv_bfloat16* __restrict__ out, long long out_ld, long long plane_stride, int transpose,
-                                    int ones_col) {
+                                    uint16_t* __restrict__ out, long long out_ld, long long plane_stride, int transpose,
+                                    int ones_col, rsb::PlaneFmt fmt) {
+  const float ps = fmt.scale();
   const long long orows = transpose ? cols : rows, ocols8 = out_ld / 8;
   const long long ones_at = ones_col ? (((transpose ? rows : cols) + 7) & ~7ll) : -1;   // first column after the padded data
   const long long total = orows * ocols8;
@@ -724,19 +737,51 @@ __global__ void split_planes_kernel(const float* __restrict__ in, long long rows
       }
       if (c0 == ones_at) x[0] = 1.f;
     }
-    __align__(16) __nv_bfloat16 p0[8], p1[8], p2[8];
+    rsb::store_planes<8>(out + r * out_ld + c0, plane_stride, x, fmt.format, ps);
+  }
+}
+
+// *amax = max(*amax, max |in|) over a [rows, cols] (ld) fp32 matrix: the bound of an FP16X2 split (common.cuh).
+// Contiguous 16-byte-aligned matrices are read as one flat float4 stream, four loads in flight per thread.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ in, long long rows, long long cols, long long ld,
+                                                     float* __restrict__ amax) {
+  float m = 0.f;
+  const bool al = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  const long long stride = (long long)gridDim.x * blockDim.x, tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (al && ld == cols && ((rows * cols) & 3) == 0) {
+    const float4* q = reinterpret_cast<const float4*>(in);
+    const long long total = rows * cols / 4;
+    for (long long i = tid; i < total; i += 4 * stride) {
+      float4 v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(x[j]);
-      const float r1 = x[j] - __bfloat162float(h0);            // exact in fp32
-      const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
-      const float r2 = r1 - __bfloat162float(h1);              // exact
-      p0[j] = h0; p1[j] = h1; p2[j] = __float2bfloat16_rn(r2);
+      for (int u = 0; u < 4; ++u) v[u] = (i + u * stride < total) ? __ldg(q + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
     }
-    __nv_bfloat16* o = out + r * out_ld + c0;
-    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(p0);
-    *reinterpret_cast<uint4*>(o + plane_stride) = *reinterpret_cast<const uint4*>(p1);
-    *reinterpret_cast<uint4*>(o + 2 * plane_stride) = *reinterpret_cast<const uint4*>(p2);
+  } else if (al && (cols & 3) == 0 && (ld & 3) == 0) {
+    const long long c4n = cols / 4, total = rows * c4n;
+    for (long long i = tid; i < total; i += stride) {
+      const long long r = i / c4n, c4 = i - r * c4n;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(in + r * ld) + c4);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    const long long total = rows * cols;
+    for (long long i = tid; i < total; i += stride) {
+      const long long r = i / cols, c = i - r * cols;
+      m = fmaxf(m, fabsf(__ldg(in + r * ld + c)));
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, wm[w]);
+    if (m > 0.f && m < 3.0e38f) rsb::atomic_max_nonneg(amax, m);
   }
 }
 
@@ -832,15 +877,16 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 static bool encode_map(CUtensorMap* map, const void* base, long long cols, long long rows, long long ld, long long plane_stride,
-                       int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+                       int box_cols, int box_rows, CUtensorMapSwizzle swz, int np) {
   // dims (innermost first): columns, rows, planes
-  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 3};
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)np};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 3};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)np};
   cuuint32_t estr[3] = {1, 1, 1};
   EncodeTiledFn encode = encode_tiled_fn();
   if (encode == nullptr) return false;
-  CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult rc = encode(map, np == 3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base),
+                       dims, strides, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return rc == CUDA_SUCCESS;
@@ -912,9 +958,56 @@ extern "C" RSB_API int64_t rsb_gemm_planes_workspace_bytes(int64_t M, int64_t N,
   return s > 1 ? (int64_t)s * batch * M * N * 4 + 256 : 256;
 }
 
+// *amax_out = max(*amax_out, mul * max |g| * max |w|): bound on the rank-1 head gradient g[r] * w[c] * mask / (1 - p)
+__global__ void __launch_bounds__(1024) rank1_bound_kernel(const float* __restrict__ g, long long m, const float* __restrict__ w,
+                                                           long long n, float mul, float* __restrict__ amax) {
+  float mg = 0.f, mw = 0.f;
+  for (long long i = threadIdx.x; i < m; i += blockDim.x) mg = fmaxf(mg, fabsf(__ldg(g + i)));
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) mw = fmaxf(mw, fabsf(__ldg(w + i)));
+  __shared__ float sg[32], sw[32];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+    mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+  }
+  if ((threadIdx.x & 31) == 0) { sg[threadIdx.x >> 5] = mg; sw[threadIdx.x >> 5] = mw; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { mg = fmaxf(mg, sg[i]); mw = fmaxf(mw, sw[i]); }
+    const float b = mg * mw * mul;
+    if (b > 0.f && b < 3.0e38f) rsb::atomic_max_nonneg(amax, b);
+  }
+}
+
+extern "C" RSB_API int rsb_rank1_absmax(const float* g_row, int64_t M, const float* w_col, int64_t N, float mul, float* amax_out,
+                                        void* stream) {
+  if (!g_row || !w_col || !amax_out || M < 0 || N < 0) return RSB_ERR_BAD_ARG;
+  if (M == 0 || N == 0) return RSB_OK;
+  rank1_bound_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g_row, M, w_col, N, mul, amax_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  return RSB_OK;
+}
+
+extern "C" RSB_API int rsb_absmax(const float* in, int64_t rows, int64_t cols, int64_t ld, float* amax_out, void* stream) {
+  if (!in || !amax_out || rows < 0 || cols < 0 || ld < cols) return RSB_ERR_BAD_ARG;
+  if (rows == 0 || cols == 0) return RSB_OK;
+  long long blocks = (rows * cols / 16 + 255) / 256;
+  const long long cap = (long long)rsb::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, rows, cols, ld, amax_out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  rsb::note_launch(1);
+  return RSB_OK;
+}
+
 extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t cols, int64_t ld, int32_t transpose, int32_t ones_col,
-                                        void* out_planes, int64_t out_ld, int64_t plane_stride, void* stream) {
-  if (!in || !out_planes || rows <= 0 || cols <= 0 || ld < (transpose ? cols : cols)) return RSB_ERR_BAD_ARG;
+                                        void* out_planes, int64_t out_ld, int64_t plane_stride, const rsb_planes_format* fmt,
+                                        void* stream) {
+  if (!in || !out_planes || rows <= 0 || cols <= 0 || ld < (transpose ? cols : cols) || !rsb::plane_fmt_ok(fmt)) return RSB_ERR_BAD_ARG;
   const int64_t ocols = transpose ? rows : cols, orows = transpose ? cols : rows;
   if (out_ld % 8 || out_ld < ocols + (ones_col ? 8 : 0) || plane_stride < orows * out_ld || plane_stride % 8 ||
       (reinterpret_cast<uintptr_t>(out_planes) & 15))
@@ -924,7 +1017,7 @@ extern "C" RSB_API int rsb_split_planes(const float* in, int64_t rows, int64_t c
   const long long cap = (long long)rsb::sm_count() * 16;
   if (blocks > cap) blocks = cap;
   split_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      in, rows, cols, ld, reinterpret_cast<__nv_bfloat16*>(out_planes), out_ld, plane_stride, transpose, ones_col);
+      in, rows, cols, ld, reinterpret_cast<uint16_t*>(out_planes), out_ld, plane_stride, transpose, ones_col, rsb::plane_fmt(fmt));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   rsb::note_launch(1);
@@ -998,6 +1091,9 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   const bool to_planes = mode == RSB_EPI_RELU_DROPOUT_PLANES || mode == RSB_EPI_MASK_PLANES;
   if (!A || !B || !A->planes || !B->planes || (!D && !to_planes) || M <= 0 || N <= 0 || K <= 0 || batch <= 0) return RSB_ERR_BAD_ARG;
   if (mode < RSB_EPI_LINEAR || mode > RSB_EPI_MASK_F32) return RSB_ERR_BAD_ARG;
+  if (A->fmt.format != B->fmt.format || !rsb::plane_fmt_ok(&A->fmt) || !rsb::plane_fmt_ok(&B->fmt)) return RSB_ERR_BAD_ARG;
+  if (epi && epi->d_amax && (to_planes || split_k > 1)) return RSB_ERR_UNSUPPORTED;   // max |D| is formed by the fp32 epilogue
+  if (epi && epi->d_amax) split_k = 1;
   if (mode != RSB_EPI_LINEAR) {
     // fused epilogues: one un-batched, un-split GEMM whose output feeds the next GEMM
     if (batch != 1 || beta != 0.f || !epi->mask || epi->p < 0.f || epi->p >= 1.f) return RSB_ERR_BAD_ARG;
@@ -1035,9 +1131,13 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   if (p.splits > p.k_blocks) p.splits = p.k_blocks;
   p.a.mn_major = A->mn_major; p.a.batch_row_step = (int)A->batch_row_step; p.a.batch_col_step = (int)A->batch_col_step;
   p.b.mn_major = B->mn_major; p.b.batch_row_step = (int)B->batch_row_step; p.b.batch_col_step = (int)B->batch_col_step;
-  p.a_stage_bytes = 3u * kBlockM * kBlockK * 2;                                           // both majors: 24 KiB
+  p.np = A->fmt.format == RSB_PLANES_FP16X2 ? 2 : 3;
+  p.fmt_a = rsb::plane_fmt(&A->fmt);
+  p.fmt_b = rsb::plane_fmt(&B->fmt);
+  const uint32_t np = (uint32_t)p.np;
+  p.a_stage_bytes = np * kBlockM * kBlockK * 2;                                           // both majors: 8 KiB per plane
   const int b_rows = two ? p.n_tile / 2 : p.n_tile;                                       // staged by one CTA
-  p.b_stage_bytes = B->mn_major ? (uint32_t)((b_rows + 63) / 64) * 3u * kBlockK * 128 : 3u * b_rows * kBlockK * 2;
+  p.b_stage_bytes = B->mn_major ? (uint32_t)((b_rows + 63) / 64) * np * kBlockK * 128 : np * b_rows * kBlockK * 2;
   p.tx_bytes = p.a_stage_bytes + p.b_stage_bytes;
   p.b_stage_bytes = (p.b_stage_bytes + 1023u) & ~1023u;                                   // keep every stage 1 KiB aligned
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
@@ -1046,7 +1146,13 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   if (p.stages < 2) return RSB_ERR_UNSUPPORTED;
   {
     static const int drain = [] { const char* v = getenv("RSB_GEMM_DRAIN"); int d = v ? atoi(v) : 1; return d < 1 ? 1 : d; }();
-    p.drain = drain;
+    // FP16X2 issues 3 MMAs per 16 k instead of 6, so the TMEM reads of the drain (64 B/clk: 1664 clk per 128 x 208 tile)
+    // weigh twice as much against the MMA time: two K groups (64 k) per drain.  Measured on 65536 x 400 x 624, error vs
+    // fp64 / time: 1 group 2.2e-7 / 0.163 ms, 2: 3.0e-7 / 0.150, 3: 4.3e-7 / 0.137, 4: 5.5e-7 / 0.135 (cuBLAS fp32 SGEMM,
+    // what the reference runs, errs 1.2e-6 on the same data); with 3 the DCN-Mix parity test sees more Adam sign flips of
+    // rounding-level gradients than it allows, so 2 it is.
+    static const int drain16 = [] { const char* v = getenv("RSB_GEMM_DRAIN_FP16"); int d = v ? atoi(v) : 2; return d < 1 ? 1 : d; }();
+    p.drain = p.np == 2 ? drain16 : drain;
     static const int prefetch = [] { const char* v = getenv("RSB_GEMM_PREFETCH"); int d = v ? atoi(v) : 0; return d < 0 ? 0 : d; }();
     p.prefetch = prefetch;
   }
@@ -1065,6 +1171,7 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
     p.out_ld = epi->out_ld; p.out_plane_stride = epi->out_plane_stride; p.ones_col = epi->ones_col;
     p.mask = epi->mask;
     p.drop_scale = 1.0f / (1.0f - epi->p);
+    p.d_amax = epi->d_amax;
   }
   p.D = D; p.ldd = ldd; p.d_batch_stride = d_batch_stride; p.C = C; p.bias = bias; p.alpha = alpha; p.beta = beta;
   if (p.splits > 1) {
@@ -1073,10 +1180,10 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
     p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
   }
   CUtensorMap ma, mb;
-  bool ok = A->mn_major ? encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
-                        : encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B);
-  ok = ok && (B->mn_major ? encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B)
-                          : encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, kBlockK, b_rows, CU_TENSOR_MAP_SWIZZLE_64B));
+  bool ok = A->mn_major ? encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B, p.np)
+                        : encode_map(&ma, A->planes, A->cols, A->rows, A->ld, A->plane_stride, kBlockK, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B, p.np);
+  ok = ok && (B->mn_major ? encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, 64, kBlockK, CU_TENSOR_MAP_SWIZZLE_128B, p.np)
+                          : encode_map(&mb, B->planes, B->cols, B->rows, B->ld, B->plane_stride, kBlockK, b_rows, CU_TENSOR_MAP_SWIZZLE_64B, p.np));
   if (!ok) return RSB_ERR_UNSUPPORTED;
   // fp32 results of the big un-batched, un-split GEMMs leave through shared memory + TMA stores when the staging
   // buffers (8 warps x 2 x 2 KiB) fit beside the pipeline stages
@@ -1131,7 +1238,8 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)rsb::sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, p.splits, batch, M, N, D, ldd, d_batch_stride, C, bias, alpha, beta);
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.partial, p.splits, batch, M, N, D, ldd, d_batch_stride, C, bias, alpha, beta,
+                                                           p.fmt_a, p.fmt_b);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     rsb::note_launch(1);

@@ -30,19 +30,30 @@ def gemm_supported(m: int, n: int, k: int, lda: int, ldb: int, ldd: int, trans_a
     return min(m, n, k) > 0 and n % 4 == 0 and ldd % 4 == 0
 
 
-def weight_planes(w: torch.Tensor, transpose: bool = False) -> P.Planes:
+def weight_planes(w: torch.Tensor, transpose: bool = False, fmt: int = P.BF16X3) -> P.Planes:
     """Planes of a parameter (or of its transpose), rebuilt only when the parameter has changed (in-place updates bump
     `_version`): one split per optimizer step.  The forward GEMM reads W [out, in] as the K-major operand; the dX GEMM
     reads the planes of W^T [in, out], K-major as well (the MN-major view of the same planes would also do, but its
-    shared-memory tiles are padded to 64 columns, which costs the room the TMA-store epilogue needs)."""
-    attr = "_rsb_planes_t" if transpose else "_rsb_planes"
+    shared-memory tiles are padded to 64 columns, which costs the room the TMA-store epilogue needs).
+    FP16X2: W and W^T share one max |W| scalar (one rsb_absmax per version)."""
+    attr = ("_rsb_planes_t" if transpose else "_rsb_planes") + ("_h" if fmt == P.FP16X2 else "")
     cached = getattr(w, attr, None)
     key = (w._version, w.data_ptr(), tuple(w.shape))
     if cached is not None and cached[0] == key:
         return cached[1]
-    pl = P.split(w.detach().reshape(-1, w.shape[-1]), transpose=transpose)
+    w2 = w.detach().reshape(-1, w.shape[-1])
+    amax = None
+    if fmt == P.FP16X2:
+        other = getattr(w, ("_rsb_planes_h" if transpose else "_rsb_planes_t_h"), None)
+        amax = other[1].amax if (other is not None and other[0] == key) else P.absmax(w2)
+    pl = P.split(w2, transpose=transpose, fmt=fmt, amax=amax)
     setattr(w, attr, (key, pl))
     return pl
+
+
+# Operand format of the fused training-mode dense tails (_MlpBatchNorm): FP16X2 halves the MMAs and the plane bytes;
+# set to P.BF16X3 for the exact-operand path.
+MLP_PLANES_FORMAT = P.FP16X2
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
@@ -72,15 +83,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool 
 
 
 def _fwd_gemm(xp: P.Planes, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """x W^T + b for W [out, in]: both operands K-major."""
+    """x W^T + b for W [out, in]: both operands K-major (the weight planes in the activation's format)."""
     n, k = weight.shape
-    return P.gemm(xp, weight_planes(weight), xp.rows, n, k, bias=bias, split_k=1)
+    return P.gemm(xp, weight_planes(weight, fmt=xp.fmt), xp.rows, n, k, bias=bias, split_k=1)
 
 
 def _dx_gemm(gp: P.Planes, weight: torch.Tensor) -> torch.Tensor:
     """g W for W [out, in]: B = the planes of W^T [in, out], K-major."""
     n_out, n_in = weight.shape
-    return P.gemm(gp, weight_planes(weight, transpose=True), gp.rows, n_in, n_out, split_k=1)
+    return P.gemm(gp, weight_planes(weight, transpose=True, fmt=gp.fmt), gp.rows, n_in, n_out, split_k=1)
 
 
 def _dw_gemm(gp: P.Planes, xp: P.Planes) -> torch.Tensor:
@@ -552,20 +563,26 @@ class _MlpBatchNorm(torch.autograd.Function):
         ws, bs = params[0:4 * n_layers:4], params[1:4 * n_layers:4]
         gammas, betas = params[2:4 * n_layers:4], params[3:4 * n_layers:4]
         w_out, b_out = params[-2], params[-1]
-        planes = [P.split(x, ones_col=True)]
+        fmt = MLP_PLANES_FORMAT
+        # FP16X2: one zeroed device scalar per activation whose planes are written (the bounds their scales derive from)
+        amaxs = torch.zeros(n_layers, 1, dtype=torch.float32, device=x.device) if fmt == P.FP16X2 else None
+        planes = [P.split(x, ones_col=True, fmt=fmt, amax=P.absmax(x, amaxs[0]) if amaxs is not None else None)]
         masks, zs, stats = [], [], []
         y = out = None
         for i in range(n_layers):
             z = _fwd_gemm(planes[-1], ws[i], bs[i])
             bn = bns[i]
+            act_amax = amaxs[i + 1] if (amaxs is not None and i < n_layers - 1) else None
             st, affine = P.bn_train_stats(z, gammas[i], betas[i], bn.eps, bn.momentum,
                                           bn.running_mean if bn.track_running_stats else None,
-                                          bn.running_var if bn.track_running_stats else None)
+                                          bn.running_var if bn.track_running_stats else None,
+                                          act_amax=act_amax, bound_mul=1.0 / (1.0 - ps[i]))
             if bn.track_running_stats and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
             if i < n_layers - 1:
                 seed, off = _dropout_stream(z.numel())
-                yp, mask = P.bn_relu_dropout_planes(z, affine, ps[i], seed, off, _DROPOUT_DEV_COUNTER, ones_col=True)
+                yp, mask = P.bn_relu_dropout_planes(z, affine, ps[i], seed, off, _DROPOUT_DEV_COUNTER, ones_col=True,
+                                                    fmt=fmt, amax=act_amax)
                 planes.append(yp)
             else:
                 y, mask, out = _relu_dropout_dot_fwd(z, ps[i], w_out.reshape(-1), b_out, affine)
@@ -594,16 +611,24 @@ class _MlpBatchNorm(torch.autograd.Function):
         if b_out is not None and need[5 + 4 * n_layers]:
             grads[-1] = g.sum().reshape(1)
         g_r, _ = _relu_dropout_bwd_rank1(g, w_out.reshape(-1), masks[-1], ps[-1], False)   # fp32 [M, H]
+        fmt = planes[0].fmt
+        # FP16X2: max |g_r| per layer (zeroed device scalars): the head's from its two factors, the others from the
+        # epilogue of the dX GEMM that produces them
+        g_amaxs = torch.zeros(n_layers, 1, dtype=torch.float32, device=g.device) if fmt == P.FP16X2 else None
+        if g_amaxs is not None:
+            P.rank1_absmax(g, w_out.reshape(-1), ps[-1], g_amaxs[n_layers - 1])
         gx = None
         for i in reversed(range(n_layers)):
-            gp, d_beta, d_gamma = P.bn_train_bwd_planes(g_r, zs[i], stats[i], gammas[i])
+            gp, d_beta, d_gamma = P.bn_train_bwd_planes(g_r, zs[i], stats[i], gammas[i], fmt=fmt,
+                                                        g_amax=g_amaxs[i] if g_amaxs is not None else None)
             if gammas[i] is not None and need[6 + 4 * i]:
                 grads[4 * i + 2] = d_gamma
             if betas[i] is not None and need[7 + 4 * i]:
                 grads[4 * i + 3] = d_beta
             g_prev = None
             if i > 0:
-                g_prev = P.dx_masked(gp, weight_planes(ws[i], transpose=True), masks[i - 1], ps[i - 1], to_planes=False)
+                g_prev = P.dx_masked(gp, weight_planes(ws[i], transpose=True, fmt=gp.fmt), masks[i - 1], ps[i - 1],
+                                     to_planes=False, d_amax=g_amaxs[i - 1] if g_amaxs is not None else None)
             elif need[0]:
                 gx = _dx_gemm(gp, ws[0])
             want_w, want_b = need[4 + 4 * i], bs[i] is not None and need[5 + 4 * i]

@@ -9,6 +9,7 @@ from recsys_benchmark_b200 import planes as P
 
 DEV = "cuda:0"
 torch.manual_seed(0)
+FMT = P.FP16X2 if "--fp16" in sys.argv else P.BF16X3
 
 
 def err(got, ref):
@@ -19,7 +20,7 @@ def check(m, n, k, a_mn, b_mn, split_k=0, bias=True):
     a = torch.randn((k, m) if a_mn else (m, k), device=DEV)
     b = torch.randn((k, n) if b_mn else (n, k), device=DEV)
     bi = torch.randn(n, device=DEV) if bias else None
-    pa, pb = P.split(a), P.split(b)
+    pa, pb = P.split(a, fmt=FMT), P.split(b, fmt=FMT)
     ea = err(pa.float(), a.double())
     out = P.gemm(pa, pb, m, n, k, a_mn_major=a_mn, b_mn_major=b_mn, bias=bi, split_k=split_k)
     A = a.double().t() if a_mn else a.double()
@@ -76,14 +77,14 @@ if not quick:
                                         "dW2 400x400x65536": (400, 400, 65536, True, True)}.items():
         a = torch.randn((k, m) if a_mn else (m, k), device=DEV)
         b = torch.randn((k, n) if b_mn else (n, k), device=DEV)
-        pa, pb = P.split(a), P.split(b)
+        pa, pb = P.split(a, fmt=FMT), P.split(b, fmt=FMT)
         out = torch.empty(m, n, device=DEV)
         ms = timeit(lambda: P.gemm(pa, pb, m, n, k, a_mn_major=a_mn, b_mn_major=b_mn, out=out))
-        ms_split = timeit(lambda: P.split(a))
+        ms_split = timeit(lambda: P.split(a, fmt=FMT))
         ms_cublas = timeit(lambda: torch.matmul(a.t() if a_mn else a, b if b_mn else b.t(), out=out))
         tf = 2.0 * m * n * k / ms / 1e9
         results["timing"].append(dict(name=name, ms=ms, tflops_fp32_equiv=tf, ms_split_a=ms_split, ms_cublas_fp32=ms_cublas))
         print(f"{name}: {ms:.4f} ms = {tf:.1f} TFLOP/s fp32-equivalent ({6 * tf:.0f} bf16 MMA TFLOP/s); split(A) {ms_split:.4f} ms; "
               f"cuBLAS fp32 {ms_cublas:.4f} ms", flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(results, open("gpurun_out/gemm_planes_check.json", "w"), indent=1)
+json.dump(results, open("gpurun_out/gemm_planes_check%s.json" % ("_fp16" if FMT == P.FP16X2 else ""), "w"), indent=1)

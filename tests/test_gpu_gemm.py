@@ -1,6 +1,8 @@
 """GPU tests of the fp32-accurate tensor-core GEMM (rsb_gemm_planes: hand-written tcgen05 kernel on bf16 planes)
 through the C ABI wrappers: every layout, batching, fused epilogue, and fp32-level accuracy
 (error vs an fp64 product must be of the same order as cuBLAS fp32 SGEMM's)."""
+import math
+
 import pytest
 import torch
 
@@ -39,6 +41,54 @@ def test_gemm_layouts_match_fp64(LA, m, n, k, ta, tb):
     assert out.shape == (m, n)
     assert e_ours < 2e-6, f"relative error {e_ours:.2e} (cuBLAS fp32: {e_cublas:.2e})"
     assert e_ours < max(4 * e_cublas, 5e-7)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 16), (256, 400, 624), (2048, 400, 400), (1000, 64, 352), (520, 352, 256),
+                                   (132, 12, 20), (4, 4, 4)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("mag_a,mag_b", [(1.0, 1.0), (3e-7, 0.05), (2e4, 1e-3)])
+def test_gemm_fp16x2_planes_match_fp64(LA, m, n, k, a_mn, b_mn, mag_a, mag_b):
+    """Two scaled fp16 planes per operand, 3 MMAs per product (RSB_PLANES_FP16X2): the scale comes from a device-side
+    max |x|, so tiny gradients (3e-7) and large activations (2e4) keep the same relative accuracy; the error against
+    fp64 stays at the level of an fp32 GEMM's own rounding."""
+    from recsys_benchmark_b200 import planes as P
+
+    if (a_mn and m % 8) or (b_mn and n % 8):
+        pytest.skip("MN-major operands need 8-aligned rows")
+    torch.manual_seed(m + n + k)
+    a = torch.randn((k, m) if a_mn else (m, k), device=DEV) * mag_a
+    b = torch.randn((k, n) if b_mn else (n, k), device=DEV) * mag_b
+    bias = torch.randn(n, device=DEV) * mag_a * mag_b
+    pa, pb = P.split(a, fmt=P.FP16X2), P.split(b, fmt=P.FP16X2)
+    assert pa.data.dtype == torch.float16 and pa.data.shape[0] == 2
+    # the planes represent the operand to ~2^-22 of its largest element
+    assert _err(pa.float(), a.double()) < 3e-7 and _err(pb.float(), b.double()) < 3e-7
+    assert float(pa.amax) == float(a.abs().max())
+    sa = float(pa.scale())
+    assert 2 ** 13 <= float(a.abs().max()) * sa < 2 ** 14 and sa == 2.0 ** round(math.log2(sa))
+    out = P.gemm(pa, pb, m, n, k, a_mn_major=a_mn, b_mn_major=b_mn, bias=bias)
+    A = a.double().t() if a_mn else a.double()
+    B = b.double() if b_mn else b.double().t()
+    ref = A @ B + bias.double()
+    assert _err(out, ref) < 6e-7, _err(out, ref)
+    # split-K (weight-gradient style) applies the scales in the reduction kernel
+    if a_mn and b_mn and k >= 256:
+        out2 = P.gemm(pa, pb, m, n, k, a_mn_major=True, b_mn_major=True, split_k=3)
+        assert _err(out2, A @ B) < 6e-7
+
+
+def test_fp16x2_ones_column_yields_the_bias_gradient(LA):
+    """gemm_dw over FP16X2 planes: the ones column stores the scale itself, so the extra output column is sum_r g[r, :]."""
+    from recsys_benchmark_b200 import planes as P
+
+    torch.manual_seed(1)
+    g = torch.randn(4096, 400, device=DEV) * 1e-5
+    x = torch.randn(4096, 624, device=DEV) * 0.03
+    gp, xp = P.split(g, fmt=P.FP16X2), P.split(x, ones_col=True, fmt=P.FP16X2)
+    assert xp.max_exp == P.ONES_SCALE_EXP and float(xp.scale()) <= 2.0 ** 14
+    dw, db = P.gemm_dw(gp, xp, True)
+    assert _err(dw, g.double().t() @ x.double()) < 6e-7
+    assert _err(db, g.double().sum(0)) < 6e-7
 
 
 def test_gemm_alpha_beta_c(LA):
@@ -329,13 +379,17 @@ def test_head_block_matches_unfused_path_with_the_same_masks(LA, with_bn, monkey
     assert abs(keep - 0.25) < 0.01                     # P(x > 0) * (1 - p)
 
 
+@pytest.mark.parametrize("fmt", ["bf16x3", "fp16x2"])
 @pytest.mark.parametrize("p", [0.0, 0.5])
-def test_fused_batchnorm_mlp_node_matches_torch(LA, monkeypatch, p):
+def test_fused_batchnorm_mlp_node_matches_torch(LA, monkeypatch, p, fmt):
     """[Linear -> BatchNorm1d -> ReLU -> Dropout] x 3 -> Linear(400, 1) as one autograd node (own batch statistics,
     BatchNorm + ReLU + dropout -> planes passes, BatchNorm backward -> planes) against torch's own modules in fp64
     driven with the masks the fused node drew; running statistics follow torch's update rule."""
     import copy
 
+    from recsys_benchmark_b200 import planes as P
+
+    monkeypatch.setattr(LA, "MLP_PLANES_FORMAT", P.FP16X2 if fmt == "fp16x2" else P.BF16X3)
     torch.manual_seed(0)
     mods = []
     width = 624
