@@ -114,7 +114,11 @@ RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx_is_i32, co
                    const void* aux, int32_t aux_mode, const int64_t* mask_d_idx,
                    const float* fc, const float* bias,
                    float* out_emb, float* out_yfm, float* out_sum, int64_t* out_rows,
-                   int32_t* err_flag, void* stream);
+                   int32_t* err_flag, float* amax_slots, void* stream);
+/* amax_slots (optional, NULL = off): device array of RSB_LOOKUP_AMAX_SLOTS zero-initialised floats; every warp raises
+ * one slot to the largest |out_emb| it wrote, so max(amax_slots) == max |out_emb| - the bound the dense tail's FP16X2
+ * operand split needs (rsb_absmax over the slots), without another pass over the [B, F*D] activation. */
+#define RSB_LOOKUP_AMAX_SLOTS 1024
 
 /* ------------------------------------------------------------------------
  * Backward, stage 1: per-lookup row gradients.
@@ -472,7 +476,8 @@ RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const in
                                    int32_t D, const float* const* table_shards, const float* fc_replicated,
                                    int32_t G, int64_t n_global, const float* bias, const float* hot_table,
                                    const int64_t* hot_map, float* out_emb, float* out_yfm,
-                                   float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream);
+                                   float* out_sum, int64_t* out_rows, int32_t* err_flag, float* amax_slots /* as rsb_lookup_fwd */,
+                                   void* stream);
 /* Backward: segmented reduction of this rank's sorted lookups (rsb_sort_rows on GLOBAL row
  * ids), each locally-unique row's sum * scale added into the owner's dense shard gradient
  * with one 128-bit red.global.add per 4 floats.  Rows of replicated fields (hot_map [n_fields, 3] as above, the row's

@@ -58,7 +58,7 @@ PROTOTYPES = {
     "rsb_launch_count": (_i64, []),
     "rsb_row_width_supported": (C.c_int, [_i32]),
     "rsb_lookup_fwd": (C.c_int, [_i32, _p, _i32, _p, _i64, _i32, _i32, _p, _i64, _i64, _p, _i64, _p, _i32, _p,
-                                 _p, _p, _p, _p, _p, _p, _p, _p]),
+                                 _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "rsb_lookup_bwd_rows": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i64, _p, _i64, _p, _i32, _p, _p, _p, _p, _p,
                                       _p, _p, _p, _p]),
     "rsb_fc_grad": (C.c_int, [_p, _p, _i64, _i32, _p, _p]),
@@ -113,9 +113,10 @@ PROTOTYPES = {
     "rsb_ipc_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "rsb_ipc_close_handle": (C.c_int, [_p]),
     "rsb_lookup_fwd_sharded": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p,
-                                         _p, _p, _p]),
+                                         _p, _p, _p, _p]),
     "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i32, _p, _p, _i64, _p]),
 }
+LOOKUP_AMAX_SLOTS = 1024      # RSB_LOOKUP_AMAX_SLOTS of include/rsb.h
 
 _lib: Optional[C.CDLL] = None
 

@@ -105,23 +105,29 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   // 32 columns x 32 partial lanes per CTA: lane (ty) folds partials ty, ty + 32, ... of column tx in fp64 - the loads of
   // a warp are 32 consecutive columns of one partial row (one line; a warp per column made every load 32 sectors and
   // the kernel latency-bound at ~20 us) - then a fixed-order fold over ty in shared memory.
+  // (the per-lane fold is a compensated fp32 sum - the fp64 pipe of this GPU made a plain double fold of 2 x 18 values
+  // per thread cost 10 us - and only the final 32-term fold and the mean / variance arithmetic run in fp64)
   __shared__ double red_a[32][33], red_b[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
-  double sa = 0.0, sb = 0.0;
+  float fa = 0.f, fb = 0.f, ca = 0.f, cb = 0.f;       // Kahan sums and their compensations
   if (c < N) {
 #pragma unroll 4
     for (int b = ty; b < nblk; b += 32) {
-      sa += (double)__ldg(partials + ((long long)b * 2) * N + c);
-      sb += (double)__ldg(partials + ((long long)b * 2 + 1) * N + c);
+      const float va = __ldg(partials + ((long long)b * 2) * N + c) - ca;
+      const float vb = __ldg(partials + ((long long)b * 2 + 1) * N + c) - cb;
+      const float ta = __fadd_rn(fa, va), tb = __fadd_rn(fb, vb);
+      ca = __fsub_rn(__fsub_rn(ta, fa), va);
+      cb = __fsub_rn(__fsub_rn(tb, fb), vb);
+      fa = ta;
+      fb = tb;
     }
   }
-  red_a[ty][tx] = sa;
-  red_b[ty][tx] = sb;
+  red_a[ty][tx] = (double)fa - (double)ca;
+  red_b[ty][tx] = (double)fb - (double)cb;
   __syncthreads();
   if (ty != 0 || c >= N) return;
-  sa = 0.0;
-  sb = 0.0;
+  double sa = 0.0, sb = 0.0;
 #pragma unroll
   for (int y = 0; y < 32; ++y) {
     sa += red_a[y][tx];
@@ -167,15 +173,16 @@ __global__ void __launch_bounds__(256) bn_apply_planes_kernel(const float* __res
                                                               const unsigned long long* __restrict__ offset_dev,
                                                               uint16_t* __restrict__ out, long long out_ld,
                                                               long long plane_stride, unsigned char* __restrict__ mask,
-                                                              int ones_col, PlaneFmt fmt) {
+                                                              int ones_col, PlaneFmt fmt, FastDiv row_div) {
   Philox rng{(unsigned)seed, (unsigned)(seed >> 32)};
   if (offset_dev) offset += *offset_dev;
   const float ps = fmt.scale();
   const int n4 = N / 4;
   const int n4o = (N + 7) / 8 * 2 + (ones_col ? 2 : 0);      // 4-column groups written per row (padding + ones column)
   const long long total = M * n4o;
+  const bool small = total < (1ll << 32);                    // 32-bit multiply-high division instead of the 64-bit one
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / n4o;
+    const long long r = small ? (long long)fastdiv((unsigned)i, row_div) : i / n4o;
     const int c4 = (int)(i - r * n4o);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 < n4) {
@@ -204,14 +211,16 @@ __global__ void __launch_bounds__(256) bn_bwd_planes_kernel(const float* __restr
                                                             long long M, int N, long long ldg, long long ldz,
                                                             const float* __restrict__ stats, const float* __restrict__ sums,
                                                             const float* __restrict__ gamma, uint16_t* __restrict__ out,
-                                                            long long out_ld, long long plane_stride, PlaneFmt fmt) {
+                                                            long long out_ld, long long plane_stride, PlaneFmt fmt,
+                                                            FastDiv row_div) {
   const float ps = fmt.scale();
   const int n4 = N / 4;
   const int n4o = (N + 7) / 8 * 2;
   const float inv_m = 1.0f / (float)M;
   const long long total = M * n4o;
+  const bool small = total < (1ll << 32);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / n4o;
+    const long long r = small ? (long long)fastdiv((unsigned)i, row_div) : i / n4o;
     const int c4 = (int)(i - r * n4o);
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c4 < n4) {
@@ -284,7 +293,7 @@ extern "C" RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int
   bn_apply_planes_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       z, M, N, ldz, affine, 1.0f / (1.0f - p), (unsigned)(p * 4294967296.0), seed, offset,
       reinterpret_cast<const unsigned long long*>(offset_dev), reinterpret_cast<uint16_t*>(out_planes), out_ld, plane_stride,
-      mask, ones_col, plane_fmt(fmt));
+      mask, ones_col, plane_fmt(fmt), make_fastdiv((unsigned long long)((N + 7) / 8 * 2 + (ones_col ? 2 : 0))));
   RSB_CHECK_LAUNCH();
   note_launch(1);
   return RSB_OK;
@@ -315,7 +324,7 @@ extern "C" RSB_API int rsb_bn_train_bwd_planes(const float* g, const float* z, i
   if (blocks > cap) blocks = cap;
   bn_bwd_planes_kernel<<<(unsigned)blocks, 256, 0, st>>>(g, z, M, N, ldg, ldz, stats, sums, gamma,
                                                          reinterpret_cast<uint16_t*>(out_planes), out_ld, plane_stride,
-                                                         plane_fmt(fmt));
+                                                         plane_fmt(fmt), make_fastdiv((unsigned long long)((N + 7) / 8 * 2)));
   RSB_CHECK_LAUNCH();
   note_launch(3);
   return RSB_OK;

@@ -24,7 +24,7 @@ namespace rsb {
 struct FastDiv {
   unsigned d, m, s1, s2;
 };
-inline FastDiv make_fastdiv(unsigned long long d64) {
+__host__ __device__ inline FastDiv make_fastdiv(unsigned long long d64) {
   FastDiv f;
   unsigned d = (unsigned)d64;
   if (d == 0) d = 1;

@@ -721,8 +721,10 @@ __global__ void split_planes_kernel(const float* __restrict__ in, long long rows
   const long long orows = transpose ? cols : rows, ocols8 = out_ld / 8;
   const long long ones_at = ones_col ? (((transpose ? rows : cols) + 7) & ~7ll) : -1;   // first column after the padded data
   const long long total = orows * ocols8;
+  const bool small = total < (1ll << 32);
+  const rsb::FastDiv row_div = rsb::make_fastdiv((unsigned long long)ocols8);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / ocols8, c0 = (i - r * ocols8) * 8;
+    const long long r = small ? (long long)rsb::fastdiv((unsigned)i, row_div) : i / ocols8, c0 = (i - r * ocols8) * 8;
     float x[8];
     const long long icols = transpose ? rows : cols;
     if (!transpose && c0 + 8 <= icols && (ld & 3) == 0) {
@@ -961,8 +963,10 @@ extern "C" RSB_API int64_t rsb_gemm_planes_workspace_bytes(int64_t M, int64_t N,
 // *amax_out = max(*amax_out, mul * max |g| * max |w|): bound on the rank-1 head gradient g[r] * w[c] * mask / (1 - p)
 __global__ void __launch_bounds__(1024) rank1_bound_kernel(const float* __restrict__ g, long long m, const float* __restrict__ w,
                                                            long long n, float mul, float* __restrict__ amax) {
+  // every CTA: its slice of g, all of w (short); max over the CTAs of mg_i * mw * mul is the bound
   float mg = 0.f, mw = 0.f;
-  for (long long i = threadIdx.x; i < m; i += blockDim.x) mg = fmaxf(mg, fabsf(__ldg(g + i)));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (long long)gridDim.x * blockDim.x)
+    mg = fmaxf(mg, fabsf(__ldg(g + i)));
   for (long long i = threadIdx.x; i < n; i += blockDim.x) mw = fmaxf(mw, fabsf(__ldg(w + i)));
   __shared__ float sg[32], sw[32];
 #pragma unroll
@@ -983,7 +987,9 @@ extern "C" RSB_API int rsb_rank1_absmax(const float* g_row, int64_t M, const flo
                                         void* stream) {
   if (!g_row || !w_col || !amax_out || M < 0 || N < 0) return RSB_ERR_BAD_ARG;
   if (M == 0 || N == 0) return RSB_OK;
-  rank1_bound_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g_row, M, w_col, N, mul, amax_out);
+  long long blocks = (M + 4095) / 4096;
+  if (blocks > 64) blocks = 64;
+  rank1_bound_kernel<<<(unsigned)blocks, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(g_row, M, w_col, N, mul, amax_out);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   rsb::note_launch(1);

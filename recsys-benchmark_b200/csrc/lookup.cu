@@ -43,6 +43,7 @@ struct LookupArgs {
   float* out_sum;
   long long* out_rows;
   int* err;
+  float* amax_slots;   // optional [RSB_LOOKUP_AMAX_SLOTS]: raised to max |out_emb| (one integer atomic per warp)
   // backward inputs / outputs
   const float* emb;
   const float* S;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const bool fm = a.out_y != nullptr || a.out_sum != nullptr;
+  float emax = 0.f;
 
   for (long long b0 = warp * SPW; b0 < a.B; b0 += nwarps * SPW) {
     const long long b = b0 + sw;
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
           for (int i = 0; i < V; ++i) {
             S.v[i] += ev[it].v[i];
             Q.v[i] = fmaf(ev[it].v[i], ev[it].v[i], Q.v[i]);
+            emax = fmaxf(emax, fabsf(ev[it].v[i]));
           }
         }
       }
@@ -296,6 +299,14 @@ __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
         a.out_y[b] = x1 + 0.5f * y2;
       }
     }
+  }
+  if (a.amax_slots != nullptr) {
+    // max |emb| of this warp's samples -> one of the slots (the dense tail's FP16X2 split takes the max over them
+    // instead of re-reading the whole activation: rsb_absmax over 1024 floats)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) emax = fmaxf(emax, __shfl_xor_sync(kFull, emax, off));
+    if (lane == 0 && emax > 0.f && emax < 3.0e38f)
+      atomic_max_nonneg(a.amax_slots + (unsigned)(warp % RSB_LOOKUP_AMAX_SLOTS), emax);
   }
 }
 
@@ -720,7 +731,8 @@ extern "C" RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx
                               int32_t F, int32_t D, const float* table, int64_t n_rows, int64_t n_global,
                               const float* table1, int64_t divider, const void* aux, int32_t aux_mode,
                               const int64_t* mask_d_idx, const float* fc, const float* bias, float* out_emb,
-                              float* out_yfm, float* out_sum, int64_t* out_rows, int32_t* err_flag, void* stream) {
+                              float* out_yfm, float* out_sum, int64_t* out_rows, int32_t* err_flag, float* amax_slots,
+                              void* stream) {
   LookupArgs a = {};
   RowShape sh;
   if (B == 0) return RSB_OK;  // empty batch: nothing to do (pointers of empty tensors may be NULL)
@@ -740,6 +752,7 @@ extern "C" RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx
   a.out_sum = out_sum;
   a.out_rows = reinterpret_cast<long long*>(out_rows);
   a.err = err_flag;
+  a.amax_slots = amax_slots;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (kind) {
     case RSB_KIND_VANILLA: return launch_fwd<RSB_KIND_VANILLA>(a, sh, s);
@@ -851,7 +864,7 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
                                               const float* fc_replicated, int32_t G, int64_t n_global,
                                               const float* bias, const float* hot_table, const int64_t* hot_map,
                                               float* out_emb, float* out_yfm, float* out_sum,
-                                              int64_t* out_rows, int32_t* err_flag, void* stream) {
+                                              int64_t* out_rows, int32_t* err_flag, float* amax_slots, void* stream) {
   LookupArgs a = {};
   RowShape sh;
   if (B == 0) return RSB_OK;
@@ -880,6 +893,7 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   a.out_sum = out_sum;
   a.out_rows = reinterpret_cast<long long*>(out_rows);
   a.err = err_flag;
+  a.amax_slots = amax_slots;
   return launch_fwd<RSB_KIND_VANILLA>(a, sh, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -55,7 +55,8 @@ class DeepFM(nn.Module):
         emb, y_fm = self.embedding.lookup(x, self.offsets, self.fc.weight, self._bias)
         b = emb.shape[0]
         scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]),
-                                                       overlap_first_dw=True)
+                                                       overlap_first_dw=True,
+                                                       x_amax_slots=getattr(emb, "_rsb_amax_slots", None))
         return scores.squeeze(-1)
 
     def get_ranks(self, x) -> torch.Tensor:

@@ -104,6 +104,22 @@ def sort_rows(rows: torch.Tensor, n_rows: int, key_div: int = 0, key_mod: int = 
     return skeys, perm
 
 
+# The gather kernels can report max |emb| (per-warp maxima in RSB_LOOKUP_AMAX_SLOTS slots): the dense tail's FP16X2
+# operand split needs that bound, and getting it here saves a pass over the [B, F*D] activation.
+EMIT_AMAX = True
+
+
+def amax_slots_for(device) -> Optional[torch.Tensor]:
+    """Zeroed slot array for a training-mode gather (None when off / not training)."""
+    if not EMIT_AMAX or not torch.is_grad_enabled():
+        return None
+    return torch.zeros(L.LOOKUP_AMAX_SLOTS, dtype=torch.float32, device=device)
+
+
+def amax_slots_of(emb: torch.Tensor) -> Optional[torch.Tensor]:
+    return getattr(emb, "_rsb_amax_slots", None)
+
+
 # ---- backward stage 2 started early --------------------------------------------------
 # The sort needs only the looked-up row ids, which exist as soon as the forward gather has run, while its
 # consumer (the segmented reduction) runs at the very end of the backward pass.  It is therefore queued on a
@@ -263,7 +279,7 @@ class _FusedLookup(torch.autograd.Function):
     """(spec, x, offsets, mask_d, table, table1, aux, fc, bias) -> (emb [B,VF,E], y_fm [B] or empty)."""
 
     @staticmethod
-    def forward(ctx, spec: LookupSpec, x, offsets, mask_d, table, table1, aux, fc, bias, presort=False):
+    def forward(ctx, spec: LookupSpec, x, offsets, mask_d, table, table1, aux, fc, bias, presort=False, amax_slots=None):
         lib = L.load()
         dev = L.require_cuda(x, table, table1, aux, fc, bias, offsets, mask_d)
         if x.dim() != 2:
@@ -290,8 +306,8 @@ class _FusedLookup(torch.autograd.Function):
               spec.kind, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, spec.dim,
               L.ptr(table), table.shape[0], spec.num_global, L.ptr(table1), spec.divider,
               L.ptr(aux_t), aux_mode, L.ptr(mask_d), L.ptr(fc), L.ptr(bias),
-              L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows), L.ptr(_err_flag(spec, dev)), L.stream_ptr(dev),
-              nbytes=nbytes)
+              L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows), L.ptr(_err_flag(spec, dev)), L.ptr(amax_slots),
+              L.stream_ptr(dev), nbytes=nbytes)
         ctx.spec = spec
         ctx.fm = fm
         ctx.shape = (b, f)
@@ -322,7 +338,7 @@ class _FusedLookup(torch.autograd.Function):
         if use_gy:
             g_y = g_y.contiguous()
         if g_emb is None and not use_gy:
-            return (None,) * 10
+            return (None,) * 11
 
         g_fc = None
         want_fc = ctx.fm and need[7] and use_gy
@@ -415,7 +431,7 @@ class _FusedLookup(torch.autograd.Function):
                     g_aux = dense_row_grad(rows, rg_aux.sum(dim=1, keepdim=True), n_rows)
             if kind == L.KIND_OPTEMBED and aux is not None and need[6]:
                 g_aux = -rg_aux.sum(dim=0)
-        return None, None, None, None, g_table, g_table1, g_aux, g_fc, g_bias, None
+        return None, None, None, None, g_table, g_table1, g_aux, g_fc, g_bias, None, None
 
 
 def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tensor], table: torch.Tensor,
@@ -428,7 +444,10 @@ def fused_lookup(spec: LookupSpec, x: torch.Tensor, offsets: Optional[torch.Tens
     # optimizer consumes it), it is started on the side stream right after the forward gather (see EARLY_SORT).
     presort = (EARLY_SORT and torch.is_grad_enabled() and table.requires_grad and spec.kind != L.KIND_QR_CAT
                and not (spec.sparse_grad and getattr(spec.module, "_rsb_fused_opt", None) is None))
-    emb, y, _rows = _FusedLookup.apply(spec, x, offsets, mask_d, table, table1, aux, fc, bias, presort)
+    slots = amax_slots_for(x.device)
+    emb, y, _rows = _FusedLookup.apply(spec, x, offsets, mask_d, table, table1, aux, fc, bias, presort, slots)
+    if slots is not None:
+        emb._rsb_amax_slots = slots       # max(slots) == max |emb| (read by the dense tail's operand split)
     return emb, (y if fc is not None else None)
 
 

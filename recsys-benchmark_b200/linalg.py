@@ -558,7 +558,7 @@ class _MlpBatchNorm(torch.autograd.Function):
     gone; what is saved for the backward is z (fp32), the planes of each layer's input, the masks and 4 N statistics."""
 
     @staticmethod
-    def forward(ctx, x, ps, side_dw, bns, *params):
+    def forward(ctx, x, ps, side_dw, bns, x_amax_slots, *params):
         n_layers = (len(params) - 2) // 4
         ws, bs = params[0:4 * n_layers:4], params[1:4 * n_layers:4]
         gammas, betas = params[2:4 * n_layers:4], params[3:4 * n_layers:4]
@@ -566,7 +566,11 @@ class _MlpBatchNorm(torch.autograd.Function):
         fmt = MLP_PLANES_FORMAT
         # FP16X2: one zeroed device scalar per activation whose planes are written (the bounds their scales derive from)
         amaxs = torch.zeros(n_layers, 1, dtype=torch.float32, device=x.device) if fmt == P.FP16X2 else None
-        planes = [P.split(x, ones_col=True, fmt=fmt, amax=P.absmax(x, amaxs[0]) if amaxs is not None else None)]
+        x_amax = None
+        if amaxs is not None:
+            # max |x|: from the gather kernel's per-warp maxima when it supplied them, else one pass over x
+            x_amax = P.absmax(x_amax_slots.view(1, -1) if x_amax_slots is not None else x, amaxs[0])
+        planes = [P.split(x, ones_col=True, fmt=fmt, amax=x_amax)]
         masks, zs, stats = [], [], []
         y = out = None
         for i in range(n_layers):
@@ -603,12 +607,12 @@ class _MlpBatchNorm(torch.autograd.Function):
         ws, bs = params[0:4 * n_layers:4], params[1:4 * n_layers:4]
         gammas, betas = params[2:4 * n_layers:4], params[3:4 * n_layers:4]
         w_out, b_out = params[-2], params[-1]
-        need = ctx.needs_input_grad                      # (x, ps, side_dw, bns, W1, b1, gamma1, beta1, ..., w_out, b_out)
+        need = ctx.needs_input_grad          # (x, ps, side_dw, bns, x_amax_slots, W1, b1, gamma1, beta1, ..., w_out, b_out)
         g = g_out.reshape(-1).contiguous()
         grads = [None] * len(params)
-        if need[4 + 4 * n_layers]:
+        if need[5 + 4 * n_layers]:
             grads[-2] = _colsum_weighted(y, g).reshape(w_out.shape)
-        if b_out is not None and need[5 + 4 * n_layers]:
+        if b_out is not None and need[6 + 4 * n_layers]:
             grads[-1] = g.sum().reshape(1)
         g_r, _ = _relu_dropout_bwd_rank1(g, w_out.reshape(-1), masks[-1], ps[-1], False)   # fp32 [M, H]
         fmt = planes[0].fmt
@@ -621,9 +625,9 @@ class _MlpBatchNorm(torch.autograd.Function):
         for i in reversed(range(n_layers)):
             gp, d_beta, d_gamma = P.bn_train_bwd_planes(g_r, zs[i], stats[i], gammas[i], fmt=fmt,
                                                         g_amax=g_amaxs[i] if g_amaxs is not None else None)
-            if gammas[i] is not None and need[6 + 4 * i]:
+            if gammas[i] is not None and need[7 + 4 * i]:
                 grads[4 * i + 2] = d_gamma
-            if betas[i] is not None and need[7 + 4 * i]:
+            if betas[i] is not None and need[8 + 4 * i]:
                 grads[4 * i + 3] = d_beta
             g_prev = None
             if i > 0:
@@ -631,7 +635,7 @@ class _MlpBatchNorm(torch.autograd.Function):
                                      to_planes=False, d_amax=g_amaxs[i - 1] if g_amaxs is not None else None)
             elif need[0]:
                 gx = _dx_gemm(gp, ws[0])
-            want_w, want_b = need[4 + 4 * i], bs[i] is not None and need[5 + 4 * i]
+            want_w, want_b = need[5 + 4 * i], bs[i] is not None and need[6 + 4 * i]
             if want_w or want_b:
                 if i == 0 and ctx.side_dw and gx is not None and _side_dw_safe(ws[0]) and \
                         (bs[0] is None or _side_dw_safe(bs[0])):
@@ -641,7 +645,7 @@ class _MlpBatchNorm(torch.autograd.Function):
                 grads[4 * i] = dw if want_w else None
                 grads[4 * i + 1] = db if want_b else None
             g_r = g_prev
-        return (gx, None, None, None, *grads)
+        return (gx, None, None, None, None, *grads)
 
 
 def _mlp_batchnorm_pattern(mods, x: torch.Tensor):
@@ -716,11 +720,13 @@ def _is_head(mod, width: int) -> bool:
             and mod.weight.data_ptr() % 16 == 0)
 
 
-def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: bool = False) -> torch.Tensor:
+def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: bool = False,
+                   x_amax_slots: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.Sequential forward of the dense tails with the same parameters / state dict, but
     Linear -> tensor-core GEMM, and (Linear ->) ReLU -> Dropout fused into single passes.
     BatchNorm1d (and anything else) runs unchanged.  overlap_first_dw: the input comes straight from the
-    embedding gather, so the first layer's weight-gradient GEMM may run beside the embedding backward."""
+    embedding gather, so the first layer's weight-gradient GEMM may run beside the embedding backward.
+    x_amax_slots: device floats whose maximum is max |x| (the gather kernels fill them, functional.EMIT_AMAX)."""
     mods = list(seq)
     i = 0
     training = seq.training
@@ -733,8 +739,8 @@ def run_sequential(seq: torch.nn.Sequential, x: torch.Tensor, overlap_first_dw: 
                 params += [lin.weight, lin.bias, bn.weight, bn.bias]
             side = overlap_first_dw and not _has_hooks(lins[0].weight) and \
                 (lins[0].bias is None or not _has_hooks(lins[0].bias))
-            return _MlpBatchNorm.apply(x.contiguous(), tuple(float(d.p) for d in drops), side, tuple(bns), *params,
-                                       head.weight, head.bias)
+            return _MlpBatchNorm.apply(x.contiguous(), tuple(float(d.p) for d in drops), side, tuple(bns), x_amax_slots,
+                                       *params, head.weight, head.bias)
         pat = _mlp_relu_dropout_pattern(mods, x)
         if pat is not None:
             lins, drops, head = pat

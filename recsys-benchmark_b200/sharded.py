@@ -184,7 +184,7 @@ class _ShardedLookup(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sg: ShardGroup, x, offsets, fc, bias, use_fm: bool, presort: bool = False, hot=None,
-                hot_map=None):
+                hot_map=None, amax_slots=None):
         lib = L.load()
         dev = L.require_cuda(x, offsets, bias)
         x = x.contiguous()
@@ -202,7 +202,7 @@ class _ShardedLookup(torch.autograd.Function):
                  L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(fc) if use_fm else None,
                  sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(hot) if hot is not None else None,
                  L.ptr(hot_map) if hot is not None else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
-                 L.ptr(sg.err_flag), L.stream_ptr(dev), nbytes=nbytes)
+                 L.ptr(sg.err_flag), L.ptr(amax_slots), L.stream_ptr(dev), nbytes=nbytes)
         ctx.sg, ctx.use_fm, ctx.shape = sg, use_fm, (b, f)
         ctx.hot_map = hot_map if hot is not None else None
         ctx.hot_shape = tuple(hot.shape) if hot is not None else None
@@ -249,7 +249,7 @@ class _ShardedLookup(torch.autograd.Function):
             if ctx.needs_input_grad[3]:
                 g_fc = RF.fc_grad(rows, g_y, b, f, ctx.fc_shape, sg.num_rows, (skeys, perm))
             g_bias = g_y.sum().reshape(1)
-        return None, None, None, g_fc, g_bias, None, None, g_hot, None
+        return None, None, None, g_fc, g_bias, None, None, g_hot, None, None
 
 
 # ------------------------------------------------------------------ modules ---
@@ -341,7 +341,10 @@ class ShardedVanillaEmbedding(IEmbedding):
         self._rsb_err_flag = self.shards.err_flag     # read by IEmbedding.train() / validate=True like the others
         presort = RF.EARLY_SORT and torch.is_grad_enabled()
         hot = getattr(self._emb_module, "hot", None)
-        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm, presort, hot, self.hot_map)
+        slots = RF.amax_slots_for(x.device)
+        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm, presort, hot, self.hot_map, slots)
+        if slots is not None:
+            emb._rsb_amax_slots = slots
         if self.validate:
             RF.check_index_errors(self)
         return emb, (y if use_fm else None)
@@ -373,7 +376,8 @@ class ShardedDeepFM(DeepFM):
     def forward(self, x):
         emb, y_fm = self.embedding.lookup(x, self.offsets, self.fc.weight, self._bias)
         b = emb.shape[0]
-        scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]))
+        scores = y_fm.unsqueeze(1) + run_sequential(self._deep_branch, emb.reshape(b, emb.shape[1] * emb.shape[2]),
+                                                    overlap_first_dw=True, x_amax_slots=RF.amax_slots_of(emb))
         return scores.squeeze(-1)
 
     # -- step protocol ---------------------------------------------------------------

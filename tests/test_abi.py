@@ -61,7 +61,7 @@ def test_workspace_queries(lib):
 def test_bad_arguments_are_rejected_before_any_launch(lib):
     BAD = 10001
     assert lib.rsb_lookup_fwd(0, None, 0, None, 4, 3, 16, None, 10, 10, None, 0, None, 0, None, None, None, None,
-                              None, None, None, None, None) == BAD
+                              None, None, None, None, None, None) == BAD
     assert lib.rsb_lookup_bwd_rows(0, None, 4, 3, 16, None, 10, None, 0, None, 0, None, None, None, None, None,
                                    None, None, None, None) == BAD
     assert lib.rsb_sort_rows(None, -1, 10, 0, 0, None, None, None, 0, None) == BAD

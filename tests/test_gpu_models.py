@@ -436,6 +436,13 @@ def test_criteo_shape_properties(R, emb_cfg, b):
     assert_close(logits.detach().cpu().numpy(), ref.detach().cpu().numpy(), what="fused vs composed", atol_scale=2e-5)
     # (2) int32 ids give bit-identical logits
     assert torch.equal(model(x.int()), logits)
+    # (2b) the gather reports max |emb| through its per-warp slots (the dense tail's operand scale comes from it)
+    import recsys_benchmark_b200.functional as RF_
+    emb_l, _ = model.embedding.lookup(x, model.offsets, model.fc.weight, model._bias)
+    slots = RF_.amax_slots_of(emb_l)
+    assert slots is not None and float(slots.max()) == float(emb_l.abs().max())
+    with torch.no_grad():
+        assert RF_.amax_slots_of(model.embedding.lookup(x, model.offsets, model.fc.weight, model._bias)[0]) is None
     # (3) gradients: fused backward == composed backward; checksum of checksums
     params = [p for p in model.embedding.parameters()] + [model.fc.weight]
     g1 = torch.autograd.grad(logits.square().sum(), params)
