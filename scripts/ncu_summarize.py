@@ -38,13 +38,19 @@ def launches(path: str, steps: int):
         per[k][0] += us
         per[k][1] += 1
     total = sum(v[0] for v in per.values())
-    ours = sum(v[0] for k, v in per.items() if "rsb" in k or "FastF32" in k or "rsb_gemm" in k)
+
+    def own(k):     # kernels compiled from recsys-benchmark_b200/csrc (namespaces rsb / pg + two free functions)
+        return "rsb::" in k or "pg::" in k or k.startswith("rank1_bound_kernel") or "rsb" in k
+
+    if steps <= 0:  # one forward gather per step
+        steps = max(1, sum(v[1] for k, v in per.items() if "lookup_fwd_kernel" in k))
+    ours = sum(v[0] for k, v in per.items() if own(k))
     print("| us/step | launches/step | share | kernel |")
     print("|---:|---:|---:|---|")
     for k, (us, n) in sorted(per.items(), key=lambda kv: -kv[1][0]):
         if us / total < 0.001:
             continue
-        mark = "**" if ("rsb" in k or "FastF32" in k) else ""
+        mark = "**" if own(k) else ""
         print(f"| {us / steps:.1f} | {n / steps:.1f} | {100 * us / total:.1f}% | {mark}`{short(k)}`{mark} |")
     print()
     print(f"Total {total / steps:.0f} us/step over {steps} captured steps; hand-written / own-instantiated kernels "

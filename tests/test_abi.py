@@ -66,6 +66,12 @@ def test_bad_arguments_are_rejected_before_any_launch(lib):
                                    None, None, None, None) == BAD
     assert lib.rsb_sort_rows(None, -1, 10, 0, 0, None, None, None, 0, None) == BAD
     assert lib.rsb_sort_rows(None, 0, 10, 0, 0, None, None, None, 0, None) == 0  # empty input is fine
+    # row ids are 32-bit sort keys and 0xffffffff is the segmented reduction's sentinel: a key space of 2^32 rows (or
+    # 2^32 lookups in one call) is refused before any launch instead of wrapping around
+    assert lib.rsb_sort_rows(None, 4, (1 << 32), 0, 0, None, None, None, 0, None) == BAD
+    assert lib.rsb_sort_rows(None, 4, (1 << 40), 0, 0, None, None, None, 0, None) == BAD
+    assert lib.rsb_sort_rows(None, (1 << 32), 10, 0, 0, None, None, None, 0, None) == BAD
+    assert lib.rsb_sort_rows(None, 4, (1 << 32) - 1, 0, 0, None, None, None, 0, None) == BAD  # (NULL buffers; size ok)
     assert lib.rsb_segment_reduce_apply(7, None, None, 4, None, 16, None, None, None, 0.0, 0.9, 0.999, 1e-8, 1,
                                         None, 0, None) == BAD
     assert lib.rsb_pep_threshold_table(None, None, 0, 4, 4, None, None, None) == BAD
