@@ -1198,6 +1198,11 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
     static const int want = [] { const char* v = getenv("RSB_GEMM_TMA_STORE"); return v ? atoi(v) : 1; }();
     const uint32_t epi_bytes = 8u * 4096u;
     const bool f32_out = (mode == RSB_EPI_LINEAR || mode == RSB_EPI_MASK_F32) && p.partial == nullptr && batch == 1 && C == nullptr;
+    // a deep ring must not crowd the staging buffers out: beyond 3 stages the ring only hides DRAM latency the MMA thread
+    // does not wait for (8 % of its time), while a direct-store epilogue exposes ~6 us per tile
+    if (want && f32_out) {
+      while (p.stages > 3 && (size_t)p.stages * stage_bytes + epi_bytes + 1024 > kSmemLimit - 2048) --p.stages;
+    }
     if (want && f32_out && (size_t)p.stages * stage_bytes + epi_bytes + 1024 <= kSmemLimit - 2048) {
       EncodeTiledFn encode = encode_tiled_fn();
       cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
