@@ -325,6 +325,11 @@ typedef struct {
   float p;                     /* dropout probability */
   float* d_amax;               /* modes 0, 3 (fp32 D, no split-K), optional: *d_amax is raised to max |D| - the bound an
                                   FP16X2 consumer of D needs (rsb_bn_train_bwd_planes), formed in the epilogue for free */
+  float* bn_partials;          /* mode 0, optional: BatchNorm batch statistics of D as per-32-row-group shifted column sums
+                                  [row_groups][3][N] = (sum (d - k), sum (d - k)^2, k = the group's first row), reduced from
+                                  the accumulator registers in the epilogue; rsb_bn_finalize_partials turns them into mean /
+                                  rstd / affine, so the statistics pass over D (rsb_bn_train_fwd_stats) disappears.
+                                  Size and availability: rsb_gemm_bn_partials_bytes */
 } rsb_gemm_epilogue;
 
 /* y = dropout_p(relu(x)) of an fp32 [M, N] activation (ldx) written as planes (+ ones column) and the 1-byte
@@ -379,6 +384,13 @@ RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t N, int64_t
                                    float eps, float momentum, float* running_mean, float* running_var, float* stats,
                                    float* affine, float bound_mul, float* act_amax, void* workspace, int64_t workspace_bytes,
                                    void* stream);
+/* bytes of the statistics buffer for rsb_gemm_epilogue.bn_partials, or -1 if this GEMM cannot carry them */
+RSB_API int64_t rsb_gemm_bn_partials_bytes(int64_t M, int64_t N, int64_t K, int32_t format);
+/* rsb_bn_train_fwd_stats' outputs from the partials a GEMM epilogue wrote: the group sums are re-based to one common shift
+ * (exact identity) and folded in fixed order; workspace >= 16 * 2 * N * 4 + 256 bytes (rsb_bn_workspace_bytes suffices) */
+RSB_API int rsb_bn_finalize_partials(const float* parts, int64_t M, int32_t N, const float* gamma, const float* beta, float eps,
+                                     float momentum, float* running_mean, float* running_var, float* stats, float* affine,
+                                     float bound_mul, float* act_amax, void* workspace, int64_t workspace_bytes, void* stream);
 RSB_API int rsb_bn_relu_dropout_planes(const float* z, int64_t M, int32_t N, int64_t ldz, const float* affine, float p,
                                        uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int32_t ones_col,
                                        void* out_planes, int64_t out_ld, int64_t plane_stride, uint8_t* mask,

@@ -46,7 +46,8 @@ class GemmEpilogue(C.Structure):
     """rsb_gemm_epilogue of include/rsb.h."""
 
     _fields_ = [("mode", C.c_int32), ("out_planes", C.c_void_p), ("out_ld", C.c_int64), ("out_plane_stride", C.c_int64),
-                ("ones_col", C.c_int32), ("mask", C.c_void_p), ("p", C.c_float), ("d_amax", C.c_void_p)]
+                ("ones_col", C.c_int32), ("mask", C.c_void_p), ("p", C.c_float), ("d_amax", C.c_void_p),
+                ("bn_partials", C.c_void_p)]
 
 
 EPI_LINEAR, EPI_RELU_DROPOUT_PLANES, EPI_MASK_PLANES, EPI_MASK_F32 = range(4)
@@ -96,6 +97,8 @@ PROTOTYPES = {
     "rsb_colsum": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _i64, _p]),
     "rsb_relu_dropout_dot_fwd": (C.c_int, [_p, _i64, _i32, _f, C.c_uint64, C.c_uint64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "rsb_bn_workspace_bytes": (_i64, [_i64, _i32]),
+    "rsb_gemm_bn_partials_bytes": (_i64, [_i64, _i64, _i64, _i32]),
+    "rsb_bn_finalize_partials": (C.c_int, [_p, _i64, _i32, _p, _p, _f, _f, _p, _p, _p, _p, _f, _p, _p, _i64, _p]),
     "rsb_bn_train_fwd_stats": (C.c_int, [_p, _i64, _i32, _i64, _p, _p, _f, _f, _p, _p, _p, _p, _f, _p, _p, _i64, _p]),
     "rsb_bn_relu_dropout_planes": (C.c_int, [_p, _i64, _i32, _i64, _p, _f, C.c_uint64, C.c_uint64, _p, _i32, _p, _i64, _i64,
                                              _p, C.POINTER(PlanesFormat), _p]),

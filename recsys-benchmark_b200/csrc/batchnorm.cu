@@ -166,6 +166,51 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   }
 }
 
+// Per-32-row-group statistics a GEMM epilogue left behind (rsb_gemm_epilogue.bn_partials: parts[g][0][c] = S1 = sum (z - k_g),
+// parts[g][1][c] = S2 = sum (z - k_g)^2 over the group's n_g valid rows, parts[g][2][c] = k_g, the group's first row)
+// -> shifted sums with ONE common shift k_0 (group 0's), folded over a slice of the groups:
+//     sum (z - k_0) = sum_g [n_g d_g + S1],   sum (z - k_0)^2 = sum_g [S2 + 2 d_g S1 + n_g d_g^2],   d_g = k_g - k_0
+// (exact identities), written as out[slice][0..1][c] - the layout bn_finalize_kernel<0> folds, with k_0 as its row 0.
+// Grid (N / 32, slices); 32 columns x 32 group lanes per CTA, coalesced loads, fixed-order fold over the lanes.
+__global__ void __launch_bounds__(1024) bn_parts_fold_kernel(const float* __restrict__ parts, long long groups, int N, long long M,
+                                                             float* __restrict__ out) {
+  __shared__ float red_a[32][33], red_b[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const long long per = (groups + gridDim.y - 1) / gridDim.y;
+  const long long g0 = per * blockIdx.y;
+  long long g1 = g0 + per;
+  if (g1 > groups) g1 = groups;
+  float t1 = 0.f, t2 = 0.f;
+  if (c < N) {
+    const float k0 = __ldg(parts + 2 * (long long)N + c);
+#pragma unroll 4
+    for (long long g = g0 + ty; g < g1; g += 32) {
+      long long n = M - g * 32;
+      n = n > 32 ? 32 : n;
+      if (n <= 0) break;
+      const float* pg = parts + g * 3 * (long long)N;
+      const float s1 = __ldg(pg + c), s2 = __ldg(pg + (long long)N + c), d = __ldg(pg + 2 * (long long)N + c) - k0;
+      const float nd = (float)n * d;
+      t1 += nd + s1;
+      t2 += fmaf(d, 2.f * s1 + nd, s2);
+    }
+  }
+  red_a[ty][tx] = t1;
+  red_b[ty][tx] = t2;
+  __syncthreads();
+  if (ty != 0 || c >= N) return;
+  t1 = 0.f;
+  t2 = 0.f;
+#pragma unroll
+  for (int y = 0; y < 32; ++y) {
+    t1 += red_a[y][tx];
+    t2 += red_b[y][tx];
+  }
+  out[((long long)blockIdx.y * 2) * N + c] = t1;
+  out[((long long)blockIdx.y * 2 + 1) * N + c] = t2;
+}
+
 // y = dropout_p(relu(z * scale + shift)) -> planes (+ ones column) + keep-and-positive mask; p = 0: no dropout
 __global__ void __launch_bounds__(256) bn_apply_planes_kernel(const float* __restrict__ z, long long M, int N, long long ldz,
                                                               const float* __restrict__ affine, float drop_scale,
@@ -272,6 +317,29 @@ extern "C" RSB_API int rsb_bn_train_fwd_stats(const float* z, int64_t M, int32_t
   RSB_CHECK_LAUNCH();
   bn_finalize_kernel<0><<<(N + 31) / 32, 1024, 0, st>>>(partials, nblk, N, M, z, gamma, beta, eps, momentum, running_mean,
                                                      running_var, stats, affine, nullptr, bound_mul, nullptr, act_amax);
+  RSB_CHECK_LAUNCH();
+  note_launch(2);
+  return RSB_OK;
+}
+
+constexpr int kBnPartSlices = 16;
+
+extern "C" RSB_API int rsb_bn_finalize_partials(const float* parts, int64_t M, int32_t N, const float* gamma, const float* beta,
+                                                float eps, float momentum, float* running_mean, float* running_var, float* stats,
+                                                float* affine, float bound_mul, float* act_amax, void* workspace,
+                                                int64_t workspace_bytes, void* stream) {
+  if (!parts || !stats || !affine || M <= 0 || N <= 0) return RSB_ERR_BAD_ARG;
+  if (!workspace || workspace_bytes < (int64_t)kBnPartSlices * 2 * N * 4 + 256) return RSB_ERR_WORKSPACE;
+  float* sl = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long groups = (M + 127) / 128 * 4;
+  int slices = kBnPartSlices;
+  if (slices > groups) slices = (int)groups;
+  bn_parts_fold_kernel<<<dim3((N + 31) / 32, slices), 1024, 0, st>>>(parts, groups, N, M, sl);
+  RSB_CHECK_LAUNCH();
+  // the slices are shifted sums w.r.t. group 0's first row (= row 0 of z): the ordinary finish applies
+  bn_finalize_kernel<0><<<(N + 31) / 32, 1024, 0, st>>>(sl, slices, N, M, parts + 2 * (long long)N, gamma, beta, eps, momentum,
+                                                     running_mean, running_var, stats, affine, nullptr, bound_mul, nullptr, act_amax);
   RSB_CHECK_LAUNCH();
   note_launch(2);
   return RSB_OK;

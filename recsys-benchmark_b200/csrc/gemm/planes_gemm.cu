@@ -80,6 +80,7 @@ struct Params {
   unsigned char* mask;
   float drop_scale;
   float* d_amax;         // fp32 outputs: *d_amax is raised to max |D| (the bound an FP16X2 consumer of D needs)
+  float* bn_part;        // TMA-store epilogue: per 32-row group shifted column sums of D, [row_groups][3][N] (see below)
 };
 
 // 8 consecutive values of one row -> three 16-byte bf16 plane stores (the fused plane epilogues write BF16X3)
@@ -582,6 +583,35 @@ epilogue_role:
               tma_store_2d(&map_d, buf, n0 + c, row0);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            if (p.bn_part != nullptr) {
+              // BatchNorm statistics of the rows this warp just produced (the batch statistics pass over D disappears):
+              // shifted sums  S1 = sum (d - k),  S2 = sum (d - k)^2  over the warp's valid rows, k = the group's first
+              // row, per column - read back from the box just staged in shared memory (lane l sums column l & 15 over
+              // rows 16 (l >> 4) .. +15: 17 shared loads and 2 shuffles per box; reducing the accumulator registers
+              // over the rows with shuffles took 48 per box and showed as +0.02 ms per GEMM).
+              const int cl = lane & 15, rh = (lane >> 4) * 16;
+              const float kshift = *reinterpret_cast<const float*>(buf + ((cl >> 2) << 4) + (cl & 3) * 4);   // row 0: no swizzle
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 16; ++rr) {
+                const int r = rh + rr;
+                const float zv = *reinterpret_cast<const float*>(buf + r * 64 + ((((uint32_t)cl >> 2) ^ (((uint32_t)r >> 1) & 3u)) << 4) +
+                                                                 (cl & 3) * 4);
+                const float dv = (row0 + r < p.M) ? zv - kshift : 0.f;
+                s1 += dv;
+                s2 = fmaf(dv, dv, s2);
+              }
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+              const int col = n0 + c + cl;
+              const long long rg = (long long)t.m_blk * (kTileM / 32) + q;
+              float* part = p.bn_part + rg * 3 * (long long)p.N;
+              if (lane < 16 && col < p.N) {
+                part[col] = s1;
+                part[p.N + col] = s2;
+                part[2 * (long long)p.N + col] = kshift;
+              }
+            }
           }
         }
         if (p.d_amax) {                      // one atomic per warp and tile (rows past M hold alpha * 0 + bias: harmless)
@@ -983,6 +1013,23 @@ __global__ void __launch_bounds__(1024) rank1_bound_kernel(const float* __restri
   }
 }
 
+// Bytes of the [row_groups][3][N] statistics buffer a GEMM with rsb_gemm_epilogue.bn_partials writes, or -1 when this
+// shape / format cannot carry the statistics (the fp32 TMA-store epilogue must fit beside >= 3 pipeline stages; K-major
+// operands; the driver's tensor-map encoder must be there).  Mirrors the stage arithmetic of rsb_gemm_planes.
+extern "C" RSB_API int64_t rsb_gemm_bn_partials_bytes(int64_t M, int64_t N, int64_t K, int32_t format) {
+  if (M <= 0 || N <= 0 || K <= 0 || N % 4 || use_pairs(M)) return -1;
+  static const int want = [] { const char* v = getenv("RSB_GEMM_TMA_STORE"); return v ? atoi(v) : 1; }();
+  if (!want || encode_tiled_fn() == nullptr) return -1;
+  int n_tiles;
+  const int n_tile = pick_n_tile(N, &n_tiles);
+  const uint32_t np = format == RSB_PLANES_FP16X2 ? 2u : 3u;
+  const uint32_t a_bytes = np * kBlockM * kBlockK * 2;
+  const uint32_t b_bytes = ((np * (uint32_t)n_tile * kBlockK * 2) + 1023u) & ~1023u;
+  if ((size_t)3 * (a_bytes + b_bytes) + 8u * 4096u + 1024 > kSmemLimit - 2048) return -1;
+  const int64_t row_groups = (M + kBlockM - 1) / kBlockM * (kBlockM / 32);
+  return row_groups * 3 * N * 4;
+}
+
 extern "C" RSB_API int rsb_rank1_absmax(const float* g_row, int64_t M, const float* w_col, int64_t N, float mul, float* amax_out,
                                         void* stream) {
   if (!g_row || !w_col || !amax_out || M < 0 || N < 0) return RSB_ERR_BAD_ARG;
@@ -1100,6 +1147,11 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
   if (A->fmt.format != B->fmt.format || !rsb::plane_fmt_ok(&A->fmt) || !rsb::plane_fmt_ok(&B->fmt)) return RSB_ERR_BAD_ARG;
   if (epi && epi->d_amax && (to_planes || split_k > 1)) return RSB_ERR_UNSUPPORTED;   // max |D| is formed by the fp32 epilogue
   if (epi && epi->d_amax) split_k = 1;
+  if (epi && epi->bn_partials) {
+    // column statistics ride the TMA-store epilogue of one plain un-batched, un-split GEMM (see rsb_gemm_bn_partials_bytes)
+    if (mode != RSB_EPI_LINEAR || batch != 1 || C != nullptr || split_k > 1 || use_pairs(M)) return RSB_ERR_UNSUPPORTED;
+    split_k = 1;
+  }
   if (mode != RSB_EPI_LINEAR) {
     // fused epilogues: one un-batched, un-split GEMM whose output feeds the next GEMM
     if (batch != 1 || beta != 0.f || !epi->mask || epi->p < 0.f || epi->p >= 1.f) return RSB_ERR_BAD_ARG;
@@ -1178,6 +1230,7 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
     p.mask = epi->mask;
     p.drop_scale = 1.0f / (1.0f - epi->p);
     p.d_amax = epi->d_amax;
+    p.bn_part = epi->bn_partials;
   }
   p.D = D; p.ldd = ldd; p.d_batch_stride = d_batch_stride; p.C = C; p.bias = bias; p.alpha = alpha; p.beta = beta;
   if (p.splits > 1) {
@@ -1217,6 +1270,7 @@ extern "C" RSB_API int rsb_gemm_planes(const rsb_planes_operand* A, const rsb_pl
       }
     }
   }
+  if (p.bn_part != nullptr && !p.tma_store) return RSB_ERR_UNSUPPORTED;
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.batch * p.splits;
   int grid = two ? rsb::sm_count() / 2 : rsb::sm_count();     // scheduling units: CTA pairs or CTAs
   if (tiles < grid) grid = (int)tiles;

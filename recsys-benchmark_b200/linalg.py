@@ -54,6 +54,10 @@ def weight_planes(w: torch.Tensor, transpose: bool = False, fmt: int = P.BF16X3)
 # Operand format of the fused training-mode dense tails (_MlpBatchNorm): FP16X2 halves the MMAs and the plane bytes;
 # set to P.BF16X3 for the exact-operand path.
 MLP_PLANES_FORMAT = P.FP16X2
+# BatchNorm batch statistics reduced in the GEMM epilogue (rsb_gemm_epilogue.bn_partials) instead of by a pass over z.
+# Correct and tested, but measured no faster on the headline step: the statistics lengthen the GEMM's exposed epilogue
+# by as much (+0.024 ms per GEMM, + 0.023 ms to combine 2048 row groups) as the separate pass costs (0.050 ms).  Off.
+BN_STATS_IN_GEMM = False
 
 
 def gemm(a: torch.Tensor, b: torch.Tensor, trans_a: bool = False, trans_b: bool = False,
@@ -574,13 +578,13 @@ class _MlpBatchNorm(torch.autograd.Function):
         masks, zs, stats = [], [], []
         y = out = None
         for i in range(n_layers):
-            z = _fwd_gemm(planes[-1], ws[i], bs[i])
             bn = bns[i]
             act_amax = amaxs[i + 1] if (amaxs is not None and i < n_layers - 1) else None
-            st, affine = P.bn_train_stats(z, gammas[i], betas[i], bn.eps, bn.momentum,
-                                          bn.running_mean if bn.track_running_stats else None,
-                                          bn.running_var if bn.track_running_stats else None,
-                                          act_amax=act_amax, bound_mul=1.0 / (1.0 - ps[i]))
+            z, st, affine = P.gemm_bn_stats(planes[-1], weight_planes(ws[i], fmt=planes[-1].fmt), bs[i], gammas[i],
+                                            betas[i], bn.eps, bn.momentum,
+                                            bn.running_mean if bn.track_running_stats else None,
+                                            bn.running_var if bn.track_running_stats else None,
+                                            act_amax=act_amax, bound_mul=1.0 / (1.0 - ps[i]), in_epilogue=BN_STATS_IN_GEMM)
             if bn.track_running_stats and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked.add_(1)
             if i < n_layers - 1:

@@ -147,7 +147,7 @@ def gemm(a: Planes, b: Planes, m: int, n: int, k: int, *, a_mn_major: bool = Fal
     oa = a.operand(a_mn_major, *a_steps)
     ob = b.operand(b_mn_major, *b_steps, cols=b_cols)
     kind = ("gemm_planes" if epilogue is None else
-            ("gemm_planes_relu_dropout", "gemm_planes_relu_dropout", "gemm_planes_masked", "gemm_planes_masked")[epilogue.mode])
+            ("gemm_planes", "gemm_planes_relu_dropout", "gemm_planes_masked", "gemm_planes_masked")[epilogue.mode])
     if a_mn_major and b_mn_major:
         kind = "gemm_planes_dw"
     if a.fmt == FP16X2:
@@ -249,6 +249,33 @@ def bn_train_stats(z: torch.Tensor, gamma: Optional[torch.Tensor], beta: Optiona
              float(momentum), L.ptr(running_mean), L.ptr(running_var), L.ptr(stats), L.ptr(affine), float(bound_mul),
              L.ptr(act_amax), L.ptr(ws), ws.numel(), L.stream_ptr(dev), nbytes=m * n * 4)
     return stats, affine
+
+
+def gemm_bn_stats(xp: Planes, wp: Planes, bias: Optional[torch.Tensor], gamma: Optional[torch.Tensor],
+                  beta: Optional[torch.Tensor], eps: float, momentum: float, running_mean: Optional[torch.Tensor],
+                  running_var: Optional[torch.Tensor], act_amax: Optional[torch.Tensor] = None, bound_mul: float = 1.0,
+                  in_epilogue: bool = True):
+    """z = x W^T + b AND the BatchNorm batch statistics of z: -> (z, stats, affine) like `gemm` + `bn_train_stats`.
+    in_epilogue (and the GEMM can carry them: fp32 TMA-store epilogue): the statistics are reduced from the staged
+    output tiles in the GEMM's epilogue (per-32-row-group shifted sums) and only a small combination follows - no pass
+    over z.  Otherwise: the GEMM, then rsb_bn_train_fwd_stats."""
+    lib = L.load()
+    m, n, k = xp.rows, wp.rows, wp.cols
+    dev = xp.data.device
+    nb = lib.rsb_gemm_bn_partials_bytes(m, n, k, xp.fmt) if in_epilogue else -1
+    if nb <= 0:
+        z = gemm(xp, wp, m, n, k, bias=bias, split_k=1)
+        return (z, *bn_train_stats(z, gamma, beta, eps, momentum, running_mean, running_var, act_amax, bound_mul))
+    parts = torch.empty(nb // 4, dtype=torch.float32, device=dev)
+    epi = L.GemmEpilogue(L.EPI_LINEAR, None, 0, 0, 0, None, 0.0, None, parts.data_ptr())
+    z = gemm(xp, wp, m, n, k, bias=bias, split_k=1, epilogue=epi)
+    stats = torch.empty(2 * n, dtype=torch.float32, device=dev)
+    affine = torch.empty(2 * n, dtype=torch.float32, device=dev)
+    ws = RF._ws(16 * 2 * n * 4 + 512, dev)
+    RF._call("bn_finalize_partials", lib.rsb_bn_finalize_partials, L.ptr(parts), m, n, L.ptr(gamma), L.ptr(beta), float(eps),
+             float(momentum), L.ptr(running_mean), L.ptr(running_var), L.ptr(stats), L.ptr(affine), float(bound_mul),
+             L.ptr(act_amax), L.ptr(ws), ws.numel(), L.stream_ptr(dev), nbytes=parts.numel() * 4)
+    return z, stats, affine
 
 
 def bn_relu_dropout_planes(z: torch.Tensor, affine: torch.Tensor, p: float, seed: int, offset: int,

@@ -91,6 +91,44 @@ def test_fp16x2_ones_column_yields_the_bias_gradient(LA):
     assert _err(db, g.double().sum(0)) < 6e-7
 
 
+@pytest.mark.parametrize("m,n,k", [(4096, 400, 624), (1000, 64, 352), (130, 48, 64), (65536, 400, 400), (32, 16, 32)])
+@pytest.mark.parametrize("fmt", ["bf16x3", "fp16x2"])
+def test_gemm_epilogue_batchnorm_statistics_match_the_separate_pass(LA, m, n, k, fmt):
+    """rsb_gemm_epilogue.bn_partials: the GEMM epilogue reduces per-32-row-group shifted column sums of its output from
+    the accumulator registers and rsb_bn_finalize_partials combines them (Chan) - same mean / rstd / affine / running
+    buffers as the pass over z (rsb_bn_train_fwd_stats) and as fp64, incl. a ragged last row group; z itself is
+    unchanged bit for bit."""
+    from recsys_benchmark_b200 import planes as P
+
+    F = P.FP16X2 if fmt == "fp16x2" else P.BF16X3
+    torch.manual_seed(m + n)
+    x = torch.randn(m, k, device=DEV) * 0.3 + 0.1
+    w = torch.randn(n, k, device=DEV) * 0.05
+    b = torch.randn(n, device=DEV) * 3.0                       # column means far from zero: |mean| >> std
+    gamma, beta = torch.rand(n, device=DEV) + 0.5, torch.randn(n, device=DEV) * 0.2
+    xp, wp = P.split(x, fmt=F), P.split(w, fmt=F)
+    lib = LA.L.load()
+    if lib.rsb_gemm_bn_partials_bytes(m, n, k, F) <= 0:
+        pytest.skip("this shape does not take the TMA-store epilogue")
+    rm1, rv1 = torch.zeros(n, device=DEV), torch.ones(n, device=DEV)
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    a1 = torch.zeros(1, device=DEV)
+    a2 = torch.zeros(1, device=DEV)
+    z1, st1, af1 = P.gemm_bn_stats(xp, wp, b, gamma, beta, 1e-5, 0.1, rm1, rv1, act_amax=a1, bound_mul=2.0)
+    z2 = P.gemm(xp, wp, m, n, k, bias=b, split_k=1)
+    st2, af2 = P.bn_train_stats(z2, gamma, beta, 1e-5, 0.1, rm2, rv2, act_amax=a2, bound_mul=2.0)
+    assert torch.equal(z1, z2)
+    z64 = z2.double()
+    mean64, var64 = z64.mean(0), z64.var(0, unbiased=False)
+    rstd64 = 1.0 / torch.sqrt(var64 + 1e-5)
+    for st in (st1, st2):
+        assert _err(st[:n], mean64) < 2e-7
+        assert float(((st[n:].double() - rstd64).abs() / rstd64).max()) < 3e-6
+    assert float(((af1 - af2).abs() / (af2.abs() + 1e-3)).max()) < 1e-5
+    assert _err(rm1, rm2.double()) < 1e-6 and _err(rv1, rv2.double()) < 1e-5
+    assert float(a1) == float(a2) > 0
+
+
 def test_gemm_alpha_beta_c(LA):
     a, b = torch.randn(256, 64, device=DEV), torch.randn(64, 128, device=DEV)
     c = torch.randn(256, 128, device=DEV)
