@@ -49,34 +49,34 @@ METRIC = "DeepFM train samples/s (Criteo shape)"
 WORKLOADS = {
     # BASELINE.json configs[1] (default)
     "deepfm_qr_criteo": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "qr", "divider": 5}, use_bn=False,
-                             p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
+                             p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb")),
     # configs[0] shape on the GPU, sparse=True variant (configs/deepfm/base_config_sparse.yaml) with the fused row update
     "deepfm_full_criteo": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla", "sparse": True}, use_bn=True,
                                p_dropout=0.5,
-                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam=True)),
+                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam="rsb")),
     "deepfm_full_criteo_dense_adam": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
-                                          p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
+                                          p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb")),
     "deepfm_full_roofline": dict(model="deepfm", dims=ROOFLINE_DIMS, emb={"name": "vanilla", "sparse": True}, use_bn=True,
                                  p_dropout=0.5,
-                                 opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam=True)),
+                                 opt=dict(learning_rate=1e-3, weight_decay=1e-6, sparse=True, fused_sparse=True, fused_adam="rsb")),
     # BASELINE.json configs[4]: full table row-sharded over the GPUs (NVLink peer gathers + shard atomics),
     # dense Adam on each shard (= configs/deepfm/base_config.yaml semantics), dense MLP grads allreduced
     "deepfm_full_criteo_sharded": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "vanilla"}, use_bn=True,
-                                       p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True), sharded=True),
+                                       p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb"), sharded=True),
     # BASELINE.json configs[3]: pruned-mask embeddings on KDD-shaped data (11 fields, 6 M ids, configs/kdd/deepfm)
     "deepfm_pep_kdd": dict(model="deepfm", dims=KDD_DIMS, emb={"name": "pep", "threshold_type": "feature_dim",
                                                                  "init_threshold": -150,
                                                                  "checkpoint_weight_dir": "/tmp/rsb_pep_ckpt"},
-                           use_bn=True, p_dropout=0.2, opt=dict(learning_rate=1e-3, weight_decay=1e-5, fused_adam=True)),
+                           use_bn=True, p_dropout=0.2, opt=dict(learning_rate=1e-3, weight_decay=1e-5, fused_adam="rsb")),
     "deepfm_optembed_kdd": dict(model="deepfm", dims=KDD_DIMS, emb={"name": "deepfm_optembed"}, use_bn=True,
-                                p_dropout=0.2, opt=dict(learning_rate=3e-5, weight_decay=1e-3, fused_adam=True)),
+                                p_dropout=0.2, opt=dict(learning_rate=3e-5, weight_decay=1e-3, fused_adam="rsb")),
     # deep hash embedding, configs/deepfm/dhe_config-50.yaml (k = 1024 codes generated in-kernel,
     # 4 x 1536 Mish/BatchNorm encoder, reference batch 2048: 79 872 encoder rows per step, ~4 TFLOP per step)
     "deepfm_dhe_criteo": dict(model="deepfm", dims=CRITEO_DIMS, batch=2048,
                               emb={"name": "dhe", "hidden_sizes": [1536, 1536, 1536, 1536], "compute_v2": False},
-                              use_bn=True, p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
+                              use_bn=True, p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb")),
     "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
-                              opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam=True)),
+                              opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb")),
 }
 
 
@@ -372,7 +372,7 @@ def small_batch_leg(args, wl, dims, cfg, dev, R, crit, batch=None):
     model = R.get_ctr_model(dims, cfg).to(dev)
     model.train()
     opt_cfg = dict(wl["opt"])
-    opt_cfg.update(capturable=True, fused_adam=True)
+    opt_cfg.update(capturable=True, fused_adam="rsb")
     opt_cfg.pop("fused_sparse", None)
     if opt_cfg.get("sparse"):
         opt_cfg.pop("sparse")          # the sparse optimizers are not capturable: dense Adam for this leg
@@ -646,6 +646,44 @@ def run_workload(args, name, wl, dev, rank, world, R, primary):
             ms_df = float(t.item())
         res["pipelined_loop"] = {"value": round(world * b / (ms_df * 1e-3), 1), "ms_per_step": round(ms_df, 4),
                                  "note": "data.DevicePrefetcher + data.DeferredScalar (loss read one step late)"}
+        # (3) the caches' record format end to end: [B, F+1] int32 blocks (label in column 0) staged by
+        #     data.RecordStager - one H2D copy + the unpack kernel on a side stream - loss through DeferredScalar
+        from recsys_benchmark_b200.data import RecordStager
+
+        rec_pool = [torch.cat([y.to(torch.int32).unsqueeze(1), x], 1).contiguous().pin_memory() for x, y in pool]
+
+        class RecCycle:
+            n = 0
+
+            def __iter__(self):
+                return (rec_pool[i % len(rec_pool)] for i in range(self.n))
+
+        rloader = RecCycle()
+        stager = RecordStager(rloader, dev)
+
+        def record_run(n):
+            rloader.n = n
+            reader = DeferredScalar(dev)
+            for xd, yd in stager:
+                reader.push(step(xd, yd))
+            return reader.flush()
+
+        record_run(3)
+        sync_all()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        record_run(steps)
+        e_ev.record()
+        sync_all()
+        ms_rs = s_ev.elapsed_time(e_ev) / steps
+        if world > 1:
+            t = torch.tensor([ms_rs], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_rs = float(t.item())
+        res["record_staged_loop"] = {"value": round(world * b / (ms_rs * 1e-3), 1), "ms_per_step": round(ms_rs, 4),
+                                     "h2d_bytes_per_step": int(rec_pool[0].numel() * 4),
+                                     "note": "lmdb record blocks [B, F+1] int32 -> data.RecordStager (pinned copy, one H2D, "
+                                             "rsb_records_unpack) + data.DeferredScalar"}
         res["clocks"] = sampler.stop() if sampler else None
 
     # ---- rooflines -----------------------------------------------------------------------------
@@ -859,7 +897,8 @@ def main_ours(args, wl):
         # the library's pipelined loop is reported beside it
         "e2e": {"value": e2e_ref["value"], "unit": "samples/s", "ms_per_step": e2e_ref["ms_per_step"],
                 "h2d_bytes_per_step": res["h2d_bytes_per_step"], "d2h_bytes_per_step": 4,
-                "loop": e2e_ref["note"], "pipelined_loop": res.get("pipelined_loop")},
+                "loop": e2e_ref["note"], "pipelined_loop": res.get("pipelined_loop"),
+                "record_staged_loop": res.get("record_staged_loop")},
         "reference_trainer_loop": e2e_ref,
         "gpu_launches": res["gpu_launches"],
         "roofline": res["roofline"],

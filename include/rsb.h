@@ -501,6 +501,38 @@ RSB_API int rsb_segment_scatter_shards(const uint32_t* sorted_keys, const uint32
                                        float scale, const int64_t* hot_map, int32_t n_fields, float* hot_grad,
                                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Input staging.  The reference's lmdb caches store one uint32 record per sample,
+ * [label, id_0 .. id_{F-1}] (src/dataset/criteo/criteo_torchfm.py:72-93, avazu_fm.py:78-97, kdd_dataset.py:53-74:
+ * `np.frombuffer(..., dtype=np.uint32)`, `arr[1:]` = ids, `arr[0]` = label).  One pass turns a staged block of records
+ * [B, F+1] (uint32 / int32, device) into what the training step consumes: ids_out [B,F] int32 (per-field ids WITHOUT
+ * offsets, the batch format rsb_lookup_fwd reads with idx_is_i32 = 1) and labels_out [B] fp32 (`labels.float()` of
+ * src/trainer/deepfm.py:52; NULL = skip).  Meant for the copy stream, right behind the H2D copy of the block. */
+RSB_API int rsb_records_unpack(const void* records, int64_t B, int32_t F, int32_t* ids_out, float* labels_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Dense Adam over every parameter of the model in one launch: the non-sparse branch of get_optimizers
+ * (src/models/deepfm.py:155-172, `torch.optim.Adam(model.parameters(), lr, weight_decay)`), arithmetic of
+ * torch/optim/adam.py::_single_tensor_adam (L2 weight decay folded into the gradient, bias corrections formed in
+ * double on the host from `step`, denom = sqrt(v) / sqrt(bc2) + eps).
+ *   h_tensors HOST array of n_tensors <= RSB_ADAM_MAX_TENSORS descriptors of DEVICE buffers (fp32, numel elements each;
+ *             param / exp_avg / exp_avg_sq updated in place).  They are passed to the kernel by value, so the caller
+ *             may rewrite the array right after the call (gradient buffers move from step to step).
+ *   block_map DEVICE int32 [n_blocks, 2]: (tensor index, chunk index); chunk c of a tensor covers elements
+ *             [c * RSB_ADAM_CHUNK, min(numel, (c + 1) * RSB_ADAM_CHUNK)).  Depends on the numels only: built once.
+ *   step      1-based step count shared by these tensors (torch keeps one per parameter; callers group equal counts). */
+#define RSB_ADAM_CHUNK 4096
+#define RSB_ADAM_MAX_TENSORS 64
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} rsb_adam_tensor;
+RSB_API int rsb_adam_dense(const rsb_adam_tensor* h_tensors, int32_t n_tensors, const int32_t* block_map, int64_t n_blocks,
+                           double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,9 +117,20 @@ PROTOTYPES = {
     "rsb_ipc_close_handle": (C.c_int, [_p]),
     "rsb_lookup_fwd_sharded": (C.c_int, [_p, _i32, _p, _i64, _i32, _i32, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, _p,
                                          _p, _p, _p, _p]),
+    "rsb_records_unpack": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
+    "rsb_adam_dense": (C.c_int, [_p, _i32, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p]),
     "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i32, _p, _p, _i64, _p]),
 }
 LOOKUP_AMAX_SLOTS = 1024      # RSB_LOOKUP_AMAX_SLOTS of include/rsb.h
+ADAM_CHUNK = 4096             # RSB_ADAM_CHUNK
+ADAM_MAX_TENSORS = 64         # RSB_ADAM_MAX_TENSORS
+
+
+class AdamTensor(C.Structure):
+    """rsb_adam_tensor of include/rsb.h."""
+
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64)]
 
 _lib: Optional[C.CDLL] = None
 

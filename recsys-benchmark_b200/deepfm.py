@@ -85,7 +85,16 @@ def get_optimizers(model: nn.Module, config: Dict) -> List[torch.optim.Optimizer
     Extra opt-in key `fused_sparse: true` (with `sparse: true`): the embedding table is
     updated by the fused segmented-reduce + SparseAdam / SGD row kernel instead of
     torch.optim.SparseAdam / SGD on a COO gradient (same arithmetic, see optim.py)."""
-    from .optim import FusedSparseAdam, FusedSparseSGD
+    from .optim import FusedDenseAdam, FusedSparseAdam, FusedSparseSGD
+
+    def dense_adam(params):
+        # `fused_adam` (opt-in): "rsb" = the one-launch Adam of this library (optim.FusedDenseAdam), true = torch's
+        # multi-tensor fused Adam; same arithmetic as the default torch.optim.Adam either way
+        if config.get("fused_adam") == "rsb" and not config.get("capturable", False):
+            return FusedDenseAdam(params, lr=config["learning_rate"], weight_decay=config["weight_decay"])
+        return torch.optim.Adam(params, lr=config["learning_rate"], weight_decay=config["weight_decay"],
+                                fused=bool(config.get("fused_adam", False)),
+                                capturable=bool(config.get("capturable", False)))
 
     sparse: bool = config.get("sparse", False)
     optimizer_name: str = config.get("optimizer", "adam")
@@ -101,14 +110,9 @@ def get_optimizers(model: nn.Module, config: Dict) -> List[torch.optim.Optimizer
     if sparse and optimizer_name == "adam":
         emb_opt = (FusedSparseAdam(model.embedding, lr=lr_emb) if fused
                    else torch.optim.SparseAdam(no_decay_param, lr=lr_emb))
-        return [emb_opt,
-                torch.optim.Adam(decay_param, lr=config["learning_rate"], weight_decay=config["weight_decay"],
-                                 fused=bool(config.get("fused_adam", False)))]
+        return [emb_opt, dense_adam(decay_param)]
     if optimizer_name == "adam":
-        # `fused_adam: true` (opt-in) selects torch's single-kernel multi-tensor Adam (same arithmetic)
-        return [torch.optim.Adam(model.parameters(), lr=config["learning_rate"],
-                                 weight_decay=config["weight_decay"], fused=bool(config.get("fused_adam", False)),
-                                 capturable=bool(config.get("capturable", False)))]
+        return [dense_adam(model.parameters())]
     if optimizer_name == "sgd":
         if not sparse:
             return [torch.optim.SGD(model.parameters(), lr=config["learning_rate"],

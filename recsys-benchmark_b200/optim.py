@@ -92,3 +92,98 @@ class FusedSparseSGD(_FusedRowOptimizer):
             skeys, perm = pair if pair is not None else RF.sort_rows(rows, p.shape[0])
             RF.segment_reduce_apply(L.APPLY_SPARSE_SGD, skeys, perm, rg, p.data, lr=group["lr"])
         return None
+
+
+class FusedDenseAdam(torch.optim.Optimizer):
+    """Dense Adam over all its parameters in ONE launch of `rsb_adam_dense` (csrc/staging.cu).
+
+    Arithmetic parity: `torch.optim.Adam(params, lr, betas, eps, weight_decay)` as the reference's `get_optimizers`
+    builds it for the non-sparse configs (src/models/deepfm.py:155-172): L2-style weight decay added to the gradient,
+    a step count per parameter, bias corrections formed in double on the host.  Parameters whose `.grad` is None are
+    skipped like torch does (e.g. DeepFM.linear_layer, which never receives a gradient); parameters with equal step
+    counts share one launch.  Selected with the opt-in config key `fused_adam: "rsb"`."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._maps = {}       # numels -> block map on the device (depends on the sizes only)
+        self._plans = {}      # group index -> launches for the current set of parameters that receive gradients
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._plans.clear()
+
+    def _block_map(self, numels, dev):
+        key = (numels, dev)
+        bm = self._maps.get(key)
+        if bm is None:
+            parts = []
+            for ti, n in enumerate(numels):
+                nchunks = (n + L.ADAM_CHUNK - 1) // L.ADAM_CHUNK
+                parts.append(torch.stack([torch.full((nchunks,), ti, dtype=torch.int32),
+                                          torch.arange(nchunks, dtype=torch.int32)], 1))
+            bm = self._maps[key] = torch.cat(parts).contiguous().to(dev)
+        return bm
+
+    def _plan(self, gi, group, mask):
+        """Launches for the parameters of `group` selected by `mask`: torch counts steps per parameter, so parameters
+        that skipped steps form their own launch; <= RSB_ADAM_MAX_TENSORS descriptors travel with one launch."""
+        by_step = {}
+        for p, has in zip(group["params"], mask):
+            if not has:
+                continue
+            st = self.state[p]
+            if len(st) == 0:
+                if p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("FusedDenseAdam needs contiguous fp32 parameters")
+                L.require_cuda(p)
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            by_step.setdefault(int(st["step"]), []).append(p)
+        launches = []
+        for step in sorted(by_step):
+            plist = by_step[step]
+            for lo in range(0, len(plist), L.ADAM_MAX_TENSORS):
+                part = plist[lo:lo + L.ADAM_MAX_TENSORS]
+                desc = (L.AdamTensor * len(part))()
+                states = []
+                for d, p in zip(desc, part):
+                    st = self.state[p]
+                    d.exp_avg, d.exp_avg_sq, d.numel = st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()
+                    states.append(st)
+                numels = tuple(p.numel() for p in part)
+                launches.append(dict(step=step, params=part, states=states, desc=desc, n=len(part),
+                                     bm=self._block_map(numels, part[0].device), nbytes=28 * sum(numels),
+                                     device=part[0].device))
+        plan = self._plans[gi] = dict(mask=mask, launches=launches)
+        return plan
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.load()
+        for gi, group in enumerate(self.param_groups):
+            mask = tuple(p.grad is not None for p in group["params"])
+            plan = self._plans.get(gi)
+            if plan is None or plan["mask"] != mask:
+                plan = self._plan(gi, group, mask)
+            b1, b2 = group["betas"]
+            for ln in plan["launches"]:
+                dev = ln["device"]
+                for d, p in zip(ln["desc"], ln["params"]):
+                    g = p.grad
+                    if g.dtype is not torch.float32 or g.layout is not torch.strided or g.device != dev or not g.is_contiguous():
+                        raise RuntimeError("FusedDenseAdam needs dense contiguous fp32 gradients on the parameter's device")
+                    d.param = p.data_ptr()
+                    d.grad = g.data_ptr()
+                step = ln["step"] = ln["step"] + 1
+                for st in ln["states"]:
+                    st["step"] = step
+                # p, g, m, v read + p, m, v written
+                RF._call("adam_dense", lib.rsb_adam_dense, ln["desc"], ln["n"], L.ptr(ln["bm"]), int(ln["bm"].shape[0]),
+                         float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), step,
+                         L.stream_ptr(dev), nbytes=ln["nbytes"])
+        return loss
