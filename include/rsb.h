@@ -490,6 +490,29 @@ RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i32, const in
                                    const int64_t* hot_map, float* out_emb, float* out_yfm,
                                    float* out_sum, int64_t* out_rows, int32_t* err_flag, float* amax_slots /* as rsb_lookup_fwd */,
                                    void* stream);
+/* The same over ANY variant ("for PEP `s`, for masks the mask rows; for QR shard emb2, replicate the
+ * <= 20-row emb1").  Sharded like the vanilla table - row r of the MAIN table (the [N, D] weight of VANILLA / PEP / MASK /
+ * OPTEMBED, emb2 of QR, n_rows rows in all) lives in shard r % G at local row r / G - are
+ *   table_shards [G]  the main table, and
+ *   aux_shards   [G]  the per-row aux array: PEP `s` for aux_mode FEATURE [N,1] / FEATURE_DIM [N,D] (fp32), the retrain
+ *                     mask [N,D] (uint8) for MASK; NULL for every other kind / mode.
+ * Replicated on every rank, passed as for rsb_lookup_fwd: table1 (QR emb1), aux for PEP GLOBAL / DIMENSION and the
+ * OPTEMBED thresholds, fc_replicated [n_global], bias.  Arguments not listed here are those of rsb_lookup_fwd. */
+RSB_API int rsb_lookup_fwd_sharded_kind(int32_t kind, const void* idx, int32_t idx_is_i32, const int64_t* offsets, int64_t B,
+                                        int32_t F, int32_t D, const float* const* table_shards, int32_t G, int64_t n_rows,
+                                        int64_t n_global, const float* table1, int64_t divider, const void* aux,
+                                        const void* const* aux_shards, int32_t aux_mode, const int64_t* mask_d_idx,
+                                        const float* fc_replicated, const float* bias, float* out_emb, float* out_yfm,
+                                        float* out_sum, int64_t* out_rows, int32_t* err_flag, float* amax_slots, void* stream);
+/* rsb_lookup_bwd_rows over the same shards (the variants' chain rules re-read the table / threshold / mask rows from
+ * their owners); the per-lookup gradients rg_main / rg_aux stay local and are then pushed to the owners with
+ * rsb_segment_scatter_shards (main table; PEP `s` with its own gradient shards), the replicated parameters' gradients
+ * are reduced locally (rsb_small_table_grad for emb1) and averaged by the caller's allreduce. */
+RSB_API int rsb_lookup_bwd_rows_sharded(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                                        const float* const* table_shards, int32_t G, int64_t n_rows, const float* table1,
+                                        int64_t divider, const void* aux, const void* const* aux_shards, int32_t aux_mode,
+                                        const int64_t* mask_d_idx, const float* emb, const float* S, const float* g_yfm,
+                                        const float* g_deep, float* rg_main, float* rg_aux, void* stream);
 /* Backward: segmented reduction of this rank's sorted lookups (rsb_sort_rows on GLOBAL row
  * ids), each locally-unique row's sum * scale added into the owner's dense shard gradient
  * with one 128-bit red.global.add per 4 floats.  Rows of replicated fields (hot_map [n_fields, 3] as above, the row's

@@ -119,6 +119,10 @@ PROTOTYPES = {
                                          _p, _p, _p, _p]),
     "rsb_records_unpack": (C.c_int, [_p, _i64, _i32, _p, _p, _p]),
     "rsb_adam_dense": (C.c_int, [_p, _i32, _p, _i64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i64, _p]),
+    "rsb_lookup_fwd_sharded_kind": (C.c_int, [_i32, _p, _i32, _p, _i64, _i32, _i32, _p, _i32, _i64, _i64, _p, _i64, _p, _p,
+                                              _i32, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "rsb_lookup_bwd_rows_sharded": (C.c_int, [_i32, _p, _i64, _i32, _i32, _p, _i32, _i64, _p, _i64, _p, _p, _i32, _p, _p,
+                                              _p, _p, _p, _p, _p, _p]),
     "rsb_segment_scatter_shards": (C.c_int, [_p, _p, _i64, _p, _i32, _p, _i32, _f, _p, _i32, _p, _p, _i64, _p]),
 }
 LOOKUP_AMAX_SLOTS = 1024      # RSB_LOOKUP_AMAX_SLOTS of include/rsb.h

@@ -54,6 +54,7 @@ struct LookupArgs {
   float* fc_grad;
   // row-sharded tables (VANILLA only): shard g holds rows r with r % G == g at r / G
   const float* const* table_shards;
+  const void* const* aux_shards;   // per-row aux arrays (PEP s of the feature / feature_dim kinds, retrain masks) sharded like the table
   int G;
   // small fields replicated on every rank instead of sharded: hot_map[f] = (lo, hi, delta) int64 - a row of field f
   // inside [lo, hi) lives at hot_table[row + delta]; hi == lo for a sharded field
@@ -89,6 +90,25 @@ __device__ __forceinline__ void qr_split(const LookupArgs& a, long long row, lon
   }
 }
 
+// Where a row of the MAIN table (and of a per-row aux array) lives: the one local table, or (owner shard, local row).
+struct RowLoc {
+  int owner;
+  long long lrow;
+};
+__device__ __forceinline__ RowLoc locate(const LookupArgs& a, long long row) {
+  RowLoc l;
+  l.owner = 0;
+  l.lrow = row;
+  if (a.table_shards != nullptr) shard_split(a, row, l.owner, l.lrow);
+  return l;
+}
+__device__ __forceinline__ const float* main_row(const LookupArgs& a, RowLoc l) {
+  return (a.table_shards != nullptr ? a.table_shards[l.owner] : a.table) + l.lrow * a.E;   // a peer shard: the load crosses NVLink
+}
+__device__ __forceinline__ const void* aux_base(const LookupArgs& a, RowLoc l) {
+  return a.aux_shards != nullptr ? a.aux_shards[l.owner] : a.aux;
+}
+
 template <int LPR>
 __device__ __forceinline__ float group_sum(float x) {
 #pragma unroll
@@ -96,13 +116,12 @@ __device__ __forceinline__ float group_sum(float x) {
   return x;
 }
 
-__device__ __forceinline__ float pep_s(const LookupArgs& a, long long row, int d) {
-  const float* s = reinterpret_cast<const float*>(a.aux);
+__device__ __forceinline__ float pep_s(const LookupArgs& a, RowLoc l, int d) {
   switch (a.aux_mode) {
-    case RSB_PEP_GLOBAL: return __ldg(s);
-    case RSB_PEP_DIMENSION: return __ldg(s + d);
-    case RSB_PEP_FEATURE: return __ldg(s + row);
-    default: return __ldg(s + row * a.E + d);
+    case RSB_PEP_GLOBAL: return __ldg(reinterpret_cast<const float*>(a.aux));
+    case RSB_PEP_DIMENSION: return __ldg(reinterpret_cast<const float*>(a.aux) + d);
+    case RSB_PEP_FEATURE: return __ldg(reinterpret_cast<const float*>(aux_base(a, l)) + l.lrow);
+    default: return __ldg(reinterpret_cast<const float*>(aux_base(a, l)) + l.lrow * a.E + d);
   }
 }
 
@@ -146,7 +165,7 @@ __device__ __forceinline__ FV<V> load_transformed(const LookupArgs& a, long long
       long long i1, i2;
       qr_split(a, row, i1, i2);
       FV<V> e1 = ldg<V>(a.table1 + i1 * a.E + d0);
-      FV<V> e2 = ldg<V>(a.table + i2 * a.E + d0);
+      FV<V> e2 = ldg<V>(main_row(a, locate(a, i2)) + d0);
 #pragma unroll
       for (int i = 0; i < V; ++i) e.v[i] = (K == RSB_KIND_QR_MULT) ? e1.v[i] * e2.v[i] : e1.v[i] + e2.v[i];
     }
@@ -154,28 +173,30 @@ __device__ __forceinline__ FV<V> load_transformed(const LookupArgs& a, long long
     if (act) {
       long long i1, i2;
       qr_split(a, row, i1, i2);
-      e = (vf < a.F) ? ldg<V>(a.table1 + i1 * a.E + d0) : ldg<V>(a.table + i2 * a.E + d0);
+      e = (vf < a.F) ? ldg<V>(a.table1 + i1 * a.E + d0) : ldg<V>(main_row(a, locate(a, i2)) + d0);
     }
   } else if (K == RSB_KIND_PEP) {
     if (act) {
-      FV<V> w = ldg<V>(a.table + row * a.E + d0);
+      const RowLoc l = locate(a, row);
+      FV<V> w = ldg<V>(main_row(a, l) + d0);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        float sg = sigmoidf_exact(pep_s(a, row, d0 + i));
+        float sg = sigmoidf_exact(pep_s(a, l, d0 + i));
         float m = fmaxf(fabsf(w.v[i]) - sg, 0.0f);
         e.v[i] = (w.v[i] > 0.f) ? m : ((w.v[i] < 0.f) ? -m : 0.0f * m);
       }
     }
   } else if (K == RSB_KIND_MASK) {
     if (act) {
-      FV<V> w = ldg<V>(a.table + row * a.E + d0);
-      const unsigned char* m = reinterpret_cast<const unsigned char*>(a.aux) + row * a.E + d0;
+      const RowLoc l = locate(a, row);
+      FV<V> w = ldg<V>(main_row(a, l) + d0);
+      const unsigned char* m = reinterpret_cast<const unsigned char*>(aux_base(a, l)) + l.lrow * a.E + d0;
 #pragma unroll
       for (int i = 0; i < V; ++i) e.v[i] = w.v[i] * (float)(m[i] != 0);
     }
   } else if (K == RSB_KIND_OPTEMBED) {
     FV<V> w = FV<V>::zero();
-    if (act) w = ldg<V>(a.table + row * a.E + d0);
+    if (act) w = ldg<V>(main_row(a, locate(a, row)) + d0);
     float keep = 1.0f;
     if (a.aux != nullptr) {
       float part = 0.f;
@@ -425,11 +446,11 @@ __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_
             long long i1, i2;
             qr_split(a, rowv[it], i1, i2);
             t1v[it] = ldg<V>(a.table1 + i1 * a.E + d0);
-            t2v[it] = ldg<V>(a.table + i2 * a.E + d0);
+            t2v[it] = ldg<V>(main_row(a, locate(a, i2)) + d0);
 #pragma unroll
             for (int i = 0; i < V; ++i) eev[it].v[i] = __fmul_rn(t1v[it].v[i], t2v[it].v[i]);
           } else if (K == RSB_KIND_PEP || K == RSB_KIND_OPTEMBED) {
-            t1v[it] = ldg<V>(a.table + rowv[it] * a.E + d0);
+            t1v[it] = ldg<V>(main_row(a, locate(a, rowv[it])) + d0);
           }
         }
       }
@@ -451,7 +472,8 @@ __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_
         if (act) st<V>(a.rg_main + p, go);
       } else if (K == RSB_KIND_MASK) {
         if (act) {
-          const unsigned char* m = reinterpret_cast<const unsigned char*>(a.aux) + row * a.E + d0;
+          const RowLoc l = locate(a, row);
+          const unsigned char* m = reinterpret_cast<const unsigned char*>(aux_base(a, l)) + l.lrow * a.E + d0;
           FV<V> r;
 #pragma unroll
           for (int i = 0; i < V; ++i) r.v[i] = go.v[i] * (float)(m[i] != 0);
@@ -501,10 +523,11 @@ __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_
       } else if (K == RSB_KIND_PEP) {
         if (act) {
           const FV<V> w = t1v[it];
+          const RowLoc l = locate(a, row);
           FV<V> rw, rs;
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            float sg = sigmoidf_exact(pep_s(a, row, d0 + i));
+            float sg = sigmoidf_exact(pep_s(a, l, d0 + i));
             bool keep = (fabsf(w.v[i]) - sg) > 0.0f;
             float sgn = (w.v[i] > 0.f) ? 1.f : ((w.v[i] < 0.f) ? -1.f : 0.f);
             rw.v[i] = keep ? go.v[i] * sgn * sgn : 0.f;
@@ -767,11 +790,17 @@ extern "C" RSB_API int rsb_lookup_fwd(int32_t kind, const void* idx, int32_t idx
 
 extern "C" RSB_API int64_t rsb_qr_bwd_fused_workspace_bytes(int64_t B, int32_t D);
 
+struct ShardInfo {
+  const float* const* table_shards;
+  const void* const* aux_shards;
+  int G;
+};
+
 static int bwd_rows_impl(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D, const float* table,
                          int64_t n_rows, const float* table1, int64_t divider, const void* aux, int32_t aux_mode,
                          const int64_t* mask_d_idx, const float* emb, const float* S, const float* g_yfm,
                          const float* g_deep, float* rg_main, float* rg_aux, float* fc_grad, float* table1_grad,
-                         void* workspace, int64_t workspace_bytes, void* stream) {
+                         void* workspace, int64_t workspace_bytes, void* stream, const ShardInfo* shards = nullptr) {
   LookupArgs a = {};
   RowShape sh;
   if (B == 0) return RSB_OK;
@@ -793,6 +822,15 @@ static int bwd_rows_impl(int32_t kind, const int64_t* rows, int64_t B, int32_t F
     // emb2 has n_rows rows, so every id is < n_rows * divider
     long double lim = (long double)n_rows * (long double)divider;
     a.small32 = (lim < 4294967296.0L && divider < (1ll << 32)) ? 1 : 0;
+  }
+  if (shards != nullptr) {
+    // rows of the main table (and of a per-row aux array) are read from the owners' shards
+    a.table = nullptr;
+    a.table_shards = shards->table_shards;
+    a.aux_shards = shards->aux_shards;
+    a.G = shards->G;
+    a.fd_g = make_fastdiv((unsigned long long)shards->G);
+    if (n_rows >= (1ll << 32)) a.small32 = 0;
   }
   a.rows_in = reinterpret_cast<const long long*>(rows);
   a.mask_d = reinterpret_cast<const long long*>(mask_d_idx);
@@ -895,6 +933,79 @@ extern "C" RSB_API int rsb_lookup_fwd_sharded(const void* idx, int32_t idx_is_i3
   a.err = err_flag;
   a.amax_slots = amax_slots;
   return launch_fwd<RSB_KIND_VANILLA>(a, sh, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Any variant over row-sharded tables: the main table (vanilla / PEP / mask / OptEmbed weight, QR emb2) and the per-row
+// aux array (PEP s of the feature / feature_dim kinds, retrain masks) live in G shards; everything small stays local.
+static bool aux_is_per_row(int kind, int aux_mode) {
+  return kind == RSB_KIND_MASK || (kind == RSB_KIND_PEP && (aux_mode == RSB_PEP_FEATURE || aux_mode == RSB_PEP_FEATURE_DIM));
+}
+
+extern "C" RSB_API int rsb_lookup_fwd_sharded_kind(int32_t kind, const void* idx, int32_t idx_is_i32, const int64_t* offsets,
+                                                   int64_t B, int32_t F, int32_t D, const float* const* table_shards,
+                                                   int32_t G, int64_t n_rows, int64_t n_global, const float* table1,
+                                                   int64_t divider, const void* aux, const void* const* aux_shards,
+                                                   int32_t aux_mode, const int64_t* mask_d_idx, const float* fc_replicated,
+                                                   const float* bias, float* out_emb, float* out_yfm, float* out_sum,
+                                                   int64_t* out_rows, int32_t* err_flag, float* amax_slots, void* stream) {
+  LookupArgs a = {};
+  RowShape sh;
+  if (B == 0) return RSB_OK;
+  if (idx == nullptr || out_emb == nullptr || table_shards == nullptr || G < 1 || n_rows <= 0) return RSB_ERR_BAD_ARG;
+  const bool per_row = aux_is_per_row(kind, aux_mode);
+  if (per_row ? (aux_shards == nullptr) : (aux_shards != nullptr)) return RSB_ERR_BAD_ARG;
+  bool al = aligned16(out_emb) && (out_sum == nullptr || aligned16(out_sum));
+  // shard base pointers come from cudaMalloc (256 B aligned); a non-null dummy stands in for the common checks
+  const void* aux_chk = per_row ? reinterpret_cast<const void*>(out_emb) : aux;
+  int rc = fill_common(a, kind, B, F, D, reinterpret_cast<const float*>(out_emb), n_rows, n_global, table1, divider, aux_chk,
+                       aux_mode, sh, al);
+  if (rc) return rc;
+  a.table = nullptr;
+  a.aux = per_row ? nullptr : aux;
+  a.table_shards = table_shards;
+  a.aux_shards = aux_shards;
+  a.G = G;
+  a.fd_g = make_fastdiv((unsigned long long)G);
+  if (n_rows >= (1ll << 32)) a.small32 = 0;
+  a.idx = idx;
+  a.idx_i32 = idx_is_i32;
+  a.offsets = reinterpret_cast<const long long*>(offsets);
+  a.mask_d = reinterpret_cast<const long long*>(mask_d_idx);
+  a.fc = fc_replicated;
+  a.bias = bias;
+  a.out_emb = out_emb;
+  a.out_y = out_yfm;
+  a.out_sum = out_sum;
+  a.out_rows = reinterpret_cast<long long*>(out_rows);
+  a.err = err_flag;
+  a.amax_slots = amax_slots;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  switch (kind) {
+    case RSB_KIND_VANILLA: return launch_fwd<RSB_KIND_VANILLA>(a, sh, s);
+    case RSB_KIND_QR_MULT: return launch_fwd<RSB_KIND_QR_MULT>(a, sh, s);
+    case RSB_KIND_QR_ADD: return launch_fwd<RSB_KIND_QR_ADD>(a, sh, s);
+    case RSB_KIND_QR_CAT: return launch_fwd<RSB_KIND_QR_CAT>(a, sh, s);
+    case RSB_KIND_PEP: return launch_fwd<RSB_KIND_PEP>(a, sh, s);
+    case RSB_KIND_MASK: return launch_fwd<RSB_KIND_MASK>(a, sh, s);
+    default: return launch_fwd<RSB_KIND_OPTEMBED>(a, sh, s);
+  }
+}
+
+extern "C" RSB_API int rsb_lookup_bwd_rows_sharded(int32_t kind, const int64_t* rows, int64_t B, int32_t F, int32_t D,
+                                                   const float* const* table_shards, int32_t G, int64_t n_rows,
+                                                   const float* table1, int64_t divider, const void* aux,
+                                                   const void* const* aux_shards, int32_t aux_mode,
+                                                   const int64_t* mask_d_idx, const float* emb, const float* S,
+                                                   const float* g_yfm, const float* g_deep, float* rg_main, float* rg_aux,
+                                                   void* stream) {
+  if (B == 0) return RSB_OK;
+  if (table_shards == nullptr || G < 1 || rg_main == nullptr) return RSB_ERR_BAD_ARG;
+  const bool per_row = aux_is_per_row(kind, aux_mode);
+  if (per_row ? (aux_shards == nullptr) : (aux_shards != nullptr)) return RSB_ERR_BAD_ARG;
+  ShardInfo si = {table_shards, aux_shards, G};
+  // non-null, 16-byte aligned stand-ins for the pointers the common checks look at
+  return bwd_rows_impl(kind, rows, B, F, D, rg_main, n_rows, table1, divider, per_row ? reinterpret_cast<const void*>(rg_main) : aux,
+                       aux_mode, mask_d_idx, emb, S, g_yfm, g_deep, rg_main, rg_aux, nullptr, nullptr, nullptr, 0, stream, &si);
 }
 
 extern "C" RSB_API int rsb_fc_grad(const int64_t* rows, const float* g_yfm, int64_t B, int32_t F, float* fc_grad,

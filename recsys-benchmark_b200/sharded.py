@@ -28,6 +28,7 @@ from torch import nn
 
 from . import _lib as L
 from . import functional as RF
+from .dcn import DCN_Mix
 from .deepfm import DeepFM
 from .embeddings import IEmbedding
 from .linalg import run_sequential
@@ -138,12 +139,11 @@ def _open(handle: bytes, device) -> int:
 
 
 class ShardGroup:
-    """The per-rank buffers (table shard and its gradient accumulator) and the device-resident pointer
-    tables to every rank's copy."""
+    """The per-rank buffers (table shard and its gradient accumulator; optionally a per-row aux array - PEP thresholds
+    or a retrain mask - and its gradient accumulator) and the device-resident pointer tables to every rank's copy."""
 
-    NAMES = ("table", "table_grad")
-
-    def __init__(self, num_rows: int, dim: int, device: torch.device, group=None):
+    def __init__(self, num_rows: int, dim: int, device: torch.device, group=None, aux_cols: int = 0,
+                 aux_is_mask: bool = False, aux_grad: bool = False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -152,18 +152,35 @@ class ShardGroup:
         self.buf: Dict[str, SharedBuffer] = {
             "table": SharedBuffer((self.n_local, dim), device),
             "table_grad": SharedBuffer((self.n_local, dim), device)}
-        handles = {k: self.buf[k].handle() for k in self.NAMES}
+        self.aux_cols, self.aux_is_mask = int(aux_cols), bool(aux_is_mask)
+        if aux_cols:
+            # a bool mask [n_local, cols] is stored in a float-typed IPC buffer and viewed as bytes
+            shape = ((self.n_local * aux_cols + 3) // 4,) if aux_is_mask else (self.n_local, aux_cols)
+            self.buf["aux"] = SharedBuffer(shape, device)
+            if aux_grad:
+                self.buf["aux_grad"] = SharedBuffer((self.n_local, aux_cols), device)
+        names = tuple(self.buf)
+        handles = {k: self.buf[k].handle() for k in names}
         if self.world > 1:
             gathered: List[Optional[dict]] = [None] * self.world
             dist.all_gather_object(gathered, handles, group=group)
         else:
             gathered = [handles]
         self.ptrs: Dict[str, torch.Tensor] = {}
-        for k in self.NAMES:
+        for k in names:
             addr = [self.buf[k].ptr if g == self.rank else _open(gathered[g][k], device) for g in range(self.world)]
             self.ptrs[k] = torch.tensor(addr, dtype=torch.int64, device=device)
         self._tick = torch.zeros(1, device=device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)   # set by the gather on an out-of-range id
+
+    def aux_tensor(self) -> Optional[torch.Tensor]:
+        """This rank's shard of the per-row aux array: fp32 [n_local, cols], or bool [n_local, cols] for a mask."""
+        if "aux" not in self.buf:
+            return None
+        t = self.buf["aux"].tensor
+        if self.aux_is_mask:
+            return t.view(torch.uint8)[: self.n_local * self.aux_cols].view(self.n_local, self.aux_cols).view(torch.bool)
+        return t
 
     def barrier(self):
         """Stream-ordered cross-rank ordering point (a 1-element allreduce, no host sync)."""
@@ -172,6 +189,8 @@ class ShardGroup:
 
     def zero_grads(self):
         self.buf["table_grad"].tensor.zero_()
+        if "aux_grad" in self.buf:
+            self.buf["aux_grad"].tensor.zero_()
 
 
 # ------------------------------------------------------------------ differentiable op ---
@@ -184,7 +203,9 @@ class _ShardedLookup(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, sg: ShardGroup, x, offsets, fc, bias, use_fm: bool, presort: bool = False, hot=None,
-                hot_map=None, amax_slots=None):
+                hot_map=None, amax_slots=None, table=None):
+        # `table` (this rank's shard parameter) is an input only so that autograd runs the backward when nothing else
+        # requires a gradient (DCN-Mix: no first-order weights, world 1: no replica); its gradient is never returned
         lib = L.load()
         dev = L.require_cuda(x, offsets, bias)
         x = x.contiguous()
@@ -249,7 +270,7 @@ class _ShardedLookup(torch.autograd.Function):
             if ctx.needs_input_grad[3]:
                 g_fc = RF.fc_grad(rows, g_y, b, f, ctx.fc_shape, sg.num_rows, (skeys, perm))
             g_bias = g_y.sum().reshape(1)
-        return None, None, None, g_fc, g_bias, None, None, g_hot, None, None
+        return None, None, None, g_fc, g_bias, None, None, g_hot, None, None, None
 
 
 # ------------------------------------------------------------------ modules ---
@@ -342,7 +363,8 @@ class ShardedVanillaEmbedding(IEmbedding):
         presort = RF.EARLY_SORT and torch.is_grad_enabled()
         hot = getattr(self._emb_module, "hot", None)
         slots = RF.amax_slots_for(x.device)
-        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm, presort, hot, self.hot_map, slots)
+        emb, y, _ = _ShardedLookup.apply(self.shards, x, offsets, fc, bias, use_fm, presort, hot, self.hot_map, slots,
+                                         self._emb_module.weight)
         if slots is not None:
             emb._rsb_amax_slots = slots
         if self.validate:
@@ -350,28 +372,289 @@ class ShardedVanillaEmbedding(IEmbedding):
         return emb, (y if use_fm else None)
 
 
-class ShardedDeepFM(DeepFM):
-    """DeepFM (src/models/deepfm.py:11-105) with the embedding table row-sharded; the first-order weights
-    `fc` (4 B per row), the MLP, `_bias` and BatchNorm are replicated (BatchNorm statistics stay per-rank).
-    Build it after `dist.init_process_group` with the device current and the same seed on every rank."""
+# ------------------------------------------------------------------ any variant, sharded ---
+_PER_ROW_PEP = (L.PEP_FEATURE, L.PEP_FEATURE_DIM)
 
-    def __init__(self, field_dims, num_factor, hidden_sizes, p_dropout=0.1, use_batchnorm=False,
-                 embedding_config=None, group=None):
-        cfg = dict(embedding_config or {"name": "vanilla"})
-        if cfg.get("name", "vanilla") != "vanilla":
-            raise NotImplementedError("row sharding covers the full (vanilla) table; compressed tables are replicated")
-        super().__init__(field_dims, num_factor, hidden_sizes, p_dropout, use_batchnorm, {"name": "vanilla"},
-                         empty_embedding=True)
-        cfg.pop("name", None)
-        cfg.pop("sparse", None)
-        self.embedding = ShardedVanillaEmbedding(field_dims, num_factor, group=group, **cfg)
+
+class _ShardedKindLookup(torch.autograd.Function):
+    """_ShardedLookup for the lightweight variants: the MAIN table (PEP / masked weight, QR emb2) and the
+    per-row aux array (PEP `s` of the feature / feature_dim kinds, retrain masks) are read from the owners' shards inside
+    the gather and inside the backward's chain-rule kernel; their gradients are pre-reduced per unique row and pushed
+    into the owners' accumulators.  Small parameters (QR emb1, PEP global / dimension thresholds, fc, bias) are
+    replicated: their gradients go back to autograd and are averaged with the other replicated gradients.
+    `table` (this rank's shard) is an input only so that autograd runs the backward; its gradient is never returned."""
+
+    @staticmethod
+    def forward(ctx, sg: ShardGroup, spec, x, offsets, table, table1, aux_rep, fc, bias, presort, amax_slots):
+        lib = L.load()
+        dev = L.require_cuda(x, offsets, table, table1, aux_rep, fc, bias)
+        x = x.contiguous()
+        b, f = x.shape
+        e = spec.row_width
+        use_fm = fc is not None
+        emb = torch.empty(b, f, e, dtype=torch.float32, device=dev)
+        y = torch.empty(b, dtype=torch.float32, device=dev) if use_fm else None
+        s = torch.empty(b, e, dtype=torch.float32, device=dev) if use_fm else None
+        rows = torch.empty(b, f, dtype=torch.int64, device=dev)
+        aux_sh = sg.ptrs.get("aux")
+        nbytes = b * (f * x.element_size() + 2 * f * e * 4 + f * 8 + (f * 4 + 4 + e * 4 if use_fm else 0))
+        RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded_kind, spec.kind, L.ptr(x), int(x.dtype == torch.int32),
+                 L.ptr(offsets), b, f, spec.dim, L.ptr(sg.ptrs["table"]), sg.world, sg.num_rows, spec.num_global,
+                 L.ptr(table1), spec.divider, L.ptr(aux_rep), L.ptr(aux_sh), spec.aux_mode, None,
+                 L.ptr(fc) if use_fm else None, L.ptr(bias) if use_fm else None, L.ptr(emb), L.ptr(y), L.ptr(s),
+                 L.ptr(rows), L.ptr(sg.err_flag), L.ptr(amax_slots), L.stream_ptr(dev), nbytes=nbytes)
+        ctx.sg, ctx.spec, ctx.use_fm, ctx.shape = sg, spec, use_fm, (b, f)
+        ctx.fc_shape = tuple(fc.shape) if fc is not None else None
+        ctx.presorted = RF.early_sort(rows, sg.num_rows, key_div=spec.divider if spec.is_qr else 0) if presort else None
+        ctx.save_for_backward(rows, emb, s, table1, aux_rep)
+        ctx.mark_non_differentiable(rows)
+        return emb, (y if use_fm else emb.new_empty(0)), rows
+
+    @staticmethod
+    def backward(ctx, g_emb, g_y, _g_rows):
+        lib = L.load()
+        sg: ShardGroup = ctx.sg
+        spec = ctx.spec
+        rows, emb, s, table1, aux_rep = ctx.saved_tensors
+        b, f = ctx.shape
+        e = spec.row_width
+        n = b * f
+        dev = rows.device
+        kind = spec.kind
+        need = ctx.needs_input_grad   # (sg, spec, x, offsets, table, table1, aux_rep, fc, bias, presort, amax_slots)
+        use_gy = ctx.use_fm and g_y is not None and g_y.numel() == b
+        g_emb = g_emb.contiguous() if g_emb is not None else None
+        g_y = g_y.contiguous() if use_gy else None
+        aux_sh = sg.ptrs.get("aux")
+        per_row_s = kind == L.KIND_PEP and spec.aux_mode in _PER_ROW_PEP and "aux_grad" in sg.buf
+        # ---- stage 1: per-lookup row gradients (the chain rule re-reads the rows from their owners) ----
+        rg_aux = None
+        if kind == L.KIND_VANILLA and not use_gy:
+            rg_main = g_emb.view(n, e)
+        else:
+            rg_main = torch.empty(n, e, dtype=torch.float32, device=dev)
+            if kind == L.KIND_QR_MULT or (kind == L.KIND_PEP and (per_row_s or need[6])):
+                rg_aux = torch.empty(n, e, dtype=torch.float32, device=dev)
+            n_out = 2 if rg_aux is not None else 1
+            nbytes = b * (f * 8 + f * e * 4 * (1 + int(use_gy)) + n_out * f * e * 4 + (e * 4 + 4 if use_gy else 0))
+            RF._call("lookup_bwd_rows", lib.rsb_lookup_bwd_rows_sharded, kind, L.ptr(rows), b, f, spec.dim,
+                     L.ptr(sg.ptrs["table"]), sg.world, sg.num_rows, L.ptr(table1), spec.divider, L.ptr(aux_rep),
+                     L.ptr(aux_sh), spec.aux_mode, None, L.ptr(emb), L.ptr(s), L.ptr(g_y), L.ptr(g_emb), L.ptr(rg_main),
+                     L.ptr(rg_aux), L.stream_ptr(dev), nbytes=nbytes)
+            if kind == L.KIND_QR_ADD:
+                rg_aux = rg_main
+        # ---- stage 2: sorted, pre-reduced per unique row, pushed to the owner ----
+        pre, ctx.presorted = ctx.presorted, None
+        skeys, perm = pre.get() if pre is not None else RF.sort_rows(rows, sg.num_rows,
+                                                                     key_div=spec.divider if spec.is_qr else 0)
+        scale = 1.0 / sg.world
+
+        def push(rg, width, target):
+            ws = RF._ws(lib.rsb_segment_workspace_bytes(n, width), dev)
+            RF._call("segment_scatter_shards", lib.rsb_segment_scatter_shards, L.ptr(skeys), L.ptr(perm), n, L.ptr(rg),
+                     width, L.ptr(sg.ptrs[target]), sg.world, scale, None, f, None, L.ptr(ws), ws.numel(),
+                     L.stream_ptr(dev), nbytes=n * (8 + 4 * width))
+
+        push(rg_main, e, "table_grad")
+        g_table1 = g_aux = g_fc = g_bias = None
+        if per_row_s:
+            if spec.aux_mode == L.PEP_FEATURE_DIM:
+                push(rg_aux, e, "aux_grad")
+            else:
+                push(rg_aux.sum(dim=1, keepdim=True).contiguous(), 1, "aux_grad")
+        elif kind == L.KIND_PEP and need[6]:
+            g_aux = rg_aux.sum(dim=0) if spec.aux_mode == L.PEP_DIMENSION else rg_aux.sum().reshape(1)
+        if spec.is_qr and need[5]:
+            g_table1 = (RF.small_table_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
+                        if (not RF.DETERMINISTIC or table1.shape[0] <= 32) else None)
+            if g_table1 is None:
+                g_table1 = RF.dense_row_grad(rows, rg_aux, table1.shape[0], key_mod=spec.divider)
+        if use_gy:
+            if need[7]:
+                g_fc = RF.fc_grad(rows, g_y, b, f, ctx.fc_shape, spec.num_global, None if spec.is_qr else (skeys, perm))
+            g_bias = g_y.sum().reshape(1)
+        return None, None, None, None, None, g_table1, g_aux, g_fc, g_bias, None, None
+
+
+class ShardedEmbedding(IEmbedding):
+    """Any of the per-row variants with its big arrays row-sharded over the process group:
+    QRHashingEmbedding mult / add (emb2 sharded, the <= divider-row emb1 replicated), PepEmbeeding (emb.weight sharded;
+    `s` sharded for the feature / feature_dim threshold types, replicated for global / dimension), RetrainPepEmbedding
+    and RetrainOptEmbed (weight and bool mask sharded).
+
+    Built FROM the single-device module (`inner`, constructed the usual way - same seed on every rank - so its
+    initialisation, kwargs and methods are the reference's): its big tensors are copied into this rank's IPC shard
+    buffers and the module's own Parameters are re-pointed at them, so parameter names stay the reference's while
+    their leading dimension becomes ceil(rows / G).  `load_full_state_dict` / `full_state_dict` convert from / to the
+    reference's single-device state dict."""
+
+    KINDS = (L.KIND_QR_MULT, L.KIND_QR_ADD, L.KIND_PEP, L.KIND_MASK)
+
+    def __init__(self, inner: IEmbedding, group=None, device=None):
+        super().__init__()
+        spec = inner._spec()
+        if spec.kind not in self.KINDS:
+            raise NotImplementedError("row sharding covers vanilla (ShardedVanillaEmbedding), QR mult / add, PEP and "
+                                      "masked-retrain tables")
+        if inner._mode is not None or spec.sparse_grad or spec.modulus:
+            raise NotImplementedError("sharded tables serve the dense-gradient [B,F,D] lookup only")
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        inner = inner.to(device)
+        table, _table1, aux = inner._tensors()
+        per_row = spec.kind == L.KIND_MASK or (spec.kind == L.KIND_PEP and spec.aux_mode in _PER_ROW_PEP)
+        self.shards = ShardGroup(table.shape[0], table.shape[1], device, group,
+                                 aux_cols=int(aux.shape[1]) if per_row else 0, aux_is_mask=spec.kind == L.KIND_MASK,
+                                 aux_grad=per_row and spec.kind == L.KIND_PEP)
+        self._per_row_aux = per_row
+        self._full_rows = int(table.shape[0])
+        self.inner = inner
+        sg = self.shards
+        with torch.no_grad():
+            sg.buf["table"].tensor.copy_(shard_of_full(table.detach(), sg.rank, sg.world))
+            table.data = sg.buf["table"].tensor
+            if per_row:
+                sg.aux_tensor().copy_(shard_of_full(aux.detach(), sg.rank, sg.world))
+                aux.data = sg.aux_tensor()
+        if hasattr(inner, "_nnz") and torch.is_tensor(inner._nnz):
+            inner._nnz = inner._nnz.to(device)
+
+    # -- what the step protocol of the sharded models needs -------------------------------
+    def shard_params(self) -> List[torch.nn.Parameter]:
+        table, _t1, aux = self.inner._tensors()
+        out = [table]
+        if self._per_row_aux and aux.requires_grad:
+            out.append(aux)
+        return out
+
+    def expose_shard_grads(self, on: bool):
+        table, _t1, aux = self.inner._tensors()
+        table.grad = self.shards.buf["table_grad"].tensor if on else None
+        if "aux_grad" in self.shards.buf:
+            aux.grad = self.shards.buf["aux_grad"].tensor if on else None
+
+    # -- conversion from / to the reference's single-device tensors --------------------------
+    def _names(self):
+        table, _t1, aux = self.inner._tensors()
+        big = {id(table): True}
+        if self._per_row_aux:
+            big[id(aux)] = True
+        return {n: id(p) in big for n, p in list(self.inner.named_parameters()) + list(self.inner.named_buffers())}
+
+    @torch.no_grad()
+    def load_full_state_dict(self, state: Dict[str, torch.Tensor]):
+        sg = self.shards
+        mine = dict(list(self.inner.named_parameters()) + list(self.inner.named_buffers()))
+        for name, sharded in self._names().items():
+            src = state[name].to(sg.device)
+            mine[name].copy_(shard_of_full(src, sg.rank, sg.world) if sharded else src)
+
+    @torch.no_grad()
+    def full_state_dict(self) -> Dict[str, torch.Tensor]:
+        sg = self.shards
+        out = {}
+        mine = dict(list(self.inner.named_parameters()) + list(self.inner.named_buffers()))
+        for name, sharded in self._names().items():
+            t = mine[name].detach()
+            if not sharded:
+                out[name] = t.clone()
+                continue
+            as_bytes = t.dtype == torch.bool
+            local = (t.view(torch.uint8) if as_bytes else t).contiguous()
+            if sg.world == 1:
+                parts = [local]
+            else:
+                parts = [torch.empty_like(local) for _ in range(sg.world)]
+                dist.all_gather(parts, local, group=sg.group)
+            full = full_from_shards(parts, self._full_rows)
+            out[name] = full.view(torch.bool) if as_bytes else full
+        return out
+
+    @torch.no_grad()
+    def get_weight(self):
+        """The effective [N, D] table the reference's get_weight returns (QR: emb1 (x) emb2, PEP: soft-thresholded,
+        retrain: weight * mask) = the lookup of every id; peer rows are read in place, no collective."""
+        ids = torch.arange(self.inner._num_item, device=self.shards.device)
+        return self(ids)
+
+    def get_num_params(self) -> int:
+        return self.inner.get_num_params()
+
+    def lookup(self, x, offsets=None, fc=None, bias=None):
+        inner = self.inner
+        spec = inner._spec()
+        table, table1, aux = inner._tensors()
+        if offsets is not None:
+            offsets = offsets.reshape(-1).long()
+        self._rsb_err_flag = self.shards.err_flag
+        presort = RF.EARLY_SORT and torch.is_grad_enabled() and table.requires_grad
+        slots = RF.amax_slots_for(x.device)
+        aux_rep = None if self._per_row_aux else aux
+        emb, y, _ = _ShardedKindLookup.apply(self.shards, spec, x, offsets, table, table1, aux_rep, fc, bias, presort, slots)
+        if slots is not None:
+            emb._rsb_amax_slots = slots
+        if self.validate:
+            RF.check_index_errors(self)
+        return emb, (y if fc is not None else None)
+
+
+class _ShardedStepMixin:
+    """The two calls a training step adds around the optimizers (see the module docstring)."""
 
     def shard_params(self):
-        return [self.embedding._emb_module.weight]
+        emb = self.embedding
+        return emb.shard_params() if isinstance(emb, ShardedEmbedding) else [emb._emb_module.weight]
 
     def replicated_params(self):
         ids = {id(p) for p in self.shard_params()}
         return [p for p in self.parameters() if id(p) not in ids and p.requires_grad]
+
+    def sync_gradients(self):
+        """Call after backward(): averages the replicated gradients over the ranks (this
+        allreduce is also the point after which every rank's pushes into our shard gradient
+        are complete) and exposes the accumulated shard gradients as `.grad`."""
+        emb = self.embedding
+        sg = emb.shards
+        allreduce_mean_([p.grad for p in self.replicated_params() if p.grad is not None], sg.group)
+        if isinstance(emb, ShardedEmbedding):
+            emb.expose_shard_grads(True)
+        else:
+            emb._emb_module.weight.grad = sg.buf["table_grad"].tensor
+
+    def finish_step(self):
+        """Call after optimizer.step(): re-zero the shard gradient accumulators and order the
+        next step's peer gathers / pushes after every rank's update."""
+        emb = self.embedding
+        sg = emb.shards
+        if isinstance(emb, ShardedEmbedding):
+            emb.expose_shard_grads(False)
+        else:
+            emb._emb_module.weight.grad = None
+        sg.zero_grads()
+        sg.barrier()
+
+
+def _sharded_embedding(embedding_config, field_dims, num_factor, field_name, group):
+    from . import get_embedding
+
+    cfg = dict(embedding_config or {"name": "vanilla"})
+    if cfg.get("name", "vanilla") == "vanilla":
+        cfg.pop("name", None)
+        cfg.pop("sparse", None)
+        return ShardedVanillaEmbedding(field_dims, num_factor, group=group, **cfg)
+    return ShardedEmbedding(get_embedding(cfg, field_dims, num_factor, mode=None, field_name=field_name), group=group)
+
+
+class ShardedDeepFM(_ShardedStepMixin, DeepFM):
+    """DeepFM (src/models/deepfm.py:11-105) with the embedding's big arrays row-sharded (vanilla table, QR emb2, PEP
+    weight + thresholds, retrain weight + mask); the first-order weights `fc` (4 B per row), the MLP, `_bias` and
+    BatchNorm are replicated (BatchNorm statistics stay per-rank).  Build it after `dist.init_process_group` with the
+    device current and the same seed on every rank."""
+
+    def __init__(self, field_dims, num_factor, hidden_sizes, p_dropout=0.1, use_batchnorm=False,
+                 embedding_config=None, group=None):
+        super().__init__(field_dims, num_factor, hidden_sizes, p_dropout, use_batchnorm, {"name": "vanilla"},
+                         empty_embedding=True)
+        self.embedding = _sharded_embedding(embedding_config, field_dims, num_factor, "deepfm", group)
 
     def forward(self, x):
         emb, y_fm = self.embedding.lookup(x, self.offsets, self.fc.weight, self._bias)
@@ -380,29 +663,22 @@ class ShardedDeepFM(DeepFM):
                                                     overlap_first_dw=True, x_amax_slots=RF.amax_slots_of(emb))
         return scores.squeeze(-1)
 
-    # -- step protocol ---------------------------------------------------------------
-    def sync_gradients(self):
-        """Call after backward(): averages the replicated gradients over the ranks (this
-        allreduce is also the point after which every rank's pushes into our shard gradient
-        are complete) and exposes the accumulated shard gradients as `.grad`."""
-        sg = self.embedding.shards
-        allreduce_mean_([p.grad for p in self.replicated_params() if p.grad is not None], sg.group)
-        self.embedding._emb_module.weight.grad = sg.buf["table_grad"].tensor
 
-    def finish_step(self):
-        """Call after optimizer.step(): re-zero the shard gradient accumulators and order the
-        next step's peer gathers / pushes after every rank's update."""
-        sg = self.embedding.shards
-        self.embedding._emb_module.weight.grad = None
-        sg.zero_grads()
-        sg.barrier()
+class ShardedDCNMix(_ShardedStepMixin, DCN_Mix):
+    """DCN_Mix (src/models/dcn.py:11-96) over a row-sharded embedding; cross layers and the MLP tail replicated."""
+
+    def __init__(self, field_dims, num_factor, hidden_sizes, num_layers=3, num_experts=4, rank=64, activation=None,
+                 embedding_config=None, p_dropout=0.5, group=None):
+        super().__init__(field_dims, num_factor, hidden_sizes, num_layers, num_experts, rank, activation,
+                         {"name": "vanilla"}, p_dropout, empty_embedding=True)
+        self.embedding = _sharded_embedding(embedding_config, field_dims, num_factor, "dcn", group)
 
 
 class ShardedStepOptimizers:
     """Facade with the `zero_grad()` / `step()` interface the reference trainer drives
     (src/trainer/deepfm.py:52-60): step() = sync_gradients -> inner optimizers -> finish_step."""
 
-    def __init__(self, model: ShardedDeepFM, optimizers: List[torch.optim.Optimizer]):
+    def __init__(self, model, optimizers: List[torch.optim.Optimizer]):
         self.model, self.optimizers = model, optimizers
 
     def zero_grad(self, set_to_none: bool = True):
