@@ -666,7 +666,7 @@ def _mlp_batchnorm_pattern(mods, x: torch.Tensor):
         h = lin.weight.shape[0]
         if lin.weight.shape[1] != width or h % 8 or width % 4 or not 0.0 <= drop.p < 1.0 or h > 2048 or \
                 lin.weight.dtype != torch.float32 or not lin.weight.is_cuda or bn.num_features != h or \
-                bn.momentum is None or (bn.weight is None) != (bn.bias is None) or \
+                bn.momentum is None or not bn.training or (bn.weight is None) != (bn.bias is None) or \
                 (bn.weight is not None and bn.weight.dtype != torch.float32):
             return None
         width = h

@@ -268,6 +268,11 @@ def _worker2(rank, world, port, ret, model_kind, name, tmp):
         from recsys_benchmark_b200 import sharded as S
 
         full, sh = _models(R, S, name, model_kind, os.path.join(tmp, str(rank)), dev)
+        # BatchNorm statistics are per rank (as with DDP): with batch statistics the global-batch run is not the
+        # reference for a rank's slice, so the DCN tail's BatchNorm layers run on their (fixed) running statistics here
+        for m in list(full.modules()) + list(sh.modules()):
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.eval()
         g = torch.Generator().manual_seed(2)
         x = _ids(128, 2)
         y = torch.randint(0, 2, (128,), generator=g).float()
