@@ -75,6 +75,18 @@ WORKLOADS = {
     "deepfm_dhe_criteo": dict(model="deepfm", dims=CRITEO_DIMS, batch=2048,
                               emb={"name": "dhe", "hidden_sizes": [1536, 1536, 1536, 1536], "compute_v2": False},
                               use_bn=True, p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb")),
+    # SURVEY 8(e) widened: the lightweight variants row-sharded too (PEP weight + per-row thresholds on the KDD shape,
+    # QR emb2 on the Criteo shape, DCN-Mix over a sharded Avazu-shaped table); --workload ... under torchrun
+    "deepfm_pep_kdd_sharded": dict(model="deepfm", dims=KDD_DIMS, emb={"name": "pep", "threshold_type": "feature_dim",
+                                                                         "init_threshold": -150,
+                                                                         "checkpoint_weight_dir": "/tmp/rsb_pep_ckpt"},
+                                   use_bn=True, p_dropout=0.2, opt=dict(learning_rate=1e-3, weight_decay=1e-5, fused_adam="rsb"),
+                                   sharded=True),
+    "deepfm_qr_criteo_sharded": dict(model="deepfm", dims=CRITEO_DIMS, emb={"name": "qr", "divider": 5}, use_bn=True,
+                                     p_dropout=0.5, opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb"),
+                                     sharded=True),
+    "dcnmix_full_avazu_sharded": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
+                                      opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb"), sharded=True),
     "dcnmix_full_avazu": dict(model="dcn_mix", dims=AVAZU_DIMS, emb={"name": "vanilla"}, use_bn=True, p_dropout=0.5,
                               opt=dict(learning_rate=1e-3, weight_decay=1e-6, fused_adam="rsb")),
 }
@@ -511,9 +523,14 @@ def run_workload(args, name, wl, dev, rank, world, R, primary):
     cfg = model_config(wl)
     sharded = bool(wl.get("sharded", False))
     if sharded:
-        from recsys_benchmark_b200.sharded import ShardedDeepFM
+        from recsys_benchmark_b200.sharded import ShardedDCNMix, ShardedDeepFM
 
-        model = ShardedDeepFM(dims, 16, [400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"]).to(dev)
+        if wl["model"] == "dcn_mix":
+            model = ShardedDCNMix(dims, 16, [400, 400, 400], p_dropout=wl["p_dropout"],
+                                  embedding_config=dict(wl["emb"])).to(dev)
+        else:
+            model = ShardedDeepFM(dims, 16, [400, 400, 400], p_dropout=wl["p_dropout"], use_batchnorm=wl["use_bn"],
+                                  embedding_config=dict(wl["emb"])).to(dev)
     else:
         model = R.get_ctr_model(dims, dict(cfg)).to(dev)     # a copy: get_ctr_model pops "name" like the reference
     model.train()
@@ -703,7 +720,9 @@ def run_workload(args, name, wl, dev, rank, world, R, primary):
     n_sharded_fields = None
     if sharded:
         from recsys_benchmark_b200.sharded import HOT_FIELD_ROWS
-        n_sharded_fields = sum(1 for d in dims if d > HOT_FIELD_ROWS) if world > 1 else len(dims)
+        # small fields are replicated for the vanilla table only; the variants shard every field
+        n_sharded_fields = (sum(1 for d in dims if d > HOT_FIELD_ROWS)
+                            if (world > 1 and wl["emb"]["name"] == "vanilla") else len(dims))
     roofs = kernel_rooflines(kern, ksteps, ms_kpass, world, b, len(dims), lambda k: traffic_tab.get(k),
                              n_sharded_fields)
     top = sorted(roofs, key=lambda k: -roofs[k]["share_of_step"])
@@ -813,7 +832,8 @@ def main_ours(args, wl):
 
     sharded = bool(wl.get("sharded", False))
     parity = None
-    if sharded and not args.no_parity_check:
+    if sharded and not args.no_parity_check and wl["model"] == "deepfm" and wl["emb"]["name"] == "vanilla":
+        # (the sharded variants are held to the single-device model by tests/test_gpu_sharded_kinds.py)
         try:
             parity = sharded_parity_check(wl["dims"], dev, rank, world, R)
         except Exception as exc:  # noqa: BLE001 - reported, never hidden

@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest "tests/test_gpu_sharded_kinds.py::test_sharded_variants_world2_match_single_gpu" tests/test_staging_and_adam.py::test_deepfm_trains_the_same_with_the_one_launch_adam -q -m gpu -k "dcn or one_launch" 2>&1 | grep -v "^  \|Warning" | grep -E "Error|error|assert|^E " | head -40 > gpurun_out/t59.log
-cat gpurun_out/t59.log
+( time timeout 900 python bench.py > gpurun_out/b61_n1.json 2> gpurun_out/b61_n1.err ) 2>&1 | tail -3
+python scripts/show_bench.py gpurun_out/b61_n1.json 2>/dev/null
+( time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b61_ref.json 2> gpurun_out/b61_ref.err ) 2>&1 | tail -3
+cat gpurun_out/b61_ref.json | head -c 600
