@@ -233,18 +233,6 @@ constexpr int kIter = 5;   // 8 lane groups x 5 = 40 lookups per batch: the 39 C
 // warp (W = 16) with KI = 3 (12 slots), and the Avazu shape (22 fields) takes W = 32, KI = 3 (24 slots).
 template <int K, int V, int LPR, int W = kWarp, int KI = kIter>
 __global__ void __launch_bounds__(256) lookup_fwd_kernel(LookupArgs a) {
-  // ONE shard (N = 1, nothing replicated): it IS the table - no owner arithmetic, no pointer-table load in front of
-  // every row load (measured: 0.69 -> 0.77 of the copy peak on the headline gather)
-  if (a.G == 1 && a.hot_map == nullptr) {
-    if (a.table_shards != nullptr) {
-      a.table = a.table_shards[0];
-      a.table_shards = nullptr;
-    }
-    if (a.aux_shards != nullptr) {
-      a.aux = a.aux_shards[0];
-      a.aux_shards = nullptr;
-    }
-  }
   constexpr int GPW = W / LPR;          // lane groups per sample
   constexpr int SPW = kWarp / W;        // samples per warp
   static_assert(W >= LPR && GPW >= 1, "a row must fit the lanes of one sample");
@@ -409,17 +397,6 @@ __global__ void __launch_bounds__(1024) partials_reduce_kernel(const float* __re
 // W / KN: lanes per sample and field iterations in flight, as in lookup_fwd_kernel (KN applies to the non-TINY variant)
 template <int K, int V, int LPR, bool TINY = false, int KT = 2, int TR = kTinyRows, int W = kWarp, int KN = kIter>
 __global__ void __launch_bounds__(256, TINY ? (KT >= 2 ? 2 : 4) : 1) lookup_bwd_rows_kernel(LookupArgs a) {
-  // one shard: it is the table (see lookup_fwd_kernel)
-  if (a.G == 1 && a.hot_map == nullptr) {
-    if (a.table_shards != nullptr) {
-      a.table = a.table_shards[0];
-      a.table_shards = nullptr;
-    }
-    if (a.aux_shards != nullptr) {
-      a.aux = a.aux_shards[0];
-      a.aux_shards = nullptr;
-    }
-  }
   constexpr int GPW = W / LPR;
   constexpr int SPW = kWarp / W;
   // the register-accumulating QR variant keeps registers for the emb1 accumulators: shallower batching there

@@ -219,11 +219,19 @@ class _ShardedLookup(torch.autograd.Function):
             raise ValueError(f"replicated small fields need one id column per field: x has {f} columns, the table "
                              f"{hot_map.shape[0]} fields")
         nbytes = b * (f * x.element_size() + 2 * f * d * 4 + f * 8 + (f * 4 + 4 + d * 4 if use_fm else 0))
-        RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded, L.ptr(x), int(x.dtype == torch.int32),
-                 L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(fc) if use_fm else None,
-                 sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(hot) if hot is not None else None,
-                 L.ptr(hot_map) if hot is not None else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
-                 L.ptr(sg.err_flag), L.ptr(amax_slots), L.stream_ptr(dev), nbytes=nbytes)
+        if sg.world == 1 and hot is None:
+            # one shard IS the table: the single-table entry point (no owner arithmetic, no pointer-table load in front
+            # of every row load: 0.69 -> 0.77 of the copy peak on the headline gather)
+            RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd, L.KIND_VANILLA, L.ptr(x), int(x.dtype == torch.int32),
+                     L.ptr(offsets), b, f, d, L.ptr(sg.buf["table"].tensor), sg.num_rows, sg.num_rows, None, 0, None, 0,
+                     None, L.ptr(fc) if use_fm else None, L.ptr(bias) if use_fm else None, L.ptr(emb), L.ptr(y), L.ptr(s),
+                     L.ptr(rows), L.ptr(sg.err_flag), L.ptr(amax_slots), L.stream_ptr(dev), nbytes=nbytes)
+        else:
+            RF._call("lookup_fwd_sharded", lib.rsb_lookup_fwd_sharded, L.ptr(x), int(x.dtype == torch.int32),
+                     L.ptr(offsets), b, f, d, L.ptr(sg.ptrs["table"]), L.ptr(fc) if use_fm else None,
+                     sg.world, sg.num_rows, L.ptr(bias) if use_fm else None, L.ptr(hot) if hot is not None else None,
+                     L.ptr(hot_map) if hot is not None else None, L.ptr(emb), L.ptr(y), L.ptr(s), L.ptr(rows),
+                     L.ptr(sg.err_flag), L.ptr(amax_slots), L.stream_ptr(dev), nbytes=nbytes)
         ctx.sg, ctx.use_fm, ctx.shape = sg, use_fm, (b, f)
         ctx.hot_map = hot_map if hot is not None else None
         ctx.hot_shape = tuple(hot.shape) if hot is not None else None
