@@ -252,6 +252,37 @@ def fc_grad(rows: torch.Tensor, g_y: torch.Tensor, b: int, f: int, shape, n_rows
     return g_fc
 
 
+# The sorted first-order gradient (3 short, latency-bound launches) depends only on the sorted lookups and g_y, like
+# the table's segmented reduction it used to follow: it runs BESIDE that reduction on its own stream and re-joins at
+# the end of the backward pass.  The gradient is handed to autograd while still being written, so this is used only when
+# AccumulateGrad will steal it (fc.grad is None, no hooks - the same rule as linalg._side_dw_safe), never under capture.
+SIDE_FC_GRAD = True
+_FC_STREAMS = {}
+
+
+def fc_grad_beside(fc_param, rows, g_y, b, f, shape, n_rows, sorted_pair):
+    safe = (SIDE_FC_GRAD and sorted_pair is not None and fc_param is not None and fc_param.grad is None
+            and not getattr(fc_param, "_backward_hooks", None) and not getattr(fc_param, "_post_accumulate_grad_hooks", None)
+            and not torch.cuda.is_current_stream_capturing() and _TIMER is None)
+    if not safe:
+        return fc_grad(rows, g_y, b, f, shape, n_rows, sorted_pair)
+    dev = rows.device
+    key = dev.index
+    if key not in _FC_STREAMS:
+        _FC_STREAMS[key] = torch.cuda.Stream(dev)
+    side = _FC_STREAMS[key]
+    main = torch.cuda.current_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        out = fc_grad(rows, g_y, b, f, shape, n_rows, sorted_pair)
+    keep = (rows, g_y, sorted_pair)       # main-pool tensors the side stream reads: alive until the join
+    try:
+        torch.autograd.Variable._execution_engine.queue_callback(lambda keep=keep: main.wait_stream(side))
+    except Exception:  # noqa: BLE001 - not inside an autograd pass: join right away
+        main.wait_stream(side)
+    return out
+
+
 def _err_flag(spec: LookupSpec, device) -> Optional[torch.Tensor]:
     mod = spec.module
     if mod is None:
@@ -310,6 +341,7 @@ class _FusedLookup(torch.autograd.Function):
               L.stream_ptr(dev), nbytes=nbytes)
         ctx.spec = spec
         ctx.fm = fm
+        ctx.fc_param = fc
         ctx.shape = (b, f)
         # the backward's row sort depends only on `rows`: start it now on the side stream (see EARLY_SORT)
         # (grad mode is always off inside Function.forward: the caller decides, see fused_lookup)
@@ -393,7 +425,7 @@ class _FusedLookup(torch.autograd.Function):
         if full_pair is None and not spec.is_qr and need[4] and n > 0 and (deferred is not None or not spec.sparse_grad):
             full_pair = sort_rows(rows, n_rows)
         if want_fc:
-            g_fc = fc_grad(rows, g_y, b, f, fc.shape, fc.shape[0], full_pair)
+            g_fc = fc_grad_beside(ctx.fc_param, rows, g_y, b, f, fc.shape, fc.shape[0], full_pair)
         if spec.is_qr:
             if need[4]:
                 g_table = dense_row_grad(rows, rg_main, n_rows, key_div=spec.divider, sorted_pair=pre)

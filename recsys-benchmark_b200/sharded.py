@@ -236,6 +236,7 @@ class _ShardedLookup(torch.autograd.Function):
         ctx.hot_map = hot_map if hot is not None else None
         ctx.hot_shape = tuple(hot.shape) if hot is not None else None
         ctx.fc_shape = tuple(fc.shape) if fc is not None else None
+        ctx.fc_param = fc
         # the backward's row sort needs only `rows`: queued on the side stream now, consumed at the end of backward
         ctx.presorted = RF.early_sort(rows, sg.num_rows) if presort else None
         ctx.save_for_backward(rows, emb, s)
@@ -264,6 +265,10 @@ class _ShardedLookup(torch.autograd.Function):
         pre, ctx.presorted = ctx.presorted, None
         skeys, perm = pre.get() if pre is not None else RF.sort_rows(rows, sg.num_rows)
         scale = 1.0 / sg.world
+        g_bias = g_fc = None
+        if use_gy and ctx.needs_input_grad[3]:
+            # beside the pushes, on its own stream (same sorted lookups, independent output)
+            g_fc = RF.fc_grad_beside(ctx.fc_param, rows, g_y, b, f, ctx.fc_shape, sg.num_rows, (skeys, perm))
         ws = RF._ws(lib.rsb_segment_workspace_bytes(n, d), dev)
         g_hot = None
         if ctx.hot_map is not None:
@@ -273,10 +278,7 @@ class _ShardedLookup(torch.autograd.Function):
                  L.ptr(sg.ptrs["table_grad"]), sg.world, scale,
                  L.ptr(ctx.hot_map) if g_hot is not None else None, f, L.ptr(g_hot) if g_hot is not None else None,
                  L.ptr(ws), ws.numel(), L.stream_ptr(dev), nbytes=n * (8 + 4 * d))
-        g_bias = g_fc = None
         if use_gy:
-            if ctx.needs_input_grad[3]:
-                g_fc = RF.fc_grad(rows, g_y, b, f, ctx.fc_shape, sg.num_rows, (skeys, perm))
             g_bias = g_y.sum().reshape(1)
         return None, None, None, g_fc, g_bias, None, None, g_hot, None, None, None
 
