@@ -174,7 +174,14 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device=None) -> int:
+    """cudaStream_t of the current stream of `device` as an integer.  Called once per kernel launch: the raw-stream query
+    (one C call) instead of building a torch.cuda.Stream object each time (~5 us of the ~20 us a launch costs the host)."""
+    if _raw_stream is not None and type(device) is torch.device and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
 
 

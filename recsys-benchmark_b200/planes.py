@@ -29,11 +29,12 @@ class Planes:
     """16-bit [P, rows, ld] (ld = cols rounded up to 8; P = 3 bf16 or 2 fp16 planes) + the logical shape of the fp32
     matrix it represents; FP16X2 also carries the device scalar `amax` its scale derives from."""
 
-    __slots__ = ("data", "rows", "cols", "fmt", "amax", "max_exp")
+    __slots__ = ("data", "rows", "cols", "fmt", "amax", "max_exp", "_ops")
 
     def __init__(self, data: torch.Tensor, rows: int, cols: int, fmt: int = BF16X3, amax: Optional[torch.Tensor] = None,
                  max_exp: int = MAX_SCALE_EXP):
         self.data, self.rows, self.cols, self.fmt, self.amax, self.max_exp = data, rows, cols, fmt, amax, max_exp
+        self._ops = None      # operand descriptors already built for this (immutable) set of planes
 
     def format(self) -> L.PlanesFormat:
         return L.PlanesFormat(self.fmt, self.max_exp, self.amax.data_ptr() if self.amax is not None else None)
@@ -55,8 +56,15 @@ class Planes:
         """`cols`: extent of the stored columns the GEMM may read (TMA zero-fills beyond it).  Default: the logical
         width - a forward GEMM must not reduce over the padding / ones column; a weight-gradient GEMM that wants the
         bias gradient passes the padded width + 8."""
-        return L.PlanesOperand(self.data.data_ptr(), self.rows, self.cols if cols is None else cols, self.ld,
-                               self.data.stride(0), int(mn_major), row_step, col_step, self.format())
+        key = (mn_major, row_step, col_step, cols)
+        ops = self._ops
+        if ops is None:
+            ops = self._ops = {}
+        op = ops.get(key)
+        if op is None:
+            op = ops[key] = L.PlanesOperand(self.data.data_ptr(), self.rows, self.cols if cols is None else cols, self.ld,
+                                            self.data.stride(0), int(mn_major), row_step, col_step, self.format())
+        return op
 
     def float(self) -> torch.Tensor:
         """The represented fp32 matrix (sum of the planes, unscaled) - for tests."""
