@@ -133,6 +133,14 @@ class SharedBuffer:
             L.check(L.load().rsb_ipc_get_handle(self.ptr, buf), "ipc_get_handle")
         return buf.raw
 
+    def free(self):
+        """cudaFree the buffer.  `self.tensor` (and every view of it) dangles afterwards: drop them first."""
+        if self.ptr:
+            with torch.cuda.device(self.device):
+                L.check(L.load().rsb_shared_free(self.ptr), "shared_free")
+            self.ptr = 0
+            self.tensor = None
+
 
 def _open(handle: bytes, device) -> int:
     p = C.c_void_p()
@@ -170,8 +178,10 @@ class ShardGroup:
         else:
             gathered = [handles]
         self.ptrs: Dict[str, torch.Tensor] = {}
+        self._peer_maps: List[int] = []          # peer buffers mapped into this process (closed by close())
         for k in names:
             addr = [self.buf[k].ptr if g == self.rank else _open(gathered[g][k], device) for g in range(self.world)]
+            self._peer_maps += [a for g, a in enumerate(addr) if g != self.rank]
             self.ptrs[k] = torch.tensor(addr, dtype=torch.int64, device=device)
         self._tick = torch.zeros(1, device=device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=device)   # set by the gather on an out-of-range id
@@ -189,6 +199,23 @@ class ShardGroup:
         """Stream-ordered cross-rank ordering point (a 1-element allreduce, no host sync)."""
         if self.world > 1:
             dist.all_reduce(self._tick, group=self.group)
+
+    def close(self):
+        """Release the shards: every rank first unmaps its peers' buffers, then (after a barrier: nobody may still
+        have a buffer mapped when its owner frees it) frees its own.  Collective; the module that owned the shards
+        must not be used afterwards (its parameters pointed into the freed buffers).  Not called implicitly - the
+        buffers live as long as the process otherwise, like the reference's parameters."""
+        torch.cuda.synchronize(self.device)
+        lib = L.load()
+        with torch.cuda.device(self.device):
+            for a in self._peer_maps:
+                L.check(lib.rsb_ipc_close_handle(a), "ipc_close_handle")
+        self._peer_maps = []
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for b in self.buf.values():
+            b.free()
+        self.ptrs = {}
 
     def zero_grads(self):
         self.buf["table_grad"].tensor.zero_()

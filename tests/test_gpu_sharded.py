@@ -87,6 +87,29 @@ def test_sharded_world1_matches_unsharded(hot_field_rows):
                  what="fc after 3 steps", atol_scale=5e-5)
 
 
+def test_shard_group_close_returns_the_ipc_buffers():
+    """ShardGroup.close() frees the cudaMalloc'ed shard + gradient buffers (they do not come from torch's allocator)."""
+    import __graft_entry__ as G
+
+    G.build()
+    from recsys_benchmark_b200.sharded import ShardGroup
+
+    dev = torch.device("cuda:0")
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(dev)
+    sg = ShardGroup(1 << 20, 16, dev, aux_cols=16, aux_grad=True)          # 4 buffers x 64 MiB
+    sg.buf["table"].tensor.fill_(1.0)
+    sg.zero_grads()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(dev)
+    assert free0 - free1 >= 4 * (1 << 20) * 16 * 4 - (8 << 20)
+    sg.close()
+    free2, _ = torch.cuda.mem_get_info(dev)
+    assert free2 - free1 >= 4 * (1 << 20) * 16 * 4 - (8 << 20)
+    assert sg.buf["table"].tensor is None and sg.ptrs == {}
+    sg.close()                                                              # idempotent
+
+
 def _worker2(rank, world, port, ret, hot_field_rows):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
