@@ -303,6 +303,18 @@ def check_index_errors(module) -> None:
         raise IndexError("index out of range in self")
 
 
+def _aux_row_bytes(spec: LookupSpec, f: int, mask_d) -> int:
+    """Per-sample bytes of the per-row aux array a lookup reads beside the table rows: PEP thresholds of the
+    feature_dim (a second row) / feature (4 B) kinds, the retrain mask (1 B per element), OptEmbed's mask-D ids."""
+    if spec.kind == L.KIND_PEP:
+        return f * spec.dim * 4 if spec.aux_mode == L.PEP_FEATURE_DIM else (f * 4 if spec.aux_mode == L.PEP_FEATURE else 0)
+    if spec.kind == L.KIND_MASK:
+        return f * spec.dim
+    if spec.kind == L.KIND_OPTEMBED and mask_d is not None:
+        return f * 8
+    return 0
+
+
 # ----------------------------------------------------------------------------
 # the differentiable op
 # ----------------------------------------------------------------------------
@@ -332,7 +344,8 @@ class _FusedLookup(torch.autograd.Function):
         aux_mode = spec.modulus if spec.is_qr else spec.aux_mode
         # algorithmic bytes: ids + rows read + emb written + rows saved (+ fc, y, S)
         r_bytes = vf * e * 4
-        nbytes = b * (f * x.element_size() + 2 * r_bytes + f * 8 + (f * 4 + 4 + e * 4 if fm else 0))
+        nbytes = b * (f * x.element_size() + 2 * r_bytes + _aux_row_bytes(spec, f, mask_d) + f * 8
+                      + (f * 4 + 4 + e * 4 if fm else 0))
         _call("lookup_fwd", lib.rsb_lookup_fwd,
               spec.kind, L.ptr(x), int(x.dtype == torch.int32), L.ptr(offsets), b, f, spec.dim,
               L.ptr(table), table.shape[0], spec.num_global, L.ptr(table1), spec.divider,
@@ -404,7 +417,10 @@ class _FusedLookup(torch.autograd.Function):
             # algorithmic bytes: rows + g_deep + emb (+S, g_y) read, row grads written (+ fc)
             r_bytes = spec.out_fields(f) * e * 4
             n_out = 2 if (rg_aux is not None and kind != L.KIND_OPTEMBED) else 1
-            nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + n_out * f * e * 4 + (e * 4 + 4 + f * 4 if use_gy else 0))
+            # the PEP / OptEmbed chain rules re-read the weight rows (and the per-row thresholds / masks)
+            reread = (r_bytes if kind in (L.KIND_PEP, L.KIND_OPTEMBED) else 0) + _aux_row_bytes(spec, f, mask_d)
+            nbytes = b * (f * 8 + r_bytes * (1 + int(use_gy)) + reread + n_out * f * e * 4
+                          + (e * 4 + 4 + f * 4 if use_gy else 0))
             _call("lookup_bwd_rows", lib.rsb_lookup_bwd_rows,
                   kind, L.ptr(rows), b, f, spec.dim, L.ptr(table), table.shape[0], L.ptr(table1), spec.divider,
                   L.ptr(aux_t), spec.modulus if spec.is_qr else spec.aux_mode, L.ptr(mask_d), L.ptr(emb), L.ptr(s),
