@@ -139,10 +139,10 @@ class FusedDenseAdam(torch.optim.Optimizer):
                 st["step"] = 0
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            by_step.setdefault(int(st["step"]), []).append(p)
+            by_step.setdefault((int(st["step"]), p.device), []).append(p)
         launches = []
-        for step in sorted(by_step):
-            plist = by_step[step]
+        for key in sorted(by_step, key=lambda k: (k[0], str(k[1]))):
+            step, plist = key[0], by_step[key]
             for lo in range(0, len(plist), L.ADAM_MAX_TENSORS):
                 part = plist[lo:lo + L.ADAM_MAX_TENSORS]
                 desc = (L.AdamTensor * len(part))()
