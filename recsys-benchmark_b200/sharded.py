@@ -616,8 +616,57 @@ class ShardedEmbedding(IEmbedding):
         ids = torch.arange(self.inner._num_item, device=self.shards.device)
         return self(ids)
 
+    # -- the plugin's bookkeeping methods, global over the shards (the scripts call them: train_deepfm_pep.py:63,71) ------
+    def __getattr__(self, name):
+        """Attributes of the wrapped module (`sparsity`, `checkpoint_weight_dir`, `threshold_type`, ...) read through."""
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            inner = self.__dict__.get("_modules", {}).get("inner")
+            if inner is None or name == "inner":
+                raise
+            return getattr(inner, name)
+
     def get_num_params(self) -> int:
-        return self.inner.get_num_params()
+        inner, sg = self.inner, self.shards
+        kind = inner._spec().kind
+        if kind == L.KIND_PEP:
+            n = int(inner.get_num_params())              # surviving weights of THIS shard (padding rows are zero)
+            if sg.world > 1:
+                t = torch.tensor([n], dtype=torch.int64, device=sg.device)
+                dist.all_reduce(t, group=sg.group)
+                n = int(t.item())
+            return n
+        if kind == L.KIND_MASK:
+            return inner.get_num_params()                # counted on the full mask when the module was built
+        sharded = self._names()
+        total = 0
+        for name, p in inner.named_parameters():
+            total += self._full_rows * (p.numel() // max(p.shape[0], 1)) if sharded[name] else p.numel()
+        return total
+
+    def get_sparsity(self, get_n_params=False):
+        inner = self.inner
+        if inner._spec().kind != L.KIND_PEP:
+            return inner.get_sparsity(get_n_params)
+        total = self._full_rows * inner._hidden_size
+        n = self.get_num_params()
+        return ((1 - n / total), n) if get_n_params else 1 - n / total
+
+    def train_callback(self):
+        """PepEmbeeding.train_callback (pep_embedding.py:132-147) on the global sparsity: when a target is crossed every
+        rank takes part in gathering the full state (a collective) and rank 0 writes `{sparsity}.pth`."""
+        inner, sg = self.inner, self.shards
+        if inner._spec().kind != L.KIND_PEP:
+            return inner.train_callback()
+        with torch.no_grad():
+            cur = self.get_sparsity()
+        while inner._cur_min_spar_idx < len(inner.sparsity) and inner.sparsity[inner._cur_min_spar_idx] < cur:
+            target = inner.sparsity[inner._cur_min_spar_idx]
+            state = self.full_state_dict()
+            if sg.rank == 0:
+                torch.save(state, os.path.join(inner.checkpoint_weight_dir, f"{target}.pth"))
+            inner._cur_min_spar_idx += 1
 
     def lookup(self, x, offsets=None, fc=None, bias=None):
         inner = self.inner

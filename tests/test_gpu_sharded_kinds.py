@@ -258,6 +258,38 @@ def test_sharded_variants_world1_match_the_single_device_model(env, tmp_path, mo
                      what="get_weight", atol_scale=5e-5)
 
 
+def test_sharded_pep_bookkeeping_matches_the_single_device_plugin(env, tmp_path):
+    """get_sparsity / get_num_params / train_callback (scripts/deepfm/train_deepfm_pep.py:63,71,242) over the shards."""
+    RF, L, S = env
+    import recsys_benchmark_b200 as R
+
+    dev = torch.device(DEV)
+    d1, d2 = str(tmp_path / "a"), str(tmp_path / "b")
+    cfg = {"name": "pep", "threshold_type": "feature_dim", "init_threshold": -4.0, "sparsity": [0.05, 0.5, 0.999]}
+    torch.manual_seed(3)
+    full = R.get_embedding(dict(cfg, checkpoint_weight_dir=d1), DIMS, D, field_name="deepfm").to(dev)
+    torch.manual_seed(3)
+    sh = S.ShardedEmbedding(R.get_embedding(dict(cfg, checkpoint_weight_dir=d2), DIMS, D, field_name="deepfm"))
+    sh.load_full_state_dict(full.state_dict())
+    assert sh.get_num_params() == full.get_num_params()
+    assert sh.get_sparsity() == full.get_sparsity()
+    assert sh.get_sparsity(True) == full.get_sparsity(True)
+    assert sh.sparsity == full.sparsity and sh.threshold_type == "feature_dim"          # read-through attributes
+    full.train_callback()
+    sh.train_callback()
+    assert sh._cur_min_spar_idx == full._cur_min_spar_idx >= 1
+    for target in full.sparsity[: full._cur_min_spar_idx]:
+        a = torch.load(os.path.join(full.checkpoint_weight_dir, f"{target}.pth"), map_location="cpu")
+        b = torch.load(os.path.join(sh.checkpoint_weight_dir, f"{target}.pth"), map_location="cpu")
+        assert a.keys() == b.keys()
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    # QR: parameter count of the FULL tables
+    qr_full = R.get_embedding({"name": "qr", "divider": 5}, DIMS, D).to(dev)
+    qr_sh = S.ShardedEmbedding(R.get_embedding({"name": "qr", "divider": 5}, DIMS, D))
+    assert qr_sh.get_num_params() == qr_full.get_num_params()
+
+
 def _worker2(rank, world, port, ret, model_kind, name, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
