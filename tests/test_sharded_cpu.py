@@ -23,6 +23,23 @@ def test_shard_round_trip(n, world):
     assert torch.equal(S.full_from_shards(shards, n), full)
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_round_trip_of_the_aux_arrays(world):
+    """The per-row aux arrays of the sharded variants: a bool retrain mask [N, D] (moved as bytes) and PEP thresholds of
+    the feature kind [N, 1]; padding rows of a shard are zero / False (a zero weight row survives no threshold)."""
+    g = torch.Generator().manual_seed(world)
+    n = 1373
+    mask = torch.rand(n, 16, generator=g) > 0.4
+    shards = [S.shard_of_full(mask, r, world) for r in range(world)]
+    assert all(s.dtype == torch.bool and s.shape == (S.shard_rows(n, world), 16) for s in shards)
+    for r, s in enumerate(shards):
+        assert not bool(s[len(range(r, n, world)):].any())
+    back = S.full_from_shards([s.view(torch.uint8) for s in shards], n).view(torch.bool)
+    assert torch.equal(back, mask)
+    col = torch.randn(n, 1, generator=g)
+    assert torch.equal(S.full_from_shards([S.shard_of_full(col, r, world) for r in range(world)], n), col)
+
+
 def test_hot_field_map_layout():
     """(lo, hi, delta) per field as the gather / scatter kernels read it: lo = the field offsets (ascending, so the
     scatter can binary-search a row's field), replicated fields packed in field order, hi == lo for sharded fields."""
