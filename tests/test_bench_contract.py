@@ -62,3 +62,10 @@ def test_workload_table_matches_the_survey_shapes():
     assert wl["dcnmix_full_avazu"]["model"] == "dcn_mix" and wl["deepfm_full_criteo_sharded"]["sharded"]
     for name, w in wl.items():
         assert w["model"] in ("deepfm", "dcn_mix") and "opt" in w and "dims" in w, name
+    # the sharded variants of SURVEY 8e keep their unsharded twins' shapes and optimizer recipes
+    for sh, base in (("deepfm_pep_kdd_sharded", "deepfm_pep_kdd"), ("dcnmix_full_avazu_sharded", "dcnmix_full_avazu")):
+        assert wl[sh]["sharded"] and wl[sh]["dims"] == wl[base]["dims"] and wl[sh]["emb"] == wl[base]["emb"]
+        assert wl[sh]["opt"] == wl[base]["opt"]
+    assert wl["deepfm_qr_criteo_sharded"]["emb"] == wl["deepfm_qr_criteo"]["emb"]
+    # every dense optimizer recipe asks for the library's one-launch Adam
+    assert all(w["opt"].get("fused_adam") == "rsb" for w in wl.values())
