@@ -60,6 +60,63 @@ def test_get_optimizers_selects_the_one_launch_adam_only_when_asked():
         opt.step()
 
 
+def test_fused_dense_adam_launch_plan(monkeypatch):
+    """Host side of the one-launch Adam without a GPU (the C call is recorded instead of made): one launch per distinct
+    step count, the (tensor, chunk) map covers every element once, descriptors follow the gradient buffers, the plan is
+    rebuilt when the set of parameters with gradients changes."""
+    import ctypes as C
+
+    from recsys_benchmark_b200 import _lib as L
+    from recsys_benchmark_b200 import functional as RF
+    from recsys_benchmark_b200.optim import FusedDenseAdam
+
+    calls = []
+
+    class FakeLib:
+        @staticmethod
+        def rsb_adam_dense(desc, n, bm_ptr, n_blocks, lr, b1, b2, eps, wd, step, stream):
+            calls.append(dict(desc=[(d.param, d.grad, d.exp_avg, d.exp_avg_sq, d.numel) for d in desc], n=n,
+                              n_blocks=n_blocks, lr=lr, wd=wd, step=step))
+            return 0
+
+    monkeypatch.setattr(L, "load", lambda: FakeLib)
+    monkeypatch.setattr(L, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(L, "stream_ptr", lambda device=None: 0)
+    monkeypatch.setattr(RF, "_TIMER", None)
+    sizes = [1, 4096, 4097, 10000]
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+    opt = FusedDenseAdam(ps, lr=3e-4, weight_decay=1e-5)
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert len(calls) == 1 and calls[0]["n"] == 4 and calls[0]["step"] == 1 and calls[0]["lr"] == 3e-4 and calls[0]["wd"] == 1e-5
+    assert calls[0]["n_blocks"] == sum((n + L.ADAM_CHUNK - 1) // L.ADAM_CHUNK for n in sizes) == 1 + 1 + 2 + 3
+    bm = next(iter(opt._maps.values()))
+    assert bm.dtype == torch.int32 and bm.tolist() == [[0, 0], [1, 0], [2, 0], [2, 1], [3, 0], [3, 1], [3, 2]]
+    for (pp, gp, mp, vp, n), p in zip(calls[0]["desc"], ps):
+        assert (pp, gp, n) == (p.data_ptr(), p.grad.data_ptr(), p.numel())
+        assert mp == opt.state[p]["exp_avg"].data_ptr() and vp == opt.state[p]["exp_avg_sq"].data_ptr()
+    # new gradient buffers: same plan object, descriptors rewritten
+    plan = opt._plans[0]
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    opt.step()
+    assert opt._plans[0] is plan and calls[1]["step"] == 2
+    assert [d[1] for d in calls[1]["desc"]] == [p.grad.data_ptr() for p in ps]
+    # a parameter without a gradient is skipped; when it comes back it has its own step count -> its own launch
+    ps[1].grad = None
+    opt.step()
+    assert calls[2]["n"] == 3 and calls[2]["step"] == 3 and opt.state[ps[1]]["step"] == 2
+    ps[1].grad = torch.ones_like(ps[1])
+    opt.step()
+    assert sorted((c["step"], c["n"]) for c in calls[3:]) == [(3, 1), (4, 3)]
+    assert [opt.state[p]["step"] for p in ps] == [4, 3, 4, 4]
+    # gradients the kernel cannot take are refused
+    ps[3].grad = torch.ones(20000)[::2]              # not contiguous
+    with pytest.raises(RuntimeError, match="contiguous"):
+        opt.step()
+
+
 # ---------------------------------------------------------------- kernels
 @pytest.mark.gpu
 @pytest.mark.parametrize("b,dims", [(1, [4]), (257, [7, 3, 11, 5, 2, 9]), (4099, [1000] * 39), (65536, [50] * 11)])
